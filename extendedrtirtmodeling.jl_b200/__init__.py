@@ -1,0 +1,12 @@
+"""B200-native Gibbs sweep engine behind the API of ExtendedRtIrtModeling.jl (hot path only).
+
+The compute path is the CUDA shared library liberirt_b200.so (csrc/, C ABI in include/erirt_b200.h); this
+package is the host-side mirror of the reference's interface for that path.  No CPU fallback exists."""
+from . import _lib  # noqa: F401
+from .api import (GibbsMlIrt, GibbsRtIrt, GibbsRtIrtCross, GibbsRtIrtCrossQr, GibbsRtIrtLatent,  # noqa: F401
+                  GibbsRtIrtLatentQr, GibbsRtIrtNull, GibbsRtIrtQuantile, sample, sample_bang)
+from .engine import Engine, ErirtError, k_nu_person, k_pg, k_philox, nccl_unique_id  # noqa: F401
+from .simulate import (getBias, getRmse, setDataMlIrt, setDataRtIrt, setDataRtIrtCross, setDataRtIrtLatent,  # noqa: F401
+                       setDataRtIrtNull, setTrueParaMlIrt, setTrueParaRtIrt, setTrueParaRtIrtCross,
+                       setTrueParaRtIrtLatent)
+from .structs import InputData, InputData4R, InputPara, OutputDic, OutputPost, SimConditions, setCond  # noqa: F401

@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's sampler API for the hot path:
+
+    Cond = setCond(nSubj=1000, nItem=15)
+    MCMC = GibbsMlIrt(Cond, Data=Data, truePara=truePara)      # README.md:70
+    sample(MCMC)                                               # sample!(MCMC), README.md:71
+    MCMC.Post.mean.b                                           # README.md:74
+
+Constructors draw the initial values exactly like setInitialValues (src/GibbsRtIrt.pl.jl:84-133,
+src/GibbsRtIrtCross.pl.jl:85-134, src/GibbsRtIrtLatent.pl.jl:78-124) and `sample` replaces the body of the
+sample! methods by calls into the C ABI (include/erirt_b200.h); the Julia package binds the same ABI through
+ccall (julia/ErirtB200.jl).  There is no CPU path here.
+"""
+import numpy as np
+
+from . import _lib
+from .engine import Engine
+from .structs import InputPara, OutputDic, OutputPost
+
+# budget for keeping the full person-level trace on the device/host (bytes); beyond it Post.ra / Post.rt hold
+# the item columns only and person parameters are summarised by running moments
+PERSON_TRACE_BUDGET = 2 << 30
+
+
+class _GibbsBase:
+    model = None            # key of _lib.MODELS
+    default_cov2one = True  # sample! keyword default
+    has_rt = True
+
+    def __init__(self, Cond, Data=None, truePara=None, rng=None):
+        self.Cond, self.Data, self.truePara = Cond, Data, truePara
+        self.Para = None
+        self.Post = OutputPost()
+        self._rng = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+        self.setInitialValues()
+        self.engine = None
+
+    def _base_init(self):
+        C = self.Cond
+        return dict(theta=self._rng.standard_normal(C.nSubj), a=np.ones(C.nItem), b=np.zeros(C.nItem))
+
+    def _rt_init(self):
+        C = self.Cond
+        return dict(zeta=self._rng.standard_normal(C.nSubj), lambda_=np.zeros(C.nItem), sigma2t=np.ones(C.nItem),
+                    Sigma_p=np.eye(2))
+
+
+class GibbsMlIrt(_GibbsBase):
+    """src/GibbsRtIrt.pl.jl:76-106"""
+    model, has_rt = "MlIrt", False
+
+    def setInitialValues(self):
+        self.Para = InputPara(**self._base_init(), beta=self._rng.standard_normal(self.Cond.nFeat + 1))
+
+
+class GibbsRtIrt(_GibbsBase):
+    """src/GibbsRtIrt.pl.jl:114-146"""
+    model = "RtIrt"
+
+    def setInitialValues(self):
+        self.Para = InputPara(**self._base_init(), **self._rt_init(),
+                              beta=self._rng.standard_normal((self.Cond.nFeat + 1, 2)))
+
+
+class GibbsRtIrtNull(_GibbsBase):
+    """src/GibbsRtIrt.pl.jl:151-183"""
+    model = "RtIrtNull"
+
+    def setInitialValues(self):
+        self.Para = InputPara(**self._base_init(), **self._rt_init())
+
+
+class GibbsRtIrtCross(_GibbsBase):
+    """src/GibbsRtIrtCross.pl.jl:77-110"""
+    model = "RtIrtCross"
+
+    def setInitialValues(self):
+        self.Para = InputPara(**self._base_init(), **self._rt_init(), rho=self._rng.standard_normal(self.Cond.nItem))
+
+
+class GibbsRtIrtCrossQr(GibbsRtIrtCross):
+    """src/GibbsRtIrtCross.pl.jl:115-147"""
+    model = "RtIrtCrossQr"
+
+
+class GibbsRtIrtLatent(_GibbsBase):
+    """src/GibbsRtIrtLatent.pl.jl:70-102"""
+    model, default_cov2one = "RtIrtLatent", False
+
+    def setInitialValues(self):
+        self.Para = InputPara(**self._base_init(), **self._rt_init(), beta=self._rng.standard_normal(self.Cond.nFeat + 2))
+
+
+class GibbsRtIrtLatentQr(GibbsRtIrtLatent):
+    """src/GibbsRtIrtLatent.pl.jl:105-137"""
+    model = "RtIrtLatentQr"
+
+
+class GibbsRtIrtQuantile(GibbsRtIrtLatentQr):
+    """README.md:95 names GibbsRtIrtQuantile; the snapshot only ships the LatentQr sampler behind that role
+    (src/ExtendedRtIrtModeling.jl:65 has the export commented out).  Alias, see SURVEY.md 0.2."""
+
+
+def _qr_layout(MCMC):
+    C = MCMC.Cond
+    p = C.nFeat + 1
+    return {"MlIrt": [("beta", p)], "RtIrt": [("beta", 2 * p), ("Sigma_p", 4)], "RtIrtNull": [("beta", 2 * p), ("Sigma_p", 4)],
+            "RtIrtCross": [("rho", C.nItem), ("Sigma_p", 4)], "RtIrtCrossQr": [("rho", C.nItem), ("Sigma_p", 4)],
+            "RtIrtLatent": [("beta", C.nFeat + 2), ("Sigma_p", 4)], "RtIrtLatentQr": [("beta", C.nFeat + 2), ("Sigma_p", 4)]}[MCMC.model]
+
+
+def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", seed=1234, chain=0, device=0,
+           person_trace=None, compat=0, use_graph=True, shard=None, progress=None, chunk=None):
+    """sample!(MCMC; intercept, itemtype, cov2one) for every Gibbs* type.
+
+    Extra keyword-only engine options: dtype ("f64" parity mode / "f32" fast mode), seed, chain (independent
+    chain id), device, person_trace, compat (quirk switches, default = as written in the reference),
+    shard = (rank, world, nccl_unique_id_bytes, subj_offset, n_subj_total) for a person-sharded chain.
+    Returns MCMC (mutated), like the reference."""
+    if itemtype not in ("1pl", "2pl"):
+        raise ValueError("Invalid input: the item type must be '1pl' or '2pl'.")  # src/GibbsRtIrt.pl.jl:212-214
+    C, D, P0 = MCMC.Cond, MCMC.Data, MCMC.Para
+    if cov2one is None:
+        cov2one = MCMC.default_cov2one
+    N, J, F = C.nSubj, C.nItem, C.nFeat
+    n_sweeps = C.nIter * C.nChain
+    if person_trace is None:
+        person_trace = n_sweeps * N * 8 * 3 <= PERSON_TRACE_BUDGET
+    n_total, offset = N, 0
+    if shard is not None:
+        offset, n_total = shard[3], shard[4]
+    eng = Engine(MCMC.model, N, J, F, n_iter=C.nIter, n_chain=C.nChain, n_burnin=C.nBurnin, q_rt=C.qRt,
+                 intercept=intercept, itemtype=itemtype, cov2one=cov2one, dtype=dtype, seed=seed, chain=chain,
+                 compat=compat, person_trace=person_trace, device=device, use_graph=use_graph,
+                 n_subj_total=n_total, subj_offset=offset)
+    MCMC.engine = eng
+    if shard is not None:
+        eng.comm_init(shard[0], shard[1], shard[2])
+    eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if F > 0 else None)
+    init = dict(theta=P0.theta, a=P0.a, b=P0.b)
+    if MCMC.has_rt:
+        init.update(zeta=P0.zeta, lambda_=P0.lambda_, sigma2=P0.sigma2t, Sigma=P0.Sigma_p)
+    if P0.beta.size:
+        init["beta"] = P0.beta
+    if P0.rho.size:
+        init["rho"] = P0.rho
+    eng.set_state(**init)
+    if chunk is None or progress is None:
+        eng.sample(n_sweeps)
+    else:  # the reference wraps the loop in @showprogress; the shim can drive a progress bar by chunks
+        done = 0
+        while done < n_sweeps:
+            step = min(chunk, n_sweeps - done)
+            eng.sample(step)
+            done += step
+            progress(done, n_sweeps)
+    _collect(MCMC, eng, person_trace)
+    return MCMC
+
+
+def _collect(MCMC, eng, person_trace):
+    C = MCMC.Cond
+    N, J = C.nSubj, C.nItem
+    Post = MCMC.Post
+    Post.person_cols = bool(person_trace)
+    c0 = 0 if person_trace else N
+    Post.ra = eng.get_trace("ra", c0, N + 2 * J - c0)
+    Post.rt = eng.get_trace("rt", c0, N + 2 * J - c0) if MCMC.has_rt else None
+    qw_small = sum(n for _, n in _qr_layout(MCMC))
+    qw = eng.trace_width("qr")
+    Post.qr = eng.get_trace("qr", 0, qw if person_trace else qw_small)
+    Post.logLike = eng.get_trace("logLike")
+    nb = C.nBurnin
+    mean = InputPara()
+    sd = InputPara()
+
+    def pm(arr, lo, hi):  # mean over [(nBurnin+1):end, lo:hi, all chains]   src/GibbsRtIrt.pl.jl:327-343
+        return arr[nb:, lo:hi, :].mean(axis=(0, 2))
+
+    o = 0
+    for name, n in _qr_layout(MCMC):
+        setattr(mean, name, pm(Post.qr, o, o + n))
+        o += n
+    ic = N - c0  # first item column inside the returned ra/rt
+    mean.a, mean.b = pm(Post.ra, ic, ic + J), pm(Post.ra, ic + J, ic + 2 * J)
+    if MCMC.has_rt:
+        mean.lambda_, mean.sigma2t = pm(Post.rt, ic, ic + J), pm(Post.rt, ic + J, ic + 2 * J)
+    if person_trace:
+        mean.theta = pm(Post.ra, 0, N)
+        if MCMC.has_rt:
+            mean.zeta = pm(Post.rt, 0, N)
+        if MCMC.model == "RtIrtLatentQr":
+            mean.nu = pm(Post.qr, qw_small, qw_small + N)
+    m, s = eng.get_moments("theta")
+    sd.theta = s
+    if not person_trace:
+        mean.theta = m
+    if MCMC.has_rt:
+        m, s = eng.get_moments("zeta")
+        sd.zeta = s
+        if not person_trace:
+            mean.zeta = m
+    if MCMC.model == "RtIrtLatentQr":
+        m, s = eng.get_moments("nu")
+        sd.nu = s
+        if not person_trace:
+            mean.nu = m
+    Post.mean, Post.sd = mean, sd
+    # the reference leaves the last state in MCMC.Para
+    Para = MCMC.Para
+    Para.theta = eng.get_state("theta")
+    if MCMC.has_rt:
+        Para.zeta = eng.get_state("zeta")
+
+
+sample_bang = sample  # `sample!` is not a Python identifier

@@ -1,0 +1,936 @@
+// erirt_b200.cu -- host orchestration and the C ABI of include/erirt_b200.h.
+//
+// Replaces the body of the seven sample! methods of the reference:
+//   for m in 1:nIter, l in 1:nChain ... end       /root/reference/src/GibbsRtIrt.pl.jl:289-324
+// by   P(0) G(1) [P(k) (allreduce) G(k+1)]_{k=1..}   on one CUDA stream, optionally replayed from a CUDA graph.
+// No CPU fallback exists: every entry point fails with ERIRT_E_CUDA when no sm_100 device is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/erirt_b200.h"
+#include "global.cuh"
+#include "layout.cuh"
+#include "person.cuh"
+
+using namespace erirt;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(ERIRT_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; single-GPU use never touches it)
+// ------------------------------------------------------------------------------------------------
+namespace nccl {
+typedef struct ncclComm* comm_t;
+typedef struct { char internal[128]; } unique_id;
+typedef int (*fn_get_unique_id)(unique_id*);
+typedef int (*fn_comm_init_rank)(comm_t*, int, unique_id, int);
+typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t);
+typedef int (*fn_comm_destroy)(comm_t);
+typedef const char* (*fn_get_error_string)(int);
+static void* lib = nullptr;
+static fn_get_unique_id get_unique_id;
+static fn_comm_init_rank comm_init_rank;
+static fn_all_reduce all_reduce;
+static fn_comm_destroy comm_destroy;
+static fn_get_error_string get_error_string;
+constexpr int kFloat64 = 8, kSum = 0;  // ncclDouble, ncclSum
+static int load() {
+  if (lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+    if (lib) break;
+  }
+  if (!lib)
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+  if (!lib) return fail(ERIRT_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  get_unique_id = (fn_get_unique_id)dlsym(lib, "ncclGetUniqueId");
+  comm_init_rank = (fn_comm_init_rank)dlsym(lib, "ncclCommInitRank");
+  all_reduce = (fn_all_reduce)dlsym(lib, "ncclAllReduce");
+  comm_destroy = (fn_comm_destroy)dlsym(lib, "ncclCommDestroy");
+  get_error_string = (fn_get_error_string)dlsym(lib, "ncclGetErrorString");
+  if (!get_unique_id || !comm_init_rank || !all_reduce || !comm_destroy || !get_error_string) {
+    lib = nullptr;
+    return fail(ERIRT_E_NCCL, "libnccl is missing required symbols");
+  }
+  return 0;
+}
+}  // namespace nccl
+#define NC(expr)                                                                                     \
+  do {                                                                                               \
+    int _e = (expr);                                                                                 \
+    if (_e != 0) return fail(ERIRT_E_NCCL, "%s failed: %s", #expr, nccl::get_error_string(_e));      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// ingest kernels (K8): Julia column-major float64 -> person-major tiles
+// ------------------------------------------------------------------------------------------------
+template <typename OutT, bool AS_U8>
+__global__ void pack_transpose_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int J, OutT* __restrict__ dst, int Jp) {
+  __shared__ double tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int j0 = blockIdx.y * 32;
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int64_t i = i0 + threadIdx.x;
+    const int j = j0 + jj;
+    tile[jj][threadIdx.x] = (i < n && j < J) ? src[i + ld * j] : 0.0;
+  }
+  __syncthreads();
+  for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+    const int64_t i = i0 + ii;
+    const int j = j0 + threadIdx.x;
+    if (i < n && j < J) {
+      const double v = tile[threadIdx.x][ii];
+      if (AS_U8) dst[i * Jp + j] = (OutT)(v > 0.5 ? 1 : 0);
+      else dst[i * Jp + j] = (OutT)v;
+    }
+  }
+}
+template <typename R>
+__global__ void pack_vec_kernel(const double* __restrict__ src, int64_t n, R* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (R)src[i];
+}
+template <typename R>
+__global__ void unpack_vec_kernel(const R* __restrict__ src, int64_t n, double* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+// row-major padded [n][Jp] <-> column-major [n][J] float64 (state get/set of omega)
+template <typename R>
+__global__ void tile_to_colmajor_kernel(const R* __restrict__ src, int64_t n, int J, int Jp, double* __restrict__ dst) {
+  const int64_t total = n * J;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t % n;
+    const int j = (int)(t / n);
+    dst[t] = (double)src[i * Jp + j];
+  }
+}
+template <typename R>
+__global__ void colmajor_to_tile_kernel(const double* __restrict__ src, int64_t n, int J, int Jp, R* __restrict__ dst) {
+  const int64_t total = n * J;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t % n;
+    const int j = (int)(t / n);
+    dst[i * Jp + j] = (R)src[t];
+  }
+}
+// column sums over persons: out[j] = sum_i f(src[i + ld*j]);  mode 0: v, 1: v^2, 2: v - 0.5
+__global__ void colsum_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int mode, double* __restrict__ out) {
+  __shared__ double red[256];
+  const int j = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = src[i + ld * j];
+    acc += mode == 0 ? v : (mode == 1 ? v * v : ((v > 0.5 ? 1.0 : 0.0) - 0.5));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[j] = red[0];
+}
+// XtX[r + pb*c] = sum_i x_ir x_ic, x = [1 X]
+__global__ void xtx_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int pb, double* __restrict__ out) {
+  __shared__ double red[256];
+  const int r = blockIdx.x % pb, c = blockIdx.x / pb;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double xr = r == 0 ? 1.0 : X[i + ld * (r - 1)];
+    const double xc = c == 0 ? 1.0 : X[i + ld * (c - 1)];
+    acc += xr * xc;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[r + pb * c] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct erirt_handle {
+  erirt_config cfg{};
+  Layout L{};
+  SmemPlan S{};
+  int tpp = 1;
+  int sm_count = 0;
+  int grid = 0;
+  size_t rsz = 4;
+  int64_t n_pad = 0;
+  int cap = 0, qw = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // device buffers
+  uint8_t* dY = nullptr;
+  void *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
+  double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
+  double *dTrRa = nullptr, *dTrRt = nullptr, *dTrQr = nullptr, *dTrLl = nullptr;
+  uint32_t* dSweep = nullptr;
+  int* dStatus = nullptr;
+  // consts vector layout (f64): T1[Jp] T2[Jp] K0[Jp] XtX[MAXD*MAXD/4 >= pb*pb] sums[2]
+  int c_T1 = 0, c_T2 = 0, c_K0 = 0, c_XtX = 0, c_sums = 0, c_count = 0;
+  bool data_set = false, consts_final = false, prologue_done = false;
+  int64_t sweeps_done = 0;
+  double last_ms = 0.0;
+  // NCCL
+  nccl::comm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // graph
+  cudaGraphExec_t graph_exec = nullptr;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt) {
+  SmemPlan S{};
+  S.P = CTA_THREADS / tpp;
+  S.tile_real_bytes = (int)(S.P * L.Jp * rsz);
+  S.tile_y_bytes = S.P * L.Jp;
+  S.Dgp = L.Dg + 2;  // + 1/nu column, padded to an odd count to spread banks
+  if ((S.Dgp & 1) == 0) ++S.Dgp;
+  size_t o = 0;
+  S.off_omega = (int)o; o = align_up(o + S.tile_real_bytes, 128);
+  S.off_logt = (int)o; if (has_rt) o = align_up(o + S.tile_real_bytes, 128);
+  S.off_y = (int)o; o = align_up(o + S.tile_y_bytes, 128);
+  S.off_par = (int)o; o = align_up(o + PAR_COUNT * L.Jp * rsz, 128);
+  S.off_u = (int)o; o = align_up(o + (size_t)S.P * S.Dgp * rsz, 128);
+  S.off_acc_item = (int)o; o = align_up(o + 5 * L.Jp * sizeof(double), 128);
+  S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
+  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
+  S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 8, 128);
+  S.total = (int)o;
+  return S;
+}
+
+template <typename R>
+static const void* person_kernel_ptr(int tpp) {
+  switch (tpp) {
+    case 1: return (const void*)person_sweep_kernel<R, 1>;
+    case 2: return (const void*)person_sweep_kernel<R, 2>;
+    case 4: return (const void*)person_sweep_kernel<R, 4>;
+    default: return (const void*)person_sweep_kernel<R, 8>;
+  }
+}
+static const void* person_kernel_for(const erirt_handle* h) {
+  return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float>(h->tpp) : person_kernel_ptr<double>(h->tpp);
+}
+
+static int qr_small_width(int model, int J, int F) {
+  switch (model) {
+    case M_MLIRT: return F + 1;
+    case M_RTIRT: case M_NULL: return 2 * (F + 1) + 4;
+    case M_CROSS: case M_CROSSQR: return J + 4;
+    default: return F + 2 + 4;
+  }
+}
+static int beta_len(int model, int F) {
+  switch (model) {
+    case M_MLIRT: return F + 1;
+    case M_RTIRT: case M_NULL: return 2 * (F + 1);
+    case M_LATENT: case M_LATENTQR: return F + 2;
+    default: return 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int erirt_version(void) { return ERIRT_ABI_VERSION; }
+extern "C" const char* erirt_last_error(void) { return g_err.c_str(); }
+
+static int free_handle(erirt_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->comm && nccl::comm_destroy) nccl::comm_destroy(h->comm);
+  void* ptrs[] = {h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
+                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+template <typename T>
+static int dalloc(T** p, size_t count, bool zero = true) {
+  CU(cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+  if (zero) CU(cudaMemset(*p, 0, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+  return 0;
+}
+
+extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
+  if (!cfg || !out) return fail(ERIRT_E_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != ERIRT_ABI_VERSION) return fail(ERIRT_E_ARG, "abi_version %d != %d", cfg->abi_version, ERIRT_ABI_VERSION);
+  if (cfg->model < 0 || cfg->model > 6) return fail(ERIRT_E_ARG, "unknown model %d", cfg->model);
+  if (cfg->model == ERIRT_RTIRT_CROSS || cfg->model == ERIRT_RTIRT_CROSSQR)
+    return fail(ERIRT_E_UNSUPPORTED, "GibbsRtIrtCross / GibbsRtIrtCrossQr are not built yet (two-kernel pipeline, SURVEY 7.1)");
+  if (cfg->n_subj < 1 || cfg->n_item < 1 || cfg->n_feat < 0) return fail(ERIRT_E_ARG, "bad dimensions");
+  if (cfg->n_subj_total < cfg->n_subj || cfg->subj_offset < 0 || cfg->subj_offset + cfg->n_subj > cfg->n_subj_total)
+    return fail(ERIRT_E_ARG, "inconsistent shard: n_subj=%lld offset=%lld total=%lld", (long long)cfg->n_subj,
+                (long long)cfg->subj_offset, (long long)cfg->n_subj_total);
+  if (cfg->n_subj_total > 0xffffffffLL) return fail(ERIRT_E_ARG, "n_subj_total exceeds the 32-bit person counter");
+  if (2 * (cfg->n_feat + 1) > MAXD) return fail(ERIRT_E_ARG, "n_feat %d too large (2*(n_feat+1) <= %d)", cfg->n_feat, MAXD);
+  if (cfg->n_item > 1000) return fail(ERIRT_E_ARG, "n_item %d too large (<= 1000)", cfg->n_item);
+  if (cfg->n_iter < 1 || cfg->n_chain < 1) return fail(ERIRT_E_ARG, "n_iter and n_chain must be >= 1");
+  if (cfg->dtype != ERIRT_F32 && cfg->dtype != ERIRT_F64) return fail(ERIRT_E_ARG, "dtype must be ERIRT_F32 or ERIRT_F64");
+  if (!(cfg->q_rt > 0.0 && cfg->q_rt < 1.0)) return fail(ERIRT_E_ARG, "qRt must be between 0 and 1");  // Draw.pl.jl:476
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(ERIRT_E_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(ERIRT_E_ARG, "device %d out of range [0,%d)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) return fail(ERIRT_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+  erirt_handle* h = new erirt_handle();
+  h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
+  h->rsz = cfg->dtype == ERIRT_F32 ? 4 : 8;
+  h->L = make_layout(cfg->n_item, cfg->n_feat);
+  const bool has_rt = cfg->model != ERIRT_MLIRT;
+  // threads per person: smallest TPP whose tile fits ~64 KB (>= 3 CTAs/SM)
+  int tpp = 1;
+  const char* env_tpp = getenv("ERIRT_TPP");
+  if (env_tpp) tpp = atoi(env_tpp);
+  else {
+    for (tpp = 1; tpp < 8; tpp *= 2) {
+      SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt);
+      if (s.total <= 72 * 1024) break;
+    }
+  }
+  if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) { delete h; return fail(ERIRT_E_ARG, "ERIRT_TPP must be 1, 2, 4 or 8"); }
+  h->tpp = tpp;
+  h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt);
+  if (h->S.total > 227 * 1024) { delete h; return fail(ERIRT_E_UNSUPPORTED, "n_item %d needs %d bytes of shared memory per CTA", cfg->n_item, h->S.total); }
+  h->n_pad = (int64_t)align_up((size_t)cfg->n_subj, 128);
+  h->cap = cfg->n_iter * cfg->n_chain;
+  h->qw = qr_small_width(cfg->model, cfg->n_item, cfg->n_feat);
+
+#define TRY(x) do { int _r = (x); if (_r) { free_handle(h); return _r; } } while (0)
+  {
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+  }
+  const size_t cells = (size_t)h->n_pad * h->L.Jp;
+  TRY(dalloc(&h->dY, cells));
+  { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dOmega = p; }
+  if (has_rt) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dLogT = p; }
+  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dTheta = p; }
+  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dZeta = p; }
+  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dNu = p; }
+  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz * (cfg->n_feat > 0 ? cfg->n_feat : 1))); h->dX = p; }
+  TRY(dalloc(&h->dMom, (size_t)6 * h->n_pad));
+  if (cfg->person_trace) { char* p; TRY(dalloc(&p, (size_t)h->cap * 3 * h->n_pad * h->rsz)); h->dPtrace = p; }
+  TRY(dalloc(&h->dParams, (size_t)h->L.p_count));
+  TRY(dalloc(&h->dStats, (size_t)h->L.s_count + 2));
+  h->c_T1 = 0; h->c_T2 = h->L.Jp; h->c_K0 = 2 * h->L.Jp; h->c_XtX = 3 * h->L.Jp; h->c_sums = h->c_XtX + MAXD * MAXD / 4;
+  h->c_count = h->c_sums + 2;
+  TRY(dalloc(&h->dConstsLocal, (size_t)h->c_count));
+  TRY(dalloc(&h->dConsts, (size_t)h->c_count));
+  TRY(dalloc(&h->dDerived, 4));
+  TRY(dalloc(&h->dTrRa, (size_t)h->cap * 2 * cfg->n_item));
+  TRY(dalloc(&h->dTrRt, (size_t)h->cap * 2 * cfg->n_item));
+  TRY(dalloc(&h->dTrQr, (size_t)h->cap * h->qw));
+  TRY(dalloc(&h->dTrLl, (size_t)h->cap));
+  TRY(dalloc(&h->dSweep, 1));
+  TRY(dalloc(&h->dStatus, 1));
+#undef TRY
+  // default parameters == setInitialValues (a = 1, sigma2 = 1, Sigma = I; src/GibbsRtIrt.pl.jl:122-133)
+  {
+    std::vector<double> p(h->L.p_count, 0.0);
+    for (int j = 0; j < cfg->n_item; ++j) { p[h->L.p_a + j] = 1.0; p[h->L.p_sigma2 + j] = 1.0; }
+    p[h->L.p_Sigma + 0] = 1.0; p[h->L.p_Sigma + 3] = 1.0;
+    cudaMemcpy(h->dParams, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  // kernel attributes / occupancy-sized persistent grid
+  const void* kfn = person_kernel_for(h);
+  cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->S.total);
+  if (ce != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "cudaFuncSetAttribute(%d bytes): %s", h->S.total, cudaGetErrorString(ce)); }
+  int occ = 0;
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, CTA_THREADS, h->S.total);
+  if (ce != cudaSuccess || occ < 1) { free_handle(h); return fail(ERIRT_E_CUDA, "person kernel does not fit on an SM: %s", cudaGetErrorString(ce)); }
+  const int n_tiles = (int)(h->n_pad / h->S.P);
+  const char* env_occ = getenv("ERIRT_CTAS_PER_SM");
+  if (env_occ && atoi(env_occ) > 0 && atoi(env_occ) < occ) occ = atoi(env_occ);
+  h->grid = std::min(n_tiles, h->sm_count * occ);
+  *out = h;
+  return 0;
+}
+
+extern "C" int erirt_destroy(erirt_handle* h) { return free_handle(h); }
+
+// ------------------------------------------------------------------------------------------------
+// data
+// ------------------------------------------------------------------------------------------------
+template <typename R>
+static void launch_pack(erirt_handle* h, const double* dYc, int64_t ldY, const double* dTc, int64_t ldT, const double* dXc, int64_t ldX) {
+  const int64_t n = h->cfg.n_subj;
+  const int J = h->cfg.n_item, Jp = h->L.Jp, F = h->cfg.n_feat;
+  dim3 blk(32, 8), grd((unsigned)((n + 31) / 32), (unsigned)((J + 31) / 32));
+  pack_transpose_kernel<uint8_t, true><<<grd, blk, 0, h->stream>>>(dYc, ldY, n, J, h->dY, Jp);
+  if (dTc) pack_transpose_kernel<R, false><<<grd, blk, 0, h->stream>>>(dTc, ldT, n, J, (R*)h->dLogT, Jp);
+  for (int f = 0; f < F; ++f)
+    pack_vec_kernel<R><<<256, 256, 0, h->stream>>>(dXc + ldX * f, n, (R*)h->dX + (int64_t)f * h->n_pad);
+}
+
+extern "C" int erirt_set_data_device(erirt_handle* h, const double* dYc, int64_t ldY, const double* dTc, int64_t ldT,
+                                     const double* dXc, int64_t ldX) {
+  if (!h || !dYc) return fail(ERIRT_E_ARG, "null argument");
+  const bool has_rt = h->cfg.model != ERIRT_MLIRT;
+  if (has_rt && !dTc) return fail(ERIRT_E_ARG, "logT is required for this model");
+  if (h->cfg.n_feat > 0 && !dXc) return fail(ERIRT_E_ARG, "X is required when n_feat > 0");
+  CU(cudaSetDevice(h->cfg.device));
+  const int64_t n = h->cfg.n_subj;
+  const int J = h->cfg.n_item, pb = h->cfg.n_feat + 1;
+  if (ldY < n || (has_rt && ldT < n) || (h->cfg.n_feat > 0 && ldX < n)) return fail(ERIRT_E_ARG, "leading dimension smaller than n_subj");
+  const size_t cells = (size_t)h->n_pad * h->L.Jp;
+  CU(cudaMemsetAsync(h->dY, 0, cells, h->stream));
+  if (has_rt) CU(cudaMemsetAsync(h->dLogT, 0, cells * h->rsz, h->stream));
+  if (h->cfg.dtype == ERIRT_F32) launch_pack<float>(h, dYc, ldY, has_rt ? dTc : nullptr, ldT, dXc, ldX);
+  else launch_pack<double>(h, dYc, ldY, has_rt ? dTc : nullptr, ldT, dXc, ldX);
+  // constants: column sums in f64 straight from the caller's float64 data
+  CU(cudaMemsetAsync(h->dConstsLocal, 0, h->c_count * sizeof(double), h->stream));
+  colsum_kernel<<<J, 256, 0, h->stream>>>(dYc, ldY, n, 2, h->dConstsLocal + h->c_K0);
+  if (has_rt) {
+    colsum_kernel<<<J, 256, 0, h->stream>>>(dTc, ldT, n, 0, h->dConstsLocal + h->c_T1);
+    colsum_kernel<<<J, 256, 0, h->stream>>>(dTc, ldT, n, 1, h->dConstsLocal + h->c_T2);
+  }
+  xtx_kernel<<<pb * pb, 256, 0, h->stream>>>(dXc, ldX, n, pb, h->dConstsLocal + h->c_XtX);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  h->data_set = true;
+  h->consts_final = false;
+  return 0;
+}
+
+extern "C" int erirt_set_data(erirt_handle* h, const double* Y, int64_t ldY, const double* logT, int64_t ldT, const double* X, int64_t ldX) {
+  if (!h || !Y) return fail(ERIRT_E_ARG, "null argument");
+  const bool has_rt = h->cfg.model != ERIRT_MLIRT;
+  if (has_rt && !logT) return fail(ERIRT_E_ARG, "logT is required for this model");
+  if (h->cfg.n_feat > 0 && !X) return fail(ERIRT_E_ARG, "X is required when n_feat > 0");
+  CU(cudaSetDevice(h->cfg.device));
+  const int64_t n = h->cfg.n_subj;
+  const int J = h->cfg.n_item, F = h->cfg.n_feat;
+  if (ldY < n || (has_rt && ldT < n) || (F > 0 && ldX < n)) return fail(ERIRT_E_ARG, "leading dimension smaller than n_subj");
+  double *dYc = nullptr, *dTc = nullptr, *dXc = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() { if (dYc) cudaFree(dYc); if (dTc) cudaFree(dTc); if (dXc) cudaFree(dXc); };
+#define CUX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(ERIRT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+  CUX(cudaMalloc((void**)&dYc, (size_t)n * J * sizeof(double)));
+  CUX(cudaMemcpy2DAsync(dYc, n * sizeof(double), Y, ldY * sizeof(double), n * sizeof(double), J, cudaMemcpyHostToDevice, h->stream));
+  if (has_rt) {
+    CUX(cudaMalloc((void**)&dTc, (size_t)n * J * sizeof(double)));
+    CUX(cudaMemcpy2DAsync(dTc, n * sizeof(double), logT, ldT * sizeof(double), n * sizeof(double), J, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (F > 0) {
+    CUX(cudaMalloc((void**)&dXc, (size_t)n * F * sizeof(double)));
+    CUX(cudaMemcpy2DAsync(dXc, n * sizeof(double), X, ldX * sizeof(double), n * sizeof(double), F, cudaMemcpyHostToDevice, h->stream));
+  }
+#undef CUX
+  rc = erirt_set_data_device(h, dYc, n, dTc, n, dXc, n);
+  cleanup();
+  return rc;
+}
+
+// all-reduce the ingest constants over shards once, derive mean/std of logT
+static int finalize_constants(erirt_handle* h) {
+  if (h->consts_final) return 0;
+  CU(cudaMemcpyAsync(h->dConsts, h->dConstsLocal, h->c_count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (h->comm) NC(nccl::all_reduce(h->dConsts, h->dConsts, (size_t)h->c_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
+  std::vector<double> c(h->c_count);
+  CU(cudaMemcpyAsync(c.data(), h->dConsts, h->c_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  double s1 = 0, s2 = 0;
+  for (int j = 0; j < h->cfg.n_item; ++j) { s1 += c[h->c_T1 + j]; s2 += c[h->c_T2 + j]; }
+  const double n = (double)h->cfg.n_subj_total * h->cfg.n_item;
+  double d[4] = {0, 1, 0, 0};
+  if (h->cfg.model != ERIRT_MLIRT) {
+    d[0] = s1 / n;                                   // mean(Data.logT)   Draw.pl.jl:215
+    d[1] = std::sqrt((s2 - s1 * s1 / n) / (n - 1.0));  // std(Data.logT)
+  }
+  CU(cudaMemcpyAsync(h->dDerived, d, sizeof(d), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->consts_final = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+static int person_vec(erirt_handle* h, int field, void** p) {
+  switch (field) {
+    case ERIRT_THETA: *p = h->dTheta; return 0;
+    case ERIRT_ZETA: *p = h->dZeta; return 0;
+    case ERIRT_NU: *p = h->dNu; return 0;
+  }
+  return -1;
+}
+static int param_slot(erirt_handle* h, int field, int* off, int* len) {
+  const Layout& L = h->L;
+  const int J = h->cfg.n_item;
+  switch (field) {
+    case ERIRT_A: *off = L.p_a; *len = J; return 0;
+    case ERIRT_B: *off = L.p_b; *len = J; return 0;
+    case ERIRT_LAMBDA: *off = L.p_lambda; *len = J; return 0;
+    case ERIRT_SIGMA2: *off = L.p_sigma2; *len = J; return 0;
+    case ERIRT_RHO: *off = L.p_rho; *len = J; return 0;
+    case ERIRT_BETA: *off = L.p_beta; *len = beta_len(h->cfg.model, h->cfg.n_feat); return 0;
+    case ERIRT_SIGMA_P: *off = L.p_Sigma; *len = 4; return 0;
+  }
+  return -1;
+}
+
+extern "C" int erirt_set_state(erirt_handle* h, int32_t field, const double* v, int64_t n) {
+  if (!h || !v) return fail(ERIRT_E_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  void* pv;
+  int off, len;
+  if (person_vec(h, field, &pv) == 0) {
+    if (n != h->cfg.n_subj) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)h->cfg.n_subj, (long long)n);
+    double* tmp;
+    CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    cudaMemcpyAsync(tmp, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (h->cfg.dtype == ERIRT_F32) pack_vec_kernel<float><<<256, 256, 0, h->stream>>>(tmp, n, (float*)pv);
+    else pack_vec_kernel<double><<<256, 256, 0, h->stream>>>(tmp, n, (double*)pv);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "set_state: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (field == ERIRT_OMEGA) {
+    const int64_t want = h->cfg.n_subj * h->cfg.n_item;
+    if (n != want) return fail(ERIRT_E_ARG, "omega expects %lld values", (long long)want);
+    double* tmp;
+    CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    cudaMemcpyAsync(tmp, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (h->cfg.dtype == ERIRT_F32) colmajor_to_tile_kernel<float><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (float*)h->dOmega);
+    else colmajor_to_tile_kernel<double><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (double*)h->dOmega);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "set_state: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (param_slot(h, field, &off, &len) == 0) {
+    if (n != len) return fail(ERIRT_E_ARG, "field %d expects %d values, got %lld", field, len, (long long)n);
+    if (len > 0) CU(cudaMemcpy(h->dParams + off, v, len * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  return fail(ERIRT_E_ARG, "unknown field %d", field);
+}
+
+extern "C" int erirt_get_state(erirt_handle* h, int32_t field, double* out, int64_t n) {
+  if (!h || !out) return fail(ERIRT_E_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  void* pv;
+  int off, len;
+  if (person_vec(h, field, &pv) == 0 || field == ERIRT_OMEGA) {
+    const bool om = field == ERIRT_OMEGA;
+    const int64_t want = om ? h->cfg.n_subj * h->cfg.n_item : h->cfg.n_subj;
+    if (n != want) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)want, (long long)n);
+    double* tmp;
+    CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    if (om) {
+      if (h->cfg.dtype == ERIRT_F32) tile_to_colmajor_kernel<float><<<1024, 256, 0, h->stream>>>((const float*)h->dOmega, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
+      else tile_to_colmajor_kernel<double><<<1024, 256, 0, h->stream>>>((const double*)h->dOmega, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
+    } else {
+      if (h->cfg.dtype == ERIRT_F32) unpack_vec_kernel<float><<<256, 256, 0, h->stream>>>((const float*)pv, n, tmp);
+      else unpack_vec_kernel<double><<<256, 256, 0, h->stream>>>((const double*)pv, n, tmp);
+    }
+    cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_state: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (param_slot(h, field, &off, &len) == 0) {
+    if (n != len) return fail(ERIRT_E_ARG, "field %d expects %d values, got %lld", field, len, (long long)n);
+    CU(cudaStreamSynchronize(h->stream));
+    if (len > 0) CU(cudaMemcpy(out, h->dParams + off, len * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  return fail(ERIRT_E_ARG, "unknown field %d", field);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling
+// ------------------------------------------------------------------------------------------------
+template <typename R>
+static PersonArgs<R> make_person_args(erirt_handle* h) {
+  PersonArgs<R> A{};
+  A.Y = h->dY;
+  A.logT = (const R*)h->dLogT;
+  A.omega = (R*)h->dOmega;
+  A.theta = (R*)h->dTheta;
+  A.zeta = (R*)h->dZeta;
+  A.nu = (R*)h->dNu;
+  A.X = (const R*)h->dX;
+  A.mom = h->dMom;
+  A.ptrace = (R*)h->dPtrace;
+  A.params = h->dParams;
+  A.stats = h->dStats;
+  A.sweep_ctr = h->dSweep;
+  A.n_local = h->cfg.n_subj;
+  A.n_pad = h->n_pad;
+  A.person_offset = (uint32_t)h->cfg.subj_offset;
+  A.n_tiles = (int)(h->n_pad / h->S.P);
+  A.L = h->L;
+  A.S = h->S;
+  A.model = h->cfg.model;
+  A.n_chain = h->cfg.n_chain;
+  A.n_burnin = h->cfg.n_burnin;
+  const double q = h->cfg.q_rt;
+  A.k1 = (1.0 - 2.0 * q) / (q * (1.0 - q));
+  A.k2 = 2.0 / (q * (1.0 - q));
+  A.key = make_key(h->cfg.seed, h->cfg.chain);
+  return A;
+}
+
+static GlobalArgs make_global_args(erirt_handle* h) {
+  GlobalArgs A{};
+  A.params = h->dParams;
+  A.stats = h->dStats;
+  A.sweep_ctr = h->dSweep;
+  A.T1 = h->dConsts + h->c_T1;
+  A.T2 = h->dConsts + h->c_T2;
+  A.K0 = h->dConsts + h->c_K0;
+  A.XtX = h->dConsts + h->c_XtX;
+  A.consts = h->dDerived;
+  A.tr_items_ra = h->dTrRa;
+  A.tr_items_rt = h->dTrRt;
+  A.tr_qr = h->dTrQr;
+  A.tr_ll = h->dTrLl;
+  A.status = h->dStatus;
+  A.n_total = h->cfg.n_subj_total;
+  A.cap = h->cap;
+  A.qw = h->qw;
+  A.L = h->L;
+  A.model = h->cfg.model;
+  A.intercept = h->cfg.intercept;
+  A.onepl = h->cfg.itemtype_1pl;
+  A.cov2one = h->cfg.cov2one;
+  A.compat = h->cfg.compat;
+  const double q = h->cfg.q_rt;
+  A.k1 = (1.0 - 2.0 * q) / (q * (1.0 - q));
+  A.k2 = 2.0 / (q * (1.0 - q));
+  A.key = make_key(h->cfg.seed, h->cfg.chain);
+  return A;
+}
+
+// one P(k) [allreduce] G(k+1) step on h->stream
+static int enqueue_step(erirt_handle* h) {
+  if (h->cfg.dtype == ERIRT_F32) {
+    PersonArgs<float> A = make_person_args<float>(h);
+    void* args[] = {&A};
+    CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+  } else {
+    PersonArgs<double> A = make_person_args<double>(h);
+    void* args[] = {&A};
+    CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+  }
+  if (h->comm) NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
+  GlobalArgs G = make_global_args(h);
+  global_draw_kernel<<<1, G_THREADS, 0, h->stream>>>(G);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
+  if (!h) return fail(ERIRT_E_ARG, "null handle");
+  if (!h->data_set) return fail(ERIRT_E_STATE, "erirt_set_data has not been called");
+  if (n_sweeps < 0) return fail(ERIRT_E_ARG, "n_sweeps < 0");
+  if (h->sweeps_done + n_sweeps > h->cap) return fail(ERIRT_E_ARG, "trace capacity exceeded: %lld + %lld > n_iter*n_chain = %d",
+                                                      (long long)h->sweeps_done, (long long)n_sweeps, h->cap);
+  CU(cudaSetDevice(h->cfg.device));
+  int rc = finalize_constants(h);
+  if (rc) return rc;
+  CU(cudaEventRecord(h->ev0, h->stream));
+  if (!h->prologue_done) {
+    CU(cudaMemsetAsync(h->dSweep, 0, sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->dStats, 0, (h->L.s_count + 2) * sizeof(double), h->stream));
+    rc = enqueue_step(h);  // P(0), G(1)
+    if (rc) return rc;
+    h->prologue_done = true;
+  }
+  if (h->cfg.use_graph && n_sweeps > 0) {
+    if (!h->graph_exec) {
+      cudaGraph_t graph;
+      CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_step(h);
+      cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+      if (rc) return rc;
+      if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    for (int64_t t = 0; t < n_sweeps; ++t) CU(cudaGraphLaunch(h->graph_exec, h->stream));
+  } else {
+    for (int64_t t = 0; t < n_sweeps; ++t) {
+      rc = enqueue_step(h);
+      if (rc) return rc;
+    }
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  h->sweeps_done += n_sweeps;
+  int status = 0;
+  CU(cudaMemcpy(&status, h->dStatus, sizeof(int), cudaMemcpyDeviceToHost));
+  if (status != 0) return fail(ERIRT_E_NUMERIC, "a posterior covariance was not positive definite at sweep %d (PosDefException in the reference)", status);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+static int64_t full_width(const erirt_handle* h, int which) {
+  const int64_t N = h->cfg.n_subj, J = h->cfg.n_item;
+  switch (which) {
+    case ERIRT_TRACE_RA: return N + 2 * J;
+    case ERIRT_TRACE_RT: return h->cfg.model == ERIRT_MLIRT ? 0 : N + 2 * J;
+    case ERIRT_TRACE_QR: return h->qw + (h->cfg.model == ERIRT_RTIRT_LATENTQR ? N : 0);
+    case ERIRT_TRACE_LOGLIKE: return 1;
+  }
+  return -1;
+}
+extern "C" int64_t erirt_trace_width(erirt_handle* h, int32_t which) { return h ? full_width(h, which) : -1; }
+
+extern "C" int erirt_get_trace(erirt_handle* h, int32_t which, int64_t first_col, int64_t n_cols, double* out) {
+  if (!h || !out) return fail(ERIRT_E_ARG, "null argument");
+  const int64_t W = full_width(h, which);
+  if (W <= 0) return fail(ERIRT_E_ARG, "trace %d does not exist for this model", which);
+  if (first_col < 0 || n_cols < 0 || first_col + n_cols > W) return fail(ERIRT_E_ARG, "columns [%lld,%lld) outside [0,%lld)", (long long)first_col, (long long)(first_col + n_cols), (long long)W);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const int64_t N = h->cfg.n_subj, J = h->cfg.n_item, nIter = h->cfg.n_iter, nChain = h->cfg.n_chain;
+  const int64_t done = h->sweeps_done;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (int64_t t = 0; t < nIter * n_cols * nChain; ++t) out[t] = nan;
+  // column ranges: person block [0,N) for ra/rt, trailing nu block for LatentQr qr
+  auto put = [&](int64_t s, int64_t col, double v) {  // sweep s (0-based), absolute column
+    const int64_t c = col - first_col;
+    if (c < 0 || c >= n_cols) return;
+    const int64_t m = s / nChain, l = s % nChain;
+    out[m + nIter * (c + n_cols * l)] = v;
+  };
+  int pfield = -1;
+  int64_t pcol0 = 0, small0 = 0;
+  const double* dsmall = nullptr;
+  int64_t small_w = 0;
+  if (which == ERIRT_TRACE_RA) { pfield = 0; pcol0 = 0; small0 = N; dsmall = h->dTrRa; small_w = 2 * J; }
+  else if (which == ERIRT_TRACE_RT) { pfield = 1; pcol0 = 0; small0 = N; dsmall = h->dTrRt; small_w = 2 * J; }
+  else if (which == ERIRT_TRACE_QR) { small0 = 0; dsmall = h->dTrQr; small_w = h->qw; if (h->cfg.model == ERIRT_RTIRT_LATENTQR) { pfield = 2; pcol0 = h->qw; } }
+  else { small0 = 0; dsmall = h->dTrLl; small_w = 1; }
+  // small (item / structural) columns
+  if (first_col < small0 + small_w && first_col + n_cols > small0 && done > 0) {
+    std::vector<double> buf((size_t)done * small_w);
+    CU(cudaMemcpy(buf.data(), dsmall, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < done; ++s)
+      for (int64_t c = 0; c < small_w; ++c) put(s, small0 + c, buf[(size_t)s * small_w + c]);
+  }
+  // person columns
+  if (pfield >= 0 && first_col < pcol0 + N && first_col + n_cols > pcol0 && done > 0) {
+    if (!h->dPtrace) return fail(ERIRT_E_STATE, "person columns requested but person_trace = 0 (use erirt_get_moments)");
+    std::vector<double> row(N);
+    const size_t rb = (size_t)h->n_pad * h->rsz;
+    std::vector<char> raw(rb);
+    for (int64_t s = 0; s < done; ++s) {
+      const char* src = (const char*)h->dPtrace + ((size_t)s * 3 + pfield) * rb;
+      CU(cudaMemcpy(raw.data(), src, rb, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < N; ++i) {
+        const double v = h->rsz == 4 ? (double)((const float*)raw.data())[i] : ((const double*)raw.data())[i];
+        put(s, pcol0 + i, v);
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n) {
+  if (!h || !mean) return fail(ERIRT_E_ARG, "null argument");
+  int slot = field == ERIRT_THETA ? 0 : (field == ERIRT_ZETA ? 1 : (field == ERIRT_NU ? 2 : -1));
+  if (slot < 0) return fail(ERIRT_E_ARG, "moments exist for THETA, ZETA and NU only");
+  if (n != h->cfg.n_subj) return fail(ERIRT_E_ARG, "expects n_subj values");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const int64_t nChain = h->cfg.n_chain;
+  const int64_t first = (int64_t)h->cfg.n_burnin * nChain;  // sweeps with m > n_burnin
+  const int64_t cnt = h->sweeps_done > first ? h->sweeps_done - first : 0;
+  std::vector<double> s1(n), s2(n);
+  CU(cudaMemcpy(s1.data(), h->dMom + (size_t)(2 * slot) * h->n_pad, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(s2.data(), h->dMom + (size_t)(2 * slot + 1) * h->n_pad, n * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) {
+    if (cnt == 0) { mean[i] = std::numeric_limits<double>::quiet_NaN(); if (sd) sd[i] = mean[i]; continue; }
+    const double m = s1[i] / cnt;
+    mean[i] = m;
+    if (sd) sd[i] = cnt > 1 ? std::sqrt(std::max(0.0, (s2[i] - cnt * m * m) / (cnt - 1))) : 0.0;
+  }
+  return 0;
+}
+
+extern "C" int erirt_loglik_current(erirt_handle*, double*) { return fail(ERIRT_E_UNSUPPORTED, "erirt_loglik_current is not part of round 1"); }
+
+extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {
+  if (!h || !out) return fail(ERIRT_E_ARG, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  memset(out, 0, sizeof(*out));
+  out->sweeps_done = h->sweeps_done;
+  out->last_sample_ms = h->last_ms;
+  out->launches_per_sweep = 2;
+  out->sm_count = h->sm_count;
+  const int64_t N = h->cfg.n_subj, J = h->cfg.n_item, F = h->cfg.n_feat;
+  const int64_t r = (int64_t)h->rsz;
+  const bool has_rt = h->cfg.model != ERIRT_MLIRT;
+  int64_t per_cell = 1 + 2 * r + (has_rt ? r : 0);
+  int nv = has_rt ? 2 : 1;
+  if (h->cfg.model == ERIRT_RTIRT_LATENTQR) nv = 3;
+  out->bytes_per_sweep = N * J * per_cell + N * r * (2 * nv + F);
+  double d[2] = {0, 0};
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(d, h->dStats + h->L.s_count, sizeof(d), cudaMemcpyDeviceToHost));
+  out->pg_deferred_frac = d[1] > 0 ? d[0] / d[1] : 0.0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL plumbing
+// ------------------------------------------------------------------------------------------------
+extern "C" int erirt_nccl_unique_id(void* id128) {
+  if (!id128) return fail(ERIRT_E_ARG, "null argument");
+  int rc = nccl::load();
+  if (rc) return rc;
+  nccl::unique_id id;
+  NC(nccl::get_unique_id(&id));
+  memcpy(id128, &id, 128);
+  return 0;
+}
+extern "C" int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, const void* id128) {
+  if (!h || !id128) return fail(ERIRT_E_ARG, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ERIRT_E_ARG, "bad rank/world");
+  if (h->prologue_done) return fail(ERIRT_E_STATE, "erirt_comm_init must precede erirt_sample");
+  int rc = nccl::load();
+  if (rc) return rc;
+  CU(cudaSetDevice(h->cfg.device));
+  nccl::unique_id id;
+  memcpy(&id, id128, 128);
+  NC(nccl::comm_init_rank(&h->comm, world, id, rank));
+  h->rank = rank;
+  h->world = world;
+  h->consts_final = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity entry points
+// ------------------------------------------------------------------------------------------------
+static int pick_device(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(ERIRT_E_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(ERIRT_E_ARG, "device out of range");
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
+extern "C" int erirt_k_pg(const double* z, int64_t rows, int32_t cols, int64_t row0, uint64_t seed, uint32_t chain,
+                          uint32_t sweep, int32_t dtype, int32_t device, double* out) {
+  if (!z || !out || rows < 0 || cols < 1) return fail(ERIRT_E_ARG, "bad argument");
+  int rc = pick_device(device);
+  if (rc) return rc;
+  const int64_t n = rows * cols;
+  if (n == 0) return 0;
+  double *dz = nullptr, *dout = nullptr;
+  CU(cudaMalloc((void**)&dz, n * sizeof(double)));
+  CU(cudaMalloc((void**)&dout, n * sizeof(double)));
+  CU(cudaMemcpy(dz, z, n * sizeof(double), cudaMemcpyHostToDevice));
+  const PhiloxKey key = make_key(seed, chain);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  if (dtype == ERIRT_F32) k_pg_kernel<float><<<grid, 256>>>(dz, rows, cols, row0, key, sweep, dout);
+  else k_pg_kernel<double><<<grid, 256>>>(dz, rows, cols, row0, key, sweep, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dz);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "erirt_k_pg: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int erirt_k_nu_person(const double* mu, double lam, int64_t n, int64_t row0, uint64_t seed, uint32_t chain,
+                                 uint32_t sweep, int32_t dtype, int32_t device, double* out) {
+  if (!mu || !out || n < 0) return fail(ERIRT_E_ARG, "bad argument");
+  int rc = pick_device(device);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  double *dm = nullptr, *dout = nullptr;
+  CU(cudaMalloc((void**)&dm, n * sizeof(double)));
+  CU(cudaMalloc((void**)&dout, n * sizeof(double)));
+  CU(cudaMemcpy(dm, mu, n * sizeof(double), cudaMemcpyHostToDevice));
+  const PhiloxKey key = make_key(seed, chain);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  if (dtype == ERIRT_F32) k_nu_person_kernel<float><<<grid, 256>>>(dm, lam, n, row0, key, sweep, dout);
+  else k_nu_person_kernel<double><<<grid, 256>>>(dm, lam, n, row0, key, sweep, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dm);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "erirt_k_nu_person: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int erirt_k_philox(const uint32_t ctr[4], const uint32_t key[2], int32_t device, uint32_t out[4]) {
+  if (!ctr || !key || !out) return fail(ERIRT_E_ARG, "bad argument");
+  int rc = pick_device(device);
+  if (rc) return rc;
+  uint32_t* d = nullptr;
+  CU(cudaMalloc((void**)&d, 10 * sizeof(uint32_t)));
+  CU(cudaMemcpy(d, ctr, 4 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d + 4, key, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  k_philox_kernel<<<1, 1>>>(d, d + 4, d + 6);
+  cudaError_t e = cudaMemcpy(out, d + 6, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "erirt_k_philox: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -1,0 +1,355 @@
+// global.cuh -- item and structural draws from the reduced sufficient statistics (K3/K4/K6/K7 of SURVEY.md 2c).
+//
+// One CTA, launched after the person kernel P(k) (and after the NCCL all-reduce when persons are sharded;
+// every GPU runs it redundantly with the same Philox key, so the new parameters need no broadcast).
+//   1. log-likelihood of state k: Bernoulli + structural parts arrive in the statistics, the response-time
+//      part is evaluated from sufficient statistics (getLogLikelihood*, GibbsRtIrt.pl.jl:262-272)
+//   2. parameters of sweep k+1 in the reference's order, every sum over persons expanded into
+//      S0,S1,S2,Ky,C, the Gram matrix and the ingest constants T1,T2,K0,X'X:
+//        beta   drawSubjCoefficients :380-393 | ...Latent :399-416 | getSubjCoefficientsMlIrt :351-357 | ...LatentQr :446-458
+//        Sigma  drawSubjCovariance :499-515 | ...Null :522-535 | ...Latent :563-579 | ...LatentQr :585-606
+//        b      drawItemDifficulty :98-105,   a  drawItemDiscrimination :88-93   (MlIrt: a before b)
+//        lambda drawItemIntensity :215-220,   sigma2  drawItemTimeResidual :257-262
+//   3. trace row k+1 (Post.ra/rt/qr item + structural columns, GibbsRtIrt.pl.jl:319-321), statistics reset.
+// All arithmetic is f64.
+#pragma once
+#include "layout.cuh"
+
+namespace erirt {
+
+constexpr int G_THREADS = 128;
+
+// ---- small dense SPD helpers (column-major, executed by one thread on shared-memory scratch) ----
+__device__ inline bool chol_lower(int n, const double* A, double* Lm) {
+  for (int t = 0; t < n * n; ++t) Lm[t] = 0.0;
+  for (int j = 0; j < n; ++j) {
+    double d = A[j + n * j];
+    for (int k = 0; k < j; ++k) d -= Lm[j + n * k] * Lm[j + n * k];
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    Lm[j + n * j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[i + n * j];
+      for (int k = 0; k < j; ++k) s -= Lm[i + n * k] * Lm[j + n * k];
+      Lm[i + n * j] = s / d;
+    }
+  }
+  return true;
+}
+// Ainv = A^{-1} through the Cholesky factor; Lm and Li are n*n scratch, none of the four may alias
+__device__ inline bool spd_inverse(int n, const double* A, double* Ainv, double* Lm, double* Li) {
+  if (!chol_lower(n, A, Lm)) return false;
+  for (int t = 0; t < n * n; ++t) Li[t] = 0.0;
+  for (int j = 0; j < n; ++j) {
+    Li[j + n * j] = 1.0 / Lm[j + n * j];
+    for (int i = j + 1; i < n; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s -= Lm[i + n * k] * Li[k + n * j];
+      Li[i + n * j] = s / Lm[i + n * i];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int k = (i > j ? i : j); k < n; ++k) s += Li[k + n * i] * Li[k + n * j];
+      Ainv[i + n * j] = s;
+    }
+  return true;
+}
+__device__ inline bool spd_solve(int n, const double* A, const double* rhs, double* sol, double* Lm, double* y) {
+  if (!chol_lower(n, A, Lm)) return false;
+  for (int i = 0; i < n; ++i) {
+    double s = rhs[i];
+    for (int k = 0; k < i; ++k) s -= Lm[i + n * k] * y[k];
+    y[i] = s / Lm[i + n * i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < n; ++k) s -= Lm[k + n * i] * sol[k];
+    sol[i] = s / Lm[i + n * i];
+  }
+  return true;
+}
+// quadratic form b' M b and bilinear b' v
+__device__ inline double quad_form(int n, const double* M, const double* b) {
+  double acc = 0.0;
+  for (int r = 0; r < n; ++r) {
+    double x = 0.0;
+    for (int q = 0; q < n; ++q) x += M[r + n * q] * b[q];
+    acc += b[r] * x;
+  }
+  return acc;
+}
+__device__ inline double dotn(int n, const double* a, const double* b) {
+  double acc = 0.0;
+  for (int r = 0; r < n; ++r) acc += a[r] * b[r];
+  return acc;
+}
+
+__device__ inline void cov2one_2x2(double* S) {  // Draw.pl.jl:507-511
+  const double r12 = S[2] / sqrt(S[0]) / sqrt(S[3]), r21 = S[1] / sqrt(S[0]) / sqrt(S[3]);
+  S[0] = 1.0; S[3] = 1.0; S[2] = r12; S[1] = r21;
+}
+
+// rand(InverseWishart(df, Psi)) = inv(rand(Wishart(df, inv(Psi)))), Wishart by Bartlett's decomposition
+__device__ inline void inv_wishart2(PhiloxKey key, uint32_t sweep, double df, const double Psi[4], double out[4]) {
+  const double det = Psi[0] * Psi[3] - Psi[1] * Psi[2];
+  const double S[4] = {Psi[3] / det, -Psi[1] / det, -Psi[2] / det, Psi[0] / det};
+  const double l11 = sqrt(S[0]), l21 = S[1] / l11, l22 = sqrt(S[3] - l21 * l21);
+  const uint32_t site = make_site(DOM_GLOBAL, GK_SIGMAP);
+  const double a11 = sqrt(2.0 * site_gamma(key, 0, sweep, site, 0.5 * df));
+  const double a22 = sqrt(2.0 * site_gamma(key, 1, sweep, site, 0.5 * (df - 1.0)));
+  const double a21 = site_normal(key, 2, sweep, site);
+  const double x11 = l11 * a11, x21 = l21 * a11 + l22 * a21, x22 = l22 * a22;
+  const double w11 = x11 * x11, w21 = x21 * x11, w22 = x21 * x21 + x22 * x22;
+  const double dw = w11 * w22 - w21 * w21;
+  out[0] = w22 / dw; out[1] = -w21 / dw; out[2] = -w21 / dw; out[3] = w11 / dw;
+}
+
+struct GramView {  // accessors into the upper-triangular Gram of u = [1, X(1..F), theta, zeta, nu]
+  const double* g;
+  int Dg, F;
+  __device__ double at(int r, int c) const { return r <= c ? g[tri_index(r, c, Dg)] : g[tri_index(c, r, Dg)]; }
+  __device__ int th() const { return F + 1; }
+  __device__ int ze() const { return F + 2; }
+  __device__ int nu() const { return F + 3; }
+};
+
+struct GScratch {
+  double M[MAXD * MAXD], V[MAXD * MAXD], Lc[MAXD * MAXD], T[MAXD * MAXD], XX[MAXD * MAXD];
+  double rhs[MAXD], mean[MAXD], z[MAXD], beta[MAXD], Sigma[4];
+};
+
+// mean + chol(V).L * z with z_t ~ N(0,1) at the global beta site; returns false if V is not SPD
+__device__ inline bool mvn_draw(const GlobalArgs& A, uint32_t s, int d, GScratch& w) {
+  if (!chol_lower(d, w.V, w.Lc)) return false;
+  for (int t = 0; t < d; ++t) w.z[t] = site_normal(A.key, (uint32_t)t, s, make_site(DOM_GLOBAL, GK_BETA));
+  for (int r = 0; r < d; ++r) {
+    double acc = w.mean[r];
+    for (int q = 0; q <= r; ++q) acc += w.Lc[r + d * q] * w.z[q];
+    w.beta[r] = acc;
+  }
+  return true;
+}
+
+__device__ inline bool structural_draws(const GlobalArgs& A, uint32_t s, const GramView& Gm, const GramView& Gw, GScratch& w) {
+  const Layout& L = A.L;
+  const int F = L.F, pb = F + 1, model = A.model;
+  const double N = (double)A.n_total;
+  const int TH = Gm.th(), ZE = Gm.ze(), NU = Gm.nu();
+  const double Sth2 = Gm.at(TH, TH), Sze2 = Gm.at(ZE, ZE), Sthze = Gm.at(TH, ZE);
+  const double add = (A.compat & 1) ? 0.0 : 1.0;  // `1/σβ₀^2 .+ M` adds to EVERY element (Draw.pl.jl:386,410; quirk Q1)
+  bool ok = true;
+  if (model == M_MLIRT) {
+    for (int r = 0; r < pb; ++r) w.rhs[r] = Gm.at(r, TH);
+    ok = spd_solve(pb, A.XtX, w.rhs, w.beta, w.Lc, w.z);  // getSubjCoefficientsMlIrt
+    if (!A.intercept) w.beta[0] = 0.0;
+  } else if (model == M_RTIRT) {
+    const int d = 2 * pb;
+    const double S11 = w.Sigma[0], S12 = w.Sigma[2], S22 = w.Sigma[3], det = S11 * S22 - S12 * S12;
+    const double iO[4] = {S22 / det, -S12 / det, -S12 / det, S11 / det};
+    for (int br = 0; br < 2; ++br)
+      for (int bc = 0; bc < 2; ++bc)
+        for (int r = 0; r < pb; ++r)
+          for (int q = 0; q < pb; ++q) w.M[(br * pb + r) + d * (bc * pb + q)] = iO[br + 2 * bc] * A.XtX[r + pb * q] + add;
+    if (add == 0.0)
+      for (int t = 0; t < d; ++t) w.M[t + d * t] += 1.0;
+    ok = spd_inverse(d, w.M, w.V, w.Lc, w.T);
+    for (int c = 0; c < 2; ++c)  // vec(x'η invΩ')
+      for (int r = 0; r < pb; ++r) w.rhs[c * pb + r] = Gm.at(r, TH) * iO[c + 0] + Gm.at(r, ZE) * iO[c + 2];
+    for (int r = 0; r < d; ++r) {
+      double acc = 0.0;
+      for (int q = 0; q < d; ++q) acc += w.V[r + d * q] * w.rhs[q];
+      w.mean[r] = acc;
+    }
+    ok = ok && mvn_draw(A, s, d, w);
+    if (!A.intercept) { w.beta[0] = 0.0; w.beta[pb] = 0.0; }
+    // e'e, e = [θ ζ] - xβ   (drawSubjCovariance)
+    const double* b1 = w.beta;
+    const double* b2 = w.beta + pb;
+    double q11 = 0, q12 = 0, q22 = 0, l1t = 0, l1z = 0, l2t = 0, l2z = 0;
+    for (int r = 0; r < pb; ++r) {
+      double x1 = 0, x2 = 0;
+      for (int q = 0; q < pb; ++q) { x1 += A.XtX[r + pb * q] * b1[q]; x2 += A.XtX[r + pb * q] * b2[q]; }
+      q11 += b1[r] * x1; q12 += b1[r] * x2; q22 += b2[r] * x2;
+      l1t += b1[r] * Gm.at(r, TH); l1z += b1[r] * Gm.at(r, ZE);
+      l2t += b2[r] * Gm.at(r, TH); l2z += b2[r] * Gm.at(r, ZE);
+    }
+    const double E11 = Sth2 - 2.0 * l1t + q11, E12 = Sthze - l1z - l2t + q12, E22 = Sze2 - 2.0 * l2z + q22;
+    const double Psi[4] = {E11 + 1.0, E12, E12, E22 + 1.0};
+    inv_wishart2(A.key, s, N + 3.0, Psi, w.Sigma);
+    if (A.cov2one) cov2one_2x2(w.Sigma);
+  } else if (model == M_NULL) {
+    for (int t = 0; t < 2 * pb; ++t) w.beta[t] = 0.0;
+    const double Psi[4] = {Sth2 + 1.0, Sthze, Sthze, Sze2 + 1.0};
+    inv_wishart2(A.key, s, N + 3.0, Psi, w.Sigma);  // drawSubjCovarianceNull
+    if (A.cov2one) cov2one_2x2(w.Sigma);
+  } else if (model == M_LATENT || model == M_LATENTQR) {
+    const int d = F + 2;
+    const bool qrm = model == M_LATENTQR;
+    // x = [1 X θ]: x'x = ingest constant (f64) bordered by the θ column of the Gram
+    for (int r = 0; r < d; ++r)
+      for (int q = 0; q < d; ++q) w.XX[r + d * q] = (r < pb && q < pb) ? A.XtX[r + pb * q] : Gm.at(r, q);
+    // y = ζ (Latent) or ζ - k1 ν (LatentQr)
+    for (int r = 0; r < d; ++r) w.rhs[r] = Gm.at(r, ZE) - (qrm ? A.k1 * Gm.at(r, NU) : 0.0);
+    double yy = Sze2;
+    if (qrm) yy += -2.0 * A.k1 * Gm.at(ZE, NU) + A.k1 * A.k1 * Gm.at(NU, NU);
+    if (!qrm) {  // drawSubjCoefficientsLatent
+      const double iO = 1.0 / w.Sigma[3];
+      for (int t = 0; t < d * d; ++t) w.M[t] = iO * w.XX[t] + add;
+      if (add == 0.0)
+        for (int t = 0; t < d; ++t) w.M[t + d * t] += 1.0;
+      ok = spd_inverse(d, w.M, w.V, w.Lc, w.T);
+      for (int r = 0; r < d; ++r) {
+        double acc = 0.0;
+        for (int q = 0; q < d; ++q) acc += w.V[r + d * q] * (w.rhs[q] * iO);
+        w.mean[r] = acc;
+      }
+      ok = ok && mvn_draw(A, s, d, w);
+    } else {  // getSubjCoefficientsLatentQr: the tall Kronecker system collapses to OLS
+      ok = spd_solve(d, w.XX, w.rhs, w.beta, w.Lc, w.z);
+    }
+    if (!A.intercept) w.beta[0] = 0.0;
+    // residual sum of squares r = y - xβ
+    const double ss = yy - 2.0 * dotn(d, w.beta, w.rhs) + quad_form(d, w.XX, w.beta);
+    double parA, parB;
+    if (!qrm) {
+      parA = 1e-3 + N / 2.0;
+      parB = 1e-3 + ss / 2.0;
+    } else {
+      const double Snu = Gm.at(0, NU), Snu2 = Gm.at(NU, NU);
+      parA = 1e-3 + N * 3.0 / 2.0;
+      double scale;
+      if (A.compat & 2) {
+        // Σ r_i²/(2 k2 ν_i) from the 1/ν-weighted Gram: y/ν terms
+        for (int r = 0; r < d; ++r)
+          for (int q = 0; q < d; ++q) w.T[r + d * q] = Gw.at(r, q);
+        for (int r = 0; r < d; ++r) w.mean[r] = Gw.at(r, ZE) - A.k1 * Gm.at(0, r);  // Σ x (ζ - k1 ν)/ν
+        const double yyw = Gw.at(ZE, ZE) - 2.0 * A.k1 * Gm.at(0, ZE) + A.k1 * A.k1 * Snu;
+        const double ssw = yyw - 2.0 * dotn(d, w.beta, w.mean) + quad_form(d, w.T, w.beta);
+        scale = ssw / (2.0 * A.k2);
+      } else {
+        // as written: sum(r.^2 / (2 k2e)) with vector / vector (quirk Q2, Draw.pl.jl:594)
+        scale = ss * (2.0 * A.k2 * Snu) / (4.0 * A.k2 * A.k2 * Snu2);
+      }
+      parB = 1e-3 + scale + Snu;
+    }
+    const double sv = parB / site_gamma(A.key, 0, s, make_site(DOM_GLOBAL, GK_SIGMAP), parA);
+    w.Sigma[0] = 1.0; w.Sigma[1] = 0.0; w.Sigma[2] = 0.0; w.Sigma[3] = sv;
+    if (A.cov2one) cov2one_2x2(w.Sigma);
+  }
+  return ok;
+}
+
+__global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs A) {
+  __shared__ GScratch w;
+  __shared__ double sRed[G_THREADS];
+  const Layout& L = A.L;
+  const int J = L.J, F = L.F, Dg = L.Dg, tid = threadIdx.x;
+  const int model = A.model;
+  const bool has_rt = model != M_MLIRT;
+  const uint32_t k = *A.sweep_ctr;  // person launch P(k) just finished
+  const uint32_t s = k + 1;         // sweep whose parameters are drawn now
+  const double N = (double)A.n_total;
+  double* par = A.params;
+  double* st = A.stats;
+  const GramView Gm{st + L.s_gram, Dg, F};
+  const GramView Gw{st + L.s_gramw, Dg, F};
+  const double Sth = Gm.at(0, Gm.th());
+  const double Sze = Gm.at(0, Gm.ze()), Sze2 = Gm.at(Gm.ze(), Gm.ze());
+  const double LOG2PI = 1.8378770664093454835606594728112;
+
+  // ---- 1. log-likelihood of state k ----
+  if (k >= 1) {
+    double part = 0.0;
+    if (has_rt)
+      for (int j = tid; j < J; j += G_THREADS) {
+        const double lam = par[L.p_lambda + j], s2 = par[L.p_sigma2 + j];
+        const double Q = A.T2[j] - 2.0 * lam * A.T1[j] + N * lam * lam + 2.0 * (st[L.s_C + j] - lam * Sze) + Sze2;
+        part += -0.5 * N * (LOG2PI + log(s2)) - 0.5 * Q / s2;
+      }
+    sRed[tid] = part;
+    __syncthreads();
+    for (int o = G_THREADS / 2; o; o >>= 1) {
+      if (tid < o) sRed[tid] += sRed[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0 && (int)(k - 1) < A.cap) A.tr_ll[k - 1] = st[L.s_scal + SC_LL_BERN] + sRed[0] + st[L.s_scal + SC_LL_STRUCT];
+  }
+
+  // ---- 2a. structural draws (thread 0), 2b. item draws (all threads) ----
+  if (tid == 0) {
+    for (int t = 0; t < MAXD; ++t) w.beta[t] = par[L.p_beta + t];
+    for (int t = 0; t < 4; ++t) w.Sigma[t] = par[L.p_Sigma + t];
+    if (!structural_draws(A, s, Gm, Gw, w)) atomicExch(A.status, (int)s);
+  }
+  const double mu_lam = has_rt ? A.consts[0] : 0.0, sd_lam = has_rt ? A.consts[1] : 1.0;
+  for (int j = tid; j < J; j += G_THREADS) {
+    const double S0 = st[L.s_S0 + j], S1 = st[L.s_S1 + j], S2 = st[L.s_S2 + j];
+    const double K0 = A.K0[j], K1 = st[L.s_Ky + j] - 0.5 * Sth;  // Σκ, Σκθ
+    double a = par[L.p_a + j], b = par[L.p_b + j];
+    auto draw_b = [&]() {  // drawItemDifficulty
+      const double parV = 1.0 / (1.0 + a * a * S0);
+      const double parM = parV * (0.0 - (a * K0 - a * a * S1));
+      double v = parM + sqrt(parV) * site_normal(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_B));
+      b = v < -4.0 ? -4.0 : (v > 4.0 ? 4.0 : v);
+    };
+    auto draw_a = [&]() {  // drawItemDiscrimination
+      const double parV = 1.0 / (1.0 + (S2 - 2.0 * b * S1 + b * b * S0));
+      const double parM = parV * (1.0 + (K1 - b * K0));
+      a = site_tnorm_pos(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_A), parM, sqrt(parV));
+      if (A.onepl) a = 1.0;
+    };
+    if (model == M_MLIRT) { draw_a(); draw_b(); }  // GibbsRtIrt.pl.jl:233-237 (quirk Q8)
+    else { draw_b(); draw_a(); }
+    par[L.p_a + j] = a;
+    par[L.p_b + j] = b;
+    if (has_rt) {
+      const double s2 = par[L.p_sigma2 + j];
+      const double T1 = A.T1[j], T2 = A.T2[j], C = st[L.s_C + j];
+      // drawItemIntensity
+      const double pv = 1.0 / (sd_lam * sd_lam);
+      const double parV = 1.0 / (pv + N / s2);
+      const double parM = parV * (mu_lam * pv + (T1 + Sze) / s2);
+      const double lam = site_tnorm_pos(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_LAMBDA), parM, sqrt(parV));
+      // drawItemTimeResidual: Σ_i (logT - λ + ζ)²
+      const double Q = T2 - 2.0 * lam * T1 + N * lam * lam + 2.0 * (C - lam * Sze) + Sze2;
+      const double parA = 1e-3 + N / 2.0, parB = 1e-3 + Q / 2.0;
+      const double s2n = parB / site_gamma(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_SIGMA2), parA);
+      par[L.p_lambda + j] = lam;
+      par[L.p_sigma2 + j] = s2n;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int t = 0; t < MAXD; ++t) par[L.p_beta + t] = w.beta[t];
+    for (int t = 0; t < 4; ++t) par[L.p_Sigma + t] = w.Sigma[t];
+  }
+  __syncthreads();
+
+  // ---- 3. trace row of sweep s, statistics reset ----
+  if ((int)k < A.cap) {
+    for (int j = tid; j < J; j += G_THREADS) {
+      A.tr_items_ra[(size_t)k * 2 * J + j] = par[L.p_a + j];
+      A.tr_items_ra[(size_t)k * 2 * J + J + j] = par[L.p_b + j];
+      if (has_rt) {
+        A.tr_items_rt[(size_t)k * 2 * J + j] = par[L.p_lambda + j];
+        A.tr_items_rt[(size_t)k * 2 * J + J + j] = par[L.p_sigma2 + j];
+      }
+    }
+    const int nb = (model == M_MLIRT) ? F + 1 : ((model == M_RTIRT || model == M_NULL) ? 2 * (F + 1) : F + 2);
+    for (int t = tid; t < A.qw; t += G_THREADS) {
+      double v = t < nb ? par[L.p_beta + t] : par[L.p_Sigma + (t - nb)];
+      A.tr_qr[(size_t)k * A.qw + t] = v;
+    }
+  }
+  if (tid == 0) {
+    A.stats[L.s_count] = st[L.s_scal + SC_PG_DEFER];      // keep the diagnostics of the last sweep
+    A.stats[L.s_count + 1] = st[L.s_scal + SC_PG_CELLS];
+  }
+  __syncthreads();
+  for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = 0.0;
+  if (tid == 0) *A.sweep_ctr = k + 1;
+}
+
+}  // namespace erirt

@@ -1,0 +1,125 @@
+// layout.cuh -- device data layout shared by the kernels and the host orchestration (DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cstdint>
+#include "rng.cuh"
+
+namespace erirt {
+
+constexpr int CTA_THREADS = 128;  // person-sweep CTA; tile = CTA_THREADS / TPP persons
+constexpr int MAXD = 32;          // largest dense system solved in the global kernel (2*(nFeat+1) <= 32)
+constexpr int QCAP = 2048;        // PG retry-queue capacity per tile (overflow is handled inline)
+
+enum ModelId { M_MLIRT = 0, M_RTIRT = 1, M_NULL = 2, M_CROSS = 3, M_CROSSQR = 4, M_LATENT = 5, M_LATENTQR = 6 };
+
+// statistics scalars (f64), accumulated by the person kernel and consumed by the global kernel
+enum StatScalar {
+  SC_LL_BERN = 0,    // sum_ij y z - log(1+e^z) at state k
+  SC_LL_STRUCT = 1,  // sum_i structural log-density at state k
+  SC_PG_DEFER = 2,   // PG cells that left the fast path (diagnostic)
+  SC_PG_CELLS = 3,
+  SC_COUNT = 8
+};
+
+// Offsets (in f64 elements) into the parameter vector written by the global kernel and the statistics
+// vector written by the person kernel.  Jp = padded item count (row pitch of the tiles, multiple of 4, odd
+// number of 16-byte quads so that row-strided 128-bit shared-memory accesses are conflict free).
+struct Layout {
+  int J, Jp, F, Dg, ntri;
+  int p_a, p_b, p_lambda, p_sigma2, p_rho, p_beta, p_Sigma, p_count;
+  int s_S0, s_S1, s_S2, s_Ky, s_C, s_gram, s_gramw, s_scal, s_count;
+};
+
+__host__ __device__ inline int tri_index(int r, int c, int Dg) {  // r <= c, row-major upper triangle
+  return r * Dg - (r * (r - 1)) / 2 + (c - r);
+}
+
+inline Layout make_layout(int J, int F) {
+  Layout L;
+  L.J = J;
+  L.F = F;
+  int q = (J + 3) / 4;
+  if ((q & 1) == 0) ++q;
+  L.Jp = 4 * q;
+  L.Dg = F + 4;  // u_i = [1, X_i(1..F), theta_i, zeta_i, nu_i]
+  L.ntri = L.Dg * (L.Dg + 1) / 2;
+  int o = 0;
+  L.p_a = o; o += L.Jp;
+  L.p_b = o; o += L.Jp;
+  L.p_lambda = o; o += L.Jp;
+  L.p_sigma2 = o; o += L.Jp;
+  L.p_rho = o; o += L.Jp;
+  L.p_beta = o; o += MAXD;
+  L.p_Sigma = o; o += 4;
+  L.p_count = o;
+  o = 0;
+  L.s_S0 = o; o += L.Jp;
+  L.s_S1 = o; o += L.Jp;
+  L.s_S2 = o; o += L.Jp;
+  L.s_Ky = o; o += L.Jp;
+  L.s_C = o; o += L.Jp;
+  L.s_gram = o; o += L.ntri;
+  L.s_gramw = o; o += L.ntri;
+  L.s_scal = o; o += SC_COUNT;
+  L.s_count = o;
+  return L;
+}
+
+// dynamic shared-memory plan of the person kernel (byte offsets)
+struct SmemPlan {
+  int P;  // persons per tile
+  int tile_real_bytes, tile_y_bytes;
+  int off_omega, off_logt, off_y, off_par, off_u, off_acc_item, off_acc_gram, off_queue, off_misc, total;
+  int Dgp;  // pitch of the U tile (elements)
+};
+
+template <typename R>
+struct PersonArgs {
+  // tiles, person-major, row pitch Jp, n_pad rows (n_pad multiple of 128; padding rows are zero)
+  const uint8_t* Y;
+  const R* logT;
+  R* omega;
+  // person vectors (n_pad) and covariates, column-major [F][n_pad]
+  R* theta;
+  R* zeta;
+  R* nu;
+  const R* X;
+  double* mom;    // [6][n_pad] running sum / sum of squares of theta, zeta, nu (post burn-in)
+  R* ptrace;      // optional [cap][3][n_pad] person trace (theta, zeta, nu) or nullptr
+  const double* params;
+  double* stats;
+  const uint32_t* sweep_ctr;  // k: this launch draws theta_k, zeta_k (k >= 1) and omega_{k+1}, nu_{k+1}
+  int64_t n_local, n_pad;
+  uint32_t person_offset;
+  int n_tiles;
+  Layout L;
+  SmemPlan S;
+  int model, n_chain, n_burnin;
+  double k1, k2;
+  PhiloxKey key;
+};
+
+struct GlobalArgs {
+  double* params;
+  double* stats;
+  uint32_t* sweep_ctr;
+  // constants from ingest (already all-reduced over shards)
+  const double* T1;   // sum_i logT_ij
+  const double* T2;   // sum_i logT_ij^2
+  const double* K0;   // sum_i kappa_ij
+  const double* XtX;  // [1 X]'[1 X], (F+1)^2 column-major
+  const double* consts;  // [0]=mean(logT) [1]=std(logT)
+  // traces, row per sweep
+  double* tr_items_ra;  // [cap][2J]  a, b
+  double* tr_items_rt;  // [cap][2J]  lambda, sigma2
+  double* tr_qr;        // [cap][qw]
+  double* tr_ll;        // [cap]
+  int* status;          // sticky numeric error flag
+  int64_t n_total;
+  int cap, qw;
+  Layout L;
+  int model, intercept, onepl, cov2one, compat;
+  double k1, k2;
+  PhiloxKey key;
+};
+
+}  // namespace erirt

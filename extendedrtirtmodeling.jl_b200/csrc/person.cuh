@@ -1,0 +1,536 @@
+// person.cuh -- the fused person-sweep kernel (K2 of SURVEY.md 2c), one launch per Gibbs sweep.
+//
+// Launch k (k = *sweep_ctr) performs, for every person row i of this GPU's shard, in the reference's
+// scan order (SURVEY 7.1 pipeline "R"):
+//   theta_k  | omega_k, a_k, b_k, beta_k, Sigma_k      drawSubjAbility / ...Null   Draw.pl.jl:49-80
+//   zeta_k   | lambda_k, sigma2_k, theta_k, beta_k, Sigma_k, nu_k   drawSubjSpeed*  Draw.pl.jl:119-174
+//   nu_{k+1} | zeta_k, theta_k, beta_k, Sigma_k        drawQrWeightsLatentQr       Draw.pl.jl:325-343
+//   omega_{k+1} | a_k, b_k, theta_k                    drawRaPgRandomVariable      Draw.pl.jl:36-40
+// and accumulates every sum over persons that the item / structural draws of sweep k+1 need
+// (S0,S1,S2 = sum omega [1,theta,theta^2]; Ky = sum y theta; C = sum logT zeta; Gram of [1 X theta zeta nu])
+// plus the Bernoulli and structural log-likelihood of state k (getLogLikelihood*, GibbsRtIrt.pl.jl:195-272).
+// (k = 0 is the prologue: only the sweep-1 auxiliaries are drawn from the initial state.)
+//
+// Mapping: CTA = 128 threads = P persons x TPP threads; a tile of P rows of Y (u8), logT and omega is
+// staged in shared memory with 1-D TMA bulk copies (the rows of a tile are contiguous in HBM), each
+// thread walks 4-item groups of its own row with 128-bit shared loads, and the per-item statistics are
+// reduced by re-reading the tile transposed (thread per item group).  omega is updated in place and
+// written back with one TMA bulk store.  HBM traffic per cell: 1 B (Y) + 4 B (logT) + 4+4 B (omega) in f32.
+#pragma once
+#include "layout.cuh"
+#include "pg.cuh"
+
+namespace erirt {
+
+// ---------------- PTX helpers: mbarrier + 1-D TMA bulk copies ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------- 4-element group access ----------------
+template <typename R>
+struct Quad {
+  R v[4];
+};
+__device__ __forceinline__ Quad<float> ld4(const float* p) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  Quad<float> q;
+  q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+  return q;
+}
+__device__ __forceinline__ Quad<double> ld4(const double* p) {
+  double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+  Quad<double> q;
+  q.v[0] = t0.x; q.v[1] = t0.y; q.v[2] = t1.x; q.v[3] = t1.y;
+  return q;
+}
+__device__ __forceinline__ void st4(float* p, const Quad<float>& q) {
+  *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
+  *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+}
+
+// item-parameter arrays staged in shared memory (each Jp long, zero beyond J)
+enum ParIdx { PAR_A = 0, PAR_AB = 1, PAR_A2 = 2, PAR_A2B = 3, PAR_IS2 = 4, PAR_COUNT = 5 };
+// per-CTA scalars in the misc block (f64)
+enum MiscD { MD_SUM_IS2 = 0, MD_SUM_LIS2 = 1, MD_COUNT = 2 };
+
+// group index handled by thread q at step k: the TPP threads of one person and the persons of a quarter
+// warp touch 8 distinct 16-byte bank groups (row pitch is an odd number of quads)
+template <int TPP>
+__device__ __forceinline__ int group_of(int q, int k) {
+  constexpr int chunk = 8 / TPP;
+  return (k / chunk) * 8 + q * chunk + (k % chunk);
+}
+
+template <typename R, int TPP>
+__global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonArgs<R> A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int P = CTA_THREADS / TPP;
+  constexpr bool F32 = sizeof(R) == 4;
+  const Layout& L = A.L;
+  const int J = L.J, Jp = L.Jp, F = L.F, Dg = L.Dg, Dgp = A.S.Dgp, G = Jp / 4;
+  const int model = A.model;
+  const bool has_rt = model != M_MLIRT;
+  const bool latent = model == M_LATENT || model == M_LATENTQR;
+  const bool qr = model == M_LATENTQR;
+
+  R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
+  R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
+  uint8_t* s_y = smem + A.S.off_y;
+  R* s_par = reinterpret_cast<R*>(smem + A.S.off_par);
+  R* s_u = reinterpret_cast<R*>(smem + A.S.off_u);
+  double* s_acc_item = reinterpret_cast<double*>(smem + A.S.off_acc_item);
+  double* s_acc_gram = reinterpret_cast<double*>(smem + A.S.off_acc_gram);
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + A.S.off_queue);
+  double* s_miscd = reinterpret_cast<double*>(smem + A.S.off_misc);          // MD_COUNT + SC_COUNT doubles
+  double* s_scal = s_miscd + MD_COUNT;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scal + SC_COUNT);
+  uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);                 // [0] count, [1] head
+
+  const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  const uint32_t k = *A.sweep_ctr;
+  const bool do_draws = k >= 1;
+  const double* par = A.params;
+
+  // ---- stage item parameters (state k) and clear accumulators ----
+  for (int j = tid; j < Jp; j += CTA_THREADS) {
+    double a = 0, b = 0, is2 = 0;
+    if (j < J) {
+      a = par[L.p_a + j];
+      b = par[L.p_b + j];
+      if (has_rt) is2 = 1.0 / par[L.p_sigma2 + j];
+    }
+    s_par[PAR_A * Jp + j] = (R)a;
+    s_par[PAR_AB * Jp + j] = (R)(a * b);
+    s_par[PAR_A2 * Jp + j] = (R)(a * a);
+    s_par[PAR_A2B * Jp + j] = (R)(a * a * b);
+    s_par[PAR_IS2 * Jp + j] = (R)is2;
+  }
+  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
+  for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
+  if (tid < SC_COUNT) s_scal[tid] = 0.0;
+  if (tid < 32) {  // sum_j 1/sigma2_j and sum_j lambda_j/sigma2_j in f64
+    double s1 = 0, s2 = 0;
+    if (has_rt)
+      for (int j = tid; j < J; j += 32) {
+        double is2 = 1.0 / par[L.p_sigma2 + j];
+        s1 += is2;
+        s2 += par[L.p_lambda + j] * is2;
+      }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (tid == 0) {
+      s_miscd[MD_SUM_IS2] = s1;
+      s_miscd[MD_SUM_LIS2] = s2;
+      mbar_init(s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  const R sum_is2 = (R)s_miscd[MD_SUM_IS2], sum_lis2 = (R)s_miscd[MD_SUM_LIS2];
+  const R S11 = has_rt ? (R)par[L.p_Sigma + 0] : R(1);
+  const R S22 = has_rt ? (R)par[L.p_Sigma + 3] : R(1);
+  const R S12 = has_rt ? (R)par[L.p_Sigma + 2] : R(0);
+  const R k1 = (R)A.k1, k2 = (R)A.k2;
+  const int pb = F + 1;  // length of one regression block [1 X]
+  const uint32_t iter_m = do_draws ? (k - 1) / (uint32_t)A.n_chain + 1 : 0;  // m of sweep k
+  const bool post_burnin = do_draws && iter_m > (uint32_t)A.n_burnin;
+
+  double acc_ll_bern = 0.0, acc_ll_struct = 0.0;
+  uint32_t acc_defer = 0, acc_cells = 0;
+  uint32_t parity = 0;
+  const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * (has_rt ? 2 : 1) + A.S.tile_y_bytes);
+  // steps per thread = ceil(G/8) * (8/TPP)
+  const int nk = ((G + 7) / 8) * (8 / TPP);
+
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    const int64_t row0 = (int64_t)tile * P;
+    if (tid == 0) {
+      tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
+      mbar_expect_tx(s_bar, load_bytes);
+      tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
+    }
+    // ---- person scalars while the tile is in flight ----
+    const int64_t i = row0 + p;
+    const bool valid = i < A.n_local;
+    const uint32_t gid = A.person_offset + (uint32_t)i;
+    R th = A.theta[i];
+    R ze = has_rt ? A.zeta[i] : R(0);
+    R nu = qr ? A.nu[i] : R(1);
+    R xb1 = R(0), xb2 = R(0);  // regression means (before the theta term of the latent models)
+    {
+      const double* beta = par + L.p_beta;
+      if (model == M_MLIRT || model == M_RTIRT || latent) xb1 = (R)beta[0];
+      if (model == M_RTIRT) xb2 = (R)beta[pb];
+      for (int f = 0; f < F; ++f) {
+        R x = A.X[(int64_t)f * A.n_pad + i];
+        if (q == 0) s_u[p * Dgp + 1 + f] = valid ? x : R(0);
+        if (model == M_MLIRT || model == M_RTIRT || latent) xb1 = fma(x, (R)beta[1 + f], xb1);
+        if (model == M_RTIRT) xb2 = fma(x, (R)beta[pb + 1 + f], xb2);
+      }
+    }
+    mbar_wait(s_bar, parity);
+    parity ^= 1u;
+
+    R* my_om = s_om + p * Jp;
+    const R* my_lt = s_lt + p * Jp;
+    const uint8_t* my_y = s_y + p * Jp;
+
+    if (do_draws) {
+      // ---- row sums over items (Draw.pl.jl:55-56, 137-138) ----
+      R sA2 = 0, sAB = 0, sAK = 0, sLT = 0;
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+        const Quad<R> om = ld4(my_om + 4 * g);
+        const Quad<R> pA2 = ld4(s_par + PAR_A2 * Jp + 4 * g);
+        const Quad<R> pA2B = ld4(s_par + PAR_A2B * Jp + 4 * g);
+        const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sA2 = fma(pA2.v[e], om.v[e], sA2);
+          sAB = fma(pA2B.v[e], om.v[e], sAB);
+          const R kap = ((yw >> (8 * e)) & 0xffu) ? R(0.5) : R(-0.5);
+          sAK = fma(pA.v[e], kap, sAK);
+        }
+        if (has_rt) {
+          const Quad<R> lt = ld4(my_lt + 4 * g);
+          const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sLT = fma(pI.v[e], lt.v[e], sLT);
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < TPP; o <<= 1) {
+        sA2 += __shfl_xor_sync(0xffffffffu, sA2, o);
+        sAB += __shfl_xor_sync(0xffffffffu, sAB, o);
+        sAK += __shfl_xor_sync(0xffffffffu, sAK, o);
+        sLT += __shfl_xor_sync(0xffffffffu, sLT, o);
+      }
+      const uint4 w = philox(A.key, gid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
+      // theta_k
+      {
+        const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
+        const R var0 = (model == M_MLIRT) ? R(1) : S11;
+        const R parV = R(1) / (R(1) / var0 + sA2);
+        const R parM = parV * (mu0 / var0 + sAK + sAB);
+        th = parM + sqrt(parV) * normal2r<R>(w.x, w.y);
+      }
+      // zeta_k
+      R mu_z = R(0), var_z = R(1);
+      if (has_rt) {
+        if (model == M_RTIRT) { mu_z = xb2; var_z = S22; }
+        else if (latent) {
+          mu_z = fma(th, (R)par[L.p_beta + F + 1], xb1);
+          var_z = S22;
+          if (qr) { mu_z = fma(k1, nu, mu_z); var_z = S22 * (k2 * nu); }
+        } else if (model == M_NULL) { mu_z = R(0); var_z = R(1); }  // Draw.pl.jl:120-121
+        else { mu_z = R(0); var_z = S22; }
+        const R parV = R(1) / (R(1) / var_z + sum_is2);
+        const R parM = parV * (mu_z / var_z + (sum_lis2 - sLT));
+        ze = parM + sqrt(parV) * normal2r<R>(w.z, w.w);
+      }
+      // structural log-density of state k (one lane per person)
+      if (valid && q == 0) {
+        const double LOG2PI = 1.8378770664093454835606594728112;
+        double ls;
+        if (model == M_MLIRT) {
+          double r = (double)th - (double)xb1;
+          ls = -0.5 * LOG2PI - 0.5 * r * r;
+        } else if (latent) {
+          double r = (double)ze - (double)mu_z, v = (double)var_z;
+          ls = -0.5 * (LOG2PI + log(v)) - 0.5 * r * r / v;
+        } else {
+          double e1 = (double)th - (model == M_RTIRT ? (double)xb1 : 0.0);
+          double e2 = (double)ze - (model == M_RTIRT ? (double)xb2 : 0.0);
+          double s11 = S11, s12 = S12, s22 = S22, det = s11 * s22 - s12 * s12;
+          ls = -LOG2PI - 0.5 * log(det) - 0.5 * (s22 * e1 * e1 - 2.0 * s12 * e1 * e2 + s11 * e2 * e2) / det;
+        }
+        acc_ll_struct += ls;
+        A.theta[i] = th;
+        if (has_rt) A.zeta[i] = ze;
+        if (post_burnin) {
+          double* m = A.mom + i;
+          m[0] += (double)th;
+          m[A.n_pad] += (double)th * (double)th;
+          if (has_rt) {
+            m[2 * A.n_pad] += (double)ze;
+            m[3 * A.n_pad] += (double)ze * (double)ze;
+          }
+          if (qr) {
+            m[4 * A.n_pad] += (double)nu;
+            m[5 * A.n_pad] += (double)nu * (double)nu;
+          }
+        }
+        if (A.ptrace) {
+          R* t = A.ptrace + ((int64_t)(k - 1) * 3) * A.n_pad + i;
+          t[0] = th;
+          t[A.n_pad] = ze;
+          t[2 * A.n_pad] = nu;
+        }
+      }
+    }
+    // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
+    if (qr) {
+      const R xb = fma(th, (R)par[L.p_beta + F + 1], xb1);
+      const R sc = sqrt(S22 * k2);
+      const R parA = fabs(ze - xb) / sc;
+      const R parB = sqrt(R(2) * k2 + k1 * k1) / sc;
+      R mu = parB / parA;
+      if (mu < R(1e-10)) mu = R(1e-10);
+      const uint4 w = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+      const R ig = ig_msh<R>(mu, parB * parB, normal2r<R>(w.x, w.y), u01<R>(w.z));
+      nu = R(1) / ig;
+      nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
+      if (valid && q == 0) A.nu[i] = nu;
+    }
+    if (q == 0) {
+      R* u = s_u + p * Dgp;
+      u[0] = valid ? R(1) : R(0);
+      u[F + 1] = valid ? th : R(0);
+      u[F + 2] = valid ? ze : R(0);
+      u[F + 3] = (valid && qr) ? nu : R(0);
+      u[F + 4] = (valid && qr) ? R(1) / nu : R(0);  // weight of the nu-weighted Gram
+    }
+
+    // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
+    float ll_tile = 0.f;
+    uint32_t my_defer = 0;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int g = group_of<TPP>(q, kk);
+      if (g >= G) continue;
+      Quad<R> out;
+      if (!valid) {
+        out.v[0] = out.v[1] = out.v[2] = out.v[3] = R(0);
+        st4(my_om + 4 * g, out);
+        continue;
+      }
+      const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
+      const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
+      const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+      if constexpr (F32) {
+        const uint4 wA = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
+        const uint4 wB = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
+        const uint32_t ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float z = fmaf(pA.v[e], th, -pAB.v[e]);
+          const float kap = ((yw >> (8 * e)) & 0xffu) ? 0.5f : -0.5f;
+          float ll;
+          float om = pg_fast_attempt0(z, kap, ww[2 * e], ww[2 * e + 1], ll);
+          if (4 * g + e >= J) { om = 0.f; ll = 0.f; }
+          ll_tile += ll;
+          my_defer += om < 0.f;
+          out.v[e] = om;
+        }
+      } else {
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * g + e;
+          if (j >= J) { out.v[e] = R(0); continue; }
+          const R z = fma(pA.v[e], th, -pAB.v[e]);
+          const R y = ((yw >> (8 * e)) & 0xffu) ? R(1) : R(0);
+          const R az = fabs(z);
+          acc_ll_bern += (double)(y * z - (R(0.5) * (z + az) + log1p(exp(-az))));
+          uint32_t na;
+          out.v[e] = pg_draw_exact<R>(A.key, gid, k + 1, j, z, 0, &na);
+          my_defer += na > 1u;
+        }
+      }
+      st4(my_om + 4 * g, out);
+    }
+    acc_ll_bern += (double)ll_tile;
+    if (valid && q == 0) acc_cells += (uint32_t)J;
+    acc_defer += my_defer;
+
+    if constexpr (F32) {
+      // ---- retry queue: every cell that left the fast path is replayed exactly (any thread may take it) ----
+      if (tid == 0) { s_qctl[0] = 0; s_qctl[1] = 0; }
+      __syncthreads();
+      uint32_t base = 0;
+      if (my_defer) base = atomicAdd(&s_qctl[0], my_defer);
+      if (my_defer) {
+        for (int kk = 0; kk < nk; ++kk) {
+          const int g = group_of<TPP>(q, kk);
+          if (g >= G) continue;
+          const Quad<R> om = ld4(my_om + 4 * g);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (om.v[e] < R(0)) {
+              const int j = 4 * g + e;
+              const uint32_t first = (om.v[e] == R(-1)) ? 0u : 1u;
+              const uint32_t entry = (first << 31) | ((uint32_t)p << 20) | (uint32_t)j;
+              if (base < (uint32_t)QCAP) s_queue[base] = entry;
+              else {  // queue overflow: finish the cell here
+                const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)th, -(float)s_par[PAR_AB * Jp + j]);
+                my_om[j] = (R)pg_draw_exact<float>(A.key, gid, k + 1, j, z, (int)first);
+              }
+              ++base;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
+      while (true) {
+        const uint32_t idx = atomicAdd(&s_qctl[1], 1u);
+        if (idx >= qn) break;
+        const uint32_t entry = s_queue[idx];
+        const int pj = (int)(entry & 0xfffffu), pp = (int)((entry >> 20) & 0x7ffu), first = (int)(entry >> 31);
+        const float thp = (float)s_u[pp * Dgp + F + 1];
+        const float z = fmaf((float)s_par[PAR_A * Jp + pj], thp, -(float)s_par[PAR_AB * Jp + pj]);
+        const uint32_t pgid = A.person_offset + (uint32_t)(row0 + pp);
+        s_om[pp * Jp + pj] = (R)pg_draw_exact<float>(A.key, pgid, k + 1, pj, z, first);
+      }
+    }
+    __syncthreads();
+
+    // ---- per-item statistics: thread per (item group, person class), tile read transposed ----
+    {
+      const int Rc = G >= CTA_THREADS ? 1 : CTA_THREADS / G;
+      for (int slot = tid; slot < G * Rc; slot += CTA_THREADS) {
+        const int g = slot % G, r = slot / G;
+        float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
+        for (int pp = r; pp < P; pp += Rc) {
+          const float tp = (float)s_u[pp * Dgp + F + 1], zp = (float)s_u[pp * Dgp + F + 2];
+          const Quad<R> om = ld4(s_om + pp * Jp + 4 * g);
+          const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * g);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float w = (float)om.v[e];
+            const float tw = tp * w;
+            a0[e] += w;
+            a1[e] += tw;
+            a2[e] = fmaf(tp, tw, a2[e]);
+            ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : 0.f;
+          }
+          if (has_rt) {
+            const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * g);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ac[e] = fmaf((float)lt.v[e], zp, ac[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * g + e;
+          atomicAdd(&s_acc_item[0 * Jp + j], (double)a0[e]);
+          atomicAdd(&s_acc_item[1 * Jp + j], (double)a1[e]);
+          atomicAdd(&s_acc_item[2 * Jp + j], (double)a2[e]);
+          atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
+          atomicAdd(&s_acc_item[4 * Jp + j], (double)ac[e]);
+        }
+      }
+      // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin (entries owned by one thread each)
+      for (int t = tid; t < L.ntri; t += CTA_THREADS) {
+        int r = 0, rem = t;
+        while (rem >= Dg - r) { rem -= Dg - r; ++r; }
+        const int c = r + rem;
+        double g0 = 0.0, g1 = 0.0;
+        for (int pp = 0; pp < P; ++pp) {
+          const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
+          g0 += ur * uc;
+          if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
+        }
+        s_acc_gram[t] += g0;
+        if (qr) s_acc_gram[L.ntri + t] += g1;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
+  }
+
+  // ---- flush CTA accumulators ----
+  atomicAdd(&s_scal[SC_LL_BERN], acc_ll_bern);
+  if (q == 0) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
+  atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
+  if (q == 0) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
+  __syncthreads();
+  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
+    const int j = t % Jp;
+    if (j < J) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
+  }
+  for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS)
+    if (t < L.ntri || qr) atomicAdd(&A.stats[L.s_gram + t], s_acc_gram[t]);
+  if (tid < SC_COUNT) atomicAdd(&A.stats[L.s_scal + tid], s_scal[tid]);
+  if (tid == 0) tma_store_wait_all();
+}
+
+// ---------------- parity / distribution-test kernels ----------------
+template <typename R>
+__global__ void k_pg_kernel(const double* z, int64_t rows, int cols, int64_t row0, PhiloxKey key, uint32_t sweep, double* out) {
+  const int64_t n = rows * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / cols;
+    const int j = (int)(t % cols);
+    const uint32_t gid = (uint32_t)(row0 + i);
+    const R zz = (R)z[t];
+    R om;
+    if constexpr (sizeof(R) == 4) {
+      const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
+      float ll;
+      om = (j & 1) ? pg_fast_attempt0(zz, 0.5f, w.z, w.w, ll) : pg_fast_attempt0(zz, 0.5f, w.x, w.y, ll);
+      if (om < 0.f) om = pg_draw_exact<float>(key, gid, sweep, j, zz, om == -1.0f ? 0 : 1);
+    } else {
+      om = pg_draw_exact<R>(key, gid, sweep, j, zz, 0);
+    }
+    out[t] = (double)om;
+  }
+}
+
+template <typename R>
+__global__ void k_nu_person_kernel(const double* mu, double lam, int64_t n, int64_t row0, PhiloxKey key, uint32_t sweep, double* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 w = philox(key, (uint32_t)(row0 + i), sweep, make_site(DOM_PERSON, PK_NU), 0);
+    R x = ig_msh<R>((R)mu[i], (R)lam, normal2r<R>(w.x, w.y), u01<R>(w.z));
+    R nu = R(1) / x;
+    nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
+    out[i] = (double)nu;
+  }
+}
+
+__global__ void k_philox_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  PhiloxKey k{key[0], key[1]};
+  uint4 w = philox(k, ctr[0], ctr[1], ctr[2], ctr[3]);
+  out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = w.w;
+}
+
+}  // namespace erirt

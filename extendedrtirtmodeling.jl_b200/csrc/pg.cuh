@@ -1,0 +1,216 @@
+// pg.cuh -- exact Polya-Gamma PG(1, z) draw on the device.
+//
+// Replaces rand(PolyaGammaPSWSampler(1, η)) at /root/reference/src/Draw.pl.jl:38 (PolyaGammaSamplers.jl is
+// not vendored; algorithm restated from Polson-Scott-Windle 2013 / Devroye 2009, see oracle/pg.c for the
+// full statement).  PG(1,z) = J*(1,c)/4, c = |z|/2, truncation point t = 0.64:
+//   Method A (c <= 1/t): envelope = exponential tail on (t,inf) [mass p] + truncated-Levy piece on (0,t)
+//     [mass q0 = 4 Phic(1/sqrt t), sampled by inverse CDF], the tilt exp(-c^2 x/2) folded into acceptance.
+//   Method B (c > 1/t):  envelope = exponential tail + full IG(1/c,1) (Michael-Schucany-Haas), rejected if x >= t.
+// A rejected attempt restarts from the mixture choice with fresh words (attempt counter in the Philox
+// counter), so every draw is a pure function of (seed, chain, person, item, sweep).
+//
+// Two code paths share this statement:
+//   * pg_draw_exact<R>  -- complete loop, used for f64 everywhere and for the f32 retry queue;
+//   * pg_fast_attempt0  -- f32 branch-free evaluation of attempt 0 of Method A with squeeze tests that
+//     only ever say "certainly accepted"; every other outcome is replayed by pg_draw_exact<float>.
+#pragma once
+#include "pg_coeffs.h"
+#include "rng.cuh"
+
+namespace erirt {
+
+constexpr double PG_T = 0.64;
+constexpr double PG_P0 = 0.10564977366685535;     // Phic(1/sqrt(t))
+constexpr double PG_Q0 = 0.4225990946674214;      // 4 * PG_P0
+constexpr double PG_CSWITCH = 1.5625;             // 1/t
+constexpr double PI_D = 3.14159265358979323846;
+constexpr double PG_M2LNP0 = 4.4952513544286345;  // -2 ln(PG_P0)
+constexpr double PG_R1MAX_RIGHT = 0.005418509355439241;  // 3 exp(-pi^2 t): bound of a_1/a_0 on x >= t
+constexpr double PG_R1MAX_LEFT = 0.005791362408683128;   // 3 exp(-4/t):    bound of a_1/a_0 on x <= t
+
+__device__ __constant__ const float c_xq[ERIRT_XQ_DEG + 1] = ERIRT_XQ_COEFFS;
+__device__ __constant__ const float c_l1p[ERIRT_L1P_DEG + 1] = ERIRT_L1P_COEFFS;
+
+// s/Z as a polynomial in r = 1/s, s = sqrt(-2 ln y), Z = Phic^{-1}(y), y in (0, PG_P0]
+__device__ __forceinline__ float xq_poly(float r) {
+  const float x = fmaf(r, (float)ERIRT_XQ_A, (float)ERIRT_XQ_B);
+  float p = (float)c_xq[ERIRT_XQ_DEG];
+#pragma unroll
+  for (int k = ERIRT_XQ_DEG - 1; k >= 0; --k) p = fmaf(p, x, c_xq[k]);
+  return p;
+}
+// ln(1 + w), w in [0,1]
+__device__ __forceinline__ float log1p_poly(float w) {
+  const float x = fmaf(w, (float)ERIRT_L1P_A, (float)ERIRT_L1P_B);
+  float p = c_l1p[ERIRT_L1P_DEG];
+#pragma unroll
+  for (int k = ERIRT_L1P_DEG - 1; k >= 0; --k) p = fmaf(p, x, c_l1p[k]);
+  return p * w;
+}
+
+// Phic^{-1}(y) for y in (0, PG_P0]: f32 = polynomial; f64 = polynomial start + Newton on ln Phic(Z) = ln y
+template <typename R>
+__device__ __forceinline__ R inv_normal_tail(R y);
+template <>
+__device__ __forceinline__ float inv_normal_tail<float>(float y) {
+  float r = rsqrtf(-2.0f * logf(y));
+  return 1.0f / (r * xq_poly(r));
+}
+template <>
+__device__ __forceinline__ double inv_normal_tail<double>(double y) {
+  double ly = log(y);
+  float rf = rsqrtf((float)(-2.0 * ly));
+  double z = 1.0 / ((double)rf * (double)xq_poly(rf));
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    double sf = 0.5 * erfc(z * 0.70710678118654752440);
+    double pdf = 0.39894228040143267794 * exp(-0.5 * z * z);
+    z += (log(sf) - ly) * sf / pdf;
+  }
+  return z;
+}
+
+// alternating-series acceptance: U <= sum_n (-1)^n a_n(x)/a_0(x) ?
+template <typename R>
+__device__ __forceinline__ bool series_accept(R U, R x, bool right) {
+  const R e = right ? R(-0.5 * PI_D * PI_D) * x : R(-2.0) / x;
+  R S = R(1);
+#pragma unroll 1
+  for (int n = 1; n < 400; ++n) {
+    R rn = R(2 * n + 1) * exp(e * R(n * n + n));
+    if (n & 1) {
+      S -= rn;
+      if (U <= S) return true;
+    } else {
+      S += rn;
+      if (U > S) return false;
+    }
+  }
+  return false;
+}
+
+template <typename R>
+__device__ __forceinline__ bool pg_attempt_A(R c, uint32_t wa, uint32_t wb, R& X) {
+  const R um = u01<R>(wa), up = u01<R>(wb);
+  const R K = R(PI_D * PI_D / 8.0) + R(0.5) * c * c;
+  const R Rm1 = R(2.0 * PG_Q0 / PI_D) * K * exp(K * R(PG_T));  // q0 / p
+  const R v = um * (R(1) + Rm1);
+  if (v < R(1)) {
+    R x = R(PG_T) - log(up) / K;
+    if (!series_accept<R>(v, x, true)) return false;
+    X = x;
+    return true;
+  }
+  const R Z = inv_normal_tail<R>(up * R(PG_P0));
+  const R x = R(1) / (Z * Z);
+  const R ua = (v - R(1)) / Rm1;
+  const R tilt = exp(R(-0.5) * c * c * x);
+  if (ua >= tilt) return false;
+  if (!series_accept<R>(ua / tilt, x, false)) return false;
+  X = x;
+  return true;
+}
+
+template <typename R>
+__device__ __forceinline__ bool pg_attempt_B(R c, uint4 w, R& X) {
+  const R um = u01<R>(w.x);
+  const R K = R(PI_D * PI_D / 8.0) + R(0.5) * c * c;
+  const R p = (R(PI_D) / (R(2) * K)) * exp(-K * R(PG_T));
+  const R ql = R(2) * exp(-c);
+  const R Pr = p / (p + ql);
+  if (um < Pr) {
+    R x = R(PG_T) - log(u01<R>(w.y)) / K;
+    if (!series_accept<R>(um / Pr, x, true)) return false;
+    X = x;
+    return true;
+  }
+  const R ua = (um - Pr) / (R(1) - Pr);
+  const R z = normal2r<R>(w.y, w.z);
+  const R x = ig_msh<R>(R(1) / c, R(1), z, u01<R>(w.w));
+  if (!(x < R(PG_T))) return false;
+  if (!series_accept<R>(ua, x, false)) return false;
+  X = x;
+  return true;
+}
+
+constexpr uint32_t PG_MAX_ATTEMPTS = 100000u;  // bound on every device loop (NaN inputs must not hang the GPU)
+
+// Complete draw of omega_ij ~ PG(1, z); first_attempt = 0 replays attempt 0, 1 skips it (already known rejected).
+template <typename R>
+__device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint32_t sweep, int j, R z, int first_attempt,
+                                           uint32_t* n_attempts = nullptr) {
+  const R c = R(0.5) * fabs(z);
+  R X = R(PG_T);
+  uint32_t used = 0;
+  if (c <= R(PG_CSWITCH)) {
+    bool done = false;
+    if (first_attempt == 0) {
+      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
+      ++used;
+      done = (j & 1) ? pg_attempt_A<R>(c, w.z, w.w, X) : pg_attempt_A<R>(c, w.x, w.y, X);
+    }
+#pragma unroll 1
+    for (uint32_t a = 1; !done && a < PG_MAX_ATTEMPTS; ++a) {
+      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
+      ++used;
+      done = pg_attempt_A<R>(c, w.x, w.y, X);
+    }
+  } else {
+    bool done = false;
+#pragma unroll 1
+    for (uint32_t a = 1; !done && a < PG_MAX_ATTEMPTS; ++a) {
+      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
+      ++used;
+      done = pg_attempt_B<R>(c, w, X);
+    }
+  }
+  if (n_attempts) *n_attempts = used;
+  return R(0.25) * X;
+}
+
+// MUFU approximations (2^-22 relative error), one SASS instruction each
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// ---- f32 fast path: attempt 0 of Method A, branch-free, intrinsics only ----
+// Returns omega (= X/4) when the attempt is CERTAINLY accepted, a negative sentinel otherwise:
+//   -1: outcome undecided by the squeezes (replay attempt 0 exactly), -2: attempt 0 certainly rejected,
+//   -3: c > 1/t (Method B cell, attempts start at 1).
+// Also returns the Bernoulli log-likelihood term  y z - log(1 + e^z) = kappa z - c - ln(1 + e^{-2c}).
+__device__ __forceinline__ float pg_fast_attempt0(float z, float kappa, uint32_t wa, uint32_t wb, float& loglik) {
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const float c = 0.5f * fabsf(z);
+  const float w2c = fast_ex2(-2.0f * LOG2E * c);
+  loglik = fmaf(kappa, z, -c) - log1p_poly(w2c);
+
+  const float K = fmaf(0.5f * c, c, (float)(PI_D * PI_D / 8.0));
+  const float eKt = fast_ex2(K * (float)(PG_T * 1.4426950408889634));
+  const float Rm1 = (float)(2.0 * PG_Q0 / PI_D) * K * eKt;
+  const float um = u01f(wa), up = u01f(wb);
+  const float v = fmaf(um, Rm1, um);
+  const bool right = v < 1.0f;
+  const float L = fast_lg2(up);  // shared by both branches
+  // right: X = t + E/K, E = -ln(up)
+  const float Xr = fmaf(-LN2 * L, fast_rcp(K), (float)PG_T);
+  const bool acc_r = v <= (float)(1.0 - PG_R1MAX_RIGHT);
+  // left: y = up*P0, Lw = -2 ln y, r = rsqrt(Lw), X = (r * XQ(r))^2
+  const float Lw = fmaf(-2.0f * LN2, L, (float)PG_M2LNP0);
+  const float r = fast_rsqrt(Lw);
+  const float rz = r * xq_poly(r);
+  const float Xl = rz * rz;
+  const float tilt = fast_ex2((-0.5f * LOG2E) * c * c * Xl);
+  const float lhs = v - 1.0f;
+  const float rhs = Rm1 * tilt;
+  const bool acc_l = lhs < rhs * (float)(1.0 - PG_R1MAX_LEFT);
+  const bool rej_l = lhs >= rhs;  // ua >= tilt: no series can rescue it
+  float X = right ? Xr : Xl;
+  float out = 0.25f * X;
+  const bool acc = right ? acc_r : acc_l;
+  if (!acc) out = (!right && rej_l) ? -2.0f : -1.0f;
+  if (c > (float)PG_CSWITCH) out = -3.0f;
+  return out;
+}
+
+}  // namespace erirt

@@ -1,0 +1,154 @@
+"""Thin object wrapper over the C ABI: one Engine == one erirt_handle (one chain, or one person shard of a chain)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ErirtError, check  # noqa: F401
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Engine:
+    def __init__(self, model, n_subj, n_item, n_feat=0, *, n_iter=5000, n_chain=1, n_burnin=None, q_rt=0.5,
+                 intercept=False, itemtype="2pl", cov2one=True, dtype="f32", seed=1234, chain=0, compat=0,
+                 person_trace=False, device=0, use_graph=True, n_subj_total=None, subj_offset=0):
+        if itemtype not in ("1pl", "2pl"):
+            # same text as the reference's sample! (src/GibbsRtIrt.pl.jl:212-214)
+            raise ValueError("Invalid input: the item type must be '1pl' or '2pl'.")
+        L = _lib.load()
+        self.lib = L
+        mid = _lib.MODELS[model] if isinstance(model, str) else int(model)
+        cfg = _lib.Config()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.model = mid
+        cfg.n_subj = n_subj
+        cfg.n_subj_total = n_subj if n_subj_total is None else n_subj_total
+        cfg.subj_offset = subj_offset
+        cfg.n_item, cfg.n_feat = n_item, n_feat
+        cfg.n_iter, cfg.n_chain = n_iter, n_chain
+        cfg.n_burnin = int(round(n_iter / 2)) if n_burnin is None else n_burnin
+        cfg.q_rt = q_rt
+        cfg.intercept, cfg.itemtype_1pl, cfg.cov2one = int(intercept), int(itemtype == "1pl"), int(cov2one)
+        cfg.dtype = {"f32": _lib.F32, "f64": _lib.F64}[dtype]
+        cfg.seed, cfg.chain, cfg.compat = seed, chain, compat
+        cfg.person_trace, cfg.device, cfg.use_graph = int(person_trace), device, int(use_graph)
+        self.cfg = cfg
+        self.model = mid
+        self.N, self.J, self.F = n_subj, n_item, n_feat
+        self.h = C.c_void_p()
+        check(L.erirt_create(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.erirt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data / state ----
+    def set_data(self, Y, logT=None, X=None):
+        Y = np.asfortranarray(Y, dtype=np.float64)
+        assert Y.shape == (self.N, self.J), Y.shape
+        T = np.asfortranarray(logT, dtype=np.float64) if logT is not None else None
+        Xf = np.asfortranarray(X, dtype=np.float64) if (X is not None and self.F > 0) else None
+        check(self.lib.erirt_set_data(self.h, Y.ctypes.data, Y.shape[0], T.ctypes.data if T is not None else None,
+                                      T.shape[0] if T is not None else 0, Xf.ctypes.data if Xf is not None else None,
+                                      Xf.shape[0] if Xf is not None else 0))
+
+    def set_data_device(self, dY_ptr, ldY, dlogT_ptr, ldT, dX_ptr, ldX):
+        """Column-major float64 buffers already on this engine's device (e.g. torch tensors' data_ptr())."""
+        check(self.lib.erirt_set_data_device(self.h, dY_ptr, ldY, dlogT_ptr, ldT, dX_ptr, ldX))
+
+    def set_state(self, **fields):
+        for k, v in fields.items():
+            if v is None:
+                continue
+            a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel(order="F"))
+            check(self.lib.erirt_set_state(self.h, _lib.FIELDS[k.rstrip("_")], _dp(a), a.size))
+
+    def get_state(self, name):
+        fid = _lib.FIELDS[name]
+        n = {"theta": self.N, "zeta": self.N, "nu": self.N, "omega": self.N * self.J, "a": self.J, "b": self.J,
+             "lambda": self.J, "sigma2": self.J, "rho": self.J, "Sigma": 4,
+             "beta": {0: self.F + 1, 1: 2 * (self.F + 1), 2: 2 * (self.F + 1), 5: self.F + 2, 6: self.F + 2}.get(self.model, 0)}[name]
+        out = np.empty(n, dtype=np.float64)
+        check(self.lib.erirt_get_state(self.h, fid, _dp(out), n))
+        if name == "omega":
+            return out.reshape((self.N, self.J), order="F")
+        if name == "Sigma":
+            return out.reshape((2, 2), order="F")
+        return out
+
+    # ---- sampling ----
+    def sample(self, n_sweeps):
+        check(self.lib.erirt_sample(self.h, int(n_sweeps)))
+
+    def trace_width(self, which):
+        return int(self.lib.erirt_trace_width(self.h, _lib.TRACES[which]))
+
+    def get_trace(self, which, first_col=0, n_cols=None):
+        """Julia-layout array (nIter, n_cols, nChain) of Post.<which>[:, first_col:first_col+n_cols, :]."""
+        W = self.trace_width(which)
+        if n_cols is None:
+            n_cols = W - first_col
+        out = np.empty((self.cfg.n_iter, n_cols, self.cfg.n_chain), dtype=np.float64, order="F")
+        check(self.lib.erirt_get_trace(self.h, _lib.TRACES[which], first_col, n_cols, _dp(out)))
+        return out
+
+    def get_moments(self, name):
+        mean = np.empty(self.N)
+        sd = np.empty(self.N)
+        check(self.lib.erirt_get_moments(self.h, _lib.FIELDS[name], _dp(mean), _dp(sd), self.N))
+        return mean, sd
+
+    def stats(self):
+        s = _lib.Stats()
+        check(self.lib.erirt_get_stats(self.h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in _lib.Stats._fields_}
+
+    # ---- multi-GPU ----
+    def comm_init(self, rank, world, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self.lib.erirt_comm_init(self.h, rank, world, buf))
+
+
+def nccl_unique_id() -> bytes:
+    L = _lib.load()
+    buf = C.create_string_buffer(128)
+    check(L.erirt_nccl_unique_id(buf))
+    return buf.raw
+
+
+# ---- parity entry points ----
+def k_pg(z, seed=1234, chain=0, sweep=1, row0=0, dtype="f64", device=0):
+    L = _lib.load()
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    rows, cols = z.shape
+    out = np.empty_like(z)
+    check(L.erirt_k_pg(_dp(z), rows, cols, row0, seed, chain, sweep, {"f32": 0, "f64": 1}[dtype], device, _dp(out)))
+    return out
+
+
+def k_nu_person(mu, lam, seed=1234, chain=0, sweep=1, row0=0, dtype="f64", device=0):
+    L = _lib.load()
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    out = np.empty_like(mu)
+    check(L.erirt_k_nu_person(_dp(mu), lam, mu.size, row0, seed, chain, sweep, {"f32": 0, "f64": 1}[dtype], device,
+                              _dp(out)))
+    return out
+
+
+def k_philox(ctr, key, device=0):
+    L = _lib.load()
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    check(L.erirt_k_philox(c, k, device, o))
+    return [int(v) for v in o]

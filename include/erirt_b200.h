@@ -1,0 +1,141 @@
+/*
+ * erirt_b200.h -- C ABI of the B200-native Gibbs sweep engine for ExtendedRtIrtModeling.jl.
+ *
+ * Drop-in boundary: the reference has no FFI; its boundary is the Julia method table
+ *   sample!(MCMC::T; intercept, itemtype, cov2one)
+ * for T in GibbsMlIrt (/root/reference/src/GibbsRtIrt.pl.jl:210), GibbsRtIrt (:278), GibbsRtIrtNull (:367),
+ * GibbsRtIrtCross (src/GibbsRtIrtCross.pl.jl:176), GibbsRtIrtCrossQr (:265),
+ * GibbsRtIrtLatent (src/GibbsRtIrtLatent.pl.jl:168), GibbsRtIrtLatentQr (:271; README's GibbsRtIrtQuantile).
+ * A Julia `sample!` shim (julia/ErirtB200.jl) calls the functions below through `ccall`:
+ *   erirt_create      <- MCMC.Cond::SimConditions            (src/Base.pl.jl:45-62) + sample! kwargs
+ *   erirt_set_data    <- MCMC.Data::InputData Y, logT, X      (src/Base.pl.jl:67-78)
+ *   erirt_set_state   <- MCMC.Para::InputPara initial values  (setInitialValues, src/GibbsRtIrt.pl.jl:84-133)
+ *   erirt_sample      <- the `for m in 1:nIter, l in 1:nChain` loop body (src/GibbsRtIrt.pl.jl:289-324)
+ *   erirt_get_trace   -> Post.ra / Post.rt / Post.qr / Post.logLike, Julia layout [nIter, P, nChain] (:319-323)
+ *   erirt_get_moments -> Post.mean.θ / ζ / ν (and SDs) when the person trace is not kept
+ *
+ * Conventions: every function returns 0 on success or a negative ERIRT_E_* code; the message is available
+ * from erirt_last_error() (thread-local).  No C++ exception crosses this boundary.  Host buffers are owned
+ * by the caller and are not retained after a call returns.  One caller thread per handle.  There is NO CPU
+ * fallback: without a usable sm_100 CUDA device erirt_create fails with ERIRT_E_CUDA.
+ */
+#ifndef ERIRT_B200_H
+#define ERIRT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERIRT_ABI_VERSION 1
+
+enum erirt_model {
+  ERIRT_MLIRT = 0, ERIRT_RTIRT = 1, ERIRT_RTIRT_NULL = 2, ERIRT_RTIRT_CROSS = 3, ERIRT_RTIRT_CROSSQR = 4,
+  ERIRT_RTIRT_LATENT = 5, ERIRT_RTIRT_LATENTQR = 6 /* == GibbsRtIrtQuantile */
+};
+enum erirt_dtype { ERIRT_F32 = 0, ERIRT_F64 = 1 };
+enum erirt_error {
+  ERIRT_OK = 0, ERIRT_E_ARG = -1, ERIRT_E_CUDA = -2, ERIRT_E_STATE = -3, ERIRT_E_NCCL = -4, ERIRT_E_UNSUPPORTED = -5,
+  ERIRT_E_NUMERIC = -6
+};
+/* compat flags; 0 reproduces the reference source as written (SURVEY quirk register) */
+enum erirt_compat { ERIRT_COMPAT_BETA_PRIOR_DIAG = 1, ERIRT_COMPAT_LATENTQR_SCALE_ELEMENTWISE = 2 };
+
+/* state / trace selectors */
+enum erirt_field {
+  ERIRT_THETA = 0, ERIRT_ZETA = 1, ERIRT_A = 2, ERIRT_B = 3, ERIRT_LAMBDA = 4, ERIRT_SIGMA2 = 5, ERIRT_BETA = 6,
+  ERIRT_RHO = 7, ERIRT_SIGMA_P = 8, ERIRT_NU = 9, ERIRT_OMEGA = 10
+};
+enum erirt_trace { ERIRT_TRACE_RA = 0, ERIRT_TRACE_RT = 1, ERIRT_TRACE_QR = 2, ERIRT_TRACE_LOGLIKE = 3 };
+
+typedef struct erirt_handle erirt_handle;
+
+typedef struct erirt_config {
+  int32_t abi_version;    /* ERIRT_ABI_VERSION */
+  int32_t model;          /* enum erirt_model */
+  int64_t n_subj;         /* persons held by THIS handle (a shard of one chain, or all of them) */
+  int64_t n_subj_total;   /* persons of the whole chain (== n_subj when not sharded) */
+  int64_t subj_offset;    /* global id of this handle's first person (RNG counters use global ids) */
+  int32_t n_item, n_feat;
+  int32_t n_iter, n_chain; /* Cond.nIter, Cond.nChain: trace capacity is n_iter*n_chain sweeps, sweep s is
+                              (m,l) = ((s-1) / n_chain + 1, (s-1) % n_chain + 1) as in src/GibbsRtIrt.pl.jl:289 */
+  int32_t n_burnin;       /* Cond.nBurnin (the reference always passes round(nIter/2), src/Base.pl.jl:60) */
+  double q_rt;            /* Cond.qRt (Cond.qRa is never read by the reference) */
+  int32_t intercept, itemtype_1pl, cov2one; /* sample! keyword arguments */
+  int32_t dtype;          /* enum erirt_dtype: storage and per-cell arithmetic; statistics are always f64 */
+  uint64_t seed;
+  uint32_t chain;         /* independent-chain id mixed into the Philox key */
+  int32_t compat;         /* enum erirt_compat bits */
+  int32_t person_trace;   /* 1: keep theta/zeta(/nu) of every sweep on the device (small problems) */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t use_graph;      /* 1: replay sweeps from a captured CUDA graph */
+  int32_t reserved[8];
+} erirt_config;
+
+typedef struct erirt_stats {
+  int64_t sweeps_done;
+  double last_sample_ms;      /* device time of the last erirt_sample call (CUDA events) */
+  double person_kernel_ms;    /* mean duration of the person-sweep kernel in that call (0 under graph replay) */
+  int64_t bytes_per_sweep;    /* algorithmic HBM bytes of one sweep for this shard */
+  double pg_deferred_frac;    /* fraction of PG cells that needed the exact/retry path in the last sweep */
+  int32_t launches_per_sweep; /* kernels this library launches per sweep */
+  int32_t sm_count;
+} erirt_stats;
+
+int erirt_version(void);
+const char* erirt_last_error(void);
+
+int erirt_create(const erirt_config* cfg, erirt_handle** out);
+int erirt_destroy(erirt_handle* h);
+
+/* Host, column-major float64 as Julia stores them: Y[i + ldY*j] in {0,1}, logT[i + ldT*j] = log(T),
+ * X[i + ldX*k].  i runs over this handle's n_subj persons, so a shard passes a pointer offset into the
+ * full matrix with the full leading dimension.  logT may be NULL for GibbsMlIrt; X may be NULL if n_feat=0. */
+int erirt_set_data(erirt_handle* h, const double* Y, int64_t ldY, const double* logT, int64_t ldT,
+                   const double* X, int64_t ldX);
+/* Same contract with the buffers already on this handle's device (cudaMalloc'ed by the caller). */
+int erirt_set_data_device(erirt_handle* h, const double* dY, int64_t ldY, const double* dlogT, int64_t ldT,
+                          const double* dX, int64_t ldX);
+
+/* Initial / current values of one InputPara field (float64, Julia layout: beta is vec(β) column-major,
+ * SIGMA_P is vec(Σp), NU is n_subj (LatentQr) or n_subj x n_item column-major (CrossQr), OMEGA n_subj x n_item). */
+int erirt_set_state(erirt_handle* h, int32_t field, const double* v, int64_t n);
+int erirt_get_state(erirt_handle* h, int32_t field, double* out, int64_t n);
+
+/* Run n_sweeps more sweeps (blocking).  The first call also draws the sweep-1 auxiliaries from the initial state. */
+int erirt_sample(erirt_handle* h, int64_t n_sweeps);
+
+/* Copy columns [first_col, first_col+n_cols) of Post.<which> for all sweeps done so far into `out`,
+ * laid out like the Julia array restricted to those columns: out[m + n_iter*(c + n_cols*l)].
+ * Column order is the reference's: ra = [θ; a; b], rt = [ζ; λ; σ²t], qr per model.
+ * Person columns (θ, ζ, ν) need person_trace = 1. Entries of sweeps not yet run are NaN. */
+int erirt_get_trace(erirt_handle* h, int32_t which, int64_t first_col, int64_t n_cols, double* out);
+int64_t erirt_trace_width(erirt_handle* h, int32_t which);
+
+/* Post-burn-in running mean and SD (over sweeps with m > n_burnin) of THETA, ZETA or NU (person-level). */
+int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n);
+
+/* getLogLikelihood* of the CURRENT device state with the item/structural parameters given in the Julia
+ * layouts (used for DIC's D-hat at Post.mean, src/GibbsRtIrt.pl.jl:449-458): person vectors must have been
+ * set with erirt_set_state first. Not yet part of round 1 (returns ERIRT_E_UNSUPPORTED). */
+int erirt_loglik_current(erirt_handle* h, double* out);
+
+int erirt_get_stats(erirt_handle* h, erirt_stats* out);
+
+/* ---- person-sharded chains: one handle per GPU/process, item statistics all-reduced with NCCL ---- */
+int erirt_nccl_unique_id(void* id128);                 /* rank 0 creates 128 bytes, caller broadcasts them */
+int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, const void* id128);
+
+/* ---- parity entry points: one conditional kernel at a time on explicit inputs (tests only) ---- */
+/* PG(1, z) on a rows x cols row-major grid; cell (i,j) uses the sampler's counters for person row0+i, item j. */
+int erirt_k_pg(const double* z, int64_t rows, int32_t cols, int64_t row0, uint64_t seed, uint32_t chain,
+               uint32_t sweep, int32_t dtype, int32_t device, double* out);
+/* nu_i = clamp(1/IG(mu_i, lam), 1e-10, 1e10) at the person-level quantile-weight site. */
+int erirt_k_nu_person(const double* mu, double lam, int64_t n, int64_t row0, uint64_t seed, uint32_t chain,
+                      uint32_t sweep, int32_t dtype, int32_t device, double* out);
+/* Raw Philox4x32-10 block (known-answer tests). */
+int erirt_k_philox(const uint32_t ctr[4], const uint32_t key[2], int32_t device, uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
