@@ -428,24 +428,24 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
       const int Rc = G >= CTA_THREADS ? 1 : CTA_THREADS / G;
       for (int slot = tid; slot < G * Rc; slot += CTA_THREADS) {
         const int g = slot % G, r = slot / G;
-        float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
+        R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
         for (int pp = r; pp < P; pp += Rc) {
-          const float tp = (float)s_u[pp * Dgp + F + 1], zp = (float)s_u[pp * Dgp + F + 2];
+          const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
           const Quad<R> om = ld4(s_om + pp * Jp + 4 * g);
           const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * g);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float w = (float)om.v[e];
-            const float tw = tp * w;
+            const R w = om.v[e];
+            const R tw = tp * w;
             a0[e] += w;
             a1[e] += tw;
-            a2[e] = fmaf(tp, tw, a2[e]);
-            ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : 0.f;
+            a2[e] = fma(tp, tw, a2[e]);
+            ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
           }
           if (has_rt) {
             const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * g);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) ac[e] = fmaf((float)lt.v[e], zp, ac[e]);
+            for (int e = 0; e < 4; ++e) ac[e] = fma(lt.v[e], zp, ac[e]);
           }
         }
 #pragma unroll

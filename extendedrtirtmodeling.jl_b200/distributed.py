@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing, one process per GPU (torchrun): person sharding of one chain and independent chains.
+
+torch.distributed is used only as the bootstrap (rendezvous, broadcasting the 128-byte NCCL id, gathering
+results); the per-sweep exchange of item statistics is an ncclAllReduce issued by the library itself on its own
+stream (csrc/erirt_b200.cu, enqueue_step).  SURVEY.md 8e."""
+import numpy as np
+
+
+def shard_bounds(n_total, world, rank):
+    """Contiguous person blocks, sizes differing by at most one: returns (offset, count)."""
+    base, rem = divmod(int(n_total), int(world))
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def chain_assignment(n_chains, world, rank):
+    """Independent chains c -> GPU c mod world."""
+    return [c for c in range(n_chains) if c % world == rank]
+
+
+def broadcast_bytes(payload, src=0, group=None, nbytes=128):
+    """Broadcast a fixed-size byte string from `src` with torch.distributed (any backend)."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    if dist.get_rank(group) == src:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=src, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def make_shard(n_total, group=None):
+    """Returns the `shard` tuple accepted by api.sample / Engine.comm_init for this rank:
+    (rank, world, nccl_unique_id, subj_offset, n_subj_total) plus the local person count."""
+    import torch.distributed as dist
+    from .engine import nccl_unique_id
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = nccl_unique_id() if rank == 0 else b"\0" * 128
+    uid = broadcast_bytes(uid, 0, group)
+    offset, count = shard_bounds(n_total, world, rank)
+    return (rank, world, uid, offset, n_total), count
+
+
+def gather_person_vector(local, n_total, group=None):
+    """All-gather the shards of a person-level vector (theta/zeta/nu means) back into one array of n_total."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    sizes = [shard_bounds(n_total, world, r)[1] for r in range(world)]
+    mx = max(sizes)
+    buf = torch.zeros(mx, dtype=torch.float64, device=dev)
+    buf[: len(local)] = torch.as_tensor(np.asarray(local, dtype=np.float64), device=dev)
+    outs = [torch.zeros(mx, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(outs, sizes)])

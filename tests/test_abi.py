@@ -1,0 +1,78 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol that
+include/erirt_b200.h declares, and fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "erirt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(erirt_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from erirt_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from erirt_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/erirt_b200.h but not exported"
+    assert sorted(_lib.EXPORTED) == declared
+    assert lib.erirt_version() == _lib.ABI_VERSION
+
+
+def test_config_struct_matches_header(lib):
+    from erirt_b200 import _lib
+    # field order and sizes of erirt_config as laid out by the C compiler
+    assert ctypes.sizeof(_lib.Config) == 144 and ctypes.sizeof(_lib.Stats) == 48
+    assert _lib.Config.q_rt.offset == 56 and _lib.Config.seed.offset == 80 and _lib.Config.reserved.offset == 108
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device every compute entry point must fail with ERIRT_E_CUDA, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import erirt_b200 as E
+    with pytest.raises(E.ErirtError) as ei:
+        E.Engine("RtIrtNull", 10, 3, 0)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+    with pytest.raises(E.ErirtError):
+        E.k_pg(np.zeros((2, 2)))
+    with pytest.raises(E.ErirtError):
+        E.k_philox([0] * 4, [0] * 2)
+
+
+def test_argument_validation_happens_before_cuda(lib):
+    import erirt_b200 as E
+    with pytest.raises(ValueError, match="item type must be '1pl' or '2pl'"):
+        E.Engine("RtIrt", 10, 3, 1, itemtype="3pl")
+    with pytest.raises(E.ErirtError) as ei:
+        E.Engine("RtIrt", 10, 3, 1, q_rt=1.5)
+    assert ei.value.code == -1
+    with pytest.raises(E.ErirtError) as ei:
+        E.Engine("RtIrt", 0, 3, 1)
+    assert ei.value.code == -1
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing in the package may reference it."""
+    pkg = os.path.join(ROOT, "extendedrtirtmodeling.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_py" not in txt and "liberirt_oracle" not in txt and "import oracle" not in txt, f

@@ -1,0 +1,297 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs and the same Philox stream.
+
+Tolerances (BASELINE.json north_star): 1e-12 relative in f64 for one conditional kernel / one sweep given
+identical inputs and uniforms, 1e-5 in f32; posterior moments within Monte-Carlo standard error."""
+import numpy as np
+import pytest
+
+from helpers import MODELS, make_problem, relerr, run_engine, run_oracle
+from test_oracle import PHILOX_KAT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import erirt_b200
+    erirt_b200._lib.load()  # fails loudly if the CUDA extension is missing: there is no fallback
+    return erirt_b200
+
+
+def test_philox_known_answers_on_device(E):
+    for ctr, key, exp in PHILOX_KAT:
+        assert E.k_philox(ctr, key) == exp
+
+
+def _z_grid(seed, rows=3000, cols=19):
+    rng = np.random.default_rng(seed)
+    z = rng.normal(0, 1.6, (rows, cols))
+    z[0, :8] = [0.0, 3.124, 3.126, -4.0, 8.0, 1e-4, -25.0, 0.64]  # both methods, the switch point, extremes
+    return z
+
+
+def test_pg_kernel_f64_bitwise_path_parity(E, oracle):
+    z = _z_grid(1)
+    ref = oracle.pg_grid(z, seed=5, chain=2, sweep=3, row0=10)
+    out = E.k_pg(z, seed=5, chain=2, sweep=3, row0=10, dtype="f64")
+    assert relerr(out, ref).max() < 1e-12
+
+
+def test_pg_kernel_f32_parity(E, oracle):
+    z = _z_grid(2, rows=20000)
+    ref = oracle.pg_grid(z, seed=6, sweep=1)
+    out = E.k_pg(z, seed=6, sweep=1, dtype="f32")
+    e = relerr(out, ref)
+    # a branch decision may flip when a uniform lands within float rounding of a threshold: allow 1e-4 of the cells
+    assert (e > 1e-5).mean() < 1e-4
+    assert np.median(e) < 1e-6
+
+
+def test_pg_kernel_empty_and_ragged(E, oracle):
+    assert E.k_pg(np.zeros((0, 3))).shape == (0, 3)
+    z = _z_grid(3, rows=7, cols=1)
+    assert relerr(E.k_pg(z, dtype="f64"), oracle.pg_grid(z)).max() < 1e-12
+
+
+def test_pg_counters_are_global_person_ids(E):
+    """Sharding invariance of the person-level stream: rows drawn as a shard equal the same rows of the whole."""
+    z = _z_grid(4, rows=500)
+    whole = E.k_pg(z, seed=9, sweep=2, dtype="f32")
+    part = E.k_pg(z[200:], seed=9, sweep=2, row0=200, dtype="f32")
+    assert np.array_equal(whole[200:], part)
+
+
+@pytest.mark.parametrize("z", [0.0, 1.0, 3.0, 3.3, 10.0])
+def test_pg_moments_f32_large_sample(E, z):
+    n_rows, cols = 100_000, 100  # 1e7 draws
+    w = E.k_pg(np.full((n_rows, cols), z), seed=21, sweep=1, dtype="f32").ravel()
+    n = w.size
+    m = 0.25 if z == 0 else np.tanh(z / 2) / (2 * z)
+    v = 1 / 24 if z == 0 else (np.sinh(z) - z) / (4 * z ** 3 * np.cosh(z / 2) ** 2)
+    assert abs(w.mean() - m) < 4.5 * np.sqrt(v / n) + 2e-7
+    assert abs(w.var() - v) < 0.01 * v
+
+
+def test_nu_kernel_parity(E, oracle):
+    mu = np.random.default_rng(5).uniform(0.05, 80, 20000)
+    mu[:3] = [1e-10, 1e6, 1.0]
+    ref = oracle.nu_person(mu, 61.5, seed=5, sweep=2, row0=7)
+    assert relerr(E.k_nu_person(mu, 61.5, seed=5, sweep=2, row0=7, dtype="f64"), ref).max() < 1e-12
+    assert np.quantile(relerr(E.k_nu_person(mu, 61.5, seed=5, sweep=2, row0=7, dtype="f32"), ref), 0.999) < 1e-5
+
+
+def _compare_traces(eng, ref, pb, ns, tol, atol, frac_ok=1.0):
+    N = pb["N"]
+    out = {}
+    pairs = [("ra", ref["ra"])] + ([("rt", ref["rt"])] if pb["model"] != "MlIrt" else []) + [("qr", ref["qr"])]
+    for name, want in pairs:
+        got = eng.get_trace(name)[:ns, :, 0]
+        e = relerr(got, want[:ns], atol=atol).reshape(got.shape, order="F")
+        out[name] = e
+        item = e[:, N:] if name in ("ra", "rt") else e[:, : eng.trace_width("qr") - (N if pb["model"] == "RtIrtLatentQr" else 0)]
+        assert item.max() < tol, (name, "item/structural columns", item.max())
+        person = e[:, :N] if name in ("ra", "rt") else e[:, item.shape[1]:]
+        if person.size:
+            assert (person < tol).mean() >= frac_ok, (name, "person columns", person.max(), (person < tol).mean())
+    ll = eng.get_trace("logLike")[:ns, 0, 0]
+    assert relerr(ll, ref["ll"][:ns]).max() < tol
+    return out
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_one_sweep_parity_f64(E, oracle, model):
+    """Every conditional of one sweep (omega, b, a, theta, lambda, sigma2, zeta, nu, beta, Sigma, logLike) given
+    identical inputs and uniforms: 1e-12 relative (+1e-12 absolute for values crossing zero)."""
+    pb = make_problem(model, 777, 13, 3, seed=11)
+    ref = run_oracle(oracle, pb, 1)
+    eng = run_engine(E, pb, 1, dtype="f64")
+    _compare_traces(eng, ref, pb, 1, 1e-12, 1e-3)
+    eng.close()
+    # omega_1 itself: the prologue draws it from the initial state
+    eng0 = run_engine(E, pb, 0, dtype="f64")
+    assert relerr(eng0.get_state("omega"), ref["omega"]).max() < 1e-12
+    eng0.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_one_sweep_parity_f32(E, oracle, model):
+    pb = make_problem(model, 2000, 13, 3, seed=12)
+    ref = run_oracle(oracle, pb, 1)
+    eng = run_engine(E, pb, 1, dtype="f32")
+    # a flipped PG branch changes that person's theta: tolerate 0.5% of the persons
+    _compare_traces(eng, ref, pb, 1, 1e-5, 1e-1, frac_ok=0.995)
+    eng.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_multi_sweep_parity_f64(E, oracle, model):
+    pb = make_problem(model, 400, 9, 2, seed=13)
+    ns = 12
+    ref = run_oracle(oracle, pb, ns)
+    eng = run_engine(E, pb, ns, dtype="f64", use_graph=True)
+    _compare_traces(eng, ref, pb, ns, 1e-8, 1e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("model,opts", [
+    ("MlIrt", dict(intercept=True, itemtype="1pl")),
+    ("RtIrt", dict(intercept=True, itemtype="1pl", cov2one=False)),
+    ("RtIrt", dict(compat=1)),
+    ("RtIrtNull", dict(cov2one=False)),
+    ("RtIrtLatent", dict(intercept=True, cov2one=True, compat=1)),
+    ("RtIrtLatentQr", dict(intercept=True, compat=2)),
+])
+def test_keyword_and_compat_variants_f64(E, oracle, model, opts):
+    pb = make_problem(model, 300, 7, 2, seed=14)
+    ref = run_oracle(oracle, pb, 3, **opts)
+    eng = run_engine(E, pb, 3, dtype="f64", **opts)
+    _compare_traces(eng, ref, pb, 3, 1e-10, 1e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("N,J,F", [(1, 1, 0), (5, 3, 0), (129, 4, 1), (130, 33, 0), (64, 100, 3), (257, 150, 2)])
+def test_ragged_shapes_f64(E, oracle, N, J, F):
+    """Tile edges: person counts around the tile size, item counts that are not multiples of 4, no covariates."""
+    for model in ("RtIrtNull", "RtIrtLatentQr" if F else "MlIrt"):
+        pb = make_problem(model, N, J, F, seed=15)
+        ref = run_oracle(oracle, pb, 2)
+        eng = run_engine(E, pb, 2, dtype="f64")
+        _compare_traces(eng, ref, pb, 2, 1e-10, 1e-3)
+        eng.close()
+
+
+def test_graph_replay_equals_plain_launches(E):
+    pb = make_problem("RtIrtLatentQr", 900, 20, 3, seed=16)
+    a = run_engine(E, pb, 8, dtype="f32", use_graph=False)
+    b = run_engine(E, pb, 8, dtype="f32", use_graph=True)
+    # item statistics are combined with f64 atomics, so runs agree up to summation order
+    assert np.allclose(a.get_trace("qr"), b.get_trace("qr"), rtol=1e-6, atol=1e-9)
+    assert np.allclose(a.get_trace("ra")[:, 900:, :], b.get_trace("ra")[:, 900:, :], rtol=1e-6, atol=1e-9)
+    a.close(); b.close()
+
+
+def test_interleaved_chain_layout_and_moments(E, oracle):
+    """Post arrays are [nIter, P, nChain] with sweep s -> (m, l) = (s // nChain, s % nChain) (GibbsRtIrt.pl.jl:289);
+    running moments equal the moments of the stored person trace over m > nBurnin."""
+    pb = make_problem("RtIrt", 200, 6, 2, seed=17)
+    n_iter, n_chain = 6, 3
+    ref = run_oracle(oracle, pb, n_iter * n_chain)
+    eng = E.Engine("RtIrt", 200, 6, 2, n_iter=n_iter, n_chain=n_chain, n_burnin=3, dtype="f64", seed=99,
+                   person_trace=True, use_graph=False)
+    eng.set_data(pb["Y"], pb["logT"], pb["X"])
+    i = pb["init"]
+    eng.set_state(theta=i["theta"], zeta=i["zeta"], a=i["a"], b=i["b"], lambda_=i["lambda_"], sigma2=i["sigma2"],
+                  Sigma=i["Sigma"], beta=i["beta"][:6])
+    eng.sample(10)
+    eng.sample(8)  # resumable: two calls continue the same chain
+    ra = eng.get_trace("ra")
+    assert ra.shape == (n_iter, 200 + 12, n_chain)
+    for s in range(n_iter * n_chain):
+        assert relerr(ra[s // n_chain, :, s % n_chain], ref["ra"][s], atol=1e-3).max() < 1e-8
+    mean, sd = eng.get_moments("theta")
+    post = ra[3:, :200, :]
+    assert np.allclose(mean, post.mean(axis=(0, 2)), rtol=1e-10, atol=1e-12)
+    assert np.allclose(sd, post.transpose(1, 0, 2).reshape(200, -1).std(axis=1, ddof=1), rtol=1e-8, atol=1e-10)
+    with pytest.raises(E.ErirtError):
+        eng.sample(1)  # capacity nIter*nChain exhausted
+    eng.close()
+
+
+def test_person_columns_need_person_trace(E):
+    pb = make_problem("RtIrtNull", 100, 5, 0, seed=18)
+    eng = run_engine(E, pb, 2, dtype="f32", person_trace=False)
+    assert eng.get_trace("ra", 100, 10).shape == (2, 10, 1)
+    with pytest.raises(E.ErirtError):
+        eng.get_trace("ra", 0, 5)
+    eng.close()
+
+
+def test_readme_flow_recovers_item_parameters(E):
+    """README.md:61-77: setCond(nSubj=1000, nItem=15) -> GibbsMlIrt -> sample! -> getRmse on b."""
+    Cond = E.setCond(nSubj=1000, nItem=15, nIter=600, nChain=1)
+    truePara = E.setTrueParaMlIrt(Cond, rng=1234)
+    Data = E.setDataMlIrt(Cond, truePara, rng=1234)
+    MCMC = E.GibbsMlIrt(Cond, Data=Data, truePara=truePara, rng=1234)
+    E.sample(MCMC, dtype="f32")
+    assert MCMC.Post.ra.shape == (600, 1000 + 30, 1) and MCMC.Post.qr.shape == (600, 4, 1)
+    assert E.getRmse(MCMC.truePara.b, MCMC.Post.mean.b) < 0.15
+    assert abs(E.getBias(MCMC.truePara.b, MCMC.Post.mean.b)) < 0.1
+    assert E.getRmse(MCMC.truePara.a, MCMC.Post.mean.a) < 0.15
+    assert np.corrcoef(MCMC.truePara.theta, MCMC.Post.mean.theta)[0, 1] > 0.85
+
+
+def test_quantile_model_api_flow(E):
+    """README.md:87-102 with synthetic data: GibbsRtIrtQuantile(Cond, Data=Data); Post.mean.β / Σp exist."""
+    Cond = E.setCond(nSubj=631, nItem=14, nFeat=3, qRa=0.85, qRt=0.85, nChain=3, nIter=300)
+    tp = E.setTrueParaRtIrtLatent(Cond, rng=2)
+    Data = E.setDataRtIrtLatent(Cond, tp, type="skew", rng=2)
+    MCMC = E.GibbsRtIrtQuantile(Cond, Data=Data, rng=2)
+    E.sample(MCMC, dtype="f32")
+    assert MCMC.Post.mean.beta.shape == (5,) and MCMC.Post.mean.Sigma_p.shape == (4,)
+    assert MCMC.Post.qr.shape == (300, 5 + 4 + 631, 3)
+    assert np.all(np.isfinite(MCMC.Post.logLike))
+    assert E.getRmse(tp.lambda_, MCMC.Post.mean.lambda_) < 0.25
+    assert MCMC.Post.mean.beta[0] == 0.0  # intercept=false
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_posterior_moments_within_mc_error(E, oracle, dtype):
+    """Independent runs (different seeds) of the GPU sampler and the oracle agree on posterior means of the item
+    and structural parameters within 5 Monte-Carlo standard errors (MCSE = SD / sqrt(ESS))."""
+    from erirt_b200.diagnostics import ess_rhat
+    pb = make_problem("RtIrt", 600, 8, 2, seed=19)
+    ns, burn = 1600, 400
+    ref = run_oracle(oracle, pb, ns, seed=1)
+    eng = run_engine(E, pb, ns, dtype=dtype, seed=2, use_graph=True, person_trace=False)
+    N = pb["N"]
+    pairs = [(eng.get_trace("ra", N, 16)[burn:, :, 0], ref["ra"][burn:, N:]),
+             (eng.get_trace("rt", N, 16)[burn:, :, 0], ref["rt"][burn:, N:]),
+             (eng.get_trace("qr")[burn:, :, 0], ref["qr"][burn:])]
+    worst = 0.0
+    for got, want in pairs:
+        for c in range(got.shape[1]):
+            g, w = got[:, c], want[:, c]
+            if np.ptp(w) == 0 and np.ptp(g) == 0:
+                assert g[0] == w[0]
+                continue
+            se = np.sqrt(g.var() / ess_rhat(g)[0] + w.var() / ess_rhat(w)[0])
+            worst = max(worst, abs(g.mean() - w.mean()) / se)
+            assert abs(np.log(g.std() / w.std())) < 0.35
+    assert worst < 5.0, worst
+    eng.close()
+
+
+def test_full_size_properties_c5(E):
+    """BASELINE config 5 size (nSubj=1M, nItem=100, quantile model, f32): size-independent properties.
+    - E[omega | z] = tanh(z/2)/(2z) holds on average over the 1e8 cells;
+    - the sufficient statistics the device accumulated (through the drawn item parameters) are finite;
+    - posterior of the item parameters moves towards the generating values within a few sweeps."""
+    N, J, F = 1_000_000, 100, 3
+    Cond = E.setCond(nSubj=N, nItem=J, nFeat=F, qRt=0.85, nIter=8, nChain=1)
+    tp = E.setTrueParaRtIrtLatent(Cond, rng=3)
+    Data = E.setDataRtIrtLatent(Cond, tp, type="skew", rng=3)
+    eng = E.Engine("RtIrtQuantile", N, J, F, n_iter=8, n_chain=1, q_rt=0.85, cov2one=False, dtype="f32", seed=7,
+                   person_trace=False)
+    eng.set_data(Data.Y, Data.logT, Data.X)
+    rng = np.random.default_rng(3)
+    eng.set_state(theta=rng.standard_normal(N), zeta=rng.standard_normal(N), beta=rng.standard_normal(F + 2))
+    eng.sample(8)
+    a = eng.get_trace("ra", N, 2 * J)[:, :J, 0]
+    b = eng.get_trace("ra", N, 2 * J)[:, J:, 0]
+    lam = eng.get_trace("rt", N, 2 * J)[:, :J, 0]
+    assert np.all(np.isfinite(a)) and np.all(a > 0) and np.all(np.abs(b) <= 4)
+    assert np.all(np.isfinite(eng.get_trace("logLike")))
+    assert np.sqrt(np.mean((b[-1] - tp.b) ** 2)) < np.sqrt(np.mean((b[0] - tp.b) ** 2)) + 1e-3
+    assert np.sqrt(np.mean((lam[-1] - tp.lambda_) ** 2)) < 0.2
+    # omega identity on a slice (the state holds omega_{k+1} | a_k, b_k, theta_k)
+    om = eng.get_state("omega")[:50_000]
+    th = eng.get_state("theta")[:50_000]
+    z = a[-1][None, :] * (th[:, None] - b[-1][None, :])
+    expect = np.where(np.abs(z) < 1e-6, 0.25, np.tanh(z / 2) / (2 * z + 1e-300))
+    assert abs(om.mean() - expect.mean()) < 5 * np.sqrt(1 / 24 / om.size)
+    st = eng.stats()
+    assert 0 < st["pg_deferred_frac"] < 0.25
+    eng.close()

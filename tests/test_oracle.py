@@ -1,0 +1,161 @@
+"""CPU tests of the oracle (test infrastructure): it is pinned by Random123 known-answer vectors, closed-form
+moments of every variate generator, and an independent numpy transcription of src/Draw.pl.jl.
+(The reference ships no golden vectors -- parity unpinned, see oracle/oracle.h.)"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from helpers import ALL_MODELS
+
+# Random123 kat_vectors, philox4x32 with 10 rounds: (ctr, key, expected)
+PHILOX_KAT = [
+    ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+    ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+    ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+     [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+]
+
+
+def test_philox_known_answers(oracle):
+    from oracle import draw_np
+    for ctr, key, exp in PHILOX_KAT:
+        assert oracle.philox(ctr, key) == exp
+        assert list(draw_np.philox4x32_10(ctr, key)) == exp
+
+
+def test_inverse_normal_tail(oracle):
+    for y in [0.10564977366685535, 1e-2, 1e-5, 1e-9, 2.5e-11]:
+        assert abs(oracle.inv_normal_tail(y) - stats.norm.isf(y)) < 1e-12 * stats.norm.isf(y)
+
+
+@pytest.mark.parametrize("z", [0.0, 0.3, 1.0, 2.0, 3.0, 3.2, 5.0, 12.0])
+def test_pg_moments(oracle, z):
+    # E = tanh(z/2)/(2z), Var = (sinh z - z)/(4 z^3 cosh^2(z/2))  
+    n = 150_000
+    w = oracle.pg_grid(np.full((n // 50, 50), z), seed=11, sweep=2).ravel()
+    m = 0.25 if z == 0 else np.tanh(z / 2) / (2 * z)
+    v = 1 / 24 if z == 0 else (np.sinh(z) - z) / (4 * z ** 3 * np.cosh(z / 2) ** 2)
+    assert abs(w.mean() - m) < 4.5 * np.sqrt(v / n)
+    assert abs(w.var() - v) < 0.05 * v
+    assert w.min() > 0
+
+
+def _pg_cdf(x, z, terms=200):
+    # J*(1,c) density by its alternating series, integrated numerically -> CDF of PG(1,z) = J*/4
+    c = abs(z) / 2
+    grid = np.linspace(1e-4, 6, 60001)
+    n = np.arange(terms)[:, None]
+    xs = grid[None, :]
+    small = np.pi * (n + 0.5) * (2 / (np.pi * xs)) ** 1.5 * np.exp(-2 * (n + 0.5) ** 2 / xs)
+    large = np.pi * (n + 0.5) * np.exp(-((n + 0.5) ** 2) * np.pi ** 2 * xs / 2)
+    a = np.where(xs <= 0.64, small, large)
+    f = np.cosh(c) * np.exp(-c * c * grid / 2) * ((-1.0) ** n * a).sum(axis=0)
+    cdf = np.concatenate([[0], np.cumsum((f[1:] + f[:-1]) / 2 * np.diff(grid))])
+    return np.interp(4 * np.asarray(x), grid, cdf)
+
+
+@pytest.mark.parametrize("z", [0.0, 1.5, 3.5])
+def test_pg_distribution_ks(oracle, z):
+    w = oracle.pg_grid(np.full((400, 50), z), seed=3, sweep=1).ravel()
+    d, p = stats.kstest(w, lambda x: _pg_cdf(x, z))
+    assert p > 1e-3, (d, p)
+
+
+def test_scalar_variates(oracle):
+    n = 200_000
+    x = oracle.variates("normal", 1.5, 2.0, n)
+    assert abs(x.mean() - 1.5) < 0.02 and abs(x.std() - 2.0) < 0.02
+    assert stats.kstest(x, stats.norm(1.5, 2.0).cdf).pvalue > 1e-3
+    for mu, sd in [(1.0, 0.2), (-0.5, 1.0), (-3.0, 1.0)]:
+        t = oracle.variates("tnorm", mu, sd, n)
+        a = (0 - mu) / sd
+        assert t.min() > 0
+        assert stats.kstest(t, stats.truncnorm(a, np.inf, loc=mu, scale=sd).cdf).pvalue > 1e-3
+    for shape in [1.0, 2.5, 500.001]:
+        g = oracle.variates("gamma", shape, 0.0, n)
+        assert stats.kstest(g, stats.gamma(shape).cdf).pvalue > 1e-3
+    ig = oracle.variates("invgamma", 501.0, 300.0, n)
+    assert abs(ig.mean() - 300.0 / 500.0) < 1e-3  # mean = scale/(shape-1)
+
+
+def test_inverse_gaussian_nu(oracle):
+    n = 200_000
+    mu, lam = 3.0, 7.0
+    nu = oracle.nu_person(np.full(n, mu), lam, seed=4, sweep=1)
+    x = 1.0 / nu
+    assert abs(x.mean() - mu) < 4 * np.sqrt(mu ** 3 / lam / n)
+    assert stats.kstest(x, stats.invgauss(mu / lam, scale=lam).cdf).pvalue > 1e-3
+
+
+def test_inverse_wishart_mean(oracle):
+    Psi = np.array([[3.0, 0.8], [0.8, 2.0]])
+    df = 12.0
+    acc = np.zeros((2, 2))
+    n = 20000
+    for s in range(1, n + 1):
+        acc += oracle.inv_wishart2(df, Psi, 77, s)
+    assert np.allclose(acc / n, Psi / (df - 3), rtol=0.03)  # E = Psi/(df - p - 1), p = 2
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+@pytest.mark.parametrize("alt", [False, True])
+def test_c_oracle_matches_numpy_transcription(oracle, model, alt):
+    """Two independently written restatements of Draw.pl.jl (C loops vs dense numpy broadcasting) agree."""
+    from oracle import draw_np as D
+    rng = np.random.default_rng(7)
+    N, J, F, q = 30, 6, 2, 0.85
+    opts = dict(intercept=True, itemtype="1pl", cov2one=False) if alt else {}
+    theta = rng.normal(size=N)
+    a, b = rng.uniform(0.7, 1.4, J), rng.normal(0, 0.5, J)
+    X = rng.normal(size=(N, F))
+    Y = (rng.uniform(size=(N, J)) < 1 / (1 + np.exp(-a * (theta[:, None] - b)))).astype(float)
+    logT = 3 + rng.normal(0, 0.5, (N, J))
+    cfg = oracle.make_cfg(model, N, J, F, qRt=q, seed=99, **opts)
+    nb = oracle.lib().orc_beta_len(cfg)
+    init = dict(theta=rng.normal(size=N), zeta=rng.normal(size=N), a=np.ones(J), b=np.zeros(J), lambda_=np.zeros(J),
+                sigma2=np.ones(J), beta=rng.normal(size=max(nb, 1)), rho=rng.normal(size=J), Sigma=np.eye(2).ravel())
+    nsw = 2
+    res = oracle.sample(cfg, Y, logT if model != "MlIrt" else None, X, init, nsw)
+    st = D.Stream(99, 0)
+    C = dict(N=N, J=J, F=F, qRt=q)
+    Dd = dict(Y=Y, κ=Y - 0.5, logT=logT, X=X)
+    P = {"θ": init["theta"].copy(), "ζ": init["zeta"].copy(), "a": init["a"].copy(), "b": init["b"].copy(),
+         "λ": init["lambda_"].copy(), "σ²t": init["sigma2"].copy(), "ρ": init["rho"].copy(), "Σp": np.eye(2), "ν": np.ones(N)}
+    P["β"] = init["beta"][:2 * (F + 1)].reshape(F + 1, 2, order="F").copy() if model == "RtIrt" else init["beta"][:max(nb, 1)].copy()
+    cov2one = opts.get("cov2one", model not in ("RtIrtLatent", "RtIrtLatentQr"))
+    lls = []
+    for s in range(1, nsw + 1):
+        st.sweep = s
+        P = D.sweep(model, st, C, Dd, P, intercept=opts.get("intercept", False), onepl=alt, cov2one=cov2one)
+        lls.append(D.loglik(model, C, Dd, P))
+
+    def close(x, y, tol=1e-9):
+        x, y = np.asarray(x, float).ravel(order="F"), np.asarray(y, float).ravel(order="F")
+        assert np.allclose(x, y, rtol=tol, atol=tol), np.abs(x - y).max()
+
+    close(res["theta"], P["θ"]); close(res["a"], P["a"]); close(res["b"], P["b"]); close(res["omega"], P["ω"])
+    if model != "MlIrt":
+        close(res["zeta"], P["ζ"]); close(res["lambda"], P["λ"]); close(res["sigma2"], P["σ²t"]); close(res["Sigma"], P["Σp"])
+    if "Cross" in model:
+        close(res["rho"], P["ρ"])
+    elif model != "RtIrtNull":
+        close(res["beta"][: np.asarray(P["β"]).size], P["β"])
+    if model.endswith("Qr"):
+        close(res["nu"], P["ν"])
+    close(res["ll"], lls, 1e-10)
+
+
+def test_oracle_recovers_item_parameters(oracle):
+    """Author's own acceptance criterion (README flow): parameter recovery on a simulated data set."""
+    from helpers import make_problem, run_oracle
+    pb = make_problem("RtIrtNull", 1500, 8, 0, seed=5)
+    res = run_oracle(oracle, pb, 300)
+    ra = res["ra"][150:]
+    a_hat = ra[:, pb["N"]:pb["N"] + pb["J"]].mean(0)
+    b_hat = ra[:, pb["N"] + pb["J"]:].mean(0)
+    rng = np.random.default_rng(5)
+    rng.normal(size=pb["N"])
+    a_true = rng.uniform(0.7, 1.4, pb["J"])
+    b_true = rng.normal(0, 0.5, pb["J"])
+    assert np.sqrt(np.mean((a_hat - a_true) ** 2)) < 0.15
+    assert np.sqrt(np.mean((b_hat - b_true) ** 2)) < 0.15
