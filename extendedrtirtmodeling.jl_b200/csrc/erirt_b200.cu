@@ -204,7 +204,9 @@ struct erirt_handle {
   int c_T1 = 0, c_T2 = 0, c_K0 = 0, c_XtX = 0, c_sums = 0, c_count = 0;
   bool data_set = false, consts_final = false, prologue_done = false;
   int64_t sweeps_done = 0;
-  double last_ms = 0.0;
+  double last_ms = 0.0, person_ms = 0.0;
+  std::vector<cudaEvent_t> kev;  // event pairs around person launches (time_kernels)
+  size_t kev_used = 0;
   // NCCL
   nccl::comm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -280,6 +282,7 @@ static int free_handle(erirt_handle* h) {
                   h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -659,6 +662,8 @@ static GlobalArgs make_global_args(erirt_handle* h) {
 
 // one P(k) [allreduce] G(k+1) step on h->stream
 static int enqueue_step(erirt_handle* h) {
+  const bool timed = h->cfg.time_kernels && h->kev_used + 2 <= h->kev.size();
+  if (timed) CU(cudaEventRecord(h->kev[h->kev_used], h->stream));
   if (h->cfg.dtype == ERIRT_F32) {
     PersonArgs<float> A = make_person_args<float>(h);
     void* args[] = {&A};
@@ -667,6 +672,10 @@ static int enqueue_step(erirt_handle* h) {
     PersonArgs<double> A = make_person_args<double>(h);
     void* args[] = {&A};
     CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+  }
+  if (timed) {
+    CU(cudaEventRecord(h->kev[h->kev_used + 1], h->stream));
+    h->kev_used += 2;
   }
   if (h->comm) NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
   GlobalArgs G = make_global_args(h);
@@ -692,7 +701,16 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
     if (rc) return rc;
     h->prologue_done = true;
   }
-  if (h->cfg.use_graph && n_sweeps > 0) {
+  h->kev_used = 0;
+  if (h->cfg.time_kernels) {
+    const size_t want = (size_t)std::min<int64_t>(n_sweeps, 4096) * 2;
+    while (h->kev.size() < want) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      h->kev.push_back(e);
+    }
+  }
+  if (h->cfg.use_graph && !h->cfg.time_kernels && n_sweeps > 0) {
     if (!h->graph_exec) {
       cudaGraph_t graph;
       CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -716,6 +734,16 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
+  h->person_ms = 0.0;
+  if (h->kev_used) {
+    double tot = 0.0;
+    for (size_t t = 0; t + 1 < h->kev_used; t += 2) {
+      float kms = 0.f;
+      CU(cudaEventElapsedTime(&kms, h->kev[t], h->kev[t + 1]));
+      tot += kms;
+    }
+    h->person_ms = tot / (double)(h->kev_used / 2);
+  }
   h->sweeps_done += n_sweeps;
   int status = 0;
   CU(cudaMemcpy(&status, h->dStatus, sizeof(int), cudaMemcpyDeviceToHost));
@@ -819,6 +847,7 @@ extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {
   memset(out, 0, sizeof(*out));
   out->sweeps_done = h->sweeps_done;
   out->last_sample_ms = h->last_ms;
+  out->person_kernel_ms = h->person_ms;
   out->launches_per_sweep = 2;
   out->sm_count = h->sm_count;
   const int64_t N = h->cfg.n_subj, J = h->cfg.n_item, F = h->cfg.n_feat;

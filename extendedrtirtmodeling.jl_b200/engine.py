@@ -14,7 +14,7 @@ def _dp(a):
 class Engine:
     def __init__(self, model, n_subj, n_item, n_feat=0, *, n_iter=5000, n_chain=1, n_burnin=None, q_rt=0.5,
                  intercept=False, itemtype="2pl", cov2one=True, dtype="f32", seed=1234, chain=0, compat=0,
-                 person_trace=False, device=0, use_graph=True, n_subj_total=None, subj_offset=0):
+                 person_trace=False, device=0, use_graph=True, n_subj_total=None, subj_offset=0, time_kernels=False):
         if itemtype not in ("1pl", "2pl"):
             # same text as the reference's sample! (src/GibbsRtIrt.pl.jl:212-214)
             raise ValueError("Invalid input: the item type must be '1pl' or '2pl'.")
@@ -35,6 +35,7 @@ class Engine:
         cfg.dtype = {"f32": _lib.F32, "f64": _lib.F64}[dtype]
         cfg.seed, cfg.chain, cfg.compat = seed, chain, compat
         cfg.person_trace, cfg.device, cfg.use_graph = int(person_trace), device, int(use_graph)
+        cfg.time_kernels = int(time_kernels)
         self.cfg = cfg
         self.model = mid
         self.N, self.J, self.F = n_subj, n_item, n_feat

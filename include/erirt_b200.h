@@ -68,7 +68,8 @@ typedef struct erirt_config {
   int32_t person_trace;   /* 1: keep theta/zeta(/nu) of every sweep on the device (small problems) */
   int32_t device;         /* CUDA device ordinal */
   int32_t use_graph;      /* 1: replay sweeps from a captured CUDA graph */
-  int32_t reserved[8];
+  int32_t time_kernels;   /* 1: bracket every person-sweep launch with CUDA events (forces plain launches) */
+  int32_t reserved[7];
 } erirt_config;
 
 typedef struct erirt_stats {

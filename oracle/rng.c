@@ -10,6 +10,8 @@
 #include "rng.h"
 #include "oracle.h"
 
+#define ORC_MAX_ATTEMPTS 100000u /* NaN inputs must terminate (the device loops have the same bound) */
+
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
   uint32_t k0 = key[0], k1 = key[1];
@@ -44,19 +46,21 @@ double orc_site_tnorm_pos(orc_key key, uint32_t unit, uint32_t sweep, uint32_t s
   double alpha = -mu / sd;
   uint32_t w[4];
   if (alpha <= 0.5) {
-    for (uint32_t att = 0;; ++att) {
+    for (uint32_t att = 0; att < ORC_MAX_ATTEMPTS; ++att) {
       orc_philox(key, unit, sweep, site, att, w);
       double z = orc_normal2(w[0], w[1]);
       if (z >= alpha) return mu + sd * z;
     }
+    return NAN; /* NaN parameters (the reference would throw here) */
   }
   double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
-  for (uint32_t att = 0;; ++att) {
+  for (uint32_t att = 0; att < ORC_MAX_ATTEMPTS; ++att) {
     orc_philox(key, unit, sweep, site, att, w);
     double x = alpha - log(orc_u01(w[0])) / lam;
     double d = x - lam;
     if (orc_u01(w[1]) <= exp(-0.5 * d * d)) return mu + sd * x;
   }
+  return NAN;
 }
 
 /* Gamma(shape, 1), shape >= 1 (always true here: shape = delta + N/2 etc.) */
@@ -69,7 +73,7 @@ double orc_site_gamma(orc_key key, uint32_t unit, uint32_t sweep, uint32_t site,
     shape += 1.0;
   }
   double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-  for (uint32_t att = 0;; ++att) {
+  for (uint32_t att = 0; att < ORC_MAX_ATTEMPTS; ++att) {
     orc_philox(key, unit, sweep, site, att, w);
     double x = orc_normal2(w[0], w[1]);
     double v = 1.0 + c * x;
@@ -78,6 +82,7 @@ double orc_site_gamma(orc_key key, uint32_t unit, uint32_t sweep, uint32_t site,
     double u = orc_u01(w[2]);
     if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
   }
+  return NAN;
 }
 
 double orc_ig_msh(double mu, double lam, double z, double u) {

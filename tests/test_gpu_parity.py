@@ -9,7 +9,7 @@ import pytest
 from helpers import MODELS, make_problem, relerr, run_engine, run_oracle
 from test_oracle import PHILOX_KAT
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.fixture(scope="module")
@@ -29,7 +29,8 @@ def test_philox_known_answers_on_device(E):
 def _z_grid(seed, rows=3000, cols=19):
     rng = np.random.default_rng(seed)
     z = rng.normal(0, 1.6, (rows, cols))
-    z[0, :8] = [0.0, 3.124, 3.126, -4.0, 8.0, 1e-4, -25.0, 0.64]  # both methods, the switch point, extremes
+    special = [0.0, 3.124, 3.126, -4.0, 8.0, 1e-4, -25.0, 0.64]  # both methods, the switch point, extremes
+    z.ravel()[: min(8, z.size)] = special[: min(8, z.size)]
     return z
 
 
@@ -152,10 +153,12 @@ def test_keyword_and_compat_variants_f64(E, oracle, model, opts):
     eng.close()
 
 
-@pytest.mark.parametrize("N,J,F", [(1, 1, 0), (5, 3, 0), (129, 4, 1), (130, 33, 0), (64, 100, 3), (257, 150, 2)])
+@pytest.mark.parametrize("N,J,F", [(1, 1, 0), (2, 1, 0), (5, 3, 0), (129, 4, 1), (130, 33, 0), (64, 100, 3), (257, 150, 2)])
 def test_ragged_shapes_f64(E, oracle, N, J, F):
     """Tile edges: person counts around the tile size, item counts that are not multiples of 4, no covariates."""
-    for model in ("RtIrtNull", "RtIrtLatentQr" if F else "MlIrt"):
+    # N*J = 1 is only meaningful without response times (std(logT) of one element is NaN in the reference too)
+    models = ("MlIrt",) if N * J == 1 else ("RtIrtNull", "RtIrtLatentQr" if F else "MlIrt")
+    for model in models:
         pb = make_problem(model, N, J, F, seed=15)
         ref = run_oracle(oracle, pb, 2)
         eng = run_engine(E, pb, 2, dtype="f64")
