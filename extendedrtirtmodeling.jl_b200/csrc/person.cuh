@@ -82,7 +82,7 @@ __device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
 }
 
 // item-parameter arrays staged in shared memory (each Jp long, zero beyond J)
-enum ParIdx { PAR_A = 0, PAR_AB = 1, PAR_A2 = 2, PAR_A2B = 3, PAR_IS2 = 4, PAR_COUNT = 5 };
+enum ParIdx { PAR_A = 0, PAR_AB = 1, PAR_A2 = 2, PAR_A2B = 3, PAR_IS2 = 4, PAR_LAM = 5, PAR_COUNT = 6 };
 // per-CTA scalars in the misc block (f64)
 enum MiscD { MD_SUM_IS2 = 0, MD_SUM_LIS2 = 1, MD_COUNT = 2 };
 
@@ -126,17 +126,21 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
 
   // ---- stage item parameters (state k) and clear accumulators ----
   for (int j = tid; j < Jp; j += CTA_THREADS) {
-    double a = 0, b = 0, is2 = 0;
+    double a = 0, b = 0, is2 = 0, lam = 0;
     if (j < J) {
       a = par[L.p_a + j];
       b = par[L.p_b + j];
-      if (has_rt) is2 = 1.0 / par[L.p_sigma2 + j];
+      if (has_rt) {
+        is2 = 1.0 / par[L.p_sigma2 + j];
+        lam = par[L.p_lambda + j];
+      }
     }
     s_par[PAR_A * Jp + j] = (R)a;
     s_par[PAR_AB * Jp + j] = (R)(a * b);
     s_par[PAR_A2 * Jp + j] = (R)(a * a);
     s_par[PAR_A2B * Jp + j] = (R)(a * a * b);
     s_par[PAR_IS2 * Jp + j] = (R)is2;
+    s_par[PAR_LAM * Jp + j] = (R)lam;
   }
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
   }
   __syncthreads();
 
-  const R sum_is2 = (R)s_miscd[MD_SUM_IS2], sum_lis2 = (R)s_miscd[MD_SUM_LIS2];
+  const R sum_is2 = (R)s_miscd[MD_SUM_IS2];
   const R S11 = has_rt ? (R)par[L.p_Sigma + 0] : R(1);
   const R S22 = has_rt ? (R)par[L.p_Sigma + 3] : R(1);
   const R S12 = has_rt ? (R)par[L.p_Sigma + 2] : R(0);
@@ -234,8 +238,9 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
         if (has_rt) {
           const Quad<R> lt = ld4(my_lt + 4 * g);
           const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
+          const Quad<R> pL = ld4(s_par + PAR_LAM * Jp + 4 * g);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) sLT = fma(pI.v[e], lt.v[e], sLT);
+          for (int e = 0; e < 4; ++e) sLT = fma(pI.v[e], pL.v[e] - lt.v[e], sLT);  // sum_j (lambda_j - logT_ij)/sigma2_j
         }
       }
 #pragma unroll
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
         } else if (model == M_NULL) { mu_z = R(0); var_z = R(1); }  // Draw.pl.jl:120-121
         else { mu_z = R(0); var_z = S22; }
         const R parV = R(1) / (R(1) / var_z + sum_is2);
-        const R parM = parV * (mu_z / var_z + (sum_lis2 - sLT));
+        const R parM = parV * (mu_z / var_z + sLT);
         ze = parM + sqrt(parV) * normal2r<R>(w.z, w.w);
       }
       // structural log-density of state k (one lane per person)

@@ -288,7 +288,8 @@ def test_full_size_properties_c5(E):
     assert np.all(np.isfinite(a)) and np.all(a > 0) and np.all(np.abs(b) <= 4)
     assert np.all(np.isfinite(eng.get_trace("logLike")))
     assert np.sqrt(np.mean((b[-1] - tp.b) ** 2)) < np.sqrt(np.mean((b[0] - tp.b) ** 2)) + 1e-3
-    assert np.sqrt(np.mean((lam[-1] - tp.lambda_) ** 2)) < 0.2
+    # the quantile model shifts the speed intercept (k1*nu term), so lambda is compared up to a common offset
+    assert np.std((lam[-1] - tp.lambda_)) < 0.02
     # omega identity on a slice (the state holds omega_{k+1} | a_k, b_k, theta_k)
     om = eng.get_state("omega")[:50_000]
     th = eng.get_state("theta")[:50_000]
