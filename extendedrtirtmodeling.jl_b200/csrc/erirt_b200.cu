@@ -229,10 +229,12 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_y = (int)o; o = align_up(o + S.tile_y_bytes, 128);
   S.off_par = (int)o; o = align_up(o + PAR_COUNT * L.Jp * rsz, 128);
   S.off_u = (int)o; o = align_up(o + (size_t)S.P * S.Dgp * rsz, 128);
+  S.off_sum = (int)o; o = align_up(o + (size_t)S.P * 4 * rsz, 128);
+  S.off_beta = (int)o; o = align_up(o + (size_t)(MAXD + 4) * rsz, 128);
   S.off_acc_item = (int)o; o = align_up(o + 5 * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
-  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
-  S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 8, 128);
+  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + (QCAP + QCAP2) * sizeof(uint32_t), 128);
+  S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;
   return S;
 }
@@ -310,7 +312,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
                 (long long)cfg->subj_offset, (long long)cfg->n_subj_total);
   if (cfg->n_subj_total > 0xffffffffLL) return fail(ERIRT_E_ARG, "n_subj_total exceeds the 32-bit person counter");
   if (2 * (cfg->n_feat + 1) > MAXD) return fail(ERIRT_E_ARG, "n_feat %d too large (2*(n_feat+1) <= %d)", cfg->n_feat, MAXD);
-  if (cfg->n_item > 1000) return fail(ERIRT_E_ARG, "n_item %d too large (<= 1000)", cfg->n_item);
+  if (cfg->n_item > 500) return fail(ERIRT_E_ARG, "n_item %d too large (<= 500)", cfg->n_item);
   if (cfg->n_iter < 1 || cfg->n_chain < 1) return fail(ERIRT_E_ARG, "n_iter and n_chain must be >= 1");
   if (cfg->dtype != ERIRT_F32 && cfg->dtype != ERIRT_F64) return fail(ERIRT_E_ARG, "dtype must be ERIRT_F32 or ERIRT_F64");
   if (!(cfg->q_rt > 0.0 && cfg->q_rt < 1.0)) return fail(ERIRT_E_ARG, "qRt must be between 0 and 1");  // Draw.pl.jl:476
@@ -333,14 +335,16 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   // threads per person: smallest TPP whose tile fits ~64 KB (>= 3 CTAs/SM)
   int tpp = 1;
   const char* env_tpp = getenv("ERIRT_TPP");
+  const int n_groups = h->L.Jp / 4;
   if (env_tpp) tpp = atoi(env_tpp);
   else {
     for (tpp = 1; tpp < 8; tpp *= 2) {
       SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt);
-      if (s.total <= 72 * 1024) break;
+      if (s.total <= 74 * 1024 && n_groups <= 16 * tpp) break;
     }
   }
   if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) { delete h; return fail(ERIRT_E_ARG, "ERIRT_TPP must be 1, 2, 4 or 8"); }
+  if (n_groups > 16 * tpp) { delete h; return fail(ERIRT_E_ARG, "TPP=%d handles at most %d items", tpp, 64 * tpp - 4); }
   h->tpp = tpp;
   h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt);
   if (h->S.total > 227 * 1024) { delete h; return fail(ERIRT_E_UNSUPPORTED, "n_item %d needs %d bytes of shared memory per CTA", cfg->n_item, h->S.total); }

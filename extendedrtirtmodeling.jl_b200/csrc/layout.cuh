@@ -7,7 +7,8 @@ namespace erirt {
 
 constexpr int CTA_THREADS = 128;  // person-sweep CTA; tile = CTA_THREADS / TPP persons
 constexpr int MAXD = 32;          // largest dense system solved in the global kernel (2*(nFeat+1) <= 32)
-constexpr int QCAP = 2048;        // PG retry-queue capacity per tile (overflow is handled inline)
+constexpr int QCAP = 1024;        // PG fast-retry queue capacity per tile (overflow is handled inline)
+constexpr int QCAP2 = 256;        // PG exact-replay queue capacity per tile
 
 enum ModelId { M_MLIRT = 0, M_RTIRT = 1, M_NULL = 2, M_CROSS = 3, M_CROSSQR = 4, M_LATENT = 5, M_LATENTQR = 6 };
 
@@ -68,7 +69,7 @@ inline Layout make_layout(int J, int F) {
 struct SmemPlan {
   int P;  // persons per tile
   int tile_real_bytes, tile_y_bytes;
-  int off_omega, off_logt, off_y, off_par, off_u, off_acc_item, off_acc_gram, off_queue, off_misc, total;
+  int off_omega, off_logt, off_y, off_par, off_u, off_sum, off_beta, off_acc_item, off_acc_gram, off_queue, off_misc, total;
   int Dgp;  // pitch of the U tile (elements)
 };
 

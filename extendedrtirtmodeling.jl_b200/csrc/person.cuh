@@ -94,8 +94,36 @@ __device__ __forceinline__ int group_of(int q, int k) {
   return (k / chunk) * 8 + q * chunk + (k % chunk);
 }
 
+// Retry of one PG cell whose attempt 0 was certainly rejected (f32, Method A): attempts a >= first are evaluated with
+// the same branch-free fast evaluation as the main pass.  Returns omega >= 0, or -(a+1) when attempt a is undecided by
+// the squeeze tests (the caller hands the cell to the exact queue, which replays that attempt with the full series).
+// Kept out of line: the retry path is cold relative to the main pass and inlining it thrashes the instruction cache.
+__device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z, int first) {
+#pragma unroll 1
+  for (uint32_t a = (uint32_t)first; a < 250u; ++a) {
+    const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
+    float ll;
+    const float om = pg_fast_attempt0(z, 0.f, w.x, w.y, ll);
+    if (om >= 0.f) return om;
+    if (om == -1.0f) return -(float)(a + 1u);
+  }
+  return -251.0f;  // hand over to the exact loop
+}
+__device__ __noinline__ float pg_exact_cell_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z, int first) {
+  return pg_draw_exact<float>(key, gid, sweep, j, z, first);
+}
+__device__ __noinline__ double pg_draw_cell_f64(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, double z, uint32_t* na) {
+  return pg_draw_exact<double>(key, gid, sweep, j, z, 0, na);
+}
+
+constexpr int STAT_FLUSH_TILES = 8;  // item statistics live in registers and are folded into f64 every 8 tiles
+
+// resident CTAs per SM the register allocation is tuned for: the tile of TPP=2 leaves room for 3 CTAs, TPP=4 for 5, TPP=8 for 7
+template <int TPP>
+constexpr int min_ctas_per_sm() { return TPP >= 8 ? 7 : (TPP == 4 ? 5 : 3); }
+
 template <typename R, int TPP>
-__global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonArgs<R> A) {
+__global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sweep_kernel(const PersonArgs<R> A) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int P = CTA_THREADS / TPP;
   constexpr bool F32 = sizeof(R) == 4;
@@ -105,26 +133,29 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
   const bool has_rt = model != M_MLIRT;
   const bool latent = model == M_LATENT || model == M_LATENTQR;
   const bool qr = model == M_LATENTQR;
+  const bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
 
   R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
   R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
   uint8_t* s_y = smem + A.S.off_y;
   R* s_par = reinterpret_cast<R*>(smem + A.S.off_par);
   R* s_u = reinterpret_cast<R*>(smem + A.S.off_u);
+  R* s_sum = reinterpret_cast<R*>(smem + A.S.off_sum);    // [P][4] row sums handed to the person phase
+  R* s_beta = reinterpret_cast<R*>(smem + A.S.off_beta);  // beta (MAXD) then vec(Sigma) (4)
   double* s_acc_item = reinterpret_cast<double*>(smem + A.S.off_acc_item);
   double* s_acc_gram = reinterpret_cast<double*>(smem + A.S.off_acc_gram);
   uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + A.S.off_queue);
-  double* s_miscd = reinterpret_cast<double*>(smem + A.S.off_misc);          // MD_COUNT + SC_COUNT doubles
+  double* s_miscd = reinterpret_cast<double*>(smem + A.S.off_misc);  // MD_COUNT + SC_COUNT doubles
   double* s_scal = s_miscd + MD_COUNT;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scal + SC_COUNT);
-  uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);                 // [0] count, [1] head
+  uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);         // fast queue [0] count [1] head, exact queue [2] count [3] head
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
   const uint32_t k = *A.sweep_ctr;
   const bool do_draws = k >= 1;
   const double* par = A.params;
 
-  // ---- stage item parameters (state k) and clear accumulators ----
+  // ---- stage item / structural parameters (state k) and clear accumulators ----
   for (int j = tid; j < Jp; j += CTA_THREADS) {
     double a = 0, b = 0, is2 = 0, lam = 0;
     if (j < J) {
@@ -142,24 +173,18 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
     s_par[PAR_IS2 * Jp + j] = (R)is2;
     s_par[PAR_LAM * Jp + j] = (R)lam;
   }
+  if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
+  if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
   if (tid < SC_COUNT) s_scal[tid] = 0.0;
-  if (tid < 32) {  // sum_j 1/sigma2_j and sum_j lambda_j/sigma2_j in f64
-    double s1 = 0, s2 = 0;
+  if (tid < 32) {  // sum_j 1/sigma2_j in f64
+    double s1 = 0;
     if (has_rt)
-      for (int j = tid; j < J; j += 32) {
-        double is2 = 1.0 / par[L.p_sigma2 + j];
-        s1 += is2;
-        s2 += par[L.p_lambda + j] * is2;
-      }
-    for (int o = 16; o; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
+      for (int j = tid; j < J; j += 32) s1 += 1.0 / par[L.p_sigma2 + j];
+    for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     if (tid == 0) {
       s_miscd[MD_SUM_IS2] = s1;
-      s_miscd[MD_SUM_LIS2] = s2;
       mbar_init(s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -167,9 +192,7 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
   __syncthreads();
 
   const R sum_is2 = (R)s_miscd[MD_SUM_IS2];
-  const R S11 = has_rt ? (R)par[L.p_Sigma + 0] : R(1);
-  const R S22 = has_rt ? (R)par[L.p_Sigma + 3] : R(1);
-  const R S12 = has_rt ? (R)par[L.p_Sigma + 2] : R(0);
+  const R S11 = s_beta[MAXD + 0], S12 = s_beta[MAXD + 2], S22 = s_beta[MAXD + 3];
   const R k1 = (R)A.k1, k2 = (R)A.k2;
   const int pb = F + 1;  // length of one regression block [1 X]
   const uint32_t iter_m = do_draws ? (k - 1) / (uint32_t)A.n_chain + 1 : 0;  // m of sweep k
@@ -179,10 +202,30 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
   uint32_t acc_defer = 0, acc_cells = 0;
   uint32_t parity = 0;
   const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * (has_rt ? 2 : 1) + A.S.tile_y_bytes);
-  // steps per thread = ceil(G/8) * (8/TPP)
-  const int nk = ((G + 7) / 8) * (8 / TPP);
+  const int nk = ((G + 7) / 8) * (8 / TPP);  // steps per thread over its 4-item groups
 
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+  // transposed-statistics role of this thread: item group eg, person class er (G <= CTA_THREADS is enforced by the host)
+  const int Rc = CTA_THREADS / G;
+  const bool e_active = tid < G * Rc;
+  const int eg = tid % G, er = tid / G;
+  R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
+  auto flush_item_stats = [&]() {
+    if (e_active) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * eg + e;
+        atomicAdd(&s_acc_item[0 * Jp + j], (double)a0[e]);
+        atomicAdd(&s_acc_item[1 * Jp + j], (double)a1[e]);
+        atomicAdd(&s_acc_item[2 * Jp + j], (double)a2[e]);
+        atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
+        atomicAdd(&s_acc_item[4 * Jp + j], (double)ac[e]);
+        a0[e] = a1[e] = a2[e] = ay[e] = ac[e] = R(0);
+      }
+    }
+  };
+
+  int tiles_done = 0;
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tiles_done) {
     const int64_t row0 = (int64_t)tile * P;
     if (tid == 0) {
       tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
@@ -190,24 +233,27 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
       tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
+      s_qctl[0] = 0;
+      s_qctl[1] = 0;
+      s_qctl[2] = 0;
+      s_qctl[3] = 0;
     }
-    // ---- person scalars while the tile is in flight ----
-    const int64_t i = row0 + p;
-    const bool valid = i < A.n_local;
-    const uint32_t gid = A.person_offset + (uint32_t)i;
-    R th = A.theta[i];
-    R ze = has_rt ? A.zeta[i] : R(0);
-    R nu = qr ? A.nu[i] : R(1);
-    R xb1 = R(0), xb2 = R(0);  // regression means (before the theta term of the latent models)
-    {
-      const double* beta = par + L.p_beta;
-      if (model == M_MLIRT || model == M_RTIRT || latent) xb1 = (R)beta[0];
-      if (model == M_RTIRT) xb2 = (R)beta[pb];
+    // ---- person phase, part 1 (one thread per person, coalesced): state k-1 and regression means ----
+    const int64_t pi = row0 + tid;
+    const bool pvalid = tid < P && pi < A.n_local;
+    const uint32_t pgid = A.person_offset + (uint32_t)pi;
+    R th = R(0), ze = R(0), nu = R(1), xb1 = R(0), xb2 = R(0);
+    if (tid < P) {
+      th = A.theta[pi];
+      if (has_rt) ze = A.zeta[pi];
+      if (qr) nu = A.nu[pi];
+      if (reg_x) xb1 = s_beta[0];
+      if (model == M_RTIRT) xb2 = s_beta[pb];
       for (int f = 0; f < F; ++f) {
-        R x = A.X[(int64_t)f * A.n_pad + i];
-        if (q == 0) s_u[p * Dgp + 1 + f] = valid ? x : R(0);
-        if (model == M_MLIRT || model == M_RTIRT || latent) xb1 = fma(x, (R)beta[1 + f], xb1);
-        if (model == M_RTIRT) xb2 = fma(x, (R)beta[pb + 1 + f], xb2);
+        const R x = A.X[(int64_t)f * A.n_pad + pi];
+        s_u[tid * Dgp + 1 + f] = pvalid ? x : R(0);
+        if (reg_x) xb1 = fma(x, s_beta[1 + f], xb1);
+        if (model == M_RTIRT) xb2 = fma(x, s_beta[pb + 1 + f], xb2);
       }
     }
     mbar_wait(s_bar, parity);
@@ -218,7 +264,7 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
     const uint8_t* my_y = s_y + p * Jp;
 
     if (do_draws) {
-      // ---- row sums over items (Draw.pl.jl:55-56, 137-138) ----
+      // ---- row sums over items (Draw.pl.jl:55-56, 137-138), TPP threads per person ----
       R sA2 = 0, sAB = 0, sAK = 0, sLT = 0;
       for (int kk = 0; kk < nk; ++kk) {
         const int g = group_of<TPP>(q, kk);
@@ -250,95 +296,109 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
         sAK += __shfl_xor_sync(0xffffffffu, sAK, o);
         sLT += __shfl_xor_sync(0xffffffffu, sLT, o);
       }
-      const uint4 w = philox(A.key, gid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
-      // theta_k
-      {
-        const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
-        const R var0 = (model == M_MLIRT) ? R(1) : S11;
-        const R parV = R(1) / (R(1) / var0 + sA2);
-        const R parM = parV * (mu0 / var0 + sAK + sAB);
-        th = parM + sqrt(parV) * normal2r<R>(w.x, w.y);
+      if (q == 0) {
+        R* d = s_sum + 4 * p;
+        d[0] = sA2; d[1] = sAB; d[2] = sAK; d[3] = sLT;
       }
-      // zeta_k
-      R mu_z = R(0), var_z = R(1);
-      if (has_rt) {
-        if (model == M_RTIRT) { mu_z = xb2; var_z = S22; }
-        else if (latent) {
-          mu_z = fma(th, (R)par[L.p_beta + F + 1], xb1);
-          var_z = S22;
-          if (qr) { mu_z = fma(k1, nu, mu_z); var_z = S22 * (k2 * nu); }
-        } else if (model == M_NULL) { mu_z = R(0); var_z = R(1); }  // Draw.pl.jl:120-121
-        else { mu_z = R(0); var_z = S22; }
-        const R parV = R(1) / (R(1) / var_z + sum_is2);
-        const R parM = parV * (mu_z / var_z + sLT);
-        ze = parM + sqrt(parV) * normal2r<R>(w.z, w.w);
-      }
-      // structural log-density of state k (one lane per person)
-      if (valid && q == 0) {
-        const double LOG2PI = 1.8378770664093454835606594728112;
-        double ls;
-        if (model == M_MLIRT) {
-          double r = (double)th - (double)xb1;
-          ls = -0.5 * LOG2PI - 0.5 * r * r;
-        } else if (latent) {
-          double r = (double)ze - (double)mu_z, v = (double)var_z;
-          ls = -0.5 * (LOG2PI + log(v)) - 0.5 * r * r / v;
-        } else {
-          double e1 = (double)th - (model == M_RTIRT ? (double)xb1 : 0.0);
-          double e2 = (double)ze - (model == M_RTIRT ? (double)xb2 : 0.0);
-          double s11 = S11, s12 = S12, s22 = S22, det = s11 * s22 - s12 * s12;
-          ls = -LOG2PI - 0.5 * log(det) - 0.5 * (s22 * e1 * e1 - 2.0 * s12 * e1 * e2 + s11 * e2 * e2) / det;
+      __syncthreads();
+      // ---- person phase, part 2: theta_k, zeta_k, structural log-density, moments ----
+      if (tid < P) {
+        const R* d = s_sum + 4 * tid;
+        const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
+        {
+          const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
+          const R var0 = (model == M_MLIRT) ? R(1) : S11;
+          const R iv0 = rdiv(R(1), var0);
+          const R parV = rdiv(R(1), iv0 + d[0]);
+          const R parM = parV * (mu0 * iv0 + d[2] + d[1]);
+          th = parM + rsqrt_of(parV) * normal2r<R>(w.x, w.y);
         }
-        acc_ll_struct += ls;
-        A.theta[i] = th;
-        if (has_rt) A.zeta[i] = ze;
-        if (post_burnin) {
-          double* m = A.mom + i;
-          m[0] += (double)th;
-          m[A.n_pad] += (double)th * (double)th;
-          if (has_rt) {
-            m[2 * A.n_pad] += (double)ze;
-            m[3 * A.n_pad] += (double)ze * (double)ze;
+        R mu_z = R(0), var_z = R(1);
+        if (has_rt) {
+          if (model == M_RTIRT) { mu_z = xb2; var_z = S22; }
+          else if (latent) {
+            mu_z = fma(th, s_beta[F + 1], xb1);
+            var_z = S22;
+            if (qr) { mu_z = fma(k1, nu, mu_z); var_z = S22 * (k2 * nu); }
+          } else if (model == M_NULL) { mu_z = R(0); var_z = R(1); }  // Draw.pl.jl:120-121
+          else { mu_z = R(0); var_z = S22; }
+          const R ivz = rdiv(R(1), var_z);
+          const R parV = rdiv(R(1), ivz + sum_is2);
+          const R parM = parV * (mu_z * ivz + d[3]);
+          ze = parM + rsqrt_of(parV) * normal2r<R>(w.z, w.w);
+        }
+        if (pvalid) {
+          const double LOG2PI = 1.8378770664093454835606594728112;
+          double ls;
+          if (model == M_MLIRT) {
+            double r = (double)th - (double)xb1;
+            ls = -0.5 * LOG2PI - 0.5 * r * r;
+          } else if (latent) {
+            double r = (double)ze - (double)mu_z, v = (double)var_z;
+            ls = -0.5 * (LOG2PI + log(v)) - 0.5 * r * r / v;
+          } else {
+            double e1 = (double)th - (model == M_RTIRT ? (double)xb1 : 0.0);
+            double e2 = (double)ze - (model == M_RTIRT ? (double)xb2 : 0.0);
+            double s11 = S11, s12 = S12, s22 = S22, det = s11 * s22 - s12 * s12;
+            ls = -LOG2PI - 0.5 * log(det) - 0.5 * (s22 * e1 * e1 - 2.0 * s12 * e1 * e2 + s11 * e2 * e2) / det;
           }
-          if (qr) {
-            m[4 * A.n_pad] += (double)nu;
-            m[5 * A.n_pad] += (double)nu * (double)nu;
+          acc_ll_struct += ls;
+          A.theta[pi] = th;
+          if (has_rt) A.zeta[pi] = ze;
+          if (post_burnin) {
+            double* m = A.mom + pi;
+            m[0] += (double)th;
+            m[A.n_pad] += (double)th * (double)th;
+            if (has_rt) {
+              m[2 * A.n_pad] += (double)ze;
+              m[3 * A.n_pad] += (double)ze * (double)ze;
+            }
+            if (qr) {
+              m[4 * A.n_pad] += (double)nu;
+              m[5 * A.n_pad] += (double)nu * (double)nu;
+            }
           }
-        }
-        if (A.ptrace) {
-          R* t = A.ptrace + ((int64_t)(k - 1) * 3) * A.n_pad + i;
-          t[0] = th;
-          t[A.n_pad] = ze;
-          t[2 * A.n_pad] = nu;
+          if (A.ptrace) {
+            R* t = A.ptrace + ((int64_t)(k - 1) * 3) * A.n_pad + pi;
+            t[0] = th;
+            t[A.n_pad] = ze;
+            t[2 * A.n_pad] = nu;
+          }
         }
       }
     }
-    // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
-    if (qr) {
-      const R xb = fma(th, (R)par[L.p_beta + F + 1], xb1);
-      const R sc = sqrt(S22 * k2);
-      const R parA = fabs(ze - xb) / sc;
-      const R parB = sqrt(R(2) * k2 + k1 * k1) / sc;
-      R mu = parB / parA;
-      if (mu < R(1e-10)) mu = R(1e-10);
-      const uint4 w = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
-      const R ig = ig_msh<R>(mu, parB * parB, normal2r<R>(w.x, w.y), u01<R>(w.z));
-      nu = R(1) / ig;
-      nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
-      if (valid && q == 0) A.nu[i] = nu;
+    if (tid < P) {
+      // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
+      if (qr) {
+        const R xb = fma(th, s_beta[F + 1], xb1);
+        const R isc = rdiv(R(1), rsqrt_of(S22 * k2));
+        const R parA = fabs(ze - xb) * isc;
+        const R parB = rsqrt_of(R(2) * k2 + k1 * k1) * isc;
+        R mu = rdiv(parB, parA);
+        if (!(mu >= R(1e-10))) mu = R(1e-10);
+        const uint4 w = philox(A.key, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+        const R ig = ig_msh<R>(mu, parB * parB, normal2r<R>(w.x, w.y), u01<R>(w.z));
+        nu = rdiv(R(1), ig);
+        nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
+        if (pvalid) A.nu[pi] = nu;
+      }
+      R* u = s_u + tid * Dgp;
+      u[0] = pvalid ? R(1) : R(0);
+      u[F + 1] = pvalid ? th : R(0);
+      u[F + 2] = pvalid ? ze : R(0);
+      u[F + 3] = (pvalid && qr) ? nu : R(0);
+      u[F + 4] = (pvalid && qr) ? rdiv(R(1), nu) : R(0);  // weight of the nu-weighted Gram
+      if (pvalid) acc_cells += (uint32_t)J;
     }
-    if (q == 0) {
-      R* u = s_u + p * Dgp;
-      u[0] = valid ? R(1) : R(0);
-      u[F + 1] = valid ? th : R(0);
-      u[F + 2] = valid ? ze : R(0);
-      u[F + 3] = (valid && qr) ? nu : R(0);
-      u[F + 4] = (valid && qr) ? R(1) / nu : R(0);  // weight of the nu-weighted Gram
-    }
+    __syncthreads();
 
     // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
+    const bool valid = (row0 + p) < A.n_local;
+    const uint32_t gid = A.person_offset + (uint32_t)(row0 + p);
+    const R thp = s_u[p * Dgp + F + 1];
     float ll_tile = 0.f;
     uint32_t my_defer = 0;
+    unsigned long long defer_mask = 0ull;  // bit 4*kk+e: cell left the fast path (nk <= 16 by the TPP choice)
     for (int kk = 0; kk < nk; ++kk) {
       const int g = group_of<TPP>(q, kk);
       if (g >= G) continue;
@@ -355,139 +415,160 @@ __global__ void __launch_bounds__(CTA_THREADS) person_sweep_kernel(const PersonA
         const uint4 wA = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
         const uint4 wB = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
         const uint32_t ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+        const int npad = 4 * g + 4 - J;  // > 0 only in groups holding padding cells
+        float llg = 0.f;
+        uint32_t m4 = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float z = fmaf(pA.v[e], th, -pAB.v[e]);
+          const float z = fmaf(pA.v[e], thp, -pAB.v[e]);
           const float kap = ((yw >> (8 * e)) & 0xffu) ? 0.5f : -0.5f;
           float ll;
           float om = pg_fast_attempt0(z, kap, ww[2 * e], ww[2 * e + 1], ll);
-          if (4 * g + e >= J) { om = 0.f; ll = 0.f; }
-          ll_tile += ll;
-          my_defer += om < 0.f;
+          if (npad > 0 && e >= 4 - npad) { om = 0.f; ll = 0.f; }  // padding cells never count
+          llg += ll;
+          if (om < 0.f) m4 |= 1u << e;
           out.v[e] = om;
         }
+        ll_tile += llg;
+        defer_mask |= (unsigned long long)m4 << (4 * kk);
       } else {
 #pragma unroll 1
         for (int e = 0; e < 4; ++e) {
           const int j = 4 * g + e;
           if (j >= J) { out.v[e] = R(0); continue; }
-          const R z = fma(pA.v[e], th, -pAB.v[e]);
+          const R z = fma(pA.v[e], thp, -pAB.v[e]);
           const R y = ((yw >> (8 * e)) & 0xffu) ? R(1) : R(0);
           const R az = fabs(z);
           acc_ll_bern += (double)(y * z - (R(0.5) * (z + az) + log1p(exp(-az))));
           uint32_t na;
-          out.v[e] = pg_draw_exact<R>(A.key, gid, k + 1, j, z, 0, &na);
+          out.v[e] = (R)pg_draw_cell_f64(A.key, gid, k + 1, j, (double)z, &na);
           my_defer += na > 1u;
         }
       }
       st4(my_om + 4 * g, out);
     }
     acc_ll_bern += (double)ll_tile;
-    if (valid && q == 0) acc_cells += (uint32_t)J;
-    acc_defer += my_defer;
-
     if constexpr (F32) {
-      // ---- retry queue: every cell that left the fast path is replayed exactly (any thread may take it) ----
-      if (tid == 0) { s_qctl[0] = 0; s_qctl[1] = 0; }
-      __syncthreads();
-      uint32_t base = 0;
-      if (my_defer) base = atomicAdd(&s_qctl[0], my_defer);
-      if (my_defer) {
-        for (int kk = 0; kk < nk; ++kk) {
-          const int g = group_of<TPP>(q, kk);
-          if (g >= G) continue;
-          const Quad<R> om = ld4(my_om + 4 * g);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (om.v[e] < R(0)) {
-              const int j = 4 * g + e;
-              const uint32_t first = (om.v[e] == R(-1)) ? 0u : 1u;
-              const uint32_t entry = (first << 31) | ((uint32_t)p << 20) | (uint32_t)j;
-              if (base < (uint32_t)QCAP) s_queue[base] = entry;
-              else {  // queue overflow: finish the cell here
-                const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)th, -(float)s_par[PAR_AB * Jp + j]);
-                my_om[j] = (R)pg_draw_exact<float>(A.key, gid, k + 1, j, z, (int)first);
-              }
-              ++base;
-            }
+      // ---- hand the cells that left the fast path to the queues: rejected -> fast retry, undecided / Method B -> exact ----
+      my_defer = (uint32_t)__popcll(defer_mask);
+      while (defer_mask) {
+        const int bit = __ffsll((long long)defer_mask) - 1;
+        defer_mask &= defer_mask - 1ull;
+        const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
+        const float code = (float)my_om[j];
+        const uint32_t entry = ((uint32_t)p << 16) | (uint32_t)j;
+        if (code == -2.0f) {
+          const uint32_t slot = atomicAdd(&s_qctl[0], 1u);
+          if (slot < (uint32_t)QCAP) s_queue[slot] = entry | (1u << 24);
+          else {  // queue overflow: finish the cell here
+            const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+            my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, 1);
+          }
+        } else {
+          const uint32_t first = code == -1.0f ? 0u : 1u;
+          const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
+          if (slot < (uint32_t)QCAP2) s_queue[QCAP + slot] = entry | (first << 24);
+          else {
+            const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+            my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, (int)first);
           }
         }
-      }
-      __syncthreads();
-      const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
-      while (true) {
-        const uint32_t idx = atomicAdd(&s_qctl[1], 1u);
-        if (idx >= qn) break;
-        const uint32_t entry = s_queue[idx];
-        const int pj = (int)(entry & 0xfffffu), pp = (int)((entry >> 20) & 0x7ffu), first = (int)(entry >> 31);
-        const float thp = (float)s_u[pp * Dgp + F + 1];
-        const float z = fmaf((float)s_par[PAR_A * Jp + pj], thp, -(float)s_par[PAR_AB * Jp + pj]);
-        const uint32_t pgid = A.person_offset + (uint32_t)(row0 + pp);
-        s_om[pp * Jp + pj] = (R)pg_draw_exact<float>(A.key, pgid, k + 1, pj, z, first);
       }
     }
+    acc_defer += my_defer;
     __syncthreads();
 
-    // ---- per-item statistics: thread per (item group, person class), tile read transposed ----
-    {
-      const int Rc = G >= CTA_THREADS ? 1 : CTA_THREADS / G;
-      for (int slot = tid; slot < G * Rc; slot += CTA_THREADS) {
-        const int g = slot % G, r = slot / G;
-        R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
-        for (int pp = r; pp < P; pp += Rc) {
-          const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
-          const Quad<R> om = ld4(s_om + pp * Jp + 4 * g);
-          const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * g);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const R w = om.v[e];
-            const R tw = tp * w;
-            a0[e] += w;
-            a1[e] += tw;
-            a2[e] = fma(tp, tw, a2[e]);
-            ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
+    if constexpr (F32) {
+      // ---- stage 1: fast retries, any free thread takes the next cell ----
+      const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
+      if (qn) {
+        while (true) {
+          const uint32_t idx = atomicAdd(&s_qctl[1], 1u);
+          if (idx >= qn) break;
+          const uint32_t entry = s_queue[idx];
+          const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
+          const float thq = (float)s_u[pp * Dgp + F + 1];
+          const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
+          const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
+          float om = pg_retry_fast_f32(A.key, qgid, k + 1, pj, z, first);
+          if (om < 0.f) {  // attempt -(om)-1 is undecided: exact queue
+            const uint32_t a = (uint32_t)(-om) - 1u;
+            const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
+            if (slot < (uint32_t)QCAP2) {
+              s_queue[QCAP + slot] = (entry & 0xffffffu) | (a << 24);
+              continue;
+            }
+            om = pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, (int)a);
           }
-          if (has_rt) {
-            const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * g);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) ac[e] = fma(lt.v[e], zp, ac[e]);
-          }
+          s_om[pp * Jp + pj] = (R)om;
         }
+      }
+      __syncthreads();
+      // ---- stage 2: exact replays (undecided attempts, Method-B cells) ----
+      const uint32_t qn2 = min(s_qctl[2], (uint32_t)QCAP2);
+      if (qn2) {
+        while (true) {
+          const uint32_t idx = atomicAdd(&s_qctl[3], 1u);
+          if (idx >= qn2) break;
+          const uint32_t entry = s_queue[QCAP + idx];
+          const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
+          const float thq = (float)s_u[pp * Dgp + F + 1];
+          const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
+          const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
+          s_om[pp * Jp + pj] = (R)pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, first);
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
+    if (e_active) {
+      for (int pp = er; pp < P; pp += Rc) {
+        const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
+        const Quad<R> om = ld4(s_om + pp * Jp + 4 * eg);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * eg);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int j = 4 * g + e;
-          atomicAdd(&s_acc_item[0 * Jp + j], (double)a0[e]);
-          atomicAdd(&s_acc_item[1 * Jp + j], (double)a1[e]);
-          atomicAdd(&s_acc_item[2 * Jp + j], (double)a2[e]);
-          atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
-          atomicAdd(&s_acc_item[4 * Jp + j], (double)ac[e]);
+          const R w = om.v[e];
+          const R tw = tp * w;
+          a0[e] += w;
+          a1[e] += tw;
+          a2[e] = fma(tp, tw, a2[e]);
+          ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
+        }
+        if (has_rt) {
+          const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * eg);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ac[e] = fma(lt.v[e], zp, ac[e]);
         }
       }
-      // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin (entries owned by one thread each)
-      for (int t = tid; t < L.ntri; t += CTA_THREADS) {
-        int r = 0, rem = t;
-        while (rem >= Dg - r) { rem -= Dg - r; ++r; }
-        const int c = r + rem;
-        double g0 = 0.0, g1 = 0.0;
-        for (int pp = 0; pp < P; ++pp) {
-          const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
-          g0 += ur * uc;
-          if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
-        }
-        s_acc_gram[t] += g0;
-        if (qr) s_acc_gram[L.ntri + t] += g1;
+    }
+    if ((tiles_done % STAT_FLUSH_TILES) == STAT_FLUSH_TILES - 1) flush_item_stats();
+    // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin (entries owned by one thread each)
+    for (int t = tid; t < L.ntri; t += CTA_THREADS) {
+      int r = 0, rem = t;
+      while (rem >= Dg - r) { rem -= Dg - r; ++r; }
+      const int c = r + rem;
+      double g0 = 0.0, g1 = 0.0;
+      for (int pp = 0; pp < P; ++pp) {
+        const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
+        g0 += ur * uc;
+        if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
       }
+      s_acc_gram[t] += g0;
+      if (qr) s_acc_gram[L.ntri + t] += g1;
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
   }
+  flush_item_stats();
 
   // ---- flush CTA accumulators ----
   atomicAdd(&s_scal[SC_LL_BERN], acc_ll_bern);
-  if (q == 0) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
+  if (tid < P) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
   atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
-  if (q == 0) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
+  if (tid < P) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
   __syncthreads();
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
     const int j = t % Jp;

@@ -135,7 +135,8 @@ __device__ __forceinline__ bool pg_attempt_B(R c, uint4 w, R& X) {
 
 constexpr uint32_t PG_MAX_ATTEMPTS = 100000u;  // bound on every device loop (NaN inputs must not hang the GPU)
 
-// Complete draw of omega_ij ~ PG(1, z); first_attempt = 0 replays attempt 0, 1 skips it (already known rejected).
+// Complete draw of omega_ij ~ PG(1, z) starting at attempt `first_attempt` (0 = the pair-site attempt; a >= 1 = the
+// retry-site attempts, earlier ones being already known as rejected).
 template <typename R>
 __device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint32_t sweep, int j, R z, int first_attempt,
                                            uint32_t* n_attempts = nullptr) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint3
       done = (j & 1) ? pg_attempt_A<R>(c, w.z, w.w, X) : pg_attempt_A<R>(c, w.x, w.y, X);
     }
 #pragma unroll 1
-    for (uint32_t a = 1; !done && a < PG_MAX_ATTEMPTS; ++a) {
+    for (uint32_t a = first_attempt > 1 ? (uint32_t)first_attempt : 1u; !done && a < PG_MAX_ATTEMPTS; ++a) {
       uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
       ++used;
       done = pg_attempt_A<R>(c, w.x, w.y, X);
@@ -168,12 +169,6 @@ __device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint3
   return R(0.25) * X;
 }
 
-// MUFU approximations (2^-22 relative error), one SASS instruction each
-__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
 // ---- f32 fast path: attempt 0 of Method A, branch-free, intrinsics only ----
 // Returns omega (= X/4) when the attempt is CERTAINLY accepted, a negative sentinel otherwise:
 //   -1: outcome undecided by the squeezes (replay attempt 0 exactly), -2: attempt 0 certainly rejected,
@@ -183,7 +178,7 @@ __device__ __forceinline__ float pg_fast_attempt0(float z, float kappa, uint32_t
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const float c = 0.5f * fabsf(z);
   const float w2c = fast_ex2(-2.0f * LOG2E * c);
-  loglik = fmaf(kappa, z, -c) - log1p_poly(w2c);
+  loglik = fmaf(-LN2, fast_lg2(1.0f + w2c), fmaf(kappa, z, -c));  // kappa z - c - ln(1 + e^{-2c})
 
   const float K = fmaf(0.5f * c, c, (float)(PI_D * PI_D / 8.0));
   const float eKt = fast_ex2(K * (float)(PG_T * 1.4426950408889634));

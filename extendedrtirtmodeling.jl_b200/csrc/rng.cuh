@@ -69,13 +69,25 @@ __device__ __forceinline__ double u01<double>(uint32_t w) { return u01d(w); }
 template <>
 __device__ __forceinline__ float u01<float>(uint32_t w) { return u01f(w); }
 
+// MUFU approximations (2^-22 relative error), one SASS instruction each
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// f32 uses the approximate reciprocal / rsqrt (well inside the 1e-5 contract), f64 the IEEE operations
+__device__ __forceinline__ float rdiv(float a, float b) { return a * fast_rcp(b); }
+__device__ __forceinline__ double rdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ float rsqrt_of(float x) { return x * fast_rsqrt(x); }  // sqrt(x), x > 0
+__device__ __forceinline__ double rsqrt_of(double x) { return sqrt(x); }
+
 // Box-Muller cosine branch
 __device__ __forceinline__ double normal2(uint32_t w0, uint32_t w1) {
   return sqrt(-2.0 * log(u01d(w0))) * cospi(2.0 * u01d(w1));
 }
 __device__ __forceinline__ float normal2f(uint32_t w0, uint32_t w1) {
-  float u = fminf(u01f(w0), 0.99999994f);
-  return sqrtf(-2.0f * logf(u)) * cospif(2.0f * u01f(w1));
+  const float u = fminf(u01f(w0), 0.99999994f);
+  const float t = -1.3862943611198906f * fast_lg2(u);  // -2 ln u > 0
+  return t * fast_rsqrt(t) * __cosf(6.283185307179586f * u01f(w1));
 }
 template <typename R>
 __device__ __forceinline__ R normal2r(uint32_t w0, uint32_t w1);
@@ -135,10 +147,10 @@ __device__ inline double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep
 template <typename R>
 __device__ __forceinline__ R ig_msh(R mu, R lam, R z, R u) {
   R y = z * z;
-  if (!isfinite(mu)) return lam / y;
+  if (!isfinite(mu)) return rdiv(lam, y);
   R w = mu * y;
-  R x1 = R(2) * lam * mu / (R(2) * lam + w + sqrt(w * (R(4) * lam + w)));
-  return (u <= mu / (mu + x1)) ? x1 : mu * mu / x1;
+  R x1 = rdiv(R(2) * lam * mu, R(2) * lam + w + rsqrt_of(w * (R(4) * lam + w) + R(1e-30)));
+  return (u * (mu + x1) <= mu) ? x1 : rdiv(mu * mu, x1);
 }
 
 }  // namespace erirt
