@@ -266,8 +266,9 @@ def main():
         eng = E.Engine("RtIrtQuantile", n_local, N_ITEM, N_FEAT, n_iter=n_iter, n_chain=1, n_burnin=0, q_rt=Q_RT,
                        cov2one=False, dtype=args.dtype, seed=SEED, person_trace=False, device=local, use_graph=use_graph,
                        n_subj_total=N_SUBJ, subj_offset=offset, time_kernels=time_kernels)
-        if shard is not None:
-            eng.comm_init(shard[0], shard[1], shard[2])
+        if world > 1:
+            sh, _ = D.make_shard(N_SUBJ)  # a fresh NCCL id per communicator
+            eng.comm_init(sh[0], sh[1], sh[2])
         return eng
 
     def barrier():

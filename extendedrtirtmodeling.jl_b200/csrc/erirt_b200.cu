@@ -231,7 +231,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_u = (int)o; o = align_up(o + (size_t)S.P * S.Dgp * rsz, 128);
   S.off_sum = (int)o; o = align_up(o + (size_t)S.P * 4 * rsz, 128);
   S.off_beta = (int)o; o = align_up(o + (size_t)(MAXD + 4) * rsz, 128);
-  S.off_acc_item = (int)o; o = align_up(o + 5 * L.Jp * sizeof(double), 128);
+  S.off_acc_item = (int)o; o = align_up(o + N_ITEM_STATS * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
   S.off_queue = (int)o; if (rsz == 4) o = align_up(o + (QCAP + QCAP2) * sizeof(uint32_t), 128);
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
@@ -304,8 +304,8 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   *out = nullptr;
   if (cfg->abi_version != ERIRT_ABI_VERSION) return fail(ERIRT_E_ARG, "abi_version %d != %d", cfg->abi_version, ERIRT_ABI_VERSION);
   if (cfg->model < 0 || cfg->model > 6) return fail(ERIRT_E_ARG, "unknown model %d", cfg->model);
-  if (cfg->model == ERIRT_RTIRT_CROSS || cfg->model == ERIRT_RTIRT_CROSSQR)
-    return fail(ERIRT_E_UNSUPPORTED, "GibbsRtIrtCross / GibbsRtIrtCrossQr are not built yet (two-kernel pipeline, SURVEY 7.1)");
+  if (cfg->model == ERIRT_RTIRT_CROSSQR)
+    return fail(ERIRT_E_UNSUPPORTED, "GibbsRtIrtCrossQr (cell-level quantile weights) is not built yet");
   if (cfg->n_subj < 1 || cfg->n_item < 1 || cfg->n_feat < 0) return fail(ERIRT_E_ARG, "bad dimensions");
   if (cfg->n_subj_total < cfg->n_subj || cfg->subj_offset < 0 || cfg->subj_offset + cfg->n_subj > cfg->n_subj_total)
     return fail(ERIRT_E_ARG, "inconsistent shard: n_subj=%lld offset=%lld total=%lld", (long long)cfg->n_subj,
@@ -603,8 +603,9 @@ extern "C" int erirt_get_state(erirt_handle* h, int32_t field, double* out, int6
 // sampling
 // ------------------------------------------------------------------------------------------------
 template <typename R>
-static PersonArgs<R> make_person_args(erirt_handle* h) {
+static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   PersonArgs<R> A{};
+  A.stage = stage;
   A.Y = h->dY;
   A.logT = (const R*)h->dLogT;
   A.omega = (R*)h->dOmega;
@@ -633,8 +634,9 @@ static PersonArgs<R> make_person_args(erirt_handle* h) {
   return A;
 }
 
-static GlobalArgs make_global_args(erirt_handle* h) {
+static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   GlobalArgs A{};
+  A.stage = stage;
   A.params = h->dParams;
   A.stats = h->dStats;
   A.sweep_ctr = h->dSweep;
@@ -664,28 +666,42 @@ static GlobalArgs make_global_args(erirt_handle* h) {
   return A;
 }
 
-// one P(k) [allreduce] G(k+1) step on h->stream
-static int enqueue_step(erirt_handle* h) {
-  const bool timed = h->cfg.time_kernels && h->kev_used + 2 <= h->kev.size();
-  if (timed) CU(cudaEventRecord(h->kev[h->kev_used], h->stream));
+static int launch_person(erirt_handle* h, int stage) {
   if (h->cfg.dtype == ERIRT_F32) {
-    PersonArgs<float> A = make_person_args<float>(h);
+    PersonArgs<float> A = make_person_args<float>(h, stage);
     void* args[] = {&A};
     CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
   } else {
-    PersonArgs<double> A = make_person_args<double>(h);
+    PersonArgs<double> A = make_person_args<double>(h, stage);
     void* args[] = {&A};
     CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
   }
+  return 0;
+}
+static int launch_global(erirt_handle* h, int stage) {
+  if (h->comm) NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
+  GlobalArgs G = make_global_args(h, stage);
+  global_draw_kernel<<<1, G_THREADS, 0, h->stream>>>(G);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// one sweep on h->stream:  P(k) [allreduce] G(k+1);  Cross family: K_a(k) [ar] G_a(k) K_b(k) [ar] G_b(k+1)
+static int enqueue_step(erirt_handle* h, bool prologue) {
+  const bool cross = h->cfg.model == ERIRT_RTIRT_CROSS || h->cfg.model == ERIRT_RTIRT_CROSSQR;
+  const bool timed = h->cfg.time_kernels && h->kev_used + 2 <= h->kev.size();
+  int rc;
+  if (cross && !prologue) {
+    if ((rc = launch_person(h, 1))) return rc;
+    if ((rc = launch_global(h, 1))) return rc;
+  }
+  if (timed) CU(cudaEventRecord(h->kev[h->kev_used], h->stream));
+  if ((rc = launch_person(h, cross ? 2 : 0))) return rc;
   if (timed) {
     CU(cudaEventRecord(h->kev[h->kev_used + 1], h->stream));
     h->kev_used += 2;
   }
-  if (h->comm) NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
-  GlobalArgs G = make_global_args(h);
-  global_draw_kernel<<<1, G_THREADS, 0, h->stream>>>(G);
-  CU(cudaGetLastError());
-  return 0;
+  return launch_global(h, cross ? 2 : 0);
 }
 
 extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
@@ -701,7 +717,7 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
   if (!h->prologue_done) {
     CU(cudaMemsetAsync(h->dSweep, 0, sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->dStats, 0, (h->L.s_count + 2) * sizeof(double), h->stream));
-    rc = enqueue_step(h);  // P(0), G(1)
+    rc = enqueue_step(h, true);  // P(0), G(1)
     if (rc) return rc;
     h->prologue_done = true;
   }
@@ -718,7 +734,7 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
     if (!h->graph_exec) {
       cudaGraph_t graph;
       CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      rc = enqueue_step(h);
+      rc = enqueue_step(h, false);
       cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
       if (rc) return rc;
       if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -729,7 +745,7 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
     for (int64_t t = 0; t < n_sweeps; ++t) CU(cudaGraphLaunch(h->graph_exec, h->stream));
   } else {
     for (int64_t t = 0; t < n_sweeps; ++t) {
-      rc = enqueue_step(h);
+      rc = enqueue_step(h, false);
       if (rc) return rc;
     }
   }
@@ -852,12 +868,13 @@ extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {
   out->sweeps_done = h->sweeps_done;
   out->last_sample_ms = h->last_ms;
   out->person_kernel_ms = h->person_ms;
-  out->launches_per_sweep = 2;
+  out->launches_per_sweep = (h->cfg.model == ERIRT_RTIRT_CROSS || h->cfg.model == ERIRT_RTIRT_CROSSQR) ? 4 : 2;
   out->sm_count = h->sm_count;
   const int64_t N = h->cfg.n_subj, J = h->cfg.n_item, F = h->cfg.n_feat;
   const int64_t r = (int64_t)h->rsz;
   const bool has_rt = h->cfg.model != ERIRT_MLIRT;
   int64_t per_cell = 1 + 2 * r + (has_rt ? r : 0);
+  if (h->cfg.model == ERIRT_RTIRT_CROSS) per_cell = 2 * (1 + 2 * r);  // K_a reads Y, logT, omega; K_b reads Y, logT, writes omega
   int nv = has_rt ? 2 : 1;
   if (h->cfg.model == ERIRT_RTIRT_LATENTQR) nv = 3;
   out->bytes_per_sweep = N * J * per_cell + N * r * (2 * nv + F);

@@ -184,6 +184,12 @@ __device__ inline bool structural_draws(const GlobalArgs& A, uint32_t s, const G
     const double Psi[4] = {Sth2 + 1.0, Sthze, Sthze, Sze2 + 1.0};
     inv_wishart2(A.key, s, N + 3.0, Psi, w.Sigma);  // drawSubjCovarianceNull
     if (A.cov2one) cov2one_2x2(w.Sigma);
+  } else if (model == M_CROSS || model == M_CROSSQR) {
+    // drawSubjCovarianceCross, Draw.pl.jl:542-557
+    const double parA = 1e-3 + N / 2.0, parB = 1e-3 + Sze2 / 2.0;
+    const double sv = parB / site_gamma(A.key, 0, s, make_site(DOM_GLOBAL, GK_SIGMAP), parA);
+    w.Sigma[0] = 1.0; w.Sigma[1] = 0.0; w.Sigma[2] = 0.0; w.Sigma[3] = sv;
+    if (A.cov2one) cov2one_2x2(w.Sigma);
   } else if (model == M_LATENT || model == M_LATENTQR) {
     const int d = F + 2;
     const bool qrm = model == M_LATENTQR;
@@ -255,9 +261,35 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   double* st = A.stats;
   const GramView Gm{st + L.s_gram, Dg, F};
   const GramView Gw{st + L.s_gramw, Dg, F};
-  const double Sth = Gm.at(0, Gm.th());
+  const double Sth = Gm.at(0, Gm.th()), Sth2 = Gm.at(Gm.th(), Gm.th()), Sthze = Gm.at(Gm.th(), Gm.ze());
   const double Sze = Gm.at(0, Gm.ze()), Sze2 = Gm.at(Gm.ze(), Gm.ze());
   const double LOG2PI = 1.8378770664093454835606594728112;
+  const bool cross = model == M_CROSS || model == M_CROSSQR;
+  const double mu_lam = has_rt ? A.consts[0] : 0.0, sd_lam = has_rt ? A.consts[1] : 1.0;
+
+  if (A.stage == 1) {
+    // ---- G_a of the Cross family: lambda_k, sigma2_k from (theta_k, zeta_{k-1}, rho_k)   Draw.pl.jl:225-231, 267-273 ----
+    for (int j = tid; j < J; j += G_THREADS) {
+      const double s2 = par[L.p_sigma2 + j], rho = par[L.p_rho + j];
+      const double T1 = A.T1[j], T2 = A.T2[j], C = st[L.s_C + j], D = st[L.s_D + j];
+      const double pv = 1.0 / (sd_lam * sd_lam);
+      const double parV = 1.0 / (pv + N / s2);
+      const double parM = parV * (mu_lam * pv + (T1 + Sze + rho * Sth) / s2);
+      const double lam = site_tnorm_pos(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_LAMBDA), parM, sqrt(parV));
+      const double Q = T2 - 2.0 * lam * T1 + N * lam * lam + 2.0 * (C - lam * Sze) + Sze2 + rho * rho * Sth2 +
+                       2.0 * rho * (D - lam * Sth + Sthze);
+      const double s2n = (1e-3 + Q / 2.0) / site_gamma(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_SIGMA2), 1e-3 + N / 2.0);
+      par[L.p_lambda + j] = lam;
+      par[L.p_sigma2 + j] = s2n;
+      if (k >= 1 && (int)(k - 1) < A.cap) {
+        A.tr_items_rt[(size_t)(k - 1) * 2 * J + j] = lam;
+        A.tr_items_rt[(size_t)(k - 1) * 2 * J + J + j] = s2n;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = 0.0;
+    return;
+  }
 
   // ---- 1. log-likelihood of state k ----
   if (k >= 1) {
@@ -265,7 +297,11 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     if (has_rt)
       for (int j = tid; j < J; j += G_THREADS) {
         const double lam = par[L.p_lambda + j], s2 = par[L.p_sigma2 + j];
-        const double Q = A.T2[j] - 2.0 * lam * A.T1[j] + N * lam * lam + 2.0 * (st[L.s_C + j] - lam * Sze) + Sze2;
+        double Q = A.T2[j] - 2.0 * lam * A.T1[j] + N * lam * lam + 2.0 * (st[L.s_C + j] - lam * Sze) + Sze2;
+        if (cross) {  // residual logT - lambda + zeta + theta rho_j  (getLogLikelihoodRtIrtCross, GibbsRtIrtCross.pl.jl:158-169)
+          const double rho = par[L.p_rho + j];
+          Q += rho * rho * Sth2 + 2.0 * rho * (st[L.s_D + j] - lam * Sth + Sthze);
+        }
         part += -0.5 * N * (LOG2PI + log(s2)) - 0.5 * Q / s2;
       }
     sRed[tid] = part;
@@ -283,7 +319,6 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     for (int t = 0; t < 4; ++t) w.Sigma[t] = par[L.p_Sigma + t];
     if (!structural_draws(A, s, Gm, Gw, w)) atomicExch(A.status, (int)s);
   }
-  const double mu_lam = has_rt ? A.consts[0] : 0.0, sd_lam = has_rt ? A.consts[1] : 1.0;
   for (int j = tid; j < J; j += G_THREADS) {
     const double S0 = st[L.s_S0 + j], S1 = st[L.s_S1 + j], S2 = st[L.s_S2 + j];
     const double K0 = A.K0[j], K1 = st[L.s_Ky + j] - 0.5 * Sth;  // Σκ, Σκθ
@@ -304,7 +339,12 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     else { draw_b(); draw_a(); }
     par[L.p_a + j] = a;
     par[L.p_b + j] = b;
-    if (has_rt) {
+    if (cross) {  // drawSubjCorrCross, Draw.pl.jl:463-469 (state k: theta_k, zeta_k, lambda_k, sigma2_k)
+      const double s2 = par[L.p_sigma2 + j], lam = par[L.p_lambda + j];
+      const double parV = 1.0 / (1.0 + Sth2 / s2);
+      const double parM = parV * (0.0 + (lam * Sth - Sthze - st[L.s_D + j]) / s2);
+      par[L.p_rho + j] = parM + sqrt(parV) * site_normal(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_RHO));
+    } else if (has_rt) {
       const double s2 = par[L.p_sigma2 + j];
       const double T1 = A.T1[j], T2 = A.T2[j], C = st[L.s_C + j];
       // drawItemIntensity
@@ -332,14 +372,14 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     for (int j = tid; j < J; j += G_THREADS) {
       A.tr_items_ra[(size_t)k * 2 * J + j] = par[L.p_a + j];
       A.tr_items_ra[(size_t)k * 2 * J + J + j] = par[L.p_b + j];
-      if (has_rt) {
+      if (has_rt && !cross) {
         A.tr_items_rt[(size_t)k * 2 * J + j] = par[L.p_lambda + j];
         A.tr_items_rt[(size_t)k * 2 * J + J + j] = par[L.p_sigma2 + j];
       }
     }
-    const int nb = (model == M_MLIRT) ? F + 1 : ((model == M_RTIRT || model == M_NULL) ? 2 * (F + 1) : F + 2);
+    const int nb = cross ? J : ((model == M_MLIRT) ? F + 1 : ((model == M_RTIRT || model == M_NULL) ? 2 * (F + 1) : F + 2));
     for (int t = tid; t < A.qw; t += G_THREADS) {
-      double v = t < nb ? par[L.p_beta + t] : par[L.p_Sigma + (t - nb)];
+      double v = t < nb ? (cross ? par[L.p_rho + t] : par[L.p_beta + t]) : par[L.p_Sigma + (t - nb)];
       A.tr_qr[(size_t)k * A.qw + t] = v;
     }
   }

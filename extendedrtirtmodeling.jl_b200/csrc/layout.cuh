@@ -10,6 +10,7 @@ constexpr int MAXD = 32;          // largest dense system solved in the global k
 constexpr int QCAP = 1024;        // PG fast-retry queue capacity per tile (overflow is handled inline)
 constexpr int QCAP2 = 256;        // PG exact-replay queue capacity per tile
 
+constexpr int N_ITEM_STATS = 6;   // S0, S1, S2, Ky, C, D
 enum ModelId { M_MLIRT = 0, M_RTIRT = 1, M_NULL = 2, M_CROSS = 3, M_CROSSQR = 4, M_LATENT = 5, M_LATENTQR = 6 };
 
 // statistics scalars (f64), accumulated by the person kernel and consumed by the global kernel
@@ -27,7 +28,7 @@ enum StatScalar {
 struct Layout {
   int J, Jp, F, Dg, ntri;
   int p_a, p_b, p_lambda, p_sigma2, p_rho, p_beta, p_Sigma, p_count;
-  int s_S0, s_S1, s_S2, s_Ky, s_C, s_gram, s_gramw, s_scal, s_count;
+  int s_S0, s_S1, s_S2, s_Ky, s_C, s_D, s_gram, s_gramw, s_scal, s_count;
 };
 
 __host__ __device__ inline int tri_index(int r, int c, int Dg) {  // r <= c, row-major upper triangle
@@ -58,6 +59,7 @@ inline Layout make_layout(int J, int F) {
   L.s_S2 = o; o += L.Jp;
   L.s_Ky = o; o += L.Jp;
   L.s_C = o; o += L.Jp;
+  L.s_D = o; o += L.Jp;  // sum_i theta_i logT_ij (Cross family)
   L.s_gram = o; o += L.ntri;
   L.s_gramw = o; o += L.ntri;
   L.s_scal = o; o += SC_COUNT;
@@ -95,6 +97,7 @@ struct PersonArgs {
   Layout L;
   SmemPlan S;
   int model, n_chain, n_burnin;
+  int stage;  // 0: whole sweep in one launch; Cross family: 1 = K_a (theta + its statistics), 2 = K_b (zeta, omega, statistics)
   double k1, k2;
   PhiloxKey key;
 };
@@ -119,6 +122,7 @@ struct GlobalArgs {
   int cap, qw;
   Layout L;
   int model, intercept, onepl, cov2one, compat;
+  int stage;  // 0/2: full draw + trace + counter; 1 (Cross family): lambda, sigma2 only
   double k1, k2;
   PhiloxKey key;
 };

@@ -84,7 +84,7 @@ __device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
 // item-parameter arrays staged in shared memory (each Jp long, zero beyond J)
 enum ParIdx { PAR_A = 0, PAR_AB = 1, PAR_A2 = 2, PAR_A2B = 3, PAR_IS2 = 4, PAR_LAM = 5, PAR_COUNT = 6 };
 // per-CTA scalars in the misc block (f64)
-enum MiscD { MD_SUM_IS2 = 0, MD_SUM_LIS2 = 1, MD_COUNT = 2 };
+enum MiscD { MD_SUM_IS2 = 0, MD_SUM_RHO_IS2 = 1, MD_COUNT = 2 };
 
 // group index handled by thread q at step k: the TPP threads of one person and the persons of a quarter
 // warp touch 8 distinct 16-byte bank groups (row pitch is an odd number of quads)
@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   const bool latent = model == M_LATENT || model == M_LATENTQR;
   const bool qr = model == M_LATENTQR;
   const bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
+  const bool cross = model == M_CROSS || model == M_CROSSQR;
+  const int stage = A.stage;
+  const bool do_theta = stage != 2, do_zeta = has_rt && stage != 1, do_pg = stage != 1;
 
   R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
   R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
@@ -175,23 +178,31 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   }
   if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
   if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
-  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
+  for (int t = tid; t < N_ITEM_STATS * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
   if (tid < SC_COUNT) s_scal[tid] = 0.0;
   if (tid < 32) {  // sum_j 1/sigma2_j in f64
-    double s1 = 0;
+    double s1 = 0, s2 = 0;
     if (has_rt)
-      for (int j = tid; j < J; j += 32) s1 += 1.0 / par[L.p_sigma2 + j];
-    for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      for (int j = tid; j < J; j += 32) {
+        const double is2 = 1.0 / par[L.p_sigma2 + j];
+        s1 += is2;
+        if (cross) s2 += par[L.p_rho + j] * is2;
+      }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
     if (tid == 0) {
       s_miscd[MD_SUM_IS2] = s1;
+      s_miscd[MD_SUM_RHO_IS2] = s2;
       mbar_init(s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
   __syncthreads();
 
-  const R sum_is2 = (R)s_miscd[MD_SUM_IS2];
+  const R sum_is2 = (R)s_miscd[MD_SUM_IS2], sum_rho_is2 = (R)s_miscd[MD_SUM_RHO_IS2];
   const R S11 = s_beta[MAXD + 0], S12 = s_beta[MAXD + 2], S22 = s_beta[MAXD + 3];
   const R k1 = (R)A.k1, k2 = (R)A.k2;
   const int pb = F + 1;  // length of one regression block [1 X]
@@ -201,14 +212,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   double acc_ll_bern = 0.0, acc_ll_struct = 0.0;
   uint32_t acc_defer = 0, acc_cells = 0;
   uint32_t parity = 0;
-  const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * (has_rt ? 2 : 1) + A.S.tile_y_bytes);
+  const bool load_om = stage != 2;  // K_b of the Cross family only writes omega
+  const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * ((has_rt ? 1 : 0) + (load_om ? 1 : 0)) + A.S.tile_y_bytes);
   const int nk = ((G + 7) / 8) * (8 / TPP);  // steps per thread over its 4-item groups
 
   // transposed-statistics role of this thread: item group eg, person class er (G <= CTA_THREADS is enforced by the host)
   const int Rc = CTA_THREADS / G;
   const bool e_active = tid < G * Rc;
   const int eg = tid % G, er = tid / G;
-  R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
+  R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0};
   auto flush_item_stats = [&]() {
     if (e_active) {
 #pragma unroll
@@ -219,7 +231,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         atomicAdd(&s_acc_item[2 * Jp + j], (double)a2[e]);
         atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
         atomicAdd(&s_acc_item[4 * Jp + j], (double)ac[e]);
-        a0[e] = a1[e] = a2[e] = ay[e] = ac[e] = R(0);
+        if (cross) atomicAdd(&s_acc_item[5 * Jp + j], (double)ad[e]);
+        a0[e] = a1[e] = a2[e] = ay[e] = ac[e] = ad[e] = R(0);
       }
     }
   };
@@ -230,7 +243,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     if (tid == 0) {
       tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
       mbar_expect_tx(s_bar, load_bytes);
-      tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      if (load_om) tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
       s_qctl[0] = 0;
@@ -269,19 +282,21 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       for (int kk = 0; kk < nk; ++kk) {
         const int g = group_of<TPP>(q, kk);
         if (g >= G) continue;
-        const Quad<R> om = ld4(my_om + 4 * g);
-        const Quad<R> pA2 = ld4(s_par + PAR_A2 * Jp + 4 * g);
-        const Quad<R> pA2B = ld4(s_par + PAR_A2B * Jp + 4 * g);
-        const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
-        const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+        if (do_theta) {
+          const Quad<R> om = ld4(my_om + 4 * g);
+          const Quad<R> pA2 = ld4(s_par + PAR_A2 * Jp + 4 * g);
+          const Quad<R> pA2B = ld4(s_par + PAR_A2B * Jp + 4 * g);
+          const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
+          const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          sA2 = fma(pA2.v[e], om.v[e], sA2);
-          sAB = fma(pA2B.v[e], om.v[e], sAB);
-          const R kap = ((yw >> (8 * e)) & 0xffu) ? R(0.5) : R(-0.5);
-          sAK = fma(pA.v[e], kap, sAK);
+          for (int e = 0; e < 4; ++e) {
+            sA2 = fma(pA2.v[e], om.v[e], sA2);
+            sAB = fma(pA2B.v[e], om.v[e], sAB);
+            const R kap = ((yw >> (8 * e)) & 0xffu) ? R(0.5) : R(-0.5);
+            sAK = fma(pA.v[e], kap, sAK);
+          }
         }
-        if (has_rt) {
+        if (do_zeta) {
           const Quad<R> lt = ld4(my_lt + 4 * g);
           const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
           const Quad<R> pL = ld4(s_par + PAR_LAM * Jp + 4 * g);
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       if (tid < P) {
         const R* d = s_sum + 4 * tid;
         const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
-        {
+        if (do_theta) {
           const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
           const R var0 = (model == M_MLIRT) ? R(1) : S11;
           const R iv0 = rdiv(R(1), var0);
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           th = parM + rsqrt_of(parV) * normal2r<R>(w.x, w.y);
         }
         R mu_z = R(0), var_z = R(1);
-        if (has_rt) {
+        if (do_zeta) {
           if (model == M_RTIRT) { mu_z = xb2; var_z = S22; }
           else if (latent) {
             mu_z = fma(th, s_beta[F + 1], xb1);
@@ -324,10 +339,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           else { mu_z = R(0); var_z = S22; }
           const R ivz = rdiv(R(1), var_z);
           const R parV = rdiv(R(1), ivz + sum_is2);
-          const R parM = parV * (mu_z * ivz + d[3]);
+          const R parM = parV * (mu_z * ivz + (cross ? d[3] - th * sum_rho_is2 : d[3]));  // Cross: sum_j (lambda - logT - theta rho_j)/sigma2
           ze = parM + rsqrt_of(parV) * normal2r<R>(w.z, w.w);
         }
-        if (pvalid) {
+        if (pvalid && stage == 1) A.theta[pi] = th;  // K_a: theta_k only; everything else happens in K_b
+        if (pvalid && stage != 1) {
           const double LOG2PI = 1.8378770664093454835606594728112;
           double ls;
           if (model == M_MLIRT) {
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
             ls = -LOG2PI - 0.5 * log(det) - 0.5 * (s22 * e1 * e1 - 2.0 * s12 * e1 * e2 + s11 * e2 * e2) / det;
           }
           acc_ll_struct += ls;
-          A.theta[pi] = th;
+          if (do_theta) A.theta[pi] = th;
           if (has_rt) A.zeta[pi] = ze;
           if (post_burnin) {
             double* m = A.mom + pi;
@@ -388,136 +404,138 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       u[F + 2] = pvalid ? ze : R(0);
       u[F + 3] = (pvalid && qr) ? nu : R(0);
       u[F + 4] = (pvalid && qr) ? rdiv(R(1), nu) : R(0);  // weight of the nu-weighted Gram
-      if (pvalid) acc_cells += (uint32_t)J;
+      if (pvalid && do_pg) acc_cells += (uint32_t)J;
     }
     __syncthreads();
 
-    // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
-    const bool valid = (row0 + p) < A.n_local;
-    const uint32_t gid = A.person_offset + (uint32_t)(row0 + p);
-    const R thp = s_u[p * Dgp + F + 1];
-    float ll_tile = 0.f;
-    uint32_t my_defer = 0;
-    unsigned long long defer_mask = 0ull;  // bit 4*kk+e: cell left the fast path (nk <= 16 by the TPP choice)
-    for (int kk = 0; kk < nk; ++kk) {
-      const int g = group_of<TPP>(q, kk);
-      if (g >= G) continue;
-      Quad<R> out;
-      if (!valid) {
-        out.v[0] = out.v[1] = out.v[2] = out.v[3] = R(0);
-        st4(my_om + 4 * g, out);
-        continue;
-      }
-      const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
-      const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
-      const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
-      if constexpr (F32) {
-        const uint4 wA = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
-        const uint4 wB = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
-        const uint32_t ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
-        const int npad = 4 * g + 4 - J;  // > 0 only in groups holding padding cells
-        float llg = 0.f;
-        uint32_t m4 = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float z = fmaf(pA.v[e], thp, -pAB.v[e]);
-          const float kap = ((yw >> (8 * e)) & 0xffu) ? 0.5f : -0.5f;
-          float ll;
-          float om = pg_fast_attempt0(z, kap, ww[2 * e], ww[2 * e + 1], ll);
-          if (npad > 0 && e >= 4 - npad) { om = 0.f; ll = 0.f; }  // padding cells never count
-          llg += ll;
-          if (om < 0.f) m4 |= 1u << e;
-          out.v[e] = om;
+    if (do_pg) {
+      // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
+      const bool valid = (row0 + p) < A.n_local;
+      const uint32_t gid = A.person_offset + (uint32_t)(row0 + p);
+      const R thp = s_u[p * Dgp + F + 1];
+      float ll_tile = 0.f;
+      uint32_t my_defer = 0;
+      unsigned long long defer_mask = 0ull;  // bit 4*kk+e: cell left the fast path (nk <= 16 by the TPP choice)
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+        Quad<R> out;
+        if (!valid) {
+          out.v[0] = out.v[1] = out.v[2] = out.v[3] = R(0);
+          st4(my_om + 4 * g, out);
+          continue;
         }
-        ll_tile += llg;
-        defer_mask |= (unsigned long long)m4 << (4 * kk);
-      } else {
-#pragma unroll 1
-        for (int e = 0; e < 4; ++e) {
-          const int j = 4 * g + e;
-          if (j >= J) { out.v[e] = R(0); continue; }
-          const R z = fma(pA.v[e], thp, -pAB.v[e]);
-          const R y = ((yw >> (8 * e)) & 0xffu) ? R(1) : R(0);
-          const R az = fabs(z);
-          acc_ll_bern += (double)(y * z - (R(0.5) * (z + az) + log1p(exp(-az))));
-          uint32_t na;
-          out.v[e] = (R)pg_draw_cell_f64(A.key, gid, k + 1, j, (double)z, &na);
-          my_defer += na > 1u;
-        }
-      }
-      st4(my_om + 4 * g, out);
-    }
-    acc_ll_bern += (double)ll_tile;
-    if constexpr (F32) {
-      // ---- hand the cells that left the fast path to the queues: rejected -> fast retry, undecided / Method B -> exact ----
-      my_defer = (uint32_t)__popcll(defer_mask);
-      while (defer_mask) {
-        const int bit = __ffsll((long long)defer_mask) - 1;
-        defer_mask &= defer_mask - 1ull;
-        const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
-        const float code = (float)my_om[j];
-        const uint32_t entry = ((uint32_t)p << 16) | (uint32_t)j;
-        if (code == -2.0f) {
-          const uint32_t slot = atomicAdd(&s_qctl[0], 1u);
-          if (slot < (uint32_t)QCAP) s_queue[slot] = entry | (1u << 24);
-          else {  // queue overflow: finish the cell here
-            const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
-            my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, 1);
+        const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
+        const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+        if constexpr (F32) {
+          const uint4 wA = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
+          const uint4 wB = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
+          const uint32_t ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+          const int npad = 4 * g + 4 - J;  // > 0 only in groups holding padding cells
+          float llg = 0.f;
+          uint32_t m4 = 0;
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float z = fmaf(pA.v[e], thp, -pAB.v[e]);
+            const float kap = ((yw >> (8 * e)) & 0xffu) ? 0.5f : -0.5f;
+            float ll;
+            float om = pg_fast_attempt0(z, kap, ww[2 * e], ww[2 * e + 1], ll);
+            if (npad > 0 && e >= 4 - npad) { om = 0.f; ll = 0.f; }  // padding cells never count
+            llg += ll;
+            if (om < 0.f) m4 |= 1u << e;
+            out.v[e] = om;
           }
+          ll_tile += llg;
+          defer_mask |= (unsigned long long)m4 << (4 * kk);
         } else {
-          const uint32_t first = code == -1.0f ? 0u : 1u;
-          const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
-          if (slot < (uint32_t)QCAP2) s_queue[QCAP + slot] = entry | (first << 24);
-          else {
-            const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
-            my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, (int)first);
+  #pragma unroll 1
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * g + e;
+            if (j >= J) { out.v[e] = R(0); continue; }
+            const R z = fma(pA.v[e], thp, -pAB.v[e]);
+            const R y = ((yw >> (8 * e)) & 0xffu) ? R(1) : R(0);
+            const R az = fabs(z);
+            acc_ll_bern += (double)(y * z - (R(0.5) * (z + az) + log1p(exp(-az))));
+            uint32_t na;
+            out.v[e] = (R)pg_draw_cell_f64(A.key, gid, k + 1, j, (double)z, &na);
+            my_defer += na > 1u;
           }
         }
+        st4(my_om + 4 * g, out);
       }
-    }
-    acc_defer += my_defer;
-    __syncthreads();
-
-    if constexpr (F32) {
-      // ---- stage 1: fast retries, any free thread takes the next cell ----
-      const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
-      if (qn) {
-        while (true) {
-          const uint32_t idx = atomicAdd(&s_qctl[1], 1u);
-          if (idx >= qn) break;
-          const uint32_t entry = s_queue[idx];
-          const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
-          const float thq = (float)s_u[pp * Dgp + F + 1];
-          const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
-          const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
-          float om = pg_retry_fast_f32(A.key, qgid, k + 1, pj, z, first);
-          if (om < 0.f) {  // attempt -(om)-1 is undecided: exact queue
-            const uint32_t a = (uint32_t)(-om) - 1u;
-            const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
-            if (slot < (uint32_t)QCAP2) {
-              s_queue[QCAP + slot] = (entry & 0xffffffu) | (a << 24);
-              continue;
+      acc_ll_bern += (double)ll_tile;
+      if constexpr (F32) {
+        // ---- hand the cells that left the fast path to the queues: rejected -> fast retry, undecided / Method B -> exact ----
+        my_defer = (uint32_t)__popcll(defer_mask);
+        while (defer_mask) {
+          const int bit = __ffsll((long long)defer_mask) - 1;
+          defer_mask &= defer_mask - 1ull;
+          const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
+          const float code = (float)my_om[j];
+          const uint32_t entry = ((uint32_t)p << 16) | (uint32_t)j;
+          if (code == -2.0f) {
+            const uint32_t slot = atomicAdd(&s_qctl[0], 1u);
+            if (slot < (uint32_t)QCAP) s_queue[slot] = entry | (1u << 24);
+            else {  // queue overflow: finish the cell here
+              const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+              my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, 1);
             }
-            om = pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, (int)a);
+          } else {
+            const uint32_t first = code == -1.0f ? 0u : 1u;
+            const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
+            if (slot < (uint32_t)QCAP2) s_queue[QCAP + slot] = entry | (first << 24);
+            else {
+              const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+              my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, (int)first);
+            }
           }
-          s_om[pp * Jp + pj] = (R)om;
         }
       }
+      acc_defer += my_defer;
       __syncthreads();
-      // ---- stage 2: exact replays (undecided attempts, Method-B cells) ----
-      const uint32_t qn2 = min(s_qctl[2], (uint32_t)QCAP2);
-      if (qn2) {
-        while (true) {
-          const uint32_t idx = atomicAdd(&s_qctl[3], 1u);
-          if (idx >= qn2) break;
-          const uint32_t entry = s_queue[QCAP + idx];
-          const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
-          const float thq = (float)s_u[pp * Dgp + F + 1];
-          const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
-          const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
-          s_om[pp * Jp + pj] = (R)pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, first);
+
+      if constexpr (F32) {
+        // ---- stage 1: fast retries, any free thread takes the next cell ----
+        const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
+        if (qn) {
+          while (true) {
+            const uint32_t idx = atomicAdd(&s_qctl[1], 1u);
+            if (idx >= qn) break;
+            const uint32_t entry = s_queue[idx];
+            const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
+            const float thq = (float)s_u[pp * Dgp + F + 1];
+            const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
+            const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
+            float om = pg_retry_fast_f32(A.key, qgid, k + 1, pj, z, first);
+            if (om < 0.f) {  // attempt -(om)-1 is undecided: exact queue
+              const uint32_t a = (uint32_t)(-om) - 1u;
+              const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
+              if (slot < (uint32_t)QCAP2) {
+                s_queue[QCAP + slot] = (entry & 0xffffffu) | (a << 24);
+                continue;
+              }
+              om = pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, (int)a);
+            }
+            s_om[pp * Jp + pj] = (R)om;
+          }
         }
         __syncthreads();
+        // ---- stage 2: exact replays (undecided attempts, Method-B cells) ----
+        const uint32_t qn2 = min(s_qctl[2], (uint32_t)QCAP2);
+        if (qn2) {
+          while (true) {
+            const uint32_t idx = atomicAdd(&s_qctl[3], 1u);
+            if (idx >= qn2) break;
+            const uint32_t entry = s_queue[QCAP + idx];
+            const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
+            const float thq = (float)s_u[pp * Dgp + F + 1];
+            const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
+            const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
+            s_om[pp * Jp + pj] = (R)pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, first);
+          }
+          __syncthreads();
+        }
       }
     }
 
@@ -525,21 +543,27 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     if (e_active) {
       for (int pp = er; pp < P; pp += Rc) {
         const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
-        const Quad<R> om = ld4(s_om + pp * Jp + 4 * eg);
-        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * eg);
+        if (do_pg) {
+          const Quad<R> om = ld4(s_om + pp * Jp + 4 * eg);
+          const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * eg);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const R w = om.v[e];
-          const R tw = tp * w;
-          a0[e] += w;
-          a1[e] += tw;
-          a2[e] = fma(tp, tw, a2[e]);
-          ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
+          for (int e = 0; e < 4; ++e) {
+            const R w = om.v[e];
+            const R tw = tp * w;
+            a0[e] += w;
+            a1[e] += tw;
+            a2[e] = fma(tp, tw, a2[e]);
+            ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
+          }
         }
         if (has_rt) {
           const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * eg);
 #pragma unroll
           for (int e = 0; e < 4; ++e) ac[e] = fma(lt.v[e], zp, ac[e]);
+          if (cross) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ad[e] = fma(lt.v[e], tp, ad[e]);
+          }
         }
       }
     }
@@ -560,7 +584,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
+    if (tid == 0 && do_pg) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
   }
   flush_item_stats();
 
@@ -570,9 +594,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
   if (tid < P) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
   __syncthreads();
-  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
+  for (int t = tid; t < N_ITEM_STATS * Jp; t += CTA_THREADS) {
     const int j = t % Jp;
-    if (j < J) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
+    if (j < J && (cross || t < 5 * Jp)) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
   }
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS)
     if (t < L.ntri || qr) atomicAdd(&A.stats[L.s_gram + t], s_acc_gram[t]);

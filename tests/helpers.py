@@ -1,8 +1,8 @@
 """Shared test helpers: seeded synthetic data per model and oracle/engine runners."""
 import numpy as np
 
-MODELS = ["MlIrt", "RtIrt", "RtIrtNull", "RtIrtLatent", "RtIrtLatentQr"]
-ALL_MODELS = MODELS + ["RtIrtCross", "RtIrtCrossQr"]
+MODELS = ["MlIrt", "RtIrt", "RtIrtNull", "RtIrtLatent", "RtIrtLatentQr", "RtIrtCross"]  # built on the GPU
+ALL_MODELS = MODELS + ["RtIrtCrossQr"]
 
 
 def make_problem(model, N, J, F, seed=0, q=0.85):
@@ -43,6 +43,8 @@ def run_engine(E, pb, n_sweeps, seed=99, chain=0, dtype="f64", intercept=False, 
         st.update(zeta=init["zeta"], lambda_=init["lambda_"], sigma2=init["sigma2"], Sigma=init["Sigma"])
     if pb["nb"]:
         st["beta"] = init["beta"][: pb["nb"]]
+    if "Cross" in model:
+        st["rho"] = init["rho"]
     eng.set_state(**st)
     eng.sample(n_sweeps)
     return eng

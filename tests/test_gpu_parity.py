@@ -144,6 +144,7 @@ def test_multi_sweep_parity_f64(E, oracle, model):
     ("RtIrtNull", dict(cov2one=False)),
     ("RtIrtLatent", dict(intercept=True, cov2one=True, compat=1)),
     ("RtIrtLatentQr", dict(intercept=True, compat=2)),
+    ("RtIrtCross", dict(itemtype="1pl", cov2one=False)),
 ])
 def test_keyword_and_compat_variants_f64(E, oracle, model, opts):
     pb = make_problem(model, 300, 7, 2, seed=14)
