@@ -195,7 +195,7 @@ struct erirt_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // device buffers
   uint8_t* dY = nullptr;
-  void *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
+  void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
   double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
   double *dTrRa = nullptr, *dTrRt = nullptr, *dTrQr = nullptr, *dTrLl = nullptr;
   uint32_t* dSweep = nullptr;
@@ -216,7 +216,7 @@ struct erirt_handle {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt) {
+static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt, bool cqr = false) {
   SmemPlan S{};
   S.P = CTA_THREADS / tpp;
   S.tile_real_bytes = (int)(S.P * L.Jp * rsz);
@@ -226,6 +226,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   size_t o = 0;
   S.off_omega = (int)o; o = align_up(o + S.tile_real_bytes, 128);
   S.off_logt = (int)o; if (has_rt) o = align_up(o + S.tile_real_bytes, 128);
+  S.off_nuc = (int)o; if (cqr) o = align_up(o + S.tile_real_bytes, 128);
   S.off_y = (int)o; o = align_up(o + S.tile_y_bytes, 128);
   S.off_par = (int)o; o = align_up(o + PAR_COUNT * L.Jp * rsz, 128);
   S.off_u = (int)o; o = align_up(o + (size_t)S.P * S.Dgp * rsz, 128);
@@ -280,7 +281,7 @@ static int free_handle(erirt_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->comm && nccl::comm_destroy) nccl::comm_destroy(h->comm);
-  void* ptrs[] = {h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
+  void* ptrs[] = {h->dNuCell, h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
                   h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -304,8 +305,6 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   *out = nullptr;
   if (cfg->abi_version != ERIRT_ABI_VERSION) return fail(ERIRT_E_ARG, "abi_version %d != %d", cfg->abi_version, ERIRT_ABI_VERSION);
   if (cfg->model < 0 || cfg->model > 6) return fail(ERIRT_E_ARG, "unknown model %d", cfg->model);
-  if (cfg->model == ERIRT_RTIRT_CROSSQR)
-    return fail(ERIRT_E_UNSUPPORTED, "GibbsRtIrtCrossQr (cell-level quantile weights) is not built yet");
   if (cfg->n_subj < 1 || cfg->n_item < 1 || cfg->n_feat < 0) return fail(ERIRT_E_ARG, "bad dimensions");
   if (cfg->n_subj_total < cfg->n_subj || cfg->subj_offset < 0 || cfg->subj_offset + cfg->n_subj > cfg->n_subj_total)
     return fail(ERIRT_E_ARG, "inconsistent shard: n_subj=%lld offset=%lld total=%lld", (long long)cfg->n_subj,
@@ -339,14 +338,14 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   if (env_tpp) tpp = atoi(env_tpp);
   else {
     for (tpp = 1; tpp < 8; tpp *= 2) {
-      SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt);
+      SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR);
       if (s.total <= 74 * 1024 && n_groups <= 16 * tpp) break;
     }
   }
   if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) { delete h; return fail(ERIRT_E_ARG, "ERIRT_TPP must be 1, 2, 4 or 8"); }
   if (n_groups > 16 * tpp) { delete h; return fail(ERIRT_E_ARG, "TPP=%d handles at most %d items", tpp, 64 * tpp - 4); }
   h->tpp = tpp;
-  h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt);
+  h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR);
   if (h->S.total > 227 * 1024) { delete h; return fail(ERIRT_E_UNSUPPORTED, "n_item %d needs %d bytes of shared memory per CTA", cfg->n_item, h->S.total); }
   h->n_pad = (int64_t)align_up((size_t)cfg->n_subj, 128);
   h->cap = cfg->n_iter * cfg->n_chain;
@@ -363,6 +362,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   TRY(dalloc(&h->dY, cells));
   { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dOmega = p; }
   if (has_rt) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dLogT = p; }
+  if (cfg->model == ERIRT_RTIRT_CROSSQR) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dNuCell = p; }
   { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dTheta = p; }
   { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dZeta = p; }
   { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dNu = p; }
@@ -533,6 +533,7 @@ extern "C" int erirt_set_state(erirt_handle* h, int32_t field, const double* v, 
   CU(cudaSetDevice(h->cfg.device));
   void* pv;
   int off, len;
+  if (field == ERIRT_NU && h->cfg.model == ERIRT_RTIRT_CROSSQR) return fail(ERIRT_E_ARG, "CrossQr draws nu before it is read; no initial value is needed");
   if (person_vec(h, field, &pv) == 0) {
     if (n != h->cfg.n_subj) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)h->cfg.n_subj, (long long)n);
     double* tmp;
@@ -571,15 +572,17 @@ extern "C" int erirt_get_state(erirt_handle* h, int32_t field, double* out, int6
   CU(cudaSetDevice(h->cfg.device));
   void* pv;
   int off, len;
+  const bool nu_cell = field == ERIRT_NU && h->cfg.model == ERIRT_RTIRT_CROSSQR;
   if (person_vec(h, field, &pv) == 0 || field == ERIRT_OMEGA) {
-    const bool om = field == ERIRT_OMEGA;
+    const bool om = field == ERIRT_OMEGA || nu_cell;
+    const void* tile_src = nu_cell ? h->dNuCell : h->dOmega;
     const int64_t want = om ? h->cfg.n_subj * h->cfg.n_item : h->cfg.n_subj;
     if (n != want) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)want, (long long)n);
     double* tmp;
     CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
     if (om) {
-      if (h->cfg.dtype == ERIRT_F32) tile_to_colmajor_kernel<float><<<1024, 256, 0, h->stream>>>((const float*)h->dOmega, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
-      else tile_to_colmajor_kernel<double><<<1024, 256, 0, h->stream>>>((const double*)h->dOmega, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
+      if (h->cfg.dtype == ERIRT_F32) tile_to_colmajor_kernel<float><<<1024, 256, 0, h->stream>>>((const float*)tile_src, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
+      else tile_to_colmajor_kernel<double><<<1024, 256, 0, h->stream>>>((const double*)tile_src, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
     } else {
       if (h->cfg.dtype == ERIRT_F32) unpack_vec_kernel<float><<<256, 256, 0, h->stream>>>((const float*)pv, n, tmp);
       else unpack_vec_kernel<double><<<256, 256, 0, h->stream>>>((const double*)pv, n, tmp);
@@ -609,6 +612,7 @@ static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   A.Y = h->dY;
   A.logT = (const R*)h->dLogT;
   A.omega = (R*)h->dOmega;
+  A.nu_cell = (R*)h->dNuCell;
   A.theta = (R*)h->dTheta;
   A.zeta = (R*)h->dZeta;
   A.nu = (R*)h->dNu;
@@ -875,6 +879,7 @@ extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {
   const bool has_rt = h->cfg.model != ERIRT_MLIRT;
   int64_t per_cell = 1 + 2 * r + (has_rt ? r : 0);
   if (h->cfg.model == ERIRT_RTIRT_CROSS) per_cell = 2 * (1 + 2 * r);  // K_a reads Y, logT, omega; K_b reads Y, logT, writes omega
+  if (h->cfg.model == ERIRT_RTIRT_CROSSQR) per_cell = (1 + 3 * r) + (1 + 4 * r);  // K_a: Y, logT, omega, nu; K_b: Y, logT, nu r/w, omega w
   int nv = has_rt ? 2 : 1;
   if (h->cfg.model == ERIRT_RTIRT_LATENTQR) nv = 3;
   out->bytes_per_sweep = N * J * per_cell + N * r * (2 * nv + F);

@@ -271,14 +271,29 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     // ---- G_a of the Cross family: lambda_k, sigma2_k from (theta_k, zeta_{k-1}, rho_k)   Draw.pl.jl:225-231, 267-273 ----
     for (int j = tid; j < J; j += G_THREADS) {
       const double s2 = par[L.p_sigma2 + j], rho = par[L.p_rho + j];
-      const double T1 = A.T1[j], T2 = A.T2[j], C = st[L.s_C + j], D = st[L.s_D + j];
+      const double T1 = A.T1[j], T2 = A.T2[j];
       const double pv = 1.0 / (sd_lam * sd_lam);
-      const double parV = 1.0 / (pv + N / s2);
-      const double parM = parV * (mu_lam * pv + (T1 + Sze + rho * Sth) / s2);
-      const double lam = site_tnorm_pos(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_LAMBDA), parM, sqrt(parV));
-      const double Q = T2 - 2.0 * lam * T1 + N * lam * lam + 2.0 * (C - lam * Sze) + Sze2 + rho * rho * Sth2 +
-                       2.0 * rho * (D - lam * Sth + Sthze);
-      const double s2n = (1e-3 + Q / 2.0) / site_gamma(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_SIGMA2), 1e-3 + N / 2.0);
+      double lam, s2n;
+      if (model == M_CROSS) {
+        const double C = st[L.s_C + j], D = st[L.s_D + j];
+        const double parV = 1.0 / (pv + N / s2);
+        const double parM = parV * (mu_lam * pv + (T1 + Sze + rho * Sth) / s2);
+        lam = site_tnorm_pos(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_LAMBDA), parM, sqrt(parV));
+        const double Q = T2 - 2.0 * lam * T1 + N * lam * lam + 2.0 * (C - lam * Sze) + Sze2 + rho * rho * Sth2 +
+                         2.0 * rho * (D - lam * Sth + Sthze);
+        s2n = (1e-3 + Q / 2.0) / site_gamma(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_SIGMA2), 1e-3 + N / 2.0);
+      } else {
+        // CrossQr (Draw.pl.jl:239-251, 278-288): weights w = 1/nu, r = logT + zeta; A0=Σw A1=Σθw A2=Σθrw A3=Σθ²w A4=Σrw A5=Σr²w V1=Σν
+        const double A0 = st[L.s_S0 + j], A1 = st[L.s_S1 + j], A2 = st[L.s_S2 + j], A3 = st[L.s_Ky + j], A4 = st[L.s_C + j],
+                     A5 = st[L.s_D + j], V1 = st[L.s_V + j];
+        const double R1 = T1 + Sze, k1 = A.k1, k2 = A.k2;
+        const double parV = 1.0 / (pv + A0 / (s2 * k2));
+        const double parM = parV * (mu_lam * pv + (A4 + rho * A1 - k1 * N) / (s2 * k2));
+        lam = site_tnorm_pos(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_LAMBDA), parM, sqrt(parV));
+        const double SS = A5 + lam * lam * A0 + rho * rho * A3 + k1 * k1 * V1 - 2.0 * lam * A4 + 2.0 * rho * A2 - 2.0 * k1 * R1 -
+                          2.0 * lam * rho * A1 + 2.0 * lam * k1 * N - 2.0 * rho * k1 * Sth;
+        s2n = (1e-3 + SS / (2.0 * k2) + V1) / site_gamma(A.key, (uint32_t)j, k, make_site(DOM_ITEM, IK_SIGMA2), 1e-3 + N * 3.0 / 2.0);
+      }
       par[L.p_lambda + j] = lam;
       par[L.p_sigma2 + j] = s2n;
       if (k >= 1 && (int)(k - 1) < A.cap) {
@@ -294,7 +309,9 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   // ---- 1. log-likelihood of state k ----
   if (k >= 1) {
     double part = 0.0;
-    if (has_rt)
+    if (model == M_CROSSQR) {
+      if (tid == 0) part = st[L.s_scal + SC_LL_RT];
+    } else if (has_rt)
       for (int j = tid; j < J; j += G_THREADS) {
         const double lam = par[L.p_lambda + j], s2 = par[L.p_sigma2 + j];
         double Q = A.T2[j] - 2.0 * lam * A.T1[j] + N * lam * lam + 2.0 * (st[L.s_C + j] - lam * Sze) + Sze2;
@@ -341,8 +358,15 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     par[L.p_b + j] = b;
     if (cross) {  // drawSubjCorrCross, Draw.pl.jl:463-469 (state k: theta_k, zeta_k, lambda_k, sigma2_k)
       const double s2 = par[L.p_sigma2 + j], lam = par[L.p_lambda + j];
-      const double parV = 1.0 / (1.0 + Sth2 / s2);
-      const double parM = parV * (0.0 + (lam * Sth - Sthze - st[L.s_D + j]) / s2);
+      double parV, parM;
+      if (model == M_CROSS) {
+        parV = 1.0 / (1.0 + Sth2 / s2);
+        parM = parV * (0.0 + (lam * Sth - Sthze - st[L.s_D + j]) / s2);
+      } else {  // drawSubjCorrCrossQr, Draw.pl.jl:474-489 with A1'=Σθ/ν, A2'=Σθ(logT+ζ)/ν, A3'=Σθ²/ν at nu_{k+1}
+        const double A1 = st[L.s_C + j], A2 = st[L.s_D + j], A3 = st[L.s_V + j];
+        parV = 1.0 / (1.0 + A3 / (s2 * A.k2));
+        parM = parV * (0.0 + (lam * A1 - A2 + A.k1 * Sth) / (s2 * A.k2));
+      }
       par[L.p_rho + j] = parM + sqrt(parV) * site_normal(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_RHO));
     } else if (has_rt) {
       const double s2 = par[L.p_sigma2 + j];

@@ -10,7 +10,7 @@ constexpr int MAXD = 32;          // largest dense system solved in the global k
 constexpr int QCAP = 1024;        // PG fast-retry queue capacity per tile (overflow is handled inline)
 constexpr int QCAP2 = 256;        // PG exact-replay queue capacity per tile
 
-constexpr int N_ITEM_STATS = 6;   // S0, S1, S2, Ky, C, D
+constexpr int N_ITEM_STATS = 7;   // S0, S1, S2, Ky, C, D, (V);  CrossQr K_a: A0..A5, V1;  CrossQr K_b: S0, S1, S2, Ky, A1', A2', A3'
 enum ModelId { M_MLIRT = 0, M_RTIRT = 1, M_NULL = 2, M_CROSS = 3, M_CROSSQR = 4, M_LATENT = 5, M_LATENTQR = 6 };
 
 // statistics scalars (f64), accumulated by the person kernel and consumed by the global kernel
@@ -19,6 +19,7 @@ enum StatScalar {
   SC_LL_STRUCT = 1,  // sum_i structural log-density at state k
   SC_PG_DEFER = 2,   // PG cells that left the fast path (diagnostic)
   SC_PG_CELLS = 3,
+  SC_LL_RT = 4,      // response-time log-likelihood summed per cell (CrossQr only; the other models use sufficient statistics)
   SC_COUNT = 8
 };
 
@@ -28,7 +29,7 @@ enum StatScalar {
 struct Layout {
   int J, Jp, F, Dg, ntri;
   int p_a, p_b, p_lambda, p_sigma2, p_rho, p_beta, p_Sigma, p_count;
-  int s_S0, s_S1, s_S2, s_Ky, s_C, s_D, s_gram, s_gramw, s_scal, s_count;
+  int s_S0, s_S1, s_S2, s_Ky, s_C, s_D, s_V, s_gram, s_gramw, s_scal, s_count;
 };
 
 __host__ __device__ inline int tri_index(int r, int c, int Dg) {  // r <= c, row-major upper triangle
@@ -60,6 +61,7 @@ inline Layout make_layout(int J, int F) {
   L.s_Ky = o; o += L.Jp;
   L.s_C = o; o += L.Jp;
   L.s_D = o; o += L.Jp;  // sum_i theta_i logT_ij (Cross family)
+  L.s_V = o; o += L.Jp;  // seventh per-item block (CrossQr)
   L.s_gram = o; o += L.ntri;
   L.s_gramw = o; o += L.ntri;
   L.s_scal = o; o += SC_COUNT;
@@ -71,7 +73,7 @@ inline Layout make_layout(int J, int F) {
 struct SmemPlan {
   int P;  // persons per tile
   int tile_real_bytes, tile_y_bytes;
-  int off_omega, off_logt, off_y, off_par, off_u, off_sum, off_beta, off_acc_item, off_acc_gram, off_queue, off_misc, total;
+  int off_omega, off_logt, off_nuc, off_y, off_par, off_u, off_sum, off_beta, off_acc_item, off_acc_gram, off_queue, off_misc, total;
   int Dgp;  // pitch of the U tile (elements)
 };
 
@@ -81,6 +83,7 @@ struct PersonArgs {
   const uint8_t* Y;
   const R* logT;
   R* omega;
+  R* nu_cell;  // CrossQr: cell-level quantile weights, same tiling as omega
   // person vectors (n_pad) and covariates, column-major [F][n_pad]
   R* theta;
   R* zeta;

@@ -82,9 +82,10 @@ __device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
 }
 
 // item-parameter arrays staged in shared memory (each Jp long, zero beyond J)
-enum ParIdx { PAR_A = 0, PAR_AB = 1, PAR_A2 = 2, PAR_A2B = 3, PAR_IS2 = 4, PAR_LAM = 5, PAR_COUNT = 6 };
+// PAR_IS2 holds 1/sigma2_j, or 1/(sigma2_j k2) for CrossQr; PAR_ISC = 1/sqrt(sigma2_j k2) (CrossQr)
+enum ParIdx { PAR_A = 0, PAR_AB = 1, PAR_A2 = 2, PAR_A2B = 3, PAR_IS2 = 4, PAR_LAM = 5, PAR_RHO = 6, PAR_ISC = 7, PAR_COUNT = 8 };
 // per-CTA scalars in the misc block (f64)
-enum MiscD { MD_SUM_IS2 = 0, MD_SUM_RHO_IS2 = 1, MD_COUNT = 2 };
+enum MiscD { MD_SUM_IS2 = 0, MD_SUM_RHO_IS2 = 1, MD_SUM_LOGS2K = 2, MD_COUNT = 4 };
 
 // group index handled by thread q at step k: the TPP threads of one person and the persons of a quarter
 // warp touch 8 distinct 16-byte bank groups (row pitch is an odd number of quads)
@@ -92,6 +93,22 @@ template <int TPP>
 __device__ __forceinline__ int group_of(int q, int k) {
   constexpr int chunk = 8 / TPP;
   return (k / chunk) * 8 + q * chunk + (k % chunk);
+}
+
+// Box-Muller pair from two words (CrossQr cell weights: cosine branch for even items, sine branch for odd items)
+__device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, float& zc, float& zs) {
+  const float u = fminf(u01f(w0), 0.99999994f);
+  const float t = -1.3862943611198906f * fast_lg2(u);
+  const float rad = t * fast_rsqrt(t);
+  float sn, cs;
+  __sincosf(6.283185307179586f * u01f(w1), &sn, &cs);
+  zc = rad * cs;
+  zs = rad * sn;
+}
+__device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& zc, double& zs) {
+  const double rad = sqrt(-2.0 * log(u01d(w0))), ang = 6.283185307179586476925286766559 * u01d(w1);
+  zc = rad * cos(ang);
+  zs = rad * sin(ang);
 }
 
 // Retry of one PG cell whose attempt 0 was certainly rejected (f32, Method A): attempts a >= first are evaluated with
@@ -135,11 +152,13 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   const bool qr = model == M_LATENTQR;
   const bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
   const bool cross = model == M_CROSS || model == M_CROSSQR;
+  const bool cqr = model == M_CROSSQR;
   const int stage = A.stage;
   const bool do_theta = stage != 2, do_zeta = has_rt && stage != 1, do_pg = stage != 1;
 
   R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
   R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
+  R* s_nc = reinterpret_cast<R*>(smem + A.S.off_nuc);  // CrossQr nu tile
   uint8_t* s_y = smem + A.S.off_y;
   R* s_par = reinterpret_cast<R*>(smem + A.S.off_par);
   R* s_u = reinterpret_cast<R*>(smem + A.S.off_u);
@@ -160,13 +179,18 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 
   // ---- stage item / structural parameters (state k) and clear accumulators ----
   for (int j = tid; j < Jp; j += CTA_THREADS) {
-    double a = 0, b = 0, is2 = 0, lam = 0;
+    double a = 0, b = 0, is2 = 0, lam = 0, rho = 0, isc = 0;
     if (j < J) {
       a = par[L.p_a + j];
       b = par[L.p_b + j];
       if (has_rt) {
         is2 = 1.0 / par[L.p_sigma2 + j];
         lam = par[L.p_lambda + j];
+      }
+      if (cross) rho = par[L.p_rho + j];
+      if (cqr) {
+        is2 = 1.0 / (par[L.p_sigma2 + j] * A.k2);
+        isc = sqrt(is2);
       }
     }
     s_par[PAR_A * Jp + j] = (R)a;
@@ -175,6 +199,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     s_par[PAR_A2B * Jp + j] = (R)(a * a * b);
     s_par[PAR_IS2 * Jp + j] = (R)is2;
     s_par[PAR_LAM * Jp + j] = (R)lam;
+    s_par[PAR_RHO * Jp + j] = (R)rho;
+    s_par[PAR_ISC * Jp + j] = (R)isc;
   }
   if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
   if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
@@ -182,20 +208,23 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
   if (tid < SC_COUNT) s_scal[tid] = 0.0;
   if (tid < 32) {  // sum_j 1/sigma2_j in f64
-    double s1 = 0, s2 = 0;
+    double s1 = 0, s2 = 0, s3 = 0;
     if (has_rt)
       for (int j = tid; j < J; j += 32) {
-        const double is2 = 1.0 / par[L.p_sigma2 + j];
+        const double is2 = 1.0 / (cqr ? par[L.p_sigma2 + j] * A.k2 : par[L.p_sigma2 + j]);
         s1 += is2;
         if (cross) s2 += par[L.p_rho + j] * is2;
+        if (cqr) s3 += log(par[L.p_sigma2 + j] * A.k2);
       }
     for (int o = 16; o; o >>= 1) {
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      s3 += __shfl_xor_sync(0xffffffffu, s3, o);
     }
     if (tid == 0) {
       s_miscd[MD_SUM_IS2] = s1;
       s_miscd[MD_SUM_RHO_IS2] = s2;
+      s_miscd[MD_SUM_LOGS2K] = s3;
       mbar_init(s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -209,18 +238,19 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   const uint32_t iter_m = do_draws ? (k - 1) / (uint32_t)A.n_chain + 1 : 0;  // m of sweep k
   const bool post_burnin = do_draws && iter_m > (uint32_t)A.n_burnin;
 
-  double acc_ll_bern = 0.0, acc_ll_struct = 0.0;
+  double acc_ll_bern = 0.0, acc_ll_struct = 0.0, acc_ll_rt = 0.0;
   uint32_t acc_defer = 0, acc_cells = 0;
   uint32_t parity = 0;
   const bool load_om = stage != 2;  // K_b of the Cross family only writes omega
-  const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * ((has_rt ? 1 : 0) + (load_om ? 1 : 0)) + A.S.tile_y_bytes);
+  const bool load_nc = cqr && do_draws;  // the prologue has no nu yet
+  const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * ((has_rt ? 1 : 0) + (load_om ? 1 : 0) + (load_nc ? 1 : 0)) + A.S.tile_y_bytes);
   const int nk = ((G + 7) / 8) * (8 / TPP);  // steps per thread over its 4-item groups
 
   // transposed-statistics role of this thread: item group eg, person class er (G <= CTA_THREADS is enforced by the host)
   const int Rc = CTA_THREADS / G;
   const bool e_active = tid < G * Rc;
   const int eg = tid % G, er = tid / G;
-  R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0};
+  R a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, ad[4] = {0, 0, 0, 0}, av[4] = {0, 0, 0, 0};
   auto flush_item_stats = [&]() {
     if (e_active) {
 #pragma unroll
@@ -232,7 +262,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
         atomicAdd(&s_acc_item[4 * Jp + j], (double)ac[e]);
         if (cross) atomicAdd(&s_acc_item[5 * Jp + j], (double)ad[e]);
-        a0[e] = a1[e] = a2[e] = ay[e] = ac[e] = ad[e] = R(0);
+        if (cqr) atomicAdd(&s_acc_item[6 * Jp + j], (double)av[e]);
+        a0[e] = a1[e] = a2[e] = ay[e] = ac[e] = ad[e] = av[e] = R(0);
       }
     }
   };
@@ -245,6 +276,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       mbar_expect_tx(s_bar, load_bytes);
       if (load_om) tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      if (load_nc) tma_load_1d(s_nc, A.nu_cell + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
       s_qctl[0] = 0;
       s_qctl[1] = 0;
@@ -300,8 +332,22 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const Quad<R> lt = ld4(my_lt + 4 * g);
           const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
           const Quad<R> pL = ld4(s_par + PAR_LAM * Jp + 4 * g);
+          if (!cqr) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) sLT = fma(pI.v[e], pL.v[e] - lt.v[e], sLT);  // sum_j (lambda_j - logT_ij)/sigma2_j
+            for (int e = 0; e < 4; ++e) sLT = fma(pI.v[e], pL.v[e] - lt.v[e], sLT);  // sum_j (lambda_j - logT_ij)/sigma2_j
+          } else {  // drawSubjSpeedCrossQr, Draw.pl.jl:192-206: weights 1/(sigma2_j k2 nu_ij)
+            const Quad<R> nc = ld4(s_nc + p * Jp + 4 * g);
+            const Quad<R> pR = ld4(s_par + PAR_RHO * Jp + 4 * g);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (4 * g + e < J) {
+                const R t = rdiv(pI.v[e], nc.v[e]);
+                sA2 += t;                                  // sum_j 1/(sigma2 k2 nu)
+                sLT = fma(t, pL.v[e] - lt.v[e], sLT);      // sum_j (lambda - logT)/(sigma2 k2 nu)
+                sAB = fma(t, pR.v[e], sAB);                // sum_j rho/(sigma2 k2 nu)
+              }
+            }
+          }
         }
       }
 #pragma unroll
@@ -338,8 +384,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           } else if (model == M_NULL) { mu_z = R(0); var_z = R(1); }  // Draw.pl.jl:120-121
           else { mu_z = R(0); var_z = S22; }
           const R ivz = rdiv(R(1), var_z);
-          const R parV = rdiv(R(1), ivz + sum_is2);
-          const R parM = parV * (mu_z * ivz + (cross ? d[3] - th * sum_rho_is2 : d[3]));  // Cross: sum_j (lambda - logT - theta rho_j)/sigma2
+          // Cross: sum_j (lambda - logT - theta rho_j)/sigma2;  CrossQr: the same weighted by 1/(k2 nu_ij), plus k1 sum_j 1/(sigma2 k2)
+          const R prec = cqr ? d[0] : sum_is2;
+          const R num = cqr ? d[3] - th * d[1] + k1 * sum_is2 : (cross ? d[3] - th * sum_rho_is2 : d[3]);
+          const R parV = rdiv(R(1), ivz + prec);
+          const R parM = parV * (mu_z * ivz + num);
           ze = parM + rsqrt_of(parV) * normal2r<R>(w.z, w.w);
         }
         if (pvalid && stage == 1) A.theta[pi] = th;  // K_a: theta_k only; everything else happens in K_b
@@ -408,6 +457,59 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
     __syncthreads();
 
+    if (cqr && do_pg) {
+      // ---- CrossQr cell pass (thread per person row): response-time log-likelihood of state k with nu_k
+      //      (getLogLikelihoodRtIrtCrossQr, GibbsRtIrtCross.pl.jl:240-258), then nu_{k+1} | state k
+      //      (drawQrWeightsCrossQr, Draw.pl.jl:303-320), written in place ----
+      const bool cvalid = (row0 + p) < A.n_local;
+      const uint32_t cgid = A.person_offset + (uint32_t)(row0 + p);
+      const R thc = s_u[p * Dgp + F + 1], zec = s_u[p * Dgp + F + 2];
+      const R cB = rsqrt_of(R(2) * k2 + k1 * k1);
+      R llrt = R(0);
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+        Quad<R> nc;
+        if (do_draws) nc = ld4(s_nc + p * Jp + 4 * g);
+        const Quad<R> lt = ld4(my_lt + 4 * g);
+        const Quad<R> pL = ld4(s_par + PAR_LAM * Jp + 4 * g);
+        const Quad<R> pR = ld4(s_par + PAR_RHO * Jp + 4 * g);
+        const Quad<R> pC = ld4(s_par + PAR_ISC * Jp + 4 * g);
+        const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
+        const uint4 wA = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g)), 0);
+        const uint4 wB = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g + 1)), 0);
+        R zn[4];
+        normal_pair(wA.x, wA.y, zn[0], zn[1]);
+        normal_pair(wB.x, wB.y, zn[2], zn[3]);
+        const R un[4] = {u01<R>(wA.z), u01<R>(wA.w), u01<R>(wB.z), u01<R>(wB.w)};
+        Quad<R> out;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const R resid = lt.v[e] - pL.v[e] + zec + thc * pR.v[e];
+          R nun = R(1);
+          if (cvalid && 4 * g + e < J) {
+            if (do_draws) {
+              const R nu0 = nc.v[e];
+              const R res = resid - k1 * nu0;
+              llrt += R(-0.5) * (rlog(nu0) + res * res * rdiv(pI.v[e], nu0));
+            }
+            const R parA = fabs(resid) * pC.v[e];
+            const R parB = cB * pC.v[e];
+            R mu = rdiv(parB, parA);
+            if (!(mu >= R(1e-10))) mu = R(1e-10);
+            const R ig = ig_msh<R>(mu, parB * parB, zn[e], un[e]);
+            nun = rdiv(R(1), ig);
+            nun = nun < R(1e-10) ? R(1e-10) : (nun > R(1e10) ? R(1e10) : nun);
+          }
+          out.v[e] = nun;
+        }
+        st4(s_nc + p * Jp + 4 * g, out);
+      }
+#pragma unroll
+      for (int o = 1; o < TPP; o <<= 1) llrt += __shfl_xor_sync(0xffffffffu, llrt, o);
+      if (q == 0 && cvalid && do_draws)
+        acc_ll_rt += (double)llrt - 0.5 * ((double)J * 1.8378770664093454835606594728112 + s_miscd[MD_SUM_LOGS2K]);
+    }
     if (do_pg) {
       // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
       const bool valid = (row0 + p) < A.n_local;
@@ -556,13 +658,36 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
             ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
           }
         }
-        if (has_rt) {
+        if (has_rt && !cqr) {
           const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * eg);
 #pragma unroll
           for (int e = 0; e < 4; ++e) ac[e] = fma(lt.v[e], zp, ac[e]);
           if (cross) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) ad[e] = fma(lt.v[e], tp, ad[e]);
+          }
+        }
+        if (cqr && s_u[pp * Dgp] != R(0)) {  // weighted statistics, w = 1/nu_ij, r = logT_ij + zeta_i (padding persons skipped)
+          const Quad<R> lt = ld4(s_lt + pp * Jp + 4 * eg);
+          const Quad<R> nc = ld4(s_nc + pp * Jp + 4 * eg);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const R w = rdiv(R(1), nc.v[e]);
+            const R r = lt.v[e] + zp;
+            const R tw = tp * w;
+            if (stage == 1) {  // K_a: A0..A5, V1 with (theta_k, zeta_{k-1}, nu_k)
+              a0[e] += w;
+              a1[e] += tw;
+              a2[e] = fma(tw, r, a2[e]);
+              ay[e] = fma(tw, tp, ay[e]);
+              ac[e] = fma(r, w, ac[e]);
+              ad[e] = fma(r * r, w, ad[e]);
+              av[e] += nc.v[e];
+            } else {           // K_b: A1', A2', A3' with (theta_k, zeta_k, nu_{k+1})
+              ac[e] += tw;
+              ad[e] = fma(tw, r, ad[e]);
+              av[e] = fma(tw, tp, av[e]);
+            }
           }
         }
       }
@@ -584,19 +709,23 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0 && do_pg) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
+    if (tid == 0 && do_pg) {
+      tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
+      if (cqr) tma_store_1d(A.nu_cell + row0 * Jp, s_nc, (uint32_t)A.S.tile_real_bytes);
+    }
   }
   flush_item_stats();
 
   // ---- flush CTA accumulators ----
   atomicAdd(&s_scal[SC_LL_BERN], acc_ll_bern);
   if (tid < P) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
+  if (cqr) atomicAdd(&s_scal[SC_LL_RT], acc_ll_rt);
   atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
   if (tid < P) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
   __syncthreads();
   for (int t = tid; t < N_ITEM_STATS * Jp; t += CTA_THREADS) {
     const int j = t % Jp;
-    if (j < J && (cross || t < 5 * Jp)) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
+    if (j < J && (cqr || (cross && t < 6 * Jp) || t < 5 * Jp)) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
   }
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS)
     if (t < L.ntri || qr) atomicAdd(&A.stats[L.s_gram + t], s_acc_gram[t]);

@@ -19,7 +19,7 @@ constexpr uint32_t PK_NORMALS = 0;   // words 0,1 -> theta normal; words 2,3 -> 
 constexpr uint32_t PK_NU = 1;        // LatentQr nu_i: words 0,1 normal, word 2 uniform
 constexpr uint32_t PK_PG = 2;        // attempt 0 of cells (i,2*idx) [words 0,1] and (i,2*idx+1) [words 2,3]
 constexpr uint32_t PK_PG_RETRY = 3;  // attempts >= 1 of cell (i,idx), attempt number in ctr.w
-constexpr uint32_t PK_NU_CELL = 4;   // CrossQr nu_ij, idx = j
+constexpr uint32_t PK_NU_CELL = 4;   // CrossQr nu_ij, idx = j/2: words 0,1 -> Box-Muller pair (cos: j even, sin: j odd), word 2 / 3 uniform
 // item-domain kinds (unit = item)
 constexpr uint32_t IK_B = 0, IK_A = 1, IK_LAMBDA = 2, IK_SIGMA2 = 3, IK_RHO = 4;
 // global-domain kinds (unit = component)
@@ -78,6 +78,8 @@ __device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.appro
 __device__ __forceinline__ float rdiv(float a, float b) { return a * fast_rcp(b); }
 __device__ __forceinline__ double rdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ float rsqrt_of(float x) { return x * fast_rsqrt(x); }  // sqrt(x), x > 0
+__device__ __forceinline__ float rlog(float x) { return 0.6931471805599453f * fast_lg2(x); }
+__device__ __forceinline__ double rlog(double x) { return log(x); }
 __device__ __forceinline__ double rsqrt_of(double x) { return sqrt(x); }
 
 // Box-Muller cosine branch

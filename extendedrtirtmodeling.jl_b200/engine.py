@@ -76,12 +76,12 @@ class Engine:
 
     def get_state(self, name):
         fid = _lib.FIELDS[name]
-        n = {"theta": self.N, "zeta": self.N, "nu": self.N, "omega": self.N * self.J, "a": self.J, "b": self.J,
+        n = {"theta": self.N, "zeta": self.N, "nu": self.N * self.J if self.model == 4 else self.N, "omega": self.N * self.J, "a": self.J, "b": self.J,
              "lambda": self.J, "sigma2": self.J, "rho": self.J, "Sigma": 4,
              "beta": {0: self.F + 1, 1: 2 * (self.F + 1), 2: 2 * (self.F + 1), 5: self.F + 2, 6: self.F + 2}.get(self.model, 0)}[name]
         out = np.empty(n, dtype=np.float64)
         check(self.lib.erirt_get_state(self.h, fid, _dp(out), n))
-        if name == "omega":
+        if name == "omega" or (name == "nu" and self.model == 4):
             return out.reshape((self.N, self.J), order="F")
         if name == "Sigma":
             return out.reshape((2, 2), order="F")

@@ -311,8 +311,11 @@ def drawQrWeightsCrossQr(st, C, D, P):  # :303-320
     ν = np.empty((N, J))
     for i in range(N):
         for j in range(J):
-            w = st.words(i, site(DOM_PERSON, PK_NU_CELL, j))
-            ν[i, j] = 1 / ig_msh(μ[i, j], parB[i, j] ** 2, Stream.normal2(w[0], w[1]), Stream.u01(w[2]))
+            w = st.words(i, site(DOM_PERSON, PK_NU_CELL, j >> 1))
+            rad = math.sqrt(-2.0 * math.log(Stream.u01(w[0])))
+            ang = 2.0 * math.pi * Stream.u01(w[1])
+            zn = rad * math.sin(ang) if j & 1 else rad * math.cos(ang)
+            ν[i, j] = 1 / ig_msh(μ[i, j], parB[i, j] ** 2, zn, Stream.u01(w[3 if j & 1 else 2]))
     return np.clip(ν, 1e-10, 1e10)
 
 

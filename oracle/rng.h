@@ -22,7 +22,7 @@
 #define PK_NU 1       /* LatentQr nu_i: words 0,1 normal, word 2 uniform */
 #define PK_PG 2       /* attempt 0 of the PG draw of cells (i, 2*idx) [words 0,1] and (i, 2*idx+1) [words 2,3] */
 #define PK_PG_RETRY 3 /* attempts >= 1 of cell (i, idx); attempt number in ctr.w */
-#define PK_NU_CELL 4  /* CrossQr nu_ij, idx = j: words 0,1 normal, word 2 uniform */
+#define PK_NU_CELL 4  /* CrossQr nu_ij, idx = j/2: words 0,1 -> Box-Muller pair (cos: j even, sin: j odd), word 2 / 3 uniform */
 /* item-domain kinds (unit = item j) */
 #define IK_B 0
 #define IK_A 1

@@ -292,9 +292,12 @@ static void draw_nu_cell(ctx* x) {
       double parB = sqrt(2.0 * x->k2 + x->k1 * x->k1) / sc;
       double mu = parB / parA;
       if (mu < 1e-10) mu = 1e-10;
+      /* one Philox block serves the cell pair (j, j^1): Box-Muller cosine / sine branch, words 2 / 3 as the MSH uniform */
       uint32_t w4[4];
-      orc_philox(x->key, (uint32_t)i, x->sweep, SITE(DOM_PERSON, PK_NU_CELL, j), 0, w4);
-      double ig = orc_ig_msh(mu, parB * parB, orc_normal2(w4[0], w4[1]), orc_u01(w4[2]));
+      orc_philox(x->key, (uint32_t)i, x->sweep, SITE(DOM_PERSON, PK_NU_CELL, j >> 1), 0, w4);
+      double rad = sqrt(-2.0 * log(orc_u01(w4[0]))), ang = 6.283185307179586476925286766559 * orc_u01(w4[1]);
+      double zn = (j & 1) ? rad * sin(ang) : rad * cos(ang);
+      double ig = orc_ig_msh(mu, parB * parB, zn, orc_u01(w4[(j & 1) ? 3 : 2]));
       s->nu[i + (size_t)N * j] = clampd(1.0 / ig, 1e-10, 1e10);
     }
 }

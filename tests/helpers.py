@@ -1,8 +1,8 @@
 """Shared test helpers: seeded synthetic data per model and oracle/engine runners."""
 import numpy as np
 
-MODELS = ["MlIrt", "RtIrt", "RtIrtNull", "RtIrtLatent", "RtIrtLatentQr", "RtIrtCross"]  # built on the GPU
-ALL_MODELS = MODELS + ["RtIrtCrossQr"]
+MODELS = ["MlIrt", "RtIrt", "RtIrtNull", "RtIrtLatent", "RtIrtLatentQr", "RtIrtCross", "RtIrtCrossQr"]
+ALL_MODELS = MODELS
 
 
 def make_problem(model, N, J, F, seed=0, q=0.85):

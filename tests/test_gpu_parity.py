@@ -90,6 +90,8 @@ def _compare_traces(eng, ref, pb, ns, tol, atol, frac_ok=1.0):
     pairs = [("ra", ref["ra"])] + ([("rt", ref["rt"])] if pb["model"] != "MlIrt" else []) + [("qr", ref["qr"])]
     for name, want in pairs:
         got = eng.get_trace(name)[:ns, :, 0]
+        if pb["model"] == "RtIrtCrossQr" and name == "qr":
+            want = want[:, : got.shape[1]]  # the N*J block of cell-level nu is not traced by the engine
         e = relerr(got, want[:ns], atol=atol).reshape(got.shape, order="F")
         out[name] = e
         item = e[:, N:] if name in ("ra", "rt") else e[:, : eng.trace_width("qr") - (N if pb["model"] == "RtIrtLatentQr" else 0)]
@@ -130,10 +132,12 @@ def test_one_sweep_parity_f32(E, oracle, model):
 @pytest.mark.parametrize("model", MODELS)
 def test_multi_sweep_parity_f64(E, oracle, model):
     pb = make_problem(model, 400, 9, 2, seed=13)
-    ns = 12
+    # CrossQr amplifies rounding differences quickly (weights 1/nu_ij with nu clamped to [1e-10, 1e10], Draw.pl.jl:318):
+    # the two f64 implementations agree to 1e-16 at sweep 1 and drift apart by roughly 10x per sweep
+    ns, tol = (5, 1e-7) if model == "RtIrtCrossQr" else (12, 1e-8)
     ref = run_oracle(oracle, pb, ns)
     eng = run_engine(E, pb, ns, dtype="f64", use_graph=True)
-    _compare_traces(eng, ref, pb, ns, 1e-8, 1e-3)
+    _compare_traces(eng, ref, pb, ns, tol, 1e-3)
     eng.close()
 
 
@@ -145,6 +149,7 @@ def test_multi_sweep_parity_f64(E, oracle, model):
     ("RtIrtLatent", dict(intercept=True, cov2one=True, compat=1)),
     ("RtIrtLatentQr", dict(intercept=True, compat=2)),
     ("RtIrtCross", dict(itemtype="1pl", cov2one=False)),
+    ("RtIrtCrossQr", dict(cov2one=False)),
 ])
 def test_keyword_and_compat_variants_f64(E, oracle, model, opts):
     pb = make_problem(model, 300, 7, 2, seed=14)
@@ -165,6 +170,18 @@ def test_ragged_shapes_f64(E, oracle, N, J, F):
         eng = run_engine(E, pb, 2, dtype="f64")
         _compare_traces(eng, ref, pb, 2, 1e-10, 1e-3)
         eng.close()
+
+
+def test_crossqr_cell_weights_parity(E, oracle):
+    """drawQrWeightsCrossQr (Draw.pl.jl:303-320): the N x J weights nu_{k+1} held by the engine after k sweeps."""
+    pb = make_problem("RtIrtCrossQr", 333, 11, 0, seed=21)
+    ref = run_oracle(oracle, pb, 3)
+    eng = run_engine(E, pb, 2, dtype="f64")
+    assert relerr(eng.get_state("nu"), ref["nu"]).max() < 1e-9
+    eng.close()
+    eng32 = run_engine(E, pb, 2, dtype="f32")
+    assert np.quantile(relerr(eng32.get_state("nu"), ref["nu"]), 0.99) < 1e-3
+    eng32.close()
 
 
 def test_graph_replay_equals_plain_launches(E):
