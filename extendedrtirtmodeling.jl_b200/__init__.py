@@ -4,7 +4,8 @@ The compute path is the CUDA shared library liberirt_b200.so (csrc/, C ABI in in
 package is the host-side mirror of the reference's interface for that path.  No CPU fallback exists."""
 from . import _lib  # noqa: F401
 from .api import (GibbsMlIrt, GibbsRtIrt, GibbsRtIrtCross, GibbsRtIrtCrossQr, GibbsRtIrtLatent,  # noqa: F401
-                  GibbsRtIrtLatentQr, GibbsRtIrtNull, GibbsRtIrtQuantile, sample, sample_bang)
+                  GibbsRtIrtLatentQr, GibbsRtIrtNull, GibbsRtIrtQuantile, coef, getDic, getLogLikelihood, precis, sample,
+                  sample_bang)
 from .engine import Engine, ErirtError, k_nu_person, k_pg, k_philox, nccl_unique_id  # noqa: F401
 from .simulate import (getBias, getRmse, setDataMlIrt, setDataRtIrt, setDataRtIrtCross, setDataRtIrtLatent,  # noqa: F401
                        setDataRtIrtNull, setTrueParaMlIrt, setTrueParaRtIrt, setTrueParaRtIrtCross,

@@ -69,7 +69,7 @@ def load():
     L.erirt_trace_width.argtypes = [vp, C.c_int32]
     L.erirt_trace_width.restype = C.c_int64
     L.erirt_get_moments.argtypes = [vp, C.c_int32, dp, dp, C.c_int64]
-    L.erirt_loglik_current.argtypes = [vp, dp]
+    L.erirt_loglik_current.argtypes = [vp, C.POINTER(C.c_double)]
     L.erirt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.erirt_nccl_unique_id.argtypes = [vp]
     L.erirt_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]

@@ -213,3 +213,96 @@ def _collect(MCMC, eng, person_trace):
 
 
 sample_bang = sample  # `sample!` is not a Python identifier
+
+
+def getLogLikelihood(MCMC, P, dtype="f64", device=0):
+    """getLogLikelihood*(Cond, Data; P) (src/GibbsRtIrt.pl.jl:195-204, 262-272, 351-361; Cross :158-169; Latent :151-161,
+    :243-264), evaluated on the GPU for an InputPara `P` (e.g. MCMC.Post.mean)."""
+    C, D = MCMC.Cond, MCMC.Data
+    eng = Engine(MCMC.model, C.nSubj, C.nItem, C.nFeat, n_iter=1, n_chain=1, q_rt=C.qRt, dtype=dtype, device=device,
+                 person_trace=False, use_graph=False)
+    try:
+        eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if C.nFeat > 0 else None)
+        st = dict(theta=P.theta, a=P.a, b=P.b)
+        if MCMC.has_rt:
+            st.update(zeta=P.zeta, lambda_=P.lambda_, sigma2=P.sigma2t, Sigma=np.asarray(P.Sigma_p).reshape(4))
+        if P.beta.size:
+            st["beta"] = P.beta
+        if P.rho.size:
+            st["rho"] = P.rho
+        if MCMC.model == "RtIrtLatentQr":
+            st["nu"] = P.nu
+        eng.set_state(**st)
+        return eng.loglik_current()
+    finally:
+        eng.close()
+
+
+def getDic(MCMC, dtype="f64", device=0):
+    """getDic (src/GibbsRtIrt.pl.jl:432-472): D-hat = -2 loglik(Post.mean), D-bar = -2 mean(Post.logLike) over ALL
+    iterations including burn-in (quirk Q10), pD = D-bar - D-hat, DIC = D-bar + pD."""
+    Dhat = -2.0 * getLogLikelihood(MCMC, MCMC.Post.mean, dtype=dtype, device=device)
+    Dbar = -2.0 * float(np.mean(MCMC.Post.logLike))
+    dic = OutputDic()
+    dic.pD = Dbar - Dhat
+    dic.DIC = Dbar + dic.pD
+    return dic
+
+
+def _param_names(MCMC):
+    C = MCMC.Cond
+    J, F = C.nItem, C.nFeat
+    ra = [f"a{i}" for i in range(1, J + 1)] + [f"b{i}" for i in range(1, J + 1)]
+    rt = [f"λ{i}" for i in range(1, J + 1)] + [f"σ²t{i}" for i in range(1, J + 1)]
+    sig = ["Σ[1,1]", "Σ[1,2]", "Σ[2,1]", "Σ[2,2]"]
+    qr = {"MlIrt": [f"β[{i}]" for i in range(F + 1)],
+          "RtIrt": [f"β[{i},{j}]" for j in (1, 2) for i in range(F + 1)] + sig,
+          "RtIrtNull": [f"β[{i},{j}]" for j in (1, 2) for i in range(F + 1)] + sig,
+          "RtIrtCross": [f"ρ{i}" for i in range(1, J + 1)] + sig, "RtIrtCrossQr": [f"ρ{i}" for i in range(1, J + 1)] + sig,
+          "RtIrtLatent": [f"β{i}" for i in range(F + 2)] + sig, "RtIrtLatentQr": [f"β{i}" for i in range(F + 2)] + sig}[MCMC.model]
+    return ra, rt, qr
+
+
+def precis(MCMC, file=None):
+    """precis(MCMC) (src/GibbsRtIrt.pl.jl:607-675, src/Base.pl.jl:152-167): mean, std, ess, rhat, 2.5 % / 97.5 % quantiles of the
+    item and structural parameters over the post-burn-in draws.  Returns the rows (list of dicts) and prints the tables."""
+    from .diagnostics import summarize
+    C, Post = MCMC.Cond, MCMC.Post
+    nb, N = C.nBurnin, C.nSubj
+    ic = N if Post.person_cols else 0
+    ra_n, rt_n, qr_n = _param_names(MCMC)
+    blocks = [("1) Item Response Model.", Post.ra[nb:, ic:ic + 2 * C.nItem, :], ra_n)]
+    if MCMC.has_rt:
+        blocks.append(("2) Response Time Model.", Post.rt[nb:, ic:ic + 2 * C.nItem, :], rt_n))
+    blocks.append(("3) Structural Model.", Post.qr[nb:, :len(qr_n), :], qr_n))
+    out = []
+    for title, arr, names in blocks:
+        rows = summarize(arr, names)
+        out.extend(rows)
+        print(title, file=file)
+        print(f"{'':>10s} {'mean':>9s} {'std':>9s} {'ess':>9s} {'rhat':>7s} {'q025':>9s} {'q975':>9s}", file=file)
+        for r in rows:
+            sig = "" if (r["q025"] < 0 < r["q975"]) else "*"
+            print(f"{r['name']:>10s} {r['mean']:9.3f} {r['std']:9.3f} {r['ess']:9.1f} {r['rhat']:7.3f} {r['q025']:9.3f} {r['q975']:9.3f} {sig}", file=file)
+    return out
+
+
+def coef(MCMC, file=None):
+    """coef(MCMC) (src/GibbsRtIrt.pl.jl:479-601): posterior means of the item parameters, covariance, regression coefficients, DIC."""
+    m = MCMC.Post.mean
+    print(f">> Model: {type(MCMC).__name__}. {MCMC.Cond.nSubj} subjects, {MCMC.Cond.nItem} items, {MCMC.Cond.nFeat} features; "
+          f"{MCMC.Cond.nChain} chains of {MCMC.Cond.nIter} iterations, first {MCMC.Cond.nBurnin} discarded.", file=file)
+    print("1) Item Parameters.", file=file)
+    for j in range(MCMC.Cond.nItem):
+        row = f"{j + 1:5d} {m.a[j]:7.3f} {m.b[j]:7.3f}"
+        if MCMC.has_rt:
+            row += f" {m.lambda_[j]:7.3f} {m.sigma2t[j]:7.3f}"
+        print(row, file=file)
+    if MCMC.has_rt:
+        print("2) Covariance of Person Parameters.", np.asarray(m.Sigma_p).reshape(2, 2).round(3).tolist(), file=file)
+    if m.beta.size:
+        print("3) Regression Coefficients.", np.round(m.beta, 3).tolist(), file=file)
+    dic = getDic(MCMC) if MCMC.model != "RtIrtCrossQr" else None
+    if dic is not None:
+        print(f"4) Criterion. Deviance {dic.DIC - dic.pD:.3f}  DIC {dic.DIC:.3f}", file=file)
+    return dic

@@ -197,6 +197,7 @@ struct erirt_handle {
   uint8_t* dY = nullptr;
   void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
   double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
+  double* dLlOut = nullptr;
   double *dTrRa = nullptr, *dTrRt = nullptr, *dTrQr = nullptr, *dTrLl = nullptr;
   uint32_t* dSweep = nullptr;
   int* dStatus = nullptr;
@@ -214,6 +215,9 @@ struct erirt_handle {
   cudaGraphExec_t graph_exec = nullptr;
 };
 
+static int launch_person(erirt_handle* h, int stage);
+static int launch_global(erirt_handle* h, int stage);
+static int finalize_constants(erirt_handle* h);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt, bool cqr = false) {
@@ -282,7 +286,7 @@ static int free_handle(erirt_handle* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->comm && nccl::comm_destroy) nccl::comm_destroy(h->comm);
   void* ptrs[] = {h->dNuCell, h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
-                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus};
+                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
@@ -382,6 +386,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   TRY(dalloc(&h->dTrLl, (size_t)h->cap));
   TRY(dalloc(&h->dSweep, 1));
   TRY(dalloc(&h->dStatus, 1));
+  TRY(dalloc(&h->dLlOut, 1));
 #undef TRY
   // default parameters == setInitialValues (a = 1, sigma2 = 1, Sigma = I; src/GibbsRtIrt.pl.jl:122-133)
   {
@@ -654,6 +659,7 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   A.tr_qr = h->dTrQr;
   A.tr_ll = h->dTrLl;
   A.status = h->dStatus;
+  A.ll_out = h->dLlOut;
   A.n_total = h->cfg.n_subj_total;
   A.cap = h->cap;
   A.qw = h->qw;
@@ -863,7 +869,21 @@ extern "C" int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, d
   return 0;
 }
 
-extern "C" int erirt_loglik_current(erirt_handle*, double*) { return fail(ERIRT_E_UNSUPPORTED, "erirt_loglik_current is not part of round 1"); }
+extern "C" int erirt_loglik_current(erirt_handle* h, double* out) {
+  if (!h || !out) return fail(ERIRT_E_ARG, "null argument");
+  if (!h->data_set) return fail(ERIRT_E_STATE, "erirt_set_data has not been called");
+  if (h->cfg.model == ERIRT_RTIRT_CROSSQR)
+    return fail(ERIRT_E_UNSUPPORTED, "the log-likelihood at a given state needs the N x J weights nu, which CrossQr does not take as input");
+  CU(cudaSetDevice(h->cfg.device));
+  int rc = finalize_constants(h);
+  if (rc) return rc;
+  if (!h->prologue_done) CU(cudaMemsetAsync(h->dStats, 0, (h->L.s_count + 2) * sizeof(double), h->stream));
+  if ((rc = launch_person(h, 3))) return rc;
+  if ((rc = launch_global(h, 3))) return rc;
+  CU(cudaMemcpyAsync(out, h->dLlOut, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 
 extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {
   if (!h || !out) return fail(ERIRT_E_ARG, "null argument");

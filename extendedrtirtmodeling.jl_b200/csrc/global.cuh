@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   }
 
   // ---- 1. log-likelihood of state k ----
-  if (k >= 1) {
+  if (k >= 1 || A.stage == 3) {
     double part = 0.0;
     if (model == M_CROSSQR) {
       if (tid == 0) part = st[L.s_scal + SC_LL_RT];
@@ -326,6 +326,12 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     for (int o = G_THREADS / 2; o; o >>= 1) {
       if (tid < o) sRed[tid] += sRed[tid + o];
       __syncthreads();
+    }
+    if (A.stage == 3) {  // evaluation only: report and leave every parameter untouched
+      if (tid == 0) *A.ll_out = st[L.s_scal + SC_LL_BERN] + sRed[0] + st[L.s_scal + SC_LL_STRUCT];
+      __syncthreads();
+      for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = 0.0;
+      return;
     }
     if (tid == 0 && (int)(k - 1) < A.cap) A.tr_ll[k - 1] = st[L.s_scal + SC_LL_BERN] + sRed[0] + st[L.s_scal + SC_LL_STRUCT];
   }

@@ -121,6 +121,7 @@ struct GlobalArgs {
   double* tr_qr;        // [cap][qw]
   double* tr_ll;        // [cap]
   int* status;          // sticky numeric error flag
+  double* ll_out;       // stage 3: log-likelihood of the current state
   int64_t n_total;
   int cap, qw;
   Layout L;

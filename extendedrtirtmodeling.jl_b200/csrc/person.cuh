@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   const bool cross = model == M_CROSS || model == M_CROSSQR;
   const bool cqr = model == M_CROSSQR;
   const int stage = A.stage;
-  const bool do_theta = stage != 2, do_zeta = has_rt && stage != 1, do_pg = stage != 1;
+  const bool eval = stage == 3;  // log-likelihood of the current state only (DIC's D-hat): no draws, no stores
+  const bool do_theta = stage != 2 && !eval, do_zeta = has_rt && stage != 1 && !eval, do_pg = stage != 1 && !eval;
 
   R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
   R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
   const uint32_t k = *A.sweep_ctr;
-  const bool do_draws = k >= 1;
+  const bool do_draws = k >= 1 || A.stage == 3;
   const double* par = A.params;
 
   // ---- stage item / structural parameters (state k) and clear accumulators ----
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   double acc_ll_bern = 0.0, acc_ll_struct = 0.0, acc_ll_rt = 0.0;
   uint32_t acc_defer = 0, acc_cells = 0;
   uint32_t parity = 0;
-  const bool load_om = stage != 2;  // K_b of the Cross family only writes omega
+  const bool load_om = stage != 2 && !eval;  // K_b of the Cross family only writes omega
   const bool load_nc = cqr && do_draws;  // the prologue has no nu yet
   const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * ((has_rt ? 1 : 0) + (load_om ? 1 : 0) + (load_nc ? 1 : 0)) + A.S.tile_y_bytes);
   const int nk = ((G + 7) / 8) * (8 / TPP);  // steps per thread over its 4-item groups
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           th = parM + rsqrt_of(parV) * normal2r<R>(w.x, w.y);
         }
         R mu_z = R(0), var_z = R(1);
-        if (do_zeta) {
+        if (has_rt) {
           if (model == M_RTIRT) { mu_z = xb2; var_z = S22; }
           else if (latent) {
             mu_z = fma(th, s_beta[F + 1], xb1);
@@ -383,6 +384,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
             if (qr) { mu_z = fma(k1, nu, mu_z); var_z = S22 * (k2 * nu); }
           } else if (model == M_NULL) { mu_z = R(0); var_z = R(1); }  // Draw.pl.jl:120-121
           else { mu_z = R(0); var_z = S22; }
+        }
+        if (do_zeta) {
           const R ivz = rdiv(R(1), var_z);
           // Cross: sum_j (lambda - logT - theta rho_j)/sigma2;  CrossQr: the same weighted by 1/(k2 nu_ij), plus k1 sum_j 1/(sigma2 k2)
           const R prec = cqr ? d[0] : sum_is2;
@@ -409,8 +412,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           }
           acc_ll_struct += ls;
           if (do_theta) A.theta[pi] = th;
-          if (has_rt) A.zeta[pi] = ze;
-          if (post_burnin) {
+          if (do_zeta) A.zeta[pi] = ze;
+          if (post_burnin && !eval) {
             double* m = A.mom + pi;
             m[0] += (double)th;
             m[A.n_pad] += (double)th * (double)th;
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
               m[5 * A.n_pad] += (double)nu * (double)nu;
             }
           }
-          if (A.ptrace) {
+          if (A.ptrace && !eval) {
             R* t = A.ptrace + ((int64_t)(k - 1) * 3) * A.n_pad + pi;
             t[0] = th;
             t[A.n_pad] = ze;
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
     if (tid < P) {
       // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
-      if (qr) {
+      if (qr && !eval) {
         const R xb = fma(th, s_beta[F + 1], xb1);
         const R isc = rdiv(R(1), rsqrt_of(S22 * k2));
         const R parA = fabs(ze - xb) * isc;
@@ -639,6 +642,30 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           __syncthreads();
         }
       }
+    }
+
+    if (eval) {
+      // ---- Bernoulli log-likelihood of the current state (no draws) ----
+      const bool valid = (row0 + p) < A.n_local;
+      const R thp = s_u[p * Dgp + F + 1];
+      double llb = 0.0;
+      if (valid)
+        for (int kk = 0; kk < nk; ++kk) {
+          const int g = group_of<TPP>(q, kk);
+          if (g >= G) continue;
+          const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
+          const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
+          const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+#pragma unroll 1
+          for (int e = 0; e < 4; ++e) {
+            if (4 * g + e >= J) continue;
+            const double z = (double)fma(pA.v[e], thp, -pAB.v[e]);
+            const double y = ((yw >> (8 * e)) & 0xffu) ? 1.0 : 0.0;
+            const double az = fabs(z);
+            llb += y * z - (0.5 * (z + az) + log1p(exp(-az)));
+          }
+        }
+      acc_ll_bern += llb;
     }
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----

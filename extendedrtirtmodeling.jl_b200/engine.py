@@ -91,6 +91,12 @@ class Engine:
     def sample(self, n_sweeps):
         check(self.lib.erirt_sample(self.h, int(n_sweeps)))
 
+    def loglik_current(self):
+        """getLogLikelihood* of the state currently held by the engine (no draws)."""
+        out = C.c_double()
+        check(self.lib.erirt_loglik_current(self.h, C.byref(out)))
+        return out.value
+
     def trace_width(self, which):
         return int(self.lib.erirt_trace_width(self.h, _lib.TRACES[which]))
 

@@ -115,9 +115,9 @@ int64_t erirt_trace_width(erirt_handle* h, int32_t which);
 /* Post-burn-in running mean and SD (over sweeps with m > n_burnin) of THETA, ZETA or NU (person-level). */
 int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n);
 
-/* getLogLikelihood* of the CURRENT device state with the item/structural parameters given in the Julia
- * layouts (used for DIC's D-hat at Post.mean, src/GibbsRtIrt.pl.jl:449-458): person vectors must have been
- * set with erirt_set_state first. Not yet part of round 1 (returns ERIRT_E_UNSUPPORTED). */
+/* getLogLikelihood*(Cond, Data; P) of the state currently held by the handle (every InputPara field as last set
+ * with erirt_set_state, or as left by erirt_sample): used for DIC's D-hat at Post.mean,
+ * src/GibbsRtIrt.pl.jl:432-472.  No draw is made and nothing is modified.  CrossQr: ERIRT_E_UNSUPPORTED. */
 int erirt_loglik_current(erirt_handle* h, double* out);
 
 int erirt_get_stats(erirt_handle* h, erirt_stats* out);

@@ -184,6 +184,45 @@ def test_crossqr_cell_weights_parity(E, oracle):
     eng32.close()
 
 
+@pytest.mark.parametrize("model", [m for m in MODELS if m != "RtIrtCrossQr"])
+def test_loglik_at_given_state_matches_oracle(E, oracle, model):
+    """erirt_loglik_current == getLogLikelihood*(P) of the reference (DIC's D-hat), f64, no state is modified."""
+    pb = make_problem(model, 500, 9, 2, seed=23)
+    ref = run_oracle(oracle, pb, 2)
+    state = {k: ref[k] for k in ("theta", "zeta", "a", "b", "lambda", "sigma2", "beta", "rho", "Sigma", "nu")}
+    state["lambda_"] = state.pop("lambda")
+    cfg = oracle.make_cfg(model, pb["N"], pb["J"], pb["F"], qRt=pb["q"])
+    want = oracle.loglik(cfg, pb["Y"], None if model == "MlIrt" else pb["logT"], pb["X"], state)
+    assert abs(want - ref["ll"][-1]) < 1e-9 * abs(want)
+    eng = run_engine(E, pb, 0, dtype="f64")
+    st = dict(theta=ref["theta"], a=ref["a"], b=ref["b"])
+    if model != "MlIrt":
+        st.update(zeta=ref["zeta"], lambda_=ref["lambda"], sigma2=ref["sigma2"], Sigma=ref["Sigma"])
+    if pb["nb"]:
+        st["beta"] = ref["beta"][: pb["nb"]]
+    if "Cross" in model:
+        st["rho"] = ref["rho"]
+    if model == "RtIrtLatentQr":
+        st["nu"] = ref["nu"]
+    eng.set_state(**st)
+    got = eng.loglik_current()
+    assert abs(got - want) < 1e-11 * abs(want)
+    assert eng.loglik_current() == got  # idempotent: nothing was modified
+    eng.close()
+
+
+def test_dic_api(E):
+    Cond = E.setCond(nSubj=400, nItem=8, nFeat=2, nIter=200, nChain=2)
+    tp = E.setTrueParaRtIrt(Cond, rng=4)
+    Data = E.setDataRtIrt(Cond, tp, rng=4)
+    MCMC = E.GibbsRtIrt(Cond, Data=Data, rng=4)
+    E.sample(MCMC, dtype="f64")
+    dic = E.getDic(MCMC)
+    assert np.isfinite(dic.DIC) and np.isfinite(dic.pD) and dic.pD > 0
+    rows = E.precis(MCMC, file=open("/dev/null", "w"))
+    assert len(rows) == 16 + 16 + 10 and all(np.isfinite(r["mean"]) for r in rows)
+
+
 def test_graph_replay_equals_plain_launches(E):
     pb = make_problem("RtIrtLatentQr", 900, 20, 3, seed=16)
     a = run_engine(E, pb, 8, dtype="f32", use_graph=False)
