@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liberirt_b200.so")
+LIB_PATH = os.environ.get("ERIRT_B200_LIB", os.path.join(HERE, "liberirt_b200.so"))
 
 ABI_VERSION = 1
 MODELS = {"MlIrt": 0, "RtIrt": 1, "RtIrtNull": 2, "RtIrtCross": 3, "RtIrtCrossQr": 4, "RtIrtLatent": 5,

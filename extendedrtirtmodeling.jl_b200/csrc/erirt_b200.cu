@@ -220,7 +220,7 @@ static int launch_global(erirt_handle* h, int stage);
 static int finalize_constants(erirt_handle* h);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt, bool cqr = false) {
+static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt, bool cqr = false, bool cross = false) {
   SmemPlan S{};
   S.P = CTA_THREADS / tpp;
   S.tile_real_bytes = (int)(S.P * L.Jp * rsz);
@@ -232,11 +232,11 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_logt = (int)o; if (has_rt) o = align_up(o + S.tile_real_bytes, 128);
   S.off_nuc = (int)o; if (cqr) o = align_up(o + S.tile_real_bytes, 128);
   S.off_y = (int)o; o = align_up(o + S.tile_y_bytes, 128);
-  S.off_par = (int)o; o = align_up(o + PAR_COUNT * L.Jp * rsz, 128);
+  S.off_par = (int)o; o = align_up(o + (cross ? PAR_COUNT : PAR_RHO) * L.Jp * rsz, 128);
   S.off_u = (int)o; o = align_up(o + (size_t)S.P * S.Dgp * rsz, 128);
   S.off_sum = (int)o; o = align_up(o + (size_t)S.P * 4 * rsz, 128);
   S.off_beta = (int)o; o = align_up(o + (size_t)(MAXD + 4) * rsz, 128);
-  S.off_acc_item = (int)o; o = align_up(o + N_ITEM_STATS * L.Jp * sizeof(double), 128);
+  S.off_acc_item = (int)o; o = align_up(o + (cqr ? 7 : (cross ? 6 : 5)) * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
   S.off_queue = (int)o; if (rsz == 4) o = align_up(o + (QCAP + QCAP2) * sizeof(uint32_t), 128);
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
@@ -244,17 +244,19 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   return S;
 }
 
-template <typename R>
+template <typename R, int FAM>
 static const void* person_kernel_ptr(int tpp) {
   switch (tpp) {
-    case 1: return (const void*)person_sweep_kernel<R, 1>;
-    case 2: return (const void*)person_sweep_kernel<R, 2>;
-    case 4: return (const void*)person_sweep_kernel<R, 4>;
-    default: return (const void*)person_sweep_kernel<R, 8>;
+    case 1: return (const void*)person_sweep_kernel<R, 1, FAM>;
+    case 2: return (const void*)person_sweep_kernel<R, 2, FAM>;
+    case 4: return (const void*)person_sweep_kernel<R, 4, FAM>;
+    default: return (const void*)person_sweep_kernel<R, 8, FAM>;
   }
 }
-static const void* person_kernel_for(const erirt_handle* h) {
-  return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float>(h->tpp) : person_kernel_ptr<double>(h->tpp);
+// fam 0: the specialised kernel of the one-launch models; fam 1: Cross family and the evaluation stage
+static const void* person_kernel_for(const erirt_handle* h, int fam) {
+  if (fam == 0) return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 0>(h->tpp) : person_kernel_ptr<double, 0>(h->tpp);
+  return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 1>(h->tpp) : person_kernel_ptr<double, 1>(h->tpp);
 }
 
 static int qr_small_width(int model, int J, int F) {
@@ -336,22 +338,23 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   h->L = make_layout(cfg->n_item, cfg->n_feat);
   const bool has_rt = cfg->model != ERIRT_MLIRT;
   // threads per person: smallest TPP whose tile fits ~64 KB (>= 3 CTAs/SM)
+  const bool is_cross = cfg->model == ERIRT_RTIRT_CROSS || cfg->model == ERIRT_RTIRT_CROSSQR;
   int tpp = 1;
   const char* env_tpp = getenv("ERIRT_TPP");
   const int n_groups = h->L.Jp / 4;
   if (env_tpp) tpp = atoi(env_tpp);
   else {
     for (tpp = 1; tpp < 8; tpp *= 2) {
-      SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR);
+      SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR, is_cross);
       if (s.total <= 74 * 1024 && n_groups <= 16 * tpp) break;
     }
   }
   if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) { delete h; return fail(ERIRT_E_ARG, "ERIRT_TPP must be 1, 2, 4 or 8"); }
   if (n_groups > 16 * tpp) { delete h; return fail(ERIRT_E_ARG, "TPP=%d handles at most %d items", tpp, 64 * tpp - 4); }
   h->tpp = tpp;
-  h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR);
+  h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR, is_cross);
   if (h->S.total > 227 * 1024) { delete h; return fail(ERIRT_E_UNSUPPORTED, "n_item %d needs %d bytes of shared memory per CTA", cfg->n_item, h->S.total); }
-  h->n_pad = (int64_t)align_up((size_t)cfg->n_subj, 128);
+  h->n_pad = (int64_t)align_up((size_t)cfg->n_subj, CTA_THREADS > 128 ? CTA_THREADS : 128);
   h->cap = cfg->n_iter * cfg->n_chain;
   h->qw = qr_small_width(cfg->model, cfg->n_item, cfg->n_feat);
 
@@ -396,8 +399,9 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
     cudaMemcpy(h->dParams, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice);
   }
   // kernel attributes / occupancy-sized persistent grid
-  const void* kfn = person_kernel_for(h);
+  const void* kfn = person_kernel_for(h, is_cross ? 1 : 0);
   cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->S.total);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(person_kernel_for(h, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, h->S.total);
   if (ce != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "cudaFuncSetAttribute(%d bytes): %s", h->S.total, cudaGetErrorString(ce)); }
   int occ = 0;
   ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, CTA_THREADS, h->S.total);
@@ -677,14 +681,15 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
 }
 
 static int launch_person(erirt_handle* h, int stage) {
+  const void* kfn = person_kernel_for(h, stage == 0 ? 0 : 1);
   if (h->cfg.dtype == ERIRT_F32) {
     PersonArgs<float> A = make_person_args<float>(h, stage);
     void* args[] = {&A};
-    CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+    CU(cudaLaunchKernel(kfn, dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
   } else {
     PersonArgs<double> A = make_person_args<double>(h, stage);
     void* args[] = {&A};
-    CU(cudaLaunchKernel(person_kernel_for(h), dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+    CU(cudaLaunchKernel(kfn, dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
   }
   return 0;
 }

@@ -137,9 +137,13 @@ constexpr int STAT_FLUSH_TILES = 8;  // item statistics live in registers and ar
 
 // resident CTAs per SM the register allocation is tuned for: the tile of TPP=2 leaves room for 3 CTAs, TPP=4 for 5, TPP=8 for 7
 template <int TPP>
-constexpr int min_ctas_per_sm() { return TPP >= 8 ? 7 : (TPP == 4 ? 5 : 3); }
+constexpr int min_ctas_per_sm() {
+  return CTA_THREADS == 128 ? (TPP >= 8 ? 7 : (TPP == 4 ? 5 : 3)) : (TPP >= 8 ? 4 : (TPP == 4 ? 3 : 1));
+}
 
-template <typename R, int TPP>
+// FAM = 0: the one-launch-per-sweep models (MlIrt, RtIrt, RtIrtNull, Latent, LatentQr) -- the hot configuration, with the
+// Cross-family / evaluation code compiled out; FAM = 1: everything (Cross, CrossQr stages 1/2, stage 3 evaluation).
+template <typename R, int TPP, int FAM>
 __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sweep_kernel(const PersonArgs<R> A) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int P = CTA_THREADS / TPP;
@@ -151,10 +155,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   const bool latent = model == M_LATENT || model == M_LATENTQR;
   const bool qr = model == M_LATENTQR;
   const bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
-  const bool cross = model == M_CROSS || model == M_CROSSQR;
-  const bool cqr = model == M_CROSSQR;
-  const int stage = A.stage;
-  const bool eval = stage == 3;  // log-likelihood of the current state only (DIC's D-hat): no draws, no stores
+  constexpr bool XF = FAM == 1;
+  const bool cross = XF && (model == M_CROSS || model == M_CROSSQR);
+  const bool cqr = XF && model == M_CROSSQR;
+  const int stage = XF ? A.stage : 0;
+  const bool eval = XF && stage == 3;  // log-likelihood of the current state only (DIC's D-hat): no draws, no stores
   const bool do_theta = stage != 2 && !eval, do_zeta = has_rt && stage != 1 && !eval, do_pg = stage != 1 && !eval;
 
   R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
   const uint32_t k = *A.sweep_ctr;
-  const bool do_draws = k >= 1 || A.stage == 3;
+  const bool do_draws = k >= 1 || (FAM == 1 && A.stage == 3);
   const double* par = A.params;
 
   // ---- stage item / structural parameters (state k) and clear accumulators ----
@@ -200,12 +205,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     s_par[PAR_A2B * Jp + j] = (R)(a * a * b);
     s_par[PAR_IS2 * Jp + j] = (R)is2;
     s_par[PAR_LAM * Jp + j] = (R)lam;
-    s_par[PAR_RHO * Jp + j] = (R)rho;
-    s_par[PAR_ISC * Jp + j] = (R)isc;
+    if (cross) {  // these two arrays exist only in the Cross-family shared-memory plan
+      s_par[PAR_RHO * Jp + j] = (R)rho;
+      s_par[PAR_ISC * Jp + j] = (R)isc;
+    }
   }
   if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
   if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
-  for (int t = tid; t < N_ITEM_STATS * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
+  const int n_stat_blocks = cqr ? 7 : (cross ? 6 : 5);  // per-item statistic blocks of this model (shared-memory plan)
+  for (int t = tid; t < n_stat_blocks * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
   if (tid < SC_COUNT) s_scal[tid] = 0.0;
   if (tid < 32) {  // sum_j 1/sigma2_j in f64
@@ -750,9 +758,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
   if (tid < P) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
   __syncthreads();
-  for (int t = tid; t < N_ITEM_STATS * Jp; t += CTA_THREADS) {
+  for (int t = tid; t < n_stat_blocks * Jp; t += CTA_THREADS) {
     const int j = t % Jp;
-    if (j < J && (cqr || (cross && t < 6 * Jp) || t < 5 * Jp)) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
+    if (j < J) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
   }
   for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS)
     if (t < L.ntri || qr) atomicAdd(&A.stats[L.s_gram + t], s_acc_gram[t]);
