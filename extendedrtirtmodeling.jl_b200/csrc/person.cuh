@@ -297,7 +297,18 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     const bool pvalid = tid < P && pi < A.n_local;
     const uint32_t pgid = A.person_offset + (uint32_t)pi;
     R th = R(0), ze = R(0), nu = R(1), xb1 = R(0), xb2 = R(0);
+    R zn_theta = R(0), zn_zeta = R(0), zn_nu = R(0), un_nu = R(0);  // variates drawn while the tile is in flight
     if (tid < P) {
+      if (do_draws && !eval) {
+        const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
+        zn_theta = normal2r<R>(w.x, w.y);
+        zn_zeta = normal2r<R>(w.z, w.w);
+      }
+      if (qr && !eval) {
+        const uint4 w = philox(A.key, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+        zn_nu = normal2r<R>(w.x, w.y);
+        un_nu = u01<R>(w.z);
+      }
       th = A.theta[pi];
       if (has_rt) ze = A.zeta[pi];
       if (qr) nu = A.nu[pi];
@@ -374,14 +385,13 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       // ---- person phase, part 2: theta_k, zeta_k, structural log-density, moments ----
       if (tid < P) {
         const R* d = s_sum + 4 * tid;
-        const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
         if (do_theta) {
           const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
           const R var0 = (model == M_MLIRT) ? R(1) : S11;
           const R iv0 = rdiv(R(1), var0);
           const R parV = rdiv(R(1), iv0 + d[0]);
           const R parM = parV * (mu0 * iv0 + d[2] + d[1]);
-          th = parM + rsqrt_of(parV) * normal2r<R>(w.x, w.y);
+          th = parM + rsqrt_of(parV) * zn_theta;
         }
         R mu_z = R(0), var_z = R(1);
         if (has_rt) {
@@ -400,25 +410,25 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const R num = cqr ? d[3] - th * d[1] + k1 * sum_is2 : (cross ? d[3] - th * sum_rho_is2 : d[3]);
           const R parV = rdiv(R(1), ivz + prec);
           const R parM = parV * (mu_z * ivz + num);
-          ze = parM + rsqrt_of(parV) * normal2r<R>(w.z, w.w);
+          ze = parM + rsqrt_of(parV) * zn_zeta;
         }
         if (pvalid && stage == 1) A.theta[pi] = th;  // K_a: theta_k only; everything else happens in K_b
         if (pvalid && stage != 1) {
-          const double LOG2PI = 1.8378770664093454835606594728112;
-          double ls;
+          const R LOG2PI = R(1.8378770664093454835606594728112);
+          R ls;
           if (model == M_MLIRT) {
-            double r = (double)th - (double)xb1;
-            ls = -0.5 * LOG2PI - 0.5 * r * r;
+            const R r = th - xb1;
+            ls = R(-0.5) * LOG2PI - R(0.5) * r * r;
           } else if (latent) {
-            double r = (double)ze - (double)mu_z, v = (double)var_z;
-            ls = -0.5 * (LOG2PI + log(v)) - 0.5 * r * r / v;
+            const R r = ze - mu_z;
+            ls = R(-0.5) * (LOG2PI + rlog(var_z)) - R(0.5) * r * rdiv(r, var_z);
           } else {
-            double e1 = (double)th - (model == M_RTIRT ? (double)xb1 : 0.0);
-            double e2 = (double)ze - (model == M_RTIRT ? (double)xb2 : 0.0);
-            double s11 = S11, s12 = S12, s22 = S22, det = s11 * s22 - s12 * s12;
-            ls = -LOG2PI - 0.5 * log(det) - 0.5 * (s22 * e1 * e1 - 2.0 * s12 * e1 * e2 + s11 * e2 * e2) / det;
+            const R e1 = th - (model == M_RTIRT ? xb1 : R(0));
+            const R e2 = ze - (model == M_RTIRT ? xb2 : R(0));
+            const R det = S11 * S22 - S12 * S12;
+            ls = -LOG2PI - R(0.5) * rlog(det) - R(0.5) * rdiv(S22 * e1 * e1 - R(2) * S12 * e1 * e2 + S11 * e2 * e2, det);
           }
-          acc_ll_struct += ls;
+          acc_ll_struct += (double)ls;
           if (do_theta) A.theta[pi] = th;
           if (do_zeta) A.zeta[pi] = ze;
           if (post_burnin && !eval) {
@@ -452,8 +462,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         const R parB = rsqrt_of(R(2) * k2 + k1 * k1) * isc;
         R mu = rdiv(parB, parA);
         if (!(mu >= R(1e-10))) mu = R(1e-10);
-        const uint4 w = philox(A.key, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
-        const R ig = ig_msh<R>(mu, parB * parB, normal2r<R>(w.x, w.y), u01<R>(w.z));
+        const R ig = ig_msh<R>(mu, parB * parB, zn_nu, un_nu);
         nu = rdiv(R(1), ig);
         nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
         if (pvalid) A.nu[pi] = nu;
