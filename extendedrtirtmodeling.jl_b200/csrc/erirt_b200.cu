@@ -238,7 +238,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_beta = (int)o; o = align_up(o + (size_t)(MAXD + 4) * rsz, 128);
   S.off_acc_item = (int)o; o = align_up(o + (cqr ? 7 : (cross ? 6 : 5)) * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
-  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + (QCAP + QCAP2) * sizeof(uint32_t), 128);
+  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;
   return S;

@@ -10,8 +10,7 @@ namespace erirt {
 #endif
 constexpr int CTA_THREADS = ERIRT_CTA_THREADS;  // person-sweep CTA; tile = CTA_THREADS / TPP persons
 constexpr int MAXD = 32;          // largest dense system solved in the global kernel (2*(nFeat+1) <= 32)
-constexpr int QCAP = 768;         // PG fast-retry queue capacity per tile (overflow is handled inline)
-constexpr int QCAP2 = 256;        // PG exact-replay queue capacity per tile
+constexpr int QCAP = 1024;        // PG fast-retry queue capacity per tile (overflow is handled inline)
 
 constexpr int N_ITEM_STATS = 7;   // S0, S1, S2, Ky, C, D, (V);  CrossQr K_a: A0..A5, V1;  CrossQr K_b: S0, S1, S2, Ky, A1', A2', A3'
 enum ModelId { M_MLIRT = 0, M_RTIRT = 1, M_NULL = 2, M_CROSS = 3, M_CROSSQR = 4, M_LATENT = 5, M_LATENTQR = 6 };

@@ -111,28 +111,28 @@ __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& zc
   zs = rad * sin(ang);
 }
 
-// Retry of one PG cell whose attempt 0 was certainly rejected (f32, Method A): attempts a >= first are evaluated with
-// the same branch-free fast evaluation as the main pass.  Returns omega >= 0, or -(a+1) when attempt a is undecided by
-// the squeeze tests (the caller hands the cell to the exact queue, which replays that attempt with the full series).
-// Kept out of line: the retry path is cold relative to the main pass and inlining it thrashes the instruction cache.
-__device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z, int first) {
+// Retry of one PG cell whose attempt 0 was rejected, or of a Method-B cell (f32): attempts a = 1, 2, ... from the cell's
+// retry-site Philox blocks, evaluated with the same branch-free fast evaluation as the main pass.  Kept out of line: the
+// retry path is cold relative to the main pass and inlining it thrashes the instruction cache.
+__device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z) {
+  if (!(z == z)) return z;  // poisoned state: do not spin
+  const bool method_b = 0.5f * fabsf(z) > (float)PG_CSWITCH;
 #pragma unroll 1
-  for (uint32_t a = (uint32_t)first; a < 250u; ++a) {
+  for (uint32_t a = 1; a < PG_MAX_ATTEMPTS; ++a) {
     const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
     float ll;
-    const float om = pg_fast_attempt0(z, 0.f, w.x, w.y, ll);
+    const float om = method_b ? pg_fast_attemptB(z, w) : pg_fast_attempt0(z, 0.f, w.x, w.y, ll);
     if (om >= 0.f) return om;
-    if (om == -1.0f) return -(float)(a + 1u);
   }
-  return -251.0f;  // hand over to the exact loop
-}
-__device__ __noinline__ float pg_exact_cell_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z, int first) {
-  return pg_draw_exact<float>(key, gid, sweep, j, z, first);
+  return 0.25f * (float)PG_T;
 }
 __device__ __noinline__ double pg_draw_cell_f64(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, double z, uint32_t* na) {
   return pg_draw_exact<double>(key, gid, sweep, j, z, 0, na);
 }
 
+#ifndef ERIRT_DIAG
+#define ERIRT_DIAG 0  // diagnostic builds only (tools/gpu_diag.sh): bit0 no PG math, bit1 no statistics pass, bit2 no row sums
+#endif
 constexpr int STAT_FLUSH_TILES = 8;  // item statistics live in registers and are folded into f64 every 8 tiles
 
 // resident CTAs per SM the register allocation is tuned for: the tile of TPP=2 leaves room for 3 CTAs, TPP=4 for 5, TPP=8 for 7
@@ -288,9 +288,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       if (load_nc) tma_load_1d(s_nc, A.nu_cell + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
       s_qctl[0] = 0;
-      s_qctl[1] = 0;
-      s_qctl[2] = 0;
-      s_qctl[3] = 0;
     }
     // ---- person phase, part 1 (one thread per person, coalesced): state k-1 and regression means ----
     const int64_t pi = row0 + tid;
@@ -331,7 +328,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     if (do_draws) {
       // ---- row sums over items (Draw.pl.jl:55-56, 137-138), TPP threads per person ----
       R sA2 = 0, sAB = 0, sAK = 0, sLT = 0;
-      for (int kk = 0; kk < nk; ++kk) {
+      for (int kk = 0; kk < ((ERIRT_DIAG & 4) ? 0 : nk); ++kk) {
         const int g = group_of<TPP>(q, kk);
         if (g >= G) continue;
         if (do_theta) {
@@ -432,16 +429,16 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           if (do_theta) A.theta[pi] = th;
           if (do_zeta) A.zeta[pi] = ze;
           if (post_burnin && !eval) {
-            double* m = A.mom + pi;
-            m[0] += (double)th;
-            m[A.n_pad] += (double)th * (double)th;
+            double* m = A.mom + pi;  // fire-and-forget reductions (RED.ADD.F64): no round trip on the critical path
+            atomicAdd(&m[0], (double)th);
+            atomicAdd(&m[A.n_pad], (double)th * (double)th);
             if (has_rt) {
-              m[2 * A.n_pad] += (double)ze;
-              m[3 * A.n_pad] += (double)ze * (double)ze;
+              atomicAdd(&m[2 * A.n_pad], (double)ze);
+              atomicAdd(&m[3 * A.n_pad], (double)ze * (double)ze);
             }
             if (qr) {
-              m[4 * A.n_pad] += (double)nu;
-              m[5 * A.n_pad] += (double)nu * (double)nu;
+              atomicAdd(&m[4 * A.n_pad], (double)nu);
+              atomicAdd(&m[5 * A.n_pad], (double)nu * (double)nu);
             }
           }
           if (A.ptrace && !eval) {
@@ -588,105 +585,52 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       }
       acc_ll_bern += (double)ll_tile;
       if constexpr (F32) {
-        // ---- hand the cells that left the fast path to the queues: rejected -> fast retry, undecided / Method B -> exact ----
-        my_defer = (uint32_t)__popcll(defer_mask);
-        while (defer_mask) {
-          const int bit = __ffsll((long long)defer_mask) - 1;
-          defer_mask &= defer_mask - 1ull;
-          const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
-          const float code = (float)my_om[j];
-          const uint32_t entry = ((uint32_t)p << 16) | (uint32_t)j;
-          if (code == -2.0f) {
-            const uint32_t slot = atomicAdd(&s_qctl[0], 1u);
-            if (slot < (uint32_t)QCAP) s_queue[slot] = entry | (1u << 24);
-            else {  // queue overflow: finish the cell here
-              const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
-              my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, 1);
-            }
-          } else {
-            const uint32_t first = code == -1.0f ? 0u : 1u;
-            const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
-            if (slot < (uint32_t)QCAP2) s_queue[QCAP + slot] = entry | (first << 24);
-            else {
-              const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
-              my_om[j] = (R)pg_exact_cell_f32(A.key, gid, k + 1, j, z, (int)first);
-            }
-          }
-        }
+        // ---- hand the rejected / Method-B cells to the tile's retry queue: one shared-memory atomic per WARP reserves the
+      //      slots of all its lanes (warp prefix sum), then every lane writes its own entries ----
+      my_defer = (uint32_t)__popcll(defer_mask);
+      uint32_t pre = my_defer;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+        if ((tid & 31) >= o) pre += t;
       }
-      acc_defer += my_defer;
+      const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
+      uint32_t wbase = 0;
+      if ((tid & 31) == 31 && wtotal) wbase = atomicAdd(&s_qctl[0], wtotal);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      uint32_t slot = wbase + pre - my_defer;
+      while (defer_mask) {
+        const int bit = __ffsll((long long)defer_mask) - 1;
+        defer_mask &= defer_mask - 1ull;
+        const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
+        if (slot < (uint32_t)QCAP) s_queue[slot] = ((uint32_t)p << 16) | (uint32_t)j;
+        else {  // queue overflow: finish the cell here
+          const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+          my_om[j] = (R)pg_retry_fast_f32(A.key, gid, k + 1, j, z);
+        }
+        ++slot;
+      }
+    }
+    acc_defer += my_defer;
+    __syncthreads();
+
+    if constexpr (F32) {
+      // ---- drain: a strided share of the queue per thread ----
+      const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
+      for (uint32_t idx = tid; idx < qn; idx += CTA_THREADS) {
+        const uint32_t entry = s_queue[idx];
+        const int pj = (int)(entry & 0xffffu), pp = (int)(entry >> 16);
+        const float thq = (float)s_u[pp * Dgp + F + 1];
+        const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
+        const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
+        s_om[pp * Jp + pj] = (R)pg_retry_fast_f32(A.key, qgid, k + 1, pj, z);
+      }
       __syncthreads();
-
-      if constexpr (F32) {
-        // ---- stage 1: fast retries, any free thread takes the next cell ----
-        const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
-        if (qn) {
-          while (true) {
-            const uint32_t idx = atomicAdd(&s_qctl[1], 1u);
-            if (idx >= qn) break;
-            const uint32_t entry = s_queue[idx];
-            const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
-            const float thq = (float)s_u[pp * Dgp + F + 1];
-            const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
-            const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
-            float om = pg_retry_fast_f32(A.key, qgid, k + 1, pj, z, first);
-            if (om < 0.f) {  // attempt -(om)-1 is undecided: exact queue
-              const uint32_t a = (uint32_t)(-om) - 1u;
-              const uint32_t slot = atomicAdd(&s_qctl[2], 1u);
-              if (slot < (uint32_t)QCAP2) {
-                s_queue[QCAP + slot] = (entry & 0xffffffu) | (a << 24);
-                continue;
-              }
-              om = pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, (int)a);
-            }
-            s_om[pp * Jp + pj] = (R)om;
-          }
-        }
-        __syncthreads();
-        // ---- stage 2: exact replays (undecided attempts, Method-B cells) ----
-        const uint32_t qn2 = min(s_qctl[2], (uint32_t)QCAP2);
-        if (qn2) {
-          while (true) {
-            const uint32_t idx = atomicAdd(&s_qctl[3], 1u);
-            if (idx >= qn2) break;
-            const uint32_t entry = s_queue[QCAP + idx];
-            const int pj = (int)(entry & 0xffffu), pp = (int)((entry >> 16) & 0xffu), first = (int)(entry >> 24);
-            const float thq = (float)s_u[pp * Dgp + F + 1];
-            const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
-            const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
-            s_om[pp * Jp + pj] = (R)pg_exact_cell_f32(A.key, qgid, k + 1, pj, z, first);
-          }
-          __syncthreads();
-        }
-      }
     }
-
-    if (eval) {
-      // ---- Bernoulli log-likelihood of the current state (no draws) ----
-      const bool valid = (row0 + p) < A.n_local;
-      const R thp = s_u[p * Dgp + F + 1];
-      double llb = 0.0;
-      if (valid)
-        for (int kk = 0; kk < nk; ++kk) {
-          const int g = group_of<TPP>(q, kk);
-          if (g >= G) continue;
-          const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
-          const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
-          const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
-#pragma unroll 1
-          for (int e = 0; e < 4; ++e) {
-            if (4 * g + e >= J) continue;
-            const double z = (double)fma(pA.v[e], thp, -pAB.v[e]);
-            const double y = ((yw >> (8 * e)) & 0xffu) ? 1.0 : 0.0;
-            const double az = fabs(z);
-            llb += y * z - (0.5 * (z + az) + log1p(exp(-az)));
-          }
-        }
-      acc_ll_bern += llb;
-    }
+  }
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
-    if (e_active) {
+    if (e_active && !(ERIRT_DIAG & 2)) {
       for (int pp = er; pp < P; pp += Rc) {
         const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
         if (do_pg) {
@@ -791,7 +735,7 @@ __global__ void k_pg_kernel(const double* z, int64_t rows, int cols, int64_t row
       const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
       float ll;
       om = (j & 1) ? pg_fast_attempt0(zz, 0.5f, w.z, w.w, ll) : pg_fast_attempt0(zz, 0.5f, w.x, w.y, ll);
-      if (om < 0.f) om = pg_draw_exact<float>(key, gid, sweep, j, zz, om == -1.0f ? 0 : 1);
+      if (om < 0.f) om = pg_retry_fast_f32(key, gid, sweep, j, zz);  // same path as the sampler's retry queue
     } else {
       om = pg_draw_exact<R>(key, gid, sweep, j, zz, 0);
     }

@@ -108,11 +108,12 @@ __device__ inline double site_normal(PhiloxKey key, uint32_t unit, uint32_t swee
 // Robert's (1995) translated-exponential proposal otherwise.
 __device__ inline double site_tnorm_pos(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double mu, double sd) {
   double alpha = -mu / sd;
+  if (!(alpha == alpha)) return alpha;  // NaN parameters: propagate instead of spinning
   if (alpha <= 0.5) {
     for (uint32_t att = 0;; ++att) {
       uint4 w = philox(key, unit, sweep, site, att);
       double z = normal2(w.x, w.y);
-      if (z >= alpha || att > 100000u) return mu + sd * z;
+      if (z >= alpha || att > 10000u) return mu + sd * z;
     }
   }
   double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
@@ -120,12 +121,13 @@ __device__ inline double site_tnorm_pos(PhiloxKey key, uint32_t unit, uint32_t s
     uint4 w = philox(key, unit, sweep, site, att);
     double x = alpha - log(u01d(w.x)) / lam;
     double d = x - lam;
-    if (u01d(w.y) <= exp(-0.5 * d * d) || att > 100000u) return mu + sd * x;
+    if (u01d(w.y) <= exp(-0.5 * d * d) || att > 10000u) return mu + sd * x;
   }
 }
 
 // Gamma(shape, 1) by Marsaglia-Tsang (2000); shape >= 1 here (delta + N/2, (N+3)/2, ...)
 __device__ inline double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double shape) {
+  if (!(shape > 0.0)) return shape * 0.0 / 0.0;  // NaN / non-positive shape
   double boost = 1.0;
   if (shape < 1.0) {
     uint4 w = philox(key, unit, sweep, site, 0xffffffffu);
@@ -140,7 +142,7 @@ __device__ inline double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep
     if (v <= 0.0) continue;
     v = v * v * v;
     double u = u01d(w.z);
-    if (log(u) < 0.5 * x * x + d - d * v + d * log(v) || att > 100000u) return boost * d * v;
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v) || att > 10000u) return boost * d * v;
   }
 }
 
