@@ -114,7 +114,7 @@ __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& zc
 // Retry of one PG cell whose attempt 0 was rejected, or of a Method-B cell (f32): attempts a = 1, 2, ... from the cell's
 // retry-site Philox blocks, evaluated with the same branch-free fast evaluation as the main pass.  Kept out of line: the
 // retry path is cold relative to the main pass and inlining it thrashes the instruction cache.
-__device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z) {
+__device__ __forceinline__ float pg_retry_fast_f32_inl(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z) {
   if (!(z == z)) return z;  // poisoned state: do not spin
   const bool method_b = 0.5f * fabsf(z) > (float)PG_CSWITCH;
 #pragma unroll 1
@@ -125,6 +125,10 @@ __device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uin
     if (om >= 0.f) return om;
   }
   return 0.25f * (float)PG_T;
+}
+// out-of-line copy for the cold call sites (queue overflow, test kernel)
+__device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z) {
+  return pg_retry_fast_f32_inl(key, gid, sweep, j, z);
 }
 __device__ __noinline__ double pg_draw_cell_f64(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, double z, uint32_t* na) {
   return pg_draw_exact<double>(key, gid, sweep, j, z, 0, na);
@@ -328,8 +332,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     if (do_draws) {
       // ---- row sums over items (Draw.pl.jl:55-56, 137-138), TPP threads per person ----
       R sA2 = 0, sAB = 0, sAK = 0, sLT = 0;
-      for (int kk = 0; kk < ((ERIRT_DIAG & 4) ? 0 : nk); ++kk) {
-        const int g = group_of<TPP>(q, kk);
+      constexpr int CHUNK = 8 / TPP;  // consecutive groups owned by this thread inside each block of 8
+      for (int g0 = q * CHUNK; g0 < ((ERIRT_DIAG & 4) ? 0 : G); g0 += 8) {
+#pragma unroll
+      for (int cc = 0; cc < CHUNK; ++cc) {
+        const int g = g0 + cc;
         if (g >= G) continue;
         if (do_theta) {
           const Quad<R> om = ld4(my_om + 4 * g);
@@ -366,6 +373,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
             }
           }
         }
+      }
       }
 #pragma unroll
       for (int o = 1; o < TPP; o <<= 1) {
@@ -615,15 +623,34 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     __syncthreads();
 
     if constexpr (F32) {
-      // ---- drain: a strided share of the queue per thread ----
+      // ---- drain: a strided share of the queue per thread, two cells in flight per thread (two independent Philox /
+      //      attempt chains interleave, which halves the latency-bound time of this phase) ----
       const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
-      for (uint32_t idx = tid; idx < qn; idx += CTA_THREADS) {
-        const uint32_t entry = s_queue[idx];
-        const int pj = (int)(entry & 0xffffu), pp = (int)(entry >> 16);
-        const float thq = (float)s_u[pp * Dgp + F + 1];
-        const float z = fmaf((float)s_par[PAR_A * Jp + pj], thq, -(float)s_par[PAR_AB * Jp + pj]);
-        const uint32_t qgid = A.person_offset + (uint32_t)(row0 + pp);
-        s_om[pp * Jp + pj] = (R)pg_retry_fast_f32(A.key, qgid, k + 1, pj, z);
+      for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
+        const bool has2 = idx + CTA_THREADS < qn;
+        const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
+        const int j1 = (int)(e1 & 0xffffu), p1 = (int)(e1 >> 16), j2 = (int)(e2 & 0xffffu), p2 = (int)(e2 >> 16);
+        const float z1 = fmaf((float)s_par[PAR_A * Jp + j1], (float)s_u[p1 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j1]);
+        const float z2 = fmaf((float)s_par[PAR_A * Jp + j2], (float)s_u[p2 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j2]);
+        const uint32_t g1 = A.person_offset + (uint32_t)(row0 + p1), g2 = A.person_offset + (uint32_t)(row0 + p2);
+        const bool b1 = 0.5f * fabsf(z1) > (float)PG_CSWITCH, b2 = 0.5f * fabsf(z2) > (float)PG_CSWITCH;
+        float om1 = (z1 == z1) ? -2.0f : z1, om2 = (has2 && z2 == z2) ? -2.0f : 0.0f;  // NaN state is passed through
+#pragma unroll 1
+        for (uint32_t a = 1; a < PG_MAX_ATTEMPTS && (om1 < 0.f || om2 < 0.f); ++a) {
+          const uint4 w1 = philox(A.key, g1, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j1), a);
+          const uint4 w2 = philox(A.key, g2, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j2), a);
+          float ll;
+          float o1 = pg_fast_attempt0(z1, 0.f, w1.x, w1.y, ll);
+          float o2 = pg_fast_attempt0(z2, 0.f, w2.x, w2.y, ll);
+          if (b1) o1 = pg_fast_attemptB(z1, w1);
+          if (b2) o2 = pg_fast_attemptB(z2, w2);
+          if (om1 < 0.f) om1 = o1;
+          if (om2 < 0.f) om2 = o2;
+        }
+        if (om1 < 0.f) om1 = 0.25f * (float)PG_T;
+        if (om2 < 0.f) om2 = 0.25f * (float)PG_T;
+        s_om[p1 * Jp + j1] = (R)om1;
+        if (has2) s_om[p2 * Jp + j2] = (R)om2;
       }
       __syncthreads();
     }
@@ -681,19 +708,31 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       }
     }
     if ((tiles_done % STAT_FLUSH_TILES) == STAT_FLUSH_TILES - 1) flush_item_stats();
-    // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin (entries owned by one thread each)
-    for (int t = tid; t < L.ntri; t += CTA_THREADS) {
-      int r = 0, rem = t;
-      while (rem >= Dg - r) { rem -= Dg - r; ++r; }
-      const int c = r + rem;
+    // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin: entry t is shared by the 4 lanes of a quad (persons
+    // pp = lane mod 4 (mod 4)), so that all four warps of the CTA take part instead of one
+    for (int t0 = 0; t0 < L.ntri; t0 += CTA_THREADS / 4) {
+      const int t = t0 + (tid >> 2);
       double g0 = 0.0, g1 = 0.0;
-      for (int pp = 0; pp < P; ++pp) {
-        const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
-        g0 += ur * uc;
-        if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
+      if (t < L.ntri) {
+        int r = 0, rem = t;
+        while (rem >= Dg - r) { rem -= Dg - r; ++r; }
+        const int c = r + rem;
+        for (int pp = tid & 3; pp < P; pp += 4) {
+          const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
+          g0 += ur * uc;
+          if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
+        }
       }
-      s_acc_gram[t] += g0;
-      if (qr) s_acc_gram[L.ntri + t] += g1;
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 1);
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 2);
+      if (qr) {
+        g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, 2);
+      }
+      if (t < L.ntri && (tid & 3) == 0) {
+        s_acc_gram[t] += g0;
+        if (qr) s_acc_gram[L.ntri + t] += g1;
+      }
     }
     fence_proxy_async();
     __syncthreads();

@@ -6,8 +6,7 @@ import numpy as np, torch
 import erirt_b200 as E
 import bench
 names = ["issue+person part1", "mbar wait (TMA)", "row sums", "barrier 1", "person part 2 + u rows", "barrier 2", "PG main pass",
-         "queue push", "barrier 3", "fast drain", "barrier 4", "exact drain (+barrier 5)", "statistics pass", "flush + Gram",
-         "barrier 6", "store issue"]
+         "queue push", "barrier 3", "retry drain (+barrier 4)", "statistics pass", "flush + Gram", "barrier 5 + store issue", "-", "-", "-"]
 tp = bench.true_params()
 dev = torch.device("cuda", 0)
 dY, dT, dX, off, n = bench.gen_shard_torch(tp, 0, 1, dev)
