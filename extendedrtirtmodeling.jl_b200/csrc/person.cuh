@@ -656,6 +656,30 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
   }
 
+    if (eval) {
+      // ---- Bernoulli log-likelihood of the current state (no draws) ----
+      const bool valid = (row0 + p) < A.n_local;
+      const R thp = s_u[p * Dgp + F + 1];
+      double llb = 0.0;
+      if (valid)
+        for (int kk = 0; kk < nk; ++kk) {
+          const int g = group_of<TPP>(q, kk);
+          if (g >= G) continue;
+          const Quad<R> pA = ld4(s_par + PAR_A * Jp + 4 * g);
+          const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
+          const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+#pragma unroll 1
+          for (int e = 0; e < 4; ++e) {
+            if (4 * g + e >= J) continue;
+            const double z = (double)fma(pA.v[e], thp, -pAB.v[e]);
+            const double y = ((yw >> (8 * e)) & 0xffu) ? 1.0 : 0.0;
+            const double az = fabs(z);
+            llb += y * z - (0.5 * (z + az) + log1p(exp(-az)));
+          }
+        }
+      acc_ll_bern += llb;
+    }
+
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
     if (e_active && !(ERIRT_DIAG & 2)) {
       for (int pp = er; pp < P; pp += Rc) {
