@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liberirt_b200.so")
 SOURCES = ["erirt_b200.cu"]
-HEADERS = ["rng.cuh", "pg.cuh", "pg_coeffs.h", "layout.cuh", "person.cuh", "global.cuh"]
+HEADERS = ["rng.cuh", "pg.cuh", "pg_fast.cuh", "pg_coeffs.h", "layout.cuh", "person.cuh", "person_fast.cuh", "global.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 

@@ -20,6 +20,7 @@
 #include "global.cuh"
 #include "layout.cuh"
 #include "person.cuh"
+#include "person_fast.cuh"
 
 using namespace erirt;
 
@@ -239,6 +240,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_acc_item = (int)o; o = align_up(o + (cqr ? 7 : (cross ? 6 : 5)) * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
   S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
+  S.off_tab = (int)o; if (rsz == 4 && !cross) o = align_up(o + 2 * (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response tables of the f32 fast kernel
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;
   return S;
@@ -254,8 +256,16 @@ static const void* person_kernel_ptr(int tpp) {
   }
 }
 // fam 0: the specialised kernel of the one-launch models; fam 1: Cross family and the evaluation stage
+static const void* person_fast_kernel_ptr(int tpp) {
+  switch (tpp) {
+    case 1: return (const void*)person_sweep_fast_kernel<1>;
+    case 2: return (const void*)person_sweep_fast_kernel<2>;
+    case 4: return (const void*)person_sweep_fast_kernel<4>;
+    default: return (const void*)person_sweep_fast_kernel<8>;
+  }
+}
 static const void* person_kernel_for(const erirt_handle* h, int fam) {
-  if (fam == 0) return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 0>(h->tpp) : person_kernel_ptr<double, 0>(h->tpp);
+  if (fam == 0) return h->cfg.dtype == ERIRT_F32 ? person_fast_kernel_ptr(h->tpp) : person_kernel_ptr<double, 0>(h->tpp);
   return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 1>(h->tpp) : person_kernel_ptr<double, 1>(h->tpp);
 }
 
@@ -644,6 +654,7 @@ static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   A.k1 = (1.0 - 2.0 * q) / (q * (1.0 - q));
   A.k2 = 2.0 / (q * (1.0 - q));
   A.key = make_key(h->cfg.seed, h->cfg.chain);
+  A.sched = make_sched(A.key);
   return A;
 }
 
@@ -968,7 +979,7 @@ extern "C" int erirt_k_pg(const double* z, int64_t rows, int32_t cols, int64_t r
   CU(cudaMemcpy(dz, z, n * sizeof(double), cudaMemcpyHostToDevice));
   const PhiloxKey key = make_key(seed, chain);
   const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  if (dtype == ERIRT_F32) k_pg_kernel<float><<<grid, 256>>>(dz, rows, cols, row0, key, sweep, dout);
+  if (dtype == ERIRT_F32) k_pg_fast_kernel<<<grid, 256>>>(dz, rows, cols, row0, key, sweep, dout);
   else k_pg_kernel<double><<<grid, 256>>>(dz, rows, cols, row0, key, sweep, dout);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost);

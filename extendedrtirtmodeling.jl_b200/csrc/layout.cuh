@@ -75,7 +75,7 @@ inline Layout make_layout(int J, int F) {
 struct SmemPlan {
   int P;  // persons per tile
   int tile_real_bytes, tile_y_bytes;
-  int off_omega, off_logt, off_nuc, off_y, off_par, off_u, off_sum, off_beta, off_acc_item, off_acc_gram, off_queue, off_misc, total;
+  int off_omega, off_logt, off_nuc, off_y, off_par, off_u, off_sum, off_beta, off_acc_item, off_acc_gram, off_queue, off_tab, off_misc, total;
   int Dgp;  // pitch of the U tile (elements)
 };
 
@@ -105,6 +105,7 @@ struct PersonArgs {
   int stage;  // 0: whole sweep in one launch; Cross family: 1 = K_a (theta + its statistics), 2 = K_b (zeta, omega, statistics)
   double k1, k2;
   PhiloxKey key;
+  PhiloxSched sched;  // key schedule of `key` (constant-bank operands of the hot Philox rounds)
 };
 
 struct GlobalArgs {

@@ -19,6 +19,7 @@
 #pragma once
 #include "layout.cuh"
 #include "pg.cuh"
+#include "pg_fast.cuh"
 
 namespace erirt {
 
@@ -111,25 +112,6 @@ __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& zc
   zs = rad * sin(ang);
 }
 
-// Retry of one PG cell whose attempt 0 was rejected, or of a Method-B cell (f32): attempts a = 1, 2, ... from the cell's
-// retry-site Philox blocks, evaluated with the same branch-free fast evaluation as the main pass.  Kept out of line: the
-// retry path is cold relative to the main pass and inlining it thrashes the instruction cache.
-__device__ __forceinline__ float pg_retry_fast_f32_inl(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z) {
-  if (!(z == z)) return z;  // poisoned state: do not spin
-  const bool method_b = 0.5f * fabsf(z) > (float)PG_CSWITCH;
-#pragma unroll 1
-  for (uint32_t a = 1; a < PG_MAX_ATTEMPTS; ++a) {
-    const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
-    float ll;
-    const float om = method_b ? pg_fast_attemptB(z, w) : pg_fast_attempt0(z, 0.f, w.x, w.y, ll);
-    if (om >= 0.f) return om;
-  }
-  return 0.25f * (float)PG_T;
-}
-// out-of-line copy for the cold call sites (queue overflow, test kernel)
-__device__ __noinline__ float pg_retry_fast_f32(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, float z) {
-  return pg_retry_fast_f32_inl(key, gid, sweep, j, z);
-}
 __device__ __noinline__ double pg_draw_cell_f64(PhiloxKey key, uint32_t gid, uint32_t sweep, int j, double z, uint32_t* na) {
   return pg_draw_exact<double>(key, gid, sweep, j, z, 0, na);
 }
@@ -540,9 +522,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       const bool valid = (row0 + p) < A.n_local;
       const uint32_t gid = A.person_offset + (uint32_t)(row0 + p);
       const R thp = s_u[p * Dgp + F + 1];
-      float ll_tile = 0.f;
+      float ll_tile = 0.f, ll_sabs = 0.f;
+      u64 ll_prod = bc2(1.0f);
+      int ll_npad = 0;
       uint32_t my_defer = 0;
-      unsigned long long defer_mask = 0ull;  // bit 4*kk+e: cell left the fast path (nk <= 16 by the TPP choice)
+      unsigned long long defer_mask = 0ull, rej_mask = 0ull;  // bit 4*kk+e: cell not certainly accepted / certainly rejected
       for (int kk = 0; kk < nk; ++kk) {
         const int g = group_of<TPP>(q, kk);
         if (g >= G) continue;
@@ -558,23 +542,26 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         if constexpr (F32) {
           const uint4 wA = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
           const uint4 wB = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
-          const uint32_t ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
           const int npad = 4 * g + 4 - J;  // > 0 only in groups holding padding cells
-          float llg = 0.f;
-          uint32_t m4 = 0;
+          float zs[4];
   #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float z = fmaf(pA.v[e], thp, -pAB.v[e]);
-            const float kap = ((yw >> (8 * e)) & 0xffu) ? 0.5f : -0.5f;
-            float ll;
-            float om = pg_fast_attempt0(z, kap, ww[2 * e], ww[2 * e + 1], ll);
-            if (npad > 0 && e >= 4 - npad) { om = 0.f; ll = 0.f; }  // padding cells never count
-            llg += ll;
-            if (om < 0.f) m4 |= 1u << e;
-            out.v[e] = om;
+            zs[e] = fmaf(pA.v[e], thp, -pAB.v[e]);
+            ll_tile = fmaf(((yw >> (8 * e)) & 0xffu) ? 0.5f : -0.5f, zs[e], ll_tile);  // kappa z
           }
-          ll_tile += llg;
-          defer_mask |= (unsigned long long)m4 << (4 * kk);
+          uint32_t dm = 0, rm = 0;
+          float o[4];
+          pg_fast_pair<0>(pk2(zs[0], zs[1]), wA.x, wA.y, wA.z, wA.w, o[0], o[1], dm, rm, ll_prod, ll_sabs);
+          pg_fast_pair<2>(pk2(zs[2], zs[3]), wB.x, wB.y, wB.z, wB.w, o[2], o[3], dm, rm, ll_prod, ll_sabs);
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!(fabsf(zs[e]) <= PG_Z0MAX)) { o[e] = -2.0f; dm |= 1u << e; rm |= 1u << e; }  // no attempt 0 beyond |z| = 16
+            if (npad > 0 && e >= 4 - npad) { o[e] = 0.f; dm &= ~(1u << e); ++ll_npad; }          // padding cells never count
+            out.v[e] = o[e];
+          }
+          rm &= dm;
+          defer_mask |= (unsigned long long)dm << (4 * kk);
+          rej_mask |= (unsigned long long)rm << (4 * kk);
         } else {
   #pragma unroll 1
           for (int e = 0; e < 4; ++e) {
@@ -591,70 +578,53 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         }
         st4(my_om + 4 * g, out);
       }
-      acc_ll_bern += (double)ll_tile;
       if constexpr (F32) {
-        // ---- hand the rejected / Method-B cells to the tile's retry queue: one shared-memory atomic per WARP reserves the
-      //      slots of all its lanes (warp prefix sum), then every lane writes its own entries ----
-      my_defer = (uint32_t)__popcll(defer_mask);
-      uint32_t pre = my_defer;
+        // kappa z - |z|/2 - ln(1 + e^{-|z|}); a padding cell has z = 0 and contributed -ln 2 through the product
+        if (valid) acc_ll_bern += (double)(ll_tile - 0.5f * ll_sabs - PGF_LN2 * (fast_lg2(lo2(ll_prod)) + fast_lg2(hi2(ll_prod)) - (float)ll_npad));
+        // ---- hand the cells that left the fast path to the tile's work queue: one shared-memory atomic per WARP reserves the
+        //      slots of all its lanes (warp prefix sum), then every lane writes its own entries (bit 31: replay attempt 0) ----
+        my_defer = (uint32_t)__popcll(defer_mask);
+        uint32_t pre = my_defer;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
-        if ((tid & 31) >= o) pre += t;
-      }
-      const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
-      uint32_t wbase = 0;
-      if ((tid & 31) == 31 && wtotal) wbase = atomicAdd(&s_qctl[0], wtotal);
-      wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      uint32_t slot = wbase + pre - my_defer;
-      while (defer_mask) {
-        const int bit = __ffsll((long long)defer_mask) - 1;
-        defer_mask &= defer_mask - 1ull;
-        const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
-        if (slot < (uint32_t)QCAP) s_queue[slot] = ((uint32_t)p << 16) | (uint32_t)j;
-        else {  // queue overflow: finish the cell here
-          const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
-          my_om[j] = (R)pg_retry_fast_f32(A.key, gid, k + 1, j, z);
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+          if ((tid & 31) >= o) pre += t;
         }
-        ++slot;
-      }
-    }
-    acc_defer += my_defer;
-    __syncthreads();
-
-    if constexpr (F32) {
-      // ---- drain: a strided share of the queue per thread, two cells in flight per thread (two independent Philox /
-      //      attempt chains interleave, which halves the latency-bound time of this phase) ----
-      const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
-      for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
-        const bool has2 = idx + CTA_THREADS < qn;
-        const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
-        const int j1 = (int)(e1 & 0xffffu), p1 = (int)(e1 >> 16), j2 = (int)(e2 & 0xffffu), p2 = (int)(e2 >> 16);
-        const float z1 = fmaf((float)s_par[PAR_A * Jp + j1], (float)s_u[p1 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j1]);
-        const float z2 = fmaf((float)s_par[PAR_A * Jp + j2], (float)s_u[p2 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j2]);
-        const uint32_t g1 = A.person_offset + (uint32_t)(row0 + p1), g2 = A.person_offset + (uint32_t)(row0 + p2);
-        const bool b1 = 0.5f * fabsf(z1) > (float)PG_CSWITCH, b2 = 0.5f * fabsf(z2) > (float)PG_CSWITCH;
-        float om1 = (z1 == z1) ? -2.0f : z1, om2 = (has2 && z2 == z2) ? -2.0f : 0.0f;  // NaN state is passed through
-#pragma unroll 1
-        for (uint32_t a = 1; a < PG_MAX_ATTEMPTS && (om1 < 0.f || om2 < 0.f); ++a) {
-          const uint4 w1 = philox(A.key, g1, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j1), a);
-          const uint4 w2 = philox(A.key, g2, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j2), a);
-          float ll;
-          float o1 = pg_fast_attempt0(z1, 0.f, w1.x, w1.y, ll);
-          float o2 = pg_fast_attempt0(z2, 0.f, w2.x, w2.y, ll);
-          if (b1) o1 = pg_fast_attemptB(z1, w1);
-          if (b2) o2 = pg_fast_attemptB(z2, w2);
-          if (om1 < 0.f) om1 = o1;
-          if (om2 < 0.f) om2 = o2;
+        const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
+        uint32_t wbase = 0;
+        if ((tid & 31) == 31 && wtotal) wbase = atomicAdd(&s_qctl[0], wtotal);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        uint32_t slot = wbase + pre - my_defer;
+        while (defer_mask) {
+          const int bit = __ffsll((long long)defer_mask) - 1;
+          defer_mask &= defer_mask - 1ull;
+          const bool replay0 = !((rej_mask >> bit) & 1ull);
+          const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
+          if (slot < (uint32_t)QCAP) s_queue[slot] = ((uint32_t)p << 16) | (uint32_t)j | (replay0 ? 0x80000000u : 0u);
+          else {  // queue overflow: finish the cell here
+            const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+            my_om[j] = (R)pg_resolve_f32(A.key, gid, k + 1, j, z, replay0);
+          }
+          ++slot;
         }
-        if (om1 < 0.f) om1 = 0.25f * (float)PG_T;
-        if (om2 < 0.f) om2 = 0.25f * (float)PG_T;
-        s_om[p1 * Jp + j1] = (R)om1;
-        if (has2) s_om[p2 * Jp + j2] = (R)om2;
+      } else {
+        acc_ll_bern += (double)ll_tile;
       }
+      acc_defer += my_defer;
       __syncthreads();
+
+      if constexpr (F32) {
+        // ---- drain: a strided share of the queue per thread ----
+        const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
+        for (uint32_t idx = tid; idx < qn; idx += CTA_THREADS) {
+          const uint32_t e1 = s_queue[idx];
+          const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
+          const float z1 = fmaf((float)s_par[PAR_A * Jp + j1], (float)s_u[p1 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j1]);
+          s_om[p1 * Jp + j1] = (R)pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, (e1 >> 31) != 0u);
+        }
+        __syncthreads();
+      }
     }
-  }
 
     if (eval) {
       // ---- Bernoulli log-likelihood of the current state (no draws) ----
@@ -794,14 +764,7 @@ __global__ void k_pg_kernel(const double* z, int64_t rows, int cols, int64_t row
     const uint32_t gid = (uint32_t)(row0 + i);
     const R zz = (R)z[t];
     R om;
-    if constexpr (sizeof(R) == 4) {
-      const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
-      float ll;
-      om = (j & 1) ? pg_fast_attempt0(zz, 0.5f, w.z, w.w, ll) : pg_fast_attempt0(zz, 0.5f, w.x, w.y, ll);
-      if (om < 0.f) om = pg_retry_fast_f32(key, gid, sweep, j, zz);  // same path as the sampler's retry queue
-    } else {
-      om = pg_draw_exact<R>(key, gid, sweep, j, zz, 0);
-    }
+    om = pg_draw_exact<R>(key, gid, sweep, j, zz, 0);  // f64 only; the f32 test kernel is k_pg_fast_kernel (person_fast.cuh)
     out[t] = (double)om;
   }
 }

@@ -1,0 +1,579 @@
+// person_fast.cuh -- the f32 person-sweep kernel of the one-launch models (MlIrt, RtIrt, RtIrtNull, Latent, LatentQr):
+// the hot configuration (BASELINE config 5 = LatentQr, 1M x 100, f32).  Same statement, data layout, Philox stream and
+// statistics as person_sweep_kernel<float, TPP, 0> (person.cuh, which remains the f64 / Cross-family kernel); what differs
+// is the instruction schedule of the per-cell loops:
+//   * all per-cell arithmetic runs two cells per instruction on the packed FP32 pipe (FFMA2/FMUL2/FADD2, pg_fast.cuh);
+//   * attempt 0 of the PG draw decides only "certainly accepted" / "certainly rejected" with constant bounds of a_1/a_0
+//     (6 MUFU per cell instead of 10); undecided cells (0.5 %) are replayed with the a_1 term from a second work queue;
+//   * the Bernoulli log-likelihood  sum kappa z - |z|/2 - ln(1 + e^{-|z|})  is accumulated as a product of (1 + e^{-|z|})
+//     (one lg2 per row instead of one per cell) and  sum_j kappa_ij z_ij  comes from 16-entry tables indexed by the four
+//     responses of an item group (T_a[g][y] = sum_e kappa_e a_e, T_b[g][y] = -sum_e kappa_e a_e b_e), which also give the
+//     row sum  sum_j a_j kappa_ij  of drawSubjAbility (Draw.pl.jl:56) without touching the individual responses.
+#pragma once
+#include "person.cuh"
+#include "pg_fast.cuh"
+
+namespace erirt {
+
+constexpr int TAB_PITCH = 20;  // floats per item group in the response tables: groups g and g+4 fall on disjoint banks
+constexpr int QSTD = 768;      // work-queue split: [0, QSTD) certainly-rejected cells, [QSTD, QCAP) undecided / Method-B cells
+
+__device__ __forceinline__ uint32_t y_nibble(uint32_t yw) { return (yw * 0x01020408u) >> 24; }  // bytes 0/1 -> 4-bit index
+
+template <int TPP>
+__global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sweep_fast_kernel(const PersonArgs<float> A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int P = CTA_THREADS / TPP;
+  typedef float R;
+  const Layout& L = A.L;
+  const int J = L.J, Jp = L.Jp, F = L.F, Dg = L.Dg, Dgp = A.S.Dgp, G = Jp / 4;
+  const int model = A.model;
+  const bool has_rt = model != M_MLIRT;
+  const bool latent = model == M_LATENT || model == M_LATENTQR;
+  const bool qr = model == M_LATENTQR;
+  const bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
+
+  R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
+  R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
+  uint8_t* s_y = smem + A.S.off_y;
+  R* s_par = reinterpret_cast<R*>(smem + A.S.off_par);  // PAR_A: a, PAR_AB: -a b, PAR_A2: a^2, PAR_A2B: a^2 b, PAR_IS2: 1/sigma2
+  R* s_u = reinterpret_cast<R*>(smem + A.S.off_u);
+  R* s_sum = reinterpret_cast<R*>(smem + A.S.off_sum);    // [P][4] row sums handed to the person phase
+  R* s_beta = reinterpret_cast<R*>(smem + A.S.off_beta);  // beta (MAXD) then vec(Sigma) (4)
+  R* s_ta = reinterpret_cast<R*>(smem + A.S.off_tab);     // [G][TAB_PITCH]  sum_e kappa_e a_e
+  R* s_tb = s_ta + G * TAB_PITCH;                         // [G][TAB_PITCH] -sum_e kappa_e a_e b_e
+  double* s_acc_item = reinterpret_cast<double*>(smem + A.S.off_acc_item);
+  double* s_acc_gram = reinterpret_cast<double*>(smem + A.S.off_acc_gram);
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + A.S.off_queue);
+  double* s_miscd = reinterpret_cast<double*>(smem + A.S.off_misc);  // MD_COUNT + SC_COUNT doubles
+  double* s_scal = s_miscd + MD_COUNT;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scal + SC_COUNT);
+  uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);  // [0]: packed counts (low 16 bits standard, high 16 bits special)
+
+  const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  const uint32_t k = *A.sweep_ctr;
+  const bool do_draws = k >= 1;
+  const double* par = A.params;
+
+  // ---- stage item / structural parameters (state k), the response tables, and clear the accumulators ----
+  for (int j = tid; j < Jp; j += CTA_THREADS) {
+    double a = 0, b = 0, is2 = 0;
+    if (j < J) {
+      a = par[L.p_a + j];
+      b = par[L.p_b + j];
+      if (has_rt) is2 = 1.0 / par[L.p_sigma2 + j];
+    }
+    s_par[PAR_A * Jp + j] = (R)a;
+    s_par[PAR_AB * Jp + j] = (R)(-a * b);
+    s_par[PAR_A2 * Jp + j] = (R)(a * a);
+    s_par[PAR_A2B * Jp + j] = (R)(a * a * b);
+    s_par[PAR_IS2 * Jp + j] = (R)is2;
+  }
+  for (int t = tid; t < G * 16; t += CTA_THREADS) {
+    const int g = t >> 4, yb = t & 15;
+    double ta = 0, tb = 0;
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * g + e;
+      if (j < J) {
+        const double kap = ((yb >> e) & 1) ? 0.5 : -0.5, a = par[L.p_a + j];
+        ta += kap * a;
+        tb -= kap * a * par[L.p_b + j];
+      }
+    }
+    s_ta[g * TAB_PITCH + yb] = (R)ta;
+    s_tb[g * TAB_PITCH + yb] = (R)tb;
+  }
+  if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
+  if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
+  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
+  for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
+  if (tid < SC_COUNT) s_scal[tid] = 0.0;
+  if (tid < 32) {  // sum_j 1/sigma2_j, sum_j lambda_j/sigma2_j (f64), and the bound |z_ij| <= max|a| |theta_i| + max|a b|
+    double s1 = 0, s2 = 0, amax = 0, abmax = 0;
+    for (int j = tid; j < J; j += 32) {
+      const double a = par[L.p_a + j], b = par[L.p_b + j];
+      amax = fmax(amax, fabs(a));
+      abmax = fmax(abmax, fabs(a * b));
+      if (has_rt) {
+        const double is2 = 1.0 / par[L.p_sigma2 + j];
+        s1 += is2;
+        s2 += par[L.p_lambda + j] * is2;
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      abmax = fmax(abmax, __shfl_xor_sync(0xffffffffu, abmax, o));
+    }
+    if (tid == 0) {
+      s_miscd[MD_SUM_IS2] = s1;
+      s_miscd[MD_SUM_RHO_IS2] = s2;  // this kernel: sum_j lambda_j / sigma2_j
+      s_miscd[MD_SUM_LOGS2K] = amax;
+      s_miscd[MD_SUM_LOGS2K + 1] = abmax;
+      mbar_init(s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  const R sum_is2 = (R)s_miscd[MD_SUM_IS2], sum_lam_is2 = (R)s_miscd[MD_SUM_RHO_IS2];
+  const R z_amax = (R)s_miscd[MD_SUM_LOGS2K], z_abmax = (R)s_miscd[MD_SUM_LOGS2K + 1];
+  const R S11 = s_beta[MAXD + 0], S12 = s_beta[MAXD + 2], S22 = s_beta[MAXD + 3];
+  const R k1 = (R)A.k1, k2 = (R)A.k2;
+  const int pb = F + 1;  // length of one regression block [1 X]
+  const uint32_t iter_m = do_draws ? (k - 1) / (uint32_t)A.n_chain + 1 : 0;  // m of sweep k
+  const bool post_burnin = do_draws && iter_m > (uint32_t)A.n_burnin;
+
+  double acc_ll_bern = 0.0, acc_ll_struct = 0.0;
+  uint32_t acc_defer = 0, acc_cells = 0;
+  uint32_t parity = 0;
+  const uint32_t load_bytes = (uint32_t)(A.S.tile_real_bytes * (has_rt ? 2 : 1) + A.S.tile_y_bytes);
+  const int nk = ((G + 7) / 8) * (8 / TPP);  // steps per thread over its 4-item groups (nk <= 16 by the TPP choice)
+
+  // cells of this thread that are real items (bit 4*kk+e), and the number of padding cells it walks over
+  u64 valid_mask = 0ull;
+  int n_pad_cells = 0;
+  for (int kk = 0; kk < nk; ++kk) {
+    const int g = group_of<TPP>(q, kk);
+    if (g >= G) continue;
+    for (int e = 0; e < 4; ++e) {
+      if (4 * g + e < J) valid_mask |= 1ull << (4 * kk + e);
+      else ++n_pad_cells;
+    }
+  }
+
+  // transposed-statistics role of this thread: item group eg, person class er (G <= CTA_THREADS is enforced by the host)
+  const int Rc = CTA_THREADS / G;
+  const bool e_active = tid < G * Rc;
+  const int eg = tid % G, er = tid / G;
+  u64 a0l = 0ull, a0h = 0ull, a1l = 0ull, a1h = 0ull, a2l = 0ull, a2h = 0ull, acl = 0ull, ach = 0ull;  // {items 0,1} / {items 2,3}
+  R ay[4] = {0, 0, 0, 0};
+  auto flush_item_stats = [&]() {
+    if (e_active) {
+      const R v0[4] = {lo2(a0l), hi2(a0l), lo2(a0h), hi2(a0h)}, v1[4] = {lo2(a1l), hi2(a1l), lo2(a1h), hi2(a1h)};
+      const R v2[4] = {lo2(a2l), hi2(a2l), lo2(a2h), hi2(a2h)}, vc[4] = {lo2(acl), hi2(acl), lo2(ach), hi2(ach)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * eg + e;
+        atomicAdd(&s_acc_item[0 * Jp + j], (double)v0[e]);
+        atomicAdd(&s_acc_item[1 * Jp + j], (double)v1[e]);
+        atomicAdd(&s_acc_item[2 * Jp + j], (double)v2[e]);
+        atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
+        atomicAdd(&s_acc_item[4 * Jp + j], (double)vc[e]);
+        ay[e] = R(0);
+      }
+      a0l = a0h = a1l = a1h = a2l = a2h = acl = ach = 0ull;
+    }
+  };
+
+  int tiles_done = 0;
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tiles_done) {
+    const int64_t row0 = (int64_t)tile * P;
+    if (tid == 0) {
+      tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
+      mbar_expect_tx(s_bar, load_bytes);
+      tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
+      s_qctl[0] = 0;
+    }
+    // ---- person phase, part 1 (one thread per person, coalesced): state k-1, regression means, the person's variates ----
+    const int64_t pi = row0 + tid;
+    const bool pvalid = tid < P && pi < A.n_local;
+    const uint32_t pgid = A.person_offset + (uint32_t)pi;
+    R th = R(0), ze = R(0), nu = R(1), xb1 = R(0), xb2 = R(0);
+    R zn_theta = R(0), zn_zeta = R(0), zn_nu = R(0), un_nu = R(0);
+    if (tid < P) {
+      if (do_draws) {
+        const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
+        zn_theta = normal2f(w.x, w.y);
+        zn_zeta = normal2f(w.z, w.w);
+      }
+      if (qr) {
+        const uint4 w = philox(A.key, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+        zn_nu = normal2f(w.x, w.y);
+        un_nu = u01f(w.z);
+      }
+      th = A.theta[pi];
+      if (has_rt) ze = A.zeta[pi];
+      if (qr) nu = A.nu[pi];
+      if (reg_x) xb1 = s_beta[0];
+      if (model == M_RTIRT) xb2 = s_beta[pb];
+      for (int f = 0; f < F; ++f) {
+        const R x = A.X[(int64_t)f * A.n_pad + pi];
+        s_u[tid * Dgp + 1 + f] = pvalid ? x : R(0);
+        if (reg_x) xb1 = fmaf(x, s_beta[1 + f], xb1);
+        if (model == M_RTIRT) xb2 = fmaf(x, s_beta[pb + 1 + f], xb2);
+      }
+    }
+    mbar_wait(s_bar, parity);
+    parity ^= 1u;
+
+    R* my_om = s_om + p * Jp;
+    const R* my_lt = s_lt + p * Jp;
+    const uint8_t* my_y = s_y + p * Jp;
+
+    if (do_draws) {
+      // ---- row sums over items (Draw.pl.jl:55-56, 137-138), TPP threads per person, two items per instruction ----
+      u64 sA2 = 0ull, sAB = 0ull, sLT = 0ull;
+      R sAK = R(0);
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+        const float4 om = *reinterpret_cast<const float4*>(my_om + 4 * g);
+        const float4 pA2 = *reinterpret_cast<const float4*>(s_par + PAR_A2 * Jp + 4 * g);
+        const float4 pA2B = *reinterpret_cast<const float4*>(s_par + PAR_A2B * Jp + 4 * g);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+        const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w);
+        sA2 = ffma2(pk2(pA2.x, pA2.y), o01, sA2);
+        sA2 = ffma2(pk2(pA2.z, pA2.w), o23, sA2);
+        sAB = ffma2(pk2(pA2B.x, pA2B.y), o01, sAB);
+        sAB = ffma2(pk2(pA2B.z, pA2B.w), o23, sAB);
+        sAK += s_ta[g * TAB_PITCH + y_nibble(yw)];
+        if (has_rt) {
+          const float4 lt = *reinterpret_cast<const float4*>(my_lt + 4 * g);
+          const float4 pI = *reinterpret_cast<const float4*>(s_par + PAR_IS2 * Jp + 4 * g);
+          sLT = ffma2(pk2(pI.x, pI.y), pk2(lt.x, lt.y), sLT);
+          sLT = ffma2(pk2(pI.z, pI.w), pk2(lt.z, lt.w), sLT);
+        }
+      }
+      R rA2 = lo2(sA2) + hi2(sA2), rAB = lo2(sAB) + hi2(sAB), rLT = lo2(sLT) + hi2(sLT);
+#pragma unroll
+      for (int o = 1; o < TPP; o <<= 1) {
+        rA2 += __shfl_xor_sync(0xffffffffu, rA2, o);
+        rAB += __shfl_xor_sync(0xffffffffu, rAB, o);
+        sAK += __shfl_xor_sync(0xffffffffu, sAK, o);
+        rLT += __shfl_xor_sync(0xffffffffu, rLT, o);
+      }
+      if (q == 0) *reinterpret_cast<float4*>(s_sum + 4 * p) = make_float4(rA2, rAB, sAK, sum_lam_is2 - rLT);
+      __syncthreads();
+      // ---- person phase, part 2: theta_k, zeta_k, structural log-density, moments ----
+      if (tid < P) {
+        const float4 d = *reinterpret_cast<const float4*>(s_sum + 4 * tid);
+        {
+          const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
+          const R var0 = (model == M_MLIRT) ? R(1) : S11;
+          const R iv0 = rdiv(R(1), var0);
+          const R parV = rdiv(R(1), iv0 + d.x);
+          const R parM = parV * (mu0 * iv0 + d.z + d.y);
+          th = parM + rsqrt_of(parV) * zn_theta;
+        }
+        R mu_z = R(0), var_z = R(1);
+        if (has_rt) {
+          if (model == M_RTIRT) { mu_z = xb2; var_z = S22; }
+          else if (latent) {
+            mu_z = fmaf(th, s_beta[F + 1], xb1);
+            var_z = S22;
+            if (qr) { mu_z = fmaf(k1, nu, mu_z); var_z = S22 * (k2 * nu); }
+          } else { mu_z = R(0); var_z = R(1); }  // RtIrtNull, Draw.pl.jl:120-121
+          const R ivz = rdiv(R(1), var_z);
+          const R parV = rdiv(R(1), ivz + sum_is2);
+          const R parM = parV * (mu_z * ivz + d.w);
+          ze = parM + rsqrt_of(parV) * zn_zeta;
+        }
+        if (pvalid) {
+          const R LOG2PI = R(1.8378770664093454835606594728112);
+          R ls;
+          if (model == M_MLIRT) {
+            const R r = th - xb1;
+            ls = R(-0.5) * LOG2PI - R(0.5) * r * r;
+          } else if (latent) {
+            const R r = ze - mu_z;
+            ls = R(-0.5) * (LOG2PI + rlog(var_z)) - R(0.5) * r * rdiv(r, var_z);
+          } else {
+            const R e1 = th - (model == M_RTIRT ? xb1 : R(0));
+            const R e2 = ze - (model == M_RTIRT ? xb2 : R(0));
+            const R det = S11 * S22 - S12 * S12;
+            ls = -LOG2PI - R(0.5) * rlog(det) - R(0.5) * rdiv(S22 * e1 * e1 - R(2) * S12 * e1 * e2 + S11 * e2 * e2, det);
+          }
+          acc_ll_struct += (double)ls;
+          A.theta[pi] = th;
+          if (has_rt) A.zeta[pi] = ze;
+          if (post_burnin) {
+            double* m = A.mom + pi;  // fire-and-forget reductions (RED.ADD.F64): no round trip on the critical path
+            atomicAdd(&m[0], (double)th);
+            atomicAdd(&m[A.n_pad], (double)th * (double)th);
+            if (has_rt) {
+              atomicAdd(&m[2 * A.n_pad], (double)ze);
+              atomicAdd(&m[3 * A.n_pad], (double)ze * (double)ze);
+            }
+            if (qr) {
+              atomicAdd(&m[4 * A.n_pad], (double)nu);
+              atomicAdd(&m[5 * A.n_pad], (double)nu * (double)nu);
+            }
+          }
+          if (A.ptrace) {
+            R* t = A.ptrace + ((int64_t)(k - 1) * 3) * A.n_pad + pi;
+            t[0] = th;
+            t[A.n_pad] = ze;
+            t[2 * A.n_pad] = nu;
+          }
+        }
+      }
+    }
+    if (tid < P) {
+      // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
+      if (qr) {
+        const R xb = fmaf(th, s_beta[F + 1], xb1);
+        const R isc = rdiv(R(1), rsqrt_of(S22 * k2));
+        const R parA = fabsf(ze - xb) * isc;
+        const R parB = rsqrt_of(R(2) * k2 + k1 * k1) * isc;
+        R mu = rdiv(parB, parA);
+        if (!(mu >= R(1e-10))) mu = R(1e-10);
+        const R ig = ig_msh<R>(mu, parB * parB, zn_nu, un_nu);
+        nu = rdiv(R(1), ig);
+        nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
+        if (pvalid) A.nu[pi] = nu;
+      }
+      R* u = s_u + tid * Dgp;
+      u[0] = pvalid ? R(1) : R(0);
+      u[F + 1] = pvalid ? th : R(0);
+      u[F + 2] = pvalid ? ze : R(0);
+      u[F + 3] = (pvalid && qr) ? nu : R(0);
+      u[F + 4] = (pvalid && qr) ? rdiv(R(1), nu) : R(0);  // weight of the nu-weighted Gram
+      if (pvalid) acc_cells += (uint32_t)J;
+    }
+    __syncthreads();
+
+    // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
+    const bool valid = (row0 + p) < A.n_local;
+    const uint32_t gid = A.person_offset + (uint32_t)(row0 + p);
+    const R thp = s_u[p * Dgp + F + 1];
+    u64 dmask = 0ull, rmask = 0ull;  // bit 4*kk+e: cell not certainly accepted / certainly rejected
+    if (valid) {
+      const bool wide = !(fmaf(z_amax, fabsf(thp), z_abmax) <= PG_Z0MAX);  // some |z| of this row may exceed the attempt-0 range
+      const u64 TH = bc2(thp);
+      u64 prod = bc2(1.0f);
+      R sabs = R(0), skz = R(0);
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+        const float4 pA = *reinterpret_cast<const float4*>(s_par + PAR_A * Jp + 4 * g);
+        const float4 pN = *reinterpret_cast<const float4*>(s_par + PAR_AB * Jp + 4 * g);
+        const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * g));
+        skz += fmaf(thp, s_ta[g * TAB_PITCH + yb], s_tb[g * TAB_PITCH + yb]);  // sum_e kappa_e z_e of this group
+        const u64 z01 = ffma2(pk2(pA.x, pA.y), TH, pk2(pN.x, pN.y)), z23 = ffma2(pk2(pA.z, pA.w), TH, pk2(pN.z, pN.w));
+        const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
+        const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
+        float4 out;
+        uint32_t dm = 0, rm = 0;
+        pg_fast_pair<0>(z01, wA.x, wA.y, wA.z, wA.w, out.x, out.y, dm, rm, prod, sabs);
+        pg_fast_pair<2>(z23, wB.x, wB.y, wB.z, wB.w, out.z, out.w, dm, rm, prod, sabs);
+        if (wide) {  // attempt 0 does not exist beyond |z| = 16: straight to the retry blocks
+          const R zs[4] = {lo2(z01), hi2(z01), lo2(z23), hi2(z23)};
+          R* o = &out.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (!(fabsf(zs[e]) <= PG_Z0MAX)) { o[e] = -2.0f; dm |= 1u << e; rm |= 1u << e; }
+        }
+        *reinterpret_cast<float4*>(my_om + 4 * g) = out;
+        dmask |= (u64)dm << (4 * kk);
+        rmask |= (u64)rm << (4 * kk);
+      }
+      // kappa z - |z|/2 - ln(1 + e^{-|z|}); a padding cell has z = 0 and contributed -ln 2
+      const R ll_row = skz - R(0.5) * sabs - PGF_LN2 * (fast_lg2(lo2(prod)) + fast_lg2(hi2(prod)) - (R)n_pad_cells);
+      acc_ll_bern += (double)ll_row;
+      dmask &= valid_mask;
+      rmask &= dmask;
+    }
+    if (!valid || n_pad_cells) {  // padding persons / padding items hold omega = 0
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (!valid || 4 * g + e >= J) my_om[4 * g + e] = R(0);
+      }
+    }
+    {
+      // ---- hand the cells that left the fast path to the tile's work queues: one shared-memory atomic per WARP reserves the
+      //      slots of all its lanes in both queues (packed counts, warp prefix sum), then every lane writes its entries ----
+      const u64 smask = dmask & rmask, umask = dmask & ~rmask;  // standard (certainly rejected) / special (undecided)
+      const uint32_t n_std = (uint32_t)__popcll(smask), n_spc = (uint32_t)__popcll(umask);
+      acc_defer += n_std + n_spc;
+      uint32_t pre = n_std | (n_spc << 16);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+        if ((tid & 31) >= o) pre += t;
+      }
+      const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
+      uint32_t wbase = 0;
+      if ((tid & 31) == 31 && wtotal) wbase = atomicAdd(&s_qctl[0], wtotal);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      uint32_t slot_s = (wbase & 0xffffu) + (pre & 0xffffu) - n_std;
+      uint32_t slot_u = (wbase >> 16) + (pre >> 16) - n_spc;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t ms = (uint32_t)(smask >> (32 * half)), mu = (uint32_t)(umask >> (32 * half));
+        while (ms | mu) {
+          const bool special = ms == 0u;  // this lane drains its standard bits first
+          uint32_t& m = special ? mu : ms;
+          const int bit = __ffs((int)m) - 1 + 32 * half;
+          m &= m - 1u;
+          const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
+          const uint32_t entry = ((uint32_t)p << 16) | (uint32_t)j;
+          uint32_t& slot = special ? slot_u : slot_s;
+          const uint32_t cap = special ? (uint32_t)(QCAP - QSTD) : (uint32_t)QSTD;
+          if (slot < cap) s_queue[(special ? QSTD : 0) + slot] = entry | (special ? 0x80000000u : 0u);
+          else {  // queue overflow: finish the cell here
+            const float z = fmaf(s_par[PAR_A * Jp + j], thp, s_par[PAR_AB * Jp + j]);
+            my_om[j] = pg_resolve_f32(A.key, gid, k + 1, j, z, special);
+          }
+          ++slot;
+        }
+      }
+    }
+    __syncthreads();
+
+    {
+      // ---- standard queue: Method-A retry rounds, two cells in flight per thread; Method-B cells are forwarded ----
+      const uint32_t qc = s_qctl[0];
+      const uint32_t qn = min(qc & 0xffffu, (uint32_t)QSTD);
+      for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
+        const bool has2 = idx + CTA_THREADS < qn;
+        const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
+        const int j1 = (int)(e1 & 0xffffu), p1 = (int)(e1 >> 16), j2 = (int)(e2 & 0xffffu), p2 = (int)(e2 >> 16);
+        const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
+        const float z2 = fmaf(s_par[PAR_A * Jp + j2], s_u[p2 * Dgp + F + 1], s_par[PAR_AB * Jp + j2]);
+        const uint32_t g1 = A.person_offset + (uint32_t)(row0 + p1), g2 = A.person_offset + (uint32_t)(row0 + p2);
+        const bool b1 = !(0.5f * fabsf(z1) <= (float)PG_CSWITCH), b2 = !(0.5f * fabsf(z2) <= (float)PG_CSWITCH);  // Method B or NaN
+        float om1 = b1 ? 0.0f : -2.0f, om2 = (has2 && !b2) ? -2.0f : 0.0f;
+#pragma unroll 1
+        for (uint32_t r = 1; r < PG_MAX_ATTEMPTS && (om1 < 0.f || om2 < 0.f); ++r) {
+          const uint4 w1 = philox(A.sched, g1, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j1), r);
+          const uint4 w2 = philox(A.sched, g2, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j2), r);
+          const float o1 = pg_exact_pair(z1, w1.x, w1.y, w1.z, w1.w);
+          const float o2 = pg_exact_pair(z2, w2.x, w2.y, w2.z, w2.w);
+          if (om1 < 0.f) om1 = o1;
+          if (om2 < 0.f) om2 = o2;
+        }
+        if (om1 < 0.f) om1 = 0.25f * (float)PG_T;
+        if (om2 < 0.f) om2 = 0.25f * (float)PG_T;
+        if (!b1) s_om[p1 * Jp + j1] = om1;
+        if (has2 && !b2) s_om[p2 * Jp + j2] = om2;
+        if (b1 || (has2 && b2)) {  // rare: forward to the special queue (or finish here when it is full)
+          if (b1) {
+            const uint32_t s = atomicAdd(&s_qctl[0], 0x10000u) >> 16;
+            if (s < (uint32_t)(QCAP - QSTD)) s_queue[QSTD + s] = e1;
+            else s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, g1, k + 1, j1, z1, false);
+          }
+          if (has2 && b2) {
+            const uint32_t s = atomicAdd(&s_qctl[0], 0x10000u) >> 16;
+            if (s < (uint32_t)(QCAP - QSTD)) s_queue[QSTD + s] = e2;
+            else s_om[p2 * Jp + j2] = pg_resolve_f32(A.key, g2, k + 1, j2, z2, false);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    {
+      // ---- special queue: undecided attempt 0 (bit 31: replay it with the a_1 term) and Method-B cells ----
+      const uint32_t qn = min(s_qctl[0] >> 16, (uint32_t)(QCAP - QSTD));
+      for (uint32_t idx = tid; idx < qn; idx += CTA_THREADS) {
+        const uint32_t e1 = s_queue[QSTD + idx];
+        const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
+        const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
+        s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, (e1 >> 31) != 0u);
+      }
+    }
+    __syncthreads();
+
+    // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
+    if (e_active) {
+      for (int pp = er; pp < P; pp += Rc) {
+        const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
+        const float4 om = *reinterpret_cast<const float4*>(s_om + pp * Jp + 4 * eg);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * eg);
+        const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w), T1 = bc2(tp), T2 = bc2(tp * tp);
+        a0l = fadd2(a0l, o01);
+        a0h = fadd2(a0h, o23);
+        a1l = ffma2(T1, o01, a1l);
+        a1h = ffma2(T1, o23, a1h);
+        a2l = ffma2(T2, o01, a2l);
+        a2h = ffma2(T2, o23, a2h);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
+        if (has_rt) {
+          const float4 lt = *reinterpret_cast<const float4*>(s_lt + pp * Jp + 4 * eg);
+          const u64 Z = bc2(zp);
+          acl = ffma2(pk2(lt.x, lt.y), Z, acl);
+          ach = ffma2(pk2(lt.z, lt.w), Z, ach);
+        }
+      }
+    }
+    if ((tiles_done % STAT_FLUSH_TILES) == STAT_FLUSH_TILES - 1) flush_item_stats();
+    // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin: entry t is shared by the 4 lanes of a quad (persons
+    // pp = lane mod 4 (mod 4)), so that all four warps of the CTA take part instead of one
+    for (int t0 = 0; t0 < L.ntri; t0 += CTA_THREADS / 4) {
+      const int t = t0 + (tid >> 2);
+      double g0 = 0.0, g1 = 0.0;
+      if (t < L.ntri) {
+        int r = 0, rem = t;
+        while (rem >= Dg - r) { rem -= Dg - r; ++r; }
+        const int c = r + rem;
+        for (int pp = tid & 3; pp < P; pp += 4) {
+          const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
+          g0 += ur * uc;
+          if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
+        }
+      }
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 1);
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 2);
+      if (qr) {
+        g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, 2);
+      }
+      if (t < L.ntri && (tid & 3) == 0) {
+        s_acc_gram[t] += g0;
+        if (qr) s_acc_gram[L.ntri + t] += g1;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
+  }
+  flush_item_stats();
+
+  // ---- flush CTA accumulators ----
+  atomicAdd(&s_scal[SC_LL_BERN], acc_ll_bern);
+  if (tid < P) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
+  atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
+  if (tid < P) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
+  __syncthreads();
+  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
+    const int j = t % Jp;
+    if (j < J) atomicAdd(&A.stats[L.s_S0 + t], s_acc_item[t]);
+  }
+  for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS)
+    if (t < L.ntri || qr) atomicAdd(&A.stats[L.s_gram + t], s_acc_gram[t]);
+  if (tid < SC_COUNT) atomicAdd(&A.stats[L.s_scal + tid], s_scal[tid]);
+  if (tid == 0) tma_store_wait_all();
+}
+
+// ---------------- parity / distribution-test kernel of the f32 PG path: the same functions as the sampler ----------------
+__global__ void k_pg_fast_kernel(const double* z, int64_t rows, int cols, int64_t row0, PhiloxKey key, uint32_t sweep, double* out) {
+  const int pairs = (cols + 1) / 2;
+  const int64_t n = rows * pairs;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / pairs;
+    const int j0 = 2 * (int)(t % pairs);
+    const bool has1 = j0 + 1 < cols;
+    const uint32_t gid = (uint32_t)(row0 + i);
+    const float za = (float)z[i * cols + j0], zb = has1 ? (float)z[i * cols + j0 + 1] : 0.f;
+    const uint4 w = philox(key, gid, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j0 >> 1)), 0);
+    float oa, ob, sabs = 0.f;
+    uint32_t dm = 0, rm = 0;
+    u64 prod = bc2(1.0f);
+    pg_fast_pair<0>(pk2(za, zb), w.x, w.y, w.z, w.w, oa, ob, dm, rm, prod, sabs);
+    if (!(fabsf(za) <= PG_Z0MAX)) { dm |= 1u; rm |= 1u; }
+    if (!(fabsf(zb) <= PG_Z0MAX)) { dm |= 2u; rm |= 2u; }
+    if (dm & 1u) oa = pg_resolve_f32(key, gid, sweep, j0, za, !(rm & 1u));
+    if (dm & 2u) ob = pg_resolve_f32(key, gid, sweep, j0 + 1, zb, !(rm & 2u));
+    out[i * cols + j0] = (double)oa;
+    if (has1) out[i * cols + j0 + 1] = (double)ob;
+  }
+}
+
+}  // namespace erirt

@@ -10,9 +10,9 @@
 // counter), so every draw is a pure function of (seed, chain, person, item, sweep).
 //
 // Two code paths share this statement:
-//   * pg_draw_exact<R>  -- complete loop, used for f64 everywhere and for the f32 retry queue;
-//   * pg_fast_attempt0  -- f32 branch-free evaluation of attempt 0 of Method A with squeeze tests that
-//     only ever say "certainly accepted"; every other outcome is replayed by pg_draw_exact<float>.
+//   * pg_draw_exact<R>  -- complete loop in the working precision (f64 everywhere);
+//   * pg_fast.cuh       -- f32: attempt 0 of two cells per packed instruction with squeeze tests that only ever say
+//     "certainly accepted" / "certainly rejected"; every other cell is replayed with the a_1 term from a work queue.
 #pragma once
 #include "pg_coeffs.h"
 #include "rng.cuh"
@@ -135,10 +135,15 @@ __device__ __forceinline__ bool pg_attempt_B(R c, uint4 w, R& X) {
 
 constexpr uint32_t PG_MAX_ATTEMPTS = 2000u;  // bound on every device loop; acceptance is >= 0.2, so 0.8^2000 never happens
 
-// Complete draw of omega_ij ~ PG(1, z) starting at attempt `first_attempt` (0 = the pair-site attempt; a >= 1 = the
-// retry-site attempts, earlier ones being already known as rejected).
+// Complete draw of omega_ij ~ PG(1, z).  Stream layout (identical in oracle/pg.c):
+//   attempt 0            Method A from the cell pair's block (site PK_PG, index j/2; words 0,1 for even j, 2,3 for odd j),
+//                        evaluated only when |z| <= PG_Z0MAX_D (beyond that e^{Kt} leaves the f32 range of the fast path);
+//   retry block r >= 1   (site PK_PG_RETRY, index j, ctr.w = r): c <= 1/t: Method-A attempts 2r-1 (words 0,1) and 2r (words 2,3);
+//                        c > 1/t: Method-B attempt r (all four words).
+// `skip_attempt0` resumes after an attempt 0 already known to be rejected.
+constexpr double PG_Z0MAX_D = 16.0;
 template <typename R>
-__device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint32_t sweep, int j, R z, int first_attempt,
+__device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint32_t sweep, int j, R z, int skip_attempt0,
                                            uint32_t* n_attempts = nullptr) {
   const R c = R(0.5) * fabs(z);
   R X = R(PG_T);
@@ -147,88 +152,33 @@ __device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint3
     if (n_attempts) *n_attempts = 0;
     return z;
   }
+  bool done = false;
+  if (!skip_attempt0 && fabs(z) <= R(PG_Z0MAX_D)) {
+    uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
+    ++used;
+    done = (j & 1) ? pg_attempt_A<R>(c, w.z, w.w, X) : pg_attempt_A<R>(c, w.x, w.y, X);
+  }
   if (c <= R(PG_CSWITCH)) {
-    bool done = false;
-    if (first_attempt == 0) {
-      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
-      ++used;
-      done = (j & 1) ? pg_attempt_A<R>(c, w.z, w.w, X) : pg_attempt_A<R>(c, w.x, w.y, X);
-    }
 #pragma unroll 1
-    for (uint32_t a = first_attempt > 1 ? (uint32_t)first_attempt : 1u; !done && a < PG_MAX_ATTEMPTS; ++a) {
-      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
+    for (uint32_t r = 1u; !done && r < PG_MAX_ATTEMPTS; ++r) {
+      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), r);
       ++used;
       done = pg_attempt_A<R>(c, w.x, w.y, X);
+      if (!done) {
+        ++used;
+        done = pg_attempt_A<R>(c, w.z, w.w, X);
+      }
     }
   } else {
-    bool done = false;
 #pragma unroll 1
-    for (uint32_t a = 1; !done && a < PG_MAX_ATTEMPTS; ++a) {
-      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), a);
+    for (uint32_t r = 1u; !done && r < PG_MAX_ATTEMPTS; ++r) {
+      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), r);
       ++used;
       done = pg_attempt_B<R>(c, w, X);
     }
   }
   if (n_attempts) *n_attempts = used;
   return R(0.25) * X;
-}
-
-// ---- f32 fast path: one attempt, branch-free, MUFU approximations only ----
-// The alternating series is cut after its a_1 term: U <= 1 - a_1(X)/a_0(X) accepts, anything else rejects.  The neglected
-// a_2/a_0 is at most 5 e^{-3 pi^2 t} = 2.9e-8 (x > t) or 5 e^{-12/t} = 3.6e-8 (x <= t), below the resolution of an f32 uniform.
-// Return value: omega (= X/4) >= 0 when the attempt is accepted, -2 when it is rejected, -3 when c > 1/t (Method B cell).
-// Also returns the Bernoulli log-likelihood term  y z - log(1 + e^z) = kappa z - c - ln(1 + e^{-2c}).
-__device__ __forceinline__ float pg_fast_attempt0(float z, float kappa, uint32_t wa, uint32_t wb, float& loglik) {
-  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-  const float c = 0.5f * fabsf(z);
-  const float w2c = fast_ex2(-2.0f * LOG2E * c);
-  loglik = fmaf(-LN2, fast_lg2(1.0f + w2c), fmaf(kappa, z, -c));  // kappa z - c - ln(1 + e^{-2c})
-
-  const float K = fmaf(0.5f * c, c, (float)(PI_D * PI_D / 8.0));
-  const float eKt = fast_ex2(K * (float)(PG_T * 1.4426950408889634));
-  const float Rm1 = (float)(2.0 * PG_Q0 / PI_D) * K * eKt;
-  const float um = u01f(wa), up = u01f(wb);
-  const float v = fmaf(um, Rm1, um);
-  const bool right = v < 1.0f;
-  const float L = fast_lg2(up);  // shared by both branches
-  // right: X = t + E/K, E = -ln(up); accept iff v <= 1 - 3 exp(-pi^2 X)
-  const float Xr = fmaf(-LN2 * L, fast_rcp(K), (float)PG_T);
-  const float r1r = 3.0f * fast_ex2((float)(-PI_D * PI_D * 1.4426950408889634) * Xr);
-  const bool acc_r = v <= 1.0f - r1r;
-  // left: y = up*P0, Lw = -2 ln y, r = rsqrt(Lw), 1/Z = r * XQ(r), X = 1/Z^2; accept iff ua <= tilt (1 - 3 exp(-4/X))
-  const float Lw = fmaf(-2.0f * LN2, L, (float)PG_M2LNP0);
-  const float r = fast_rsqrt(Lw);
-  const float rz = r * xq_poly(r);
-  const float Xl = rz * rz;
-  const float tilt = fast_ex2((-0.5f * LOG2E) * c * c * Xl);
-  const float r1l = 3.0f * fast_ex2((-4.0f * LOG2E) * fast_rcp(Xl));
-  const bool acc_l = (v - 1.0f) < Rm1 * tilt * (1.0f - r1l);
-  const float X = right ? Xr : Xl;
-  float out = (right ? acc_r : acc_l) ? 0.25f * X : -2.0f;
-  if (c > (float)PG_CSWITCH) out = -3.0f;
-  return out;
-}
-
-// One fast attempt of Method B (c > 1/t) from the four words of a retry-site Philox block; same return convention.
-__device__ __forceinline__ float pg_fast_attemptB(float z, uint4 w) {
-  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-  const float c = 0.5f * fabsf(z);
-  const float K = fmaf(0.5f * c, c, (float)(PI_D * PI_D / 8.0));
-  const float rK = fast_rcp(K);
-  const float p = (float)(PI_D / 2.0) * rK * fast_ex2(-K * (float)(PG_T * 1.4426950408889634));
-  const float ql = 2.0f * fast_ex2(-LOG2E * c);
-  const float Pr = p * fast_rcp(p + ql);
-  const float um = u01f(w.x);
-  if (um < Pr) {
-    const float X = fmaf(-LN2 * fast_lg2(u01f(w.y)), rK, (float)PG_T);
-    const float r1 = 3.0f * fast_ex2((float)(-PI_D * PI_D * 1.4426950408889634) * X);
-    return (um <= Pr * (1.0f - r1)) ? 0.25f * X : -2.0f;
-  }
-  const float ua = (um - Pr) * fast_rcp(1.0f - Pr);
-  const float X = ig_msh<float>(fast_rcp(c), 1.0f, normal2f(w.y, w.z), u01f(w.w));
-  if (!(X < (float)PG_T)) return -2.0f;
-  const float r1 = 3.0f * fast_ex2((-4.0f * LOG2E) * fast_rcp(X));
-  return (ua <= 1.0f - r1) ? 0.25f * X : -2.0f;
 }
 
 }  // namespace erirt

@@ -59,6 +59,35 @@ __device__ __forceinline__ uint4 philox(PhiloxKey key, uint32_t unit, uint32_t s
   return make_uint4(c0, c1, c2, c3);
 }
 
+// The same block from a precomputed key schedule (round r uses rk[2r], rk[2r+1]).  The schedule lives in the kernel
+// parameters, i.e. in the constant bank, so each round key is a direct operand of the round's LOP3 instead of an add.
+struct PhiloxSched {
+  uint32_t rk[20];
+};
+__host__ __device__ inline PhiloxSched make_sched(PhiloxKey key) {
+  PhiloxSched s;
+  for (int r = 0; r < 10; ++r) {
+    s.rk[2 * r] = key.k0 + (uint32_t)r * 0x9E3779B9u;
+    s.rk[2 * r + 1] = key.k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+  return s;
+}
+__device__ __forceinline__ uint4 philox(const PhiloxSched& ks, uint32_t unit, uint32_t sweep, uint32_t site, uint32_t attempt) {
+  uint32_t c0 = unit, c1 = sweep, c2 = site, c3 = attempt;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ ks.rk[2 * r];
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ ks.rk[2 * r + 1];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 // uniforms on (0,1): f64 keeps all 32 bits (exact); f32 rounds (w + 0.5) 2^-32 to 24 bits (may return 1.0f)
 __device__ __forceinline__ double u01d(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
 __device__ __forceinline__ float u01f(uint32_t w) { return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }

@@ -152,20 +152,23 @@ def _attempt_b(c, w):
 
 
 def pg1(st, person, j, z):
+    """Stream layout of oracle/pg.c: attempt 0 = Method A from the pair block when |z| <= 16; retry block r >= 1 holds
+    Method-A attempts 2r-1, 2r (c <= 1/t) or Method-B attempt r (c > 1/t)."""
     c = 0.5 * abs(z)
-    if c <= 1 / PG_T:
+    x = None
+    if abs(z) <= 16.0:
         w = st.words(person, site(DOM_PERSON, PK_PG, j >> 1), 0)
         x = _attempt_a(c, w[(j & 1) * 2], w[(j & 1) * 2 + 1])
-        a = 1
-        while x is None:
-            w = st.words(person, site(DOM_PERSON, PK_PG_RETRY, j), a)
+    r = 1
+    while x is None:
+        w = st.words(person, site(DOM_PERSON, PK_PG_RETRY, j), r)
+        if c <= 1 / PG_T:
             x = _attempt_a(c, w[0], w[1])
-            a += 1
-    else:
-        a, x = 1, None
-        while x is None:
-            x = _attempt_b(c, st.words(person, site(DOM_PERSON, PK_PG_RETRY, j), a))
-            a += 1
+            if x is None:
+                x = _attempt_a(c, w[2], w[3])
+        else:
+            x = _attempt_b(c, w)
+        r += 1
     return 0.25 * x
 
 
