@@ -185,8 +185,10 @@ __global__ void xtx_kernel(const double* __restrict__ X, int64_t ld, int64_t n, 
 struct erirt_handle {
   erirt_config cfg{};
   Layout L{};
-  SmemPlan S{};
-  int tpp = 1;
+  SmemPlan S{};      // plan of the sampling kernel of this engine
+  SmemPlan S_gen{};  // plan of the generic kernel (== S unless the engine samples with the f32 fast kernel; used by the evaluation stage)
+  int tpp = 1, tpp_gen = 1;
+  int grid_gen = 0;
   int sm_count = 0;
   int grid = 0;
   size_t rsz = 4;
@@ -221,7 +223,8 @@ static int launch_global(erirt_handle* h, int stage);
 static int finalize_constants(erirt_handle* h);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt, bool cqr = false, bool cross = false) {
+// `fast`: plan of person_sweep_fast_kernel (f32, one-launch models): the generic plan plus the response tables
+static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt, bool cqr, bool cross, bool fast) {
   SmemPlan S{};
   S.P = CTA_THREADS / tpp;
   S.tile_real_bytes = (int)(S.P * L.Jp * rsz);
@@ -240,7 +243,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_acc_item = (int)o; o = align_up(o + (cqr ? 7 : (cross ? 6 : 5)) * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
   S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
-  S.off_tab = (int)o; if (rsz == 4 && !cross) o = align_up(o + 2 * (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response tables of the f32 fast kernel
+  S.off_tab = (int)o; if (fast) o = align_up(o + 2 * (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response tables of the f32 fast kernel
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;
   return S;
@@ -266,7 +269,7 @@ static const void* person_fast_kernel_ptr(int tpp) {
 }
 static const void* person_kernel_for(const erirt_handle* h, int fam) {
   if (fam == 0) return h->cfg.dtype == ERIRT_F32 ? person_fast_kernel_ptr(h->tpp) : person_kernel_ptr<double, 0>(h->tpp);
-  return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 1>(h->tpp) : person_kernel_ptr<double, 1>(h->tpp);
+  return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 1>(h->tpp_gen) : person_kernel_ptr<double, 1>(h->tpp_gen);
 }
 
 static int qr_small_width(int model, int J, int F) {
@@ -347,23 +350,33 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   h->rsz = cfg->dtype == ERIRT_F32 ? 4 : 8;
   h->L = make_layout(cfg->n_item, cfg->n_feat);
   const bool has_rt = cfg->model != ERIRT_MLIRT;
-  // threads per person: smallest TPP whose tile fits ~64 KB (>= 3 CTAs/SM)
+  // threads per person: smallest TPP whose shared-memory plan leaves room for >= 3 CTAs per SM (75 KB + 1 KB reserved each)
   const bool is_cross = cfg->model == ERIRT_RTIRT_CROSS || cfg->model == ERIRT_RTIRT_CROSSQR;
-  int tpp = 1;
+  const bool is_cqr = cfg->model == ERIRT_RTIRT_CROSSQR;
+  const bool fast_engine = h->rsz == 4 && !is_cross;
   const char* env_tpp = getenv("ERIRT_TPP");
   const int n_groups = h->L.Jp / 4;
-  if (env_tpp) tpp = atoi(env_tpp);
-  else {
-    for (tpp = 1; tpp < 8; tpp *= 2) {
-      SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR, is_cross);
-      if (s.total <= 74 * 1024 && n_groups <= 16 * tpp) break;
+  auto choose = [&](bool fast, int& tpp, SmemPlan& S) -> const char* {
+    if (env_tpp) tpp = atoi(env_tpp);
+    else {
+      for (tpp = 1; tpp < 8; tpp *= 2) {
+        SmemPlan s = make_smem_plan(h->L, tpp, h->rsz, has_rt, is_cqr, is_cross, fast);
+        if (s.total <= 75 * 1024 && n_groups <= 16 * tpp) break;
+      }
     }
+    if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) return "ERIRT_TPP must be 1, 2, 4 or 8";
+    if (n_groups > 16 * tpp) return "too many items for this TPP (at most 64*TPP - 4)";
+    S = make_smem_plan(h->L, tpp, h->rsz, has_rt, is_cqr, is_cross, fast);
+    if (S.total > 227 * 1024) return "n_item needs more shared memory per CTA than an SM has";
+    return nullptr;
+  };
+  if (const char* msg = choose(fast_engine, h->tpp, h->S)) { delete h; return fail(ERIRT_E_UNSUPPORTED, "%s (n_item %d)", msg, cfg->n_item); }
+  if (fast_engine) {
+    if (const char* msg = choose(false, h->tpp_gen, h->S_gen)) { delete h; return fail(ERIRT_E_UNSUPPORTED, "%s (n_item %d)", msg, cfg->n_item); }
+  } else {
+    h->tpp_gen = h->tpp;
+    h->S_gen = h->S;
   }
-  if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) { delete h; return fail(ERIRT_E_ARG, "ERIRT_TPP must be 1, 2, 4 or 8"); }
-  if (n_groups > 16 * tpp) { delete h; return fail(ERIRT_E_ARG, "TPP=%d handles at most %d items", tpp, 64 * tpp - 4); }
-  h->tpp = tpp;
-  h->S = make_smem_plan(h->L, tpp, h->rsz, has_rt, cfg->model == ERIRT_RTIRT_CROSSQR, is_cross);
-  if (h->S.total > 227 * 1024) { delete h; return fail(ERIRT_E_UNSUPPORTED, "n_item %d needs %d bytes of shared memory per CTA", cfg->n_item, h->S.total); }
   h->n_pad = (int64_t)align_up((size_t)cfg->n_subj, CTA_THREADS > 128 ? CTA_THREADS : 128);
   h->cap = cfg->n_iter * cfg->n_chain;
   h->qw = qr_small_width(cfg->model, cfg->n_item, cfg->n_feat);
@@ -411,7 +424,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   // kernel attributes / occupancy-sized persistent grid
   const void* kfn = person_kernel_for(h, is_cross ? 1 : 0);
   cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->S.total);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(person_kernel_for(h, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, h->S.total);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(person_kernel_for(h, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, h->S_gen.total);
   if (ce != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "cudaFuncSetAttribute(%d bytes): %s", h->S.total, cudaGetErrorString(ce)); }
   int occ = 0;
   ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, CTA_THREADS, h->S.total);
@@ -420,6 +433,12 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   const char* env_occ = getenv("ERIRT_CTAS_PER_SM");
   if (env_occ && atoi(env_occ) > 0 && atoi(env_occ) < occ) occ = atoi(env_occ);
   h->grid = std::min(n_tiles, h->sm_count * occ);
+  {
+    int occ_gen = 0;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen, person_kernel_for(h, 1), CTA_THREADS, h->S_gen.total);
+    if (ce != cudaSuccess || occ_gen < 1) { free_handle(h); return fail(ERIRT_E_CUDA, "generic person kernel does not fit on an SM: %s", cudaGetErrorString(ce)); }
+    h->grid_gen = std::min((int)(h->n_pad / h->S_gen.P), h->sm_count * occ_gen);
+  }
   *out = h;
   return 0;
 }
@@ -644,9 +663,10 @@ static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   A.n_local = h->cfg.n_subj;
   A.n_pad = h->n_pad;
   A.person_offset = (uint32_t)h->cfg.subj_offset;
-  A.n_tiles = (int)(h->n_pad / h->S.P);
+  const bool generic = stage != 0 || h->cfg.dtype != ERIRT_F32;  // which kernel launch_person() picks
+  A.S = generic ? h->S_gen : h->S;
+  A.n_tiles = (int)(h->n_pad / A.S.P);
   A.L = h->L;
-  A.S = h->S;
   A.model = h->cfg.model;
   A.n_chain = h->cfg.n_chain;
   A.n_burnin = h->cfg.n_burnin;
@@ -696,11 +716,11 @@ static int launch_person(erirt_handle* h, int stage) {
   if (h->cfg.dtype == ERIRT_F32) {
     PersonArgs<float> A = make_person_args<float>(h, stage);
     void* args[] = {&A};
-    CU(cudaLaunchKernel(kfn, dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+    CU(cudaLaunchKernel(kfn, dim3(stage == 0 ? h->grid : h->grid_gen), dim3(CTA_THREADS), args, A.S.total, h->stream));
   } else {
     PersonArgs<double> A = make_person_args<double>(h, stage);
     void* args[] = {&A};
-    CU(cudaLaunchKernel(kfn, dim3(h->grid), dim3(CTA_THREADS), args, h->S.total, h->stream));
+    CU(cudaLaunchKernel(kfn, dim3(stage == 0 ? h->grid : h->grid_gen), dim3(CTA_THREADS), args, A.S.total, h->stream));
   }
   return 0;
 }

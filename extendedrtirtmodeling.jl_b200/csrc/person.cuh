@@ -53,6 +53,9 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, u
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void l2_prefetch(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

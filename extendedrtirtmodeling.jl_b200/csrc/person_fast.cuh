@@ -16,7 +16,21 @@
 namespace erirt {
 
 constexpr int TAB_PITCH = 20;  // floats per item group in the response tables: groups g and g+4 fall on disjoint banks
+constexpr int FAST_FLUSH_TILES = 16;  // item statistics live in f32 registers and are folded into the f64 accumulators every 16 tiles
 constexpr int QSTD = 768;      // work-queue split: [0, QSTD) certainly-rejected cells, [QSTD, QCAP) undecided / Method-B cells
+
+// Phase timers of the diagnostic build (tools/make_tick_build.py, -DERIRT_TICKS): clock64() per warp at the phase boundaries.
+#ifdef ERIRT_TICKS
+#define PF_NTICK 16
+__device__ unsigned long long g_ticks[PF_NTICK];
+#define PF_TICK_DECL() unsigned long long _tk[PF_NTICK] = {0}; long long _t0 = clock64(), _t1
+#define PF_TICK(n) do { _t1 = clock64(); if ((threadIdx.x & 31) == 0) _tk[n] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
+#define PF_TICK_FLUSH() do { if ((threadIdx.x & 31) == 0) for (int n = 0; n < PF_NTICK; ++n) atomicAdd(&g_ticks[n], _tk[n]); } while (0)
+#else
+#define PF_TICK_DECL()
+#define PF_TICK(n)
+#define PF_TICK_FLUSH()
+#endif
 
 __device__ __forceinline__ uint32_t y_nibble(uint32_t yw) { return (yw * 0x01020408u) >> 24; }  // bytes 0/1 -> 4-bit index
 
@@ -38,7 +52,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   uint8_t* s_y = smem + A.S.off_y;
   R* s_par = reinterpret_cast<R*>(smem + A.S.off_par);  // PAR_A: a, PAR_AB: -a b, PAR_A2: a^2, PAR_A2B: a^2 b, PAR_IS2: 1/sigma2
   R* s_u = reinterpret_cast<R*>(smem + A.S.off_u);
-  R* s_sum = reinterpret_cast<R*>(smem + A.S.off_sum);    // [P][4] row sums handed to the person phase
   R* s_beta = reinterpret_cast<R*>(smem + A.S.off_beta);  // beta (MAXD) then vec(Sigma) (4)
   R* s_ta = reinterpret_cast<R*>(smem + A.S.off_tab);     // [G][TAB_PITCH]  sum_e kappa_e a_e
   R* s_tb = s_ta + G * TAB_PITCH;                         // [G][TAB_PITCH] -sum_e kappa_e a_e b_e
@@ -112,6 +125,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       s_miscd[MD_SUM_LOGS2K] = amax;
       s_miscd[MD_SUM_LOGS2K + 1] = abmax;
       mbar_init(s_bar, 1);
+      s_qctl[0] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -168,23 +182,32 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   };
 
   int tiles_done = 0;
+  PF_TICK_DECL();
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tiles_done) {
     const int64_t row0 = (int64_t)tile * P;
+    PF_TICK(13);  // tile-loop overhead / previous store issue
     if (tid == 0) {
       tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
       mbar_expect_tx(s_bar, load_bytes);
       tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
-      s_qctl[0] = 0;
+      if (tile + (int)gridDim.x < A.n_tiles) {  // pull the next tile of this CTA into L2 while this one is processed
+        const int64_t rown = row0 + (int64_t)gridDim.x * P;
+        l2_prefetch(A.omega + rown * Jp, (uint32_t)A.S.tile_real_bytes);
+        if (has_rt) l2_prefetch(A.logT + rown * Jp, (uint32_t)A.S.tile_real_bytes);
+        l2_prefetch(A.Y + rown * Jp, (uint32_t)A.S.tile_y_bytes);
+      }
     }
-    // ---- person phase, part 1 (one thread per person, coalesced): state k-1, regression means, the person's variates ----
-    const int64_t pi = row0 + tid;
-    const bool pvalid = tid < P && pi < A.n_local;
+    // ---- person phase, part 1 (the first of the TPP lanes of a person): state k-1, regression means, the person's variates.
+    //      Every warp serves its own persons, so nothing up to the work queues needs a CTA barrier ----
+    const bool lead = q == 0;
+    const int64_t pi = row0 + p;
+    const bool pvalid = lead && pi < A.n_local;
     const uint32_t pgid = A.person_offset + (uint32_t)pi;
     R th = R(0), ze = R(0), nu = R(1), xb1 = R(0), xb2 = R(0);
     R zn_theta = R(0), zn_zeta = R(0), zn_nu = R(0), un_nu = R(0);
-    if (tid < P) {
+    if (lead) {
       if (do_draws) {
         const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
         zn_theta = normal2f(w.x, w.y);
@@ -202,13 +225,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       if (model == M_RTIRT) xb2 = s_beta[pb];
       for (int f = 0; f < F; ++f) {
         const R x = A.X[(int64_t)f * A.n_pad + pi];
-        s_u[tid * Dgp + 1 + f] = pvalid ? x : R(0);
+        s_u[p * Dgp + 1 + f] = pvalid ? x : R(0);
         if (reg_x) xb1 = fmaf(x, s_beta[1 + f], xb1);
         if (model == M_RTIRT) xb2 = fmaf(x, s_beta[pb + 1 + f], xb2);
       }
     }
+    PF_TICK(0);  // TMA issue, person part 1
     mbar_wait(s_bar, parity);
     parity ^= 1u;
+    PF_TICK(1);  // TMA wait
 
     R* my_om = s_om + p * Jp;
     const R* my_lt = s_lt + p * Jp;
@@ -218,24 +243,33 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       // ---- row sums over items (Draw.pl.jl:55-56, 137-138), TPP threads per person, two items per instruction ----
       u64 sA2 = 0ull, sAB = 0ull, sLT = 0ull;
       R sAK = R(0);
-      for (int kk = 0; kk < nk; ++kk) {
-        const int g = group_of<TPP>(q, kk);
-        if (g >= G) continue;
-        const float4 om = *reinterpret_cast<const float4*>(my_om + 4 * g);
-        const float4 pA2 = *reinterpret_cast<const float4*>(s_par + PAR_A2 * Jp + 4 * g);
-        const float4 pA2B = *reinterpret_cast<const float4*>(s_par + PAR_A2B * Jp + 4 * g);
-        const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
-        const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w);
-        sA2 = ffma2(pk2(pA2.x, pA2.y), o01, sA2);
-        sA2 = ffma2(pk2(pA2.z, pA2.w), o23, sA2);
-        sAB = ffma2(pk2(pA2B.x, pA2B.y), o01, sAB);
-        sAB = ffma2(pk2(pA2B.z, pA2B.w), o23, sAB);
-        sAK += s_ta[g * TAB_PITCH + y_nibble(yw)];
-        if (has_rt) {
-          const float4 lt = *reinterpret_cast<const float4*>(my_lt + 4 * g);
-          const float4 pI = *reinterpret_cast<const float4*>(s_par + PAR_IS2 * Jp + 4 * g);
-          sLT = ffma2(pk2(pI.x, pI.y), pk2(lt.x, lt.y), sLT);
-          sLT = ffma2(pk2(pI.z, pI.w), pk2(lt.z, lt.w), sLT);
+      constexpr int CHUNK = 8 / TPP;  // consecutive groups owned by this thread inside each block of 8
+      for (int g0 = q * CHUNK; g0 < G; g0 += 8) {
+        const R* r_om = my_om + 4 * g0;
+        const R* r_lt = my_lt + 4 * g0;
+        const uint8_t* r_y = my_y + 4 * g0;
+        const R* r_par = s_par + 4 * g0;
+        const R* r_ta = s_ta + g0 * TAB_PITCH;
+#pragma unroll
+        for (int cc = 0; cc < CHUNK; ++cc) {
+          if (g0 + cc < G) {
+            const float4 om = *reinterpret_cast<const float4*>(r_om + 4 * cc);
+            const float4 pA2 = *reinterpret_cast<const float4*>(r_par + PAR_A2 * Jp + 4 * cc);
+            const float4 pA2B = *reinterpret_cast<const float4*>(r_par + PAR_A2B * Jp + 4 * cc);
+            const uint32_t yw = *reinterpret_cast<const uint32_t*>(r_y + 4 * cc);
+            const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w);
+            sA2 = ffma2(pk2(pA2.x, pA2.y), o01, sA2);
+            sA2 = ffma2(pk2(pA2.z, pA2.w), o23, sA2);
+            sAB = ffma2(pk2(pA2B.x, pA2B.y), o01, sAB);
+            sAB = ffma2(pk2(pA2B.z, pA2B.w), o23, sAB);
+            sAK += r_ta[cc * TAB_PITCH + y_nibble(yw)];
+            if (has_rt) {
+              const float4 lt = *reinterpret_cast<const float4*>(r_lt + 4 * cc);
+              const float4 pI = *reinterpret_cast<const float4*>(r_par + PAR_IS2 * Jp + 4 * cc);
+              sLT = ffma2(pk2(pI.x, pI.y), pk2(lt.x, lt.y), sLT);
+              sLT = ffma2(pk2(pI.z, pI.w), pk2(lt.z, lt.w), sLT);
+            }
+          }
         }
       }
       R rA2 = lo2(sA2) + hi2(sA2), rAB = lo2(sAB) + hi2(sAB), rLT = lo2(sLT) + hi2(sLT);
@@ -246,11 +280,10 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         sAK += __shfl_xor_sync(0xffffffffu, sAK, o);
         rLT += __shfl_xor_sync(0xffffffffu, rLT, o);
       }
-      if (q == 0) *reinterpret_cast<float4*>(s_sum + 4 * p) = make_float4(rA2, rAB, sAK, sum_lam_is2 - rLT);
-      __syncthreads();
+      const float4 d = make_float4(rA2, rAB, sAK, sum_lam_is2 - rLT);  // all TPP lanes hold the person's sums
+      PF_TICK(2);  // row sums
       // ---- person phase, part 2: theta_k, zeta_k, structural log-density, moments ----
-      if (tid < P) {
-        const float4 d = *reinterpret_cast<const float4*>(s_sum + 4 * tid);
+      if (lead) {
         {
           const R mu0 = (model == M_MLIRT || model == M_RTIRT) ? xb1 : R(0);
           const R var0 = (model == M_MLIRT) ? R(1) : S11;
@@ -312,7 +345,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         }
       }
     }
-    if (tid < P) {
+    if (lead) {
       // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
       if (qr) {
         const R xb = fmaf(th, s_beta[F + 1], xb1);
@@ -326,7 +359,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         nu = nu < R(1e-10) ? R(1e-10) : (nu > R(1e10) ? R(1e10) : nu);
         if (pvalid) A.nu[pi] = nu;
       }
-      R* u = s_u + tid * Dgp;
+      R* u = s_u + p * Dgp;
       u[0] = pvalid ? R(1) : R(0);
       u[F + 1] = pvalid ? th : R(0);
       u[F + 2] = pvalid ? ze : R(0);
@@ -334,40 +367,51 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       u[F + 4] = (pvalid && qr) ? rdiv(R(1), nu) : R(0);  // weight of the nu-weighted Gram
       if (pvalid) acc_cells += (uint32_t)J;
     }
-    __syncthreads();
+    PF_TICK(4);  // person part 2, nu, u rows
 
     // ---- omega_{k+1} ~ PG(1, a_k (theta_k - b_k)), Draw.pl.jl:36-40, and the Bernoulli log-likelihood of state k ----
     const bool valid = (row0 + p) < A.n_local;
     const uint32_t gid = A.person_offset + (uint32_t)(row0 + p);
-    const R thp = s_u[p * Dgp + F + 1];
+    const R thp = __shfl_sync(0xffffffffu, th, (tid & 31) & ~(TPP - 1));  // theta_k of this thread's person, from its first lane
     u64 dmask = 0ull, rmask = 0ull;  // bit 4*kk+e: cell not certainly accepted / certainly rejected
     if (valid) {
       const bool wide = !(fmaf(z_amax, fabsf(thp), z_abmax) <= PG_Z0MAX);  // some |z| of this row may exceed the attempt-0 range
       const u64 TH = bc2(thp);
       u64 prod = bc2(1.0f);
       R sabs = R(0), skz = R(0);
-      for (int kk = 0; kk < nk; ++kk) {
-        const int g = group_of<TPP>(q, kk);
-        if (g >= G) continue;
-        const float4 pA = *reinterpret_cast<const float4*>(s_par + PAR_A * Jp + 4 * g);
-        const float4 pN = *reinterpret_cast<const float4*>(s_par + PAR_AB * Jp + 4 * g);
-        const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * g));
-        skz += fmaf(thp, s_ta[g * TAB_PITCH + yb], s_tb[g * TAB_PITCH + yb]);  // sum_e kappa_e z_e of this group
-        const u64 z01 = ffma2(pk2(pA.x, pA.y), TH, pk2(pN.x, pN.y)), z23 = ffma2(pk2(pA.z, pA.w), TH, pk2(pN.z, pN.w));
-        const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
-        const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
-        float4 out;
+      constexpr int U = TPP <= 2 ? 2 : 1;  // groups per iteration: group_of(q, kk + 1) == group_of(q, kk) + 1 for even kk when 8/TPP is even
+      for (int kk = 0; kk < nk; kk += U) {
+        const int g0 = group_of<TPP>(q, kk);
+        if (g0 >= G) continue;
+        const R* r_par = s_par + 4 * g0;
+        const R* r_ta = s_ta + g0 * TAB_PITCH;
         uint32_t dm = 0, rm = 0;
-        pg_fast_pair<0>(z01, wA.x, wA.y, wA.z, wA.w, out.x, out.y, dm, rm, prod, sabs);
-        pg_fast_pair<2>(z23, wB.x, wB.y, wB.z, wB.w, out.z, out.w, dm, rm, prod, sabs);
-        if (wide) {  // attempt 0 does not exist beyond |z| = 16: straight to the retry blocks
-          const R zs[4] = {lo2(z01), hi2(z01), lo2(z23), hi2(z23)};
-          R* o = &out.x;
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (!(fabsf(zs[e]) <= PG_Z0MAX)) { o[e] = -2.0f; dm |= 1u << e; rm |= 1u << e; }
+        for (int u = 0; u < U; ++u) {
+          if (g0 + u < G) {
+            const float4 pA = *reinterpret_cast<const float4*>(r_par + PAR_A * Jp + 4 * u);
+            const float4 pN = *reinterpret_cast<const float4*>(r_par + PAR_AB * Jp + 4 * u);
+            const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * (g0 + u)));
+            skz += fmaf(thp, r_ta[u * TAB_PITCH + yb], r_ta[G * TAB_PITCH + u * TAB_PITCH + yb]);  // sum_e kappa_e z_e of this group
+            const u64 z01 = ffma2(pk2(pA.x, pA.y), TH, pk2(pN.x, pN.y)), z23 = ffma2(pk2(pA.z, pA.w), TH, pk2(pN.z, pN.w));
+            const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * (g0 + u))), 0);
+            const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * (g0 + u) + 1)), 0);
+            float4 out;
+            uint32_t dmu = 0, rmu = 0;
+            pg_fast_pair<0>(z01, wA.x, wA.y, wA.z, wA.w, out.x, out.y, dmu, rmu, prod, sabs);
+            pg_fast_pair<2>(z23, wB.x, wB.y, wB.z, wB.w, out.z, out.w, dmu, rmu, prod, sabs);
+            if (wide) {  // attempt 0 does not exist beyond |z| = 16: straight to the retry blocks
+              const R zs[4] = {lo2(z01), hi2(z01), lo2(z23), hi2(z23)};
+              R* o = &out.x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (!(fabsf(zs[e]) <= PG_Z0MAX)) { o[e] = -2.0f; dmu |= 1u << e; rmu |= 1u << e; }
+            }
+            *reinterpret_cast<float4*>(my_om + 4 * (g0 + u)) = out;
+            dm |= dmu << (4 * u);
+            rm |= rmu << (4 * u);
+          }
         }
-        *reinterpret_cast<float4*>(my_om + 4 * g) = out;
         dmask |= (u64)dm << (4 * kk);
         rmask |= (u64)rm << (4 * kk);
       }
@@ -386,6 +430,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           if (!valid || 4 * g + e >= J) my_om[4 * g + e] = R(0);
       }
     }
+    PF_TICK(6);  // PG main pass
     {
       // ---- hand the cells that left the fast path to the tile's work queues: one shared-memory atomic per WARP reserves the
       //      slots of all its lanes in both queues (packed counts, warp prefix sum), then every lane writes its entries ----
@@ -404,33 +449,35 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       wbase = __shfl_sync(0xffffffffu, wbase, 31);
       uint32_t slot_s = (wbase & 0xffffu) + (pre & 0xffffu) - n_std;
       uint32_t slot_u = (wbase >> 16) + (pre >> 16) - n_spc;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t ms = (uint32_t)(smask >> (32 * half)), mu = (uint32_t)(umask >> (32 * half));
-        while (ms | mu) {
-          const bool special = ms == 0u;  // this lane drains its standard bits first
-          uint32_t& m = special ? mu : ms;
-          const int bit = __ffs((int)m) - 1 + 32 * half;
+      // bit 4*kk+e of a mask -> item index: the thread owns 32/TPP consecutive items in every block of 32
+      constexpr int BPB = 32 / TPP;
+      auto push = [&](uint32_t m, int bit0, uint32_t& slot, const uint32_t cap, const uint32_t qbase, const uint32_t flag) {
+        while (m) {
+          const int bit = bit0 + __ffs((int)m) - 1;
           m &= m - 1u;
-          const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
-          const uint32_t entry = ((uint32_t)p << 16) | (uint32_t)j;
-          uint32_t& slot = special ? slot_u : slot_s;
-          const uint32_t cap = special ? (uint32_t)(QCAP - QSTD) : (uint32_t)QSTD;
-          if (slot < cap) s_queue[(special ? QSTD : 0) + slot] = entry | (special ? 0x80000000u : 0u);
+          const int j = ((bit / BPB) << 5) + q * BPB + (bit % BPB);
+          if (slot < cap) s_queue[qbase + slot] = ((uint32_t)p << 16) | (uint32_t)j | flag;
           else {  // queue overflow: finish the cell here
             const float z = fmaf(s_par[PAR_A * Jp + j], thp, s_par[PAR_AB * Jp + j]);
-            my_om[j] = pg_resolve_f32(A.key, gid, k + 1, j, z, special);
+            my_om[j] = pg_resolve_f32(A.key, gid, k + 1, j, z, flag != 0u);
           }
           ++slot;
         }
-      }
+      };
+      push((uint32_t)smask, 0, slot_s, (uint32_t)QSTD, 0u, 0u);
+      push((uint32_t)(smask >> 32), 32, slot_s, (uint32_t)QSTD, 0u, 0u);
+      push((uint32_t)umask, 0, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
+      push((uint32_t)(umask >> 32), 32, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
     }
+    PF_TICK(7);  // queue push
     __syncthreads();
+    PF_TICK(8);  // barrier
 
     {
-      // ---- standard queue: Method-A retry rounds, two cells in flight per thread; Method-B cells are forwarded ----
+      // ---- drain, one phase: standard entries (Method-A retry rounds, two cells in flight per thread) are dealt from thread 0
+      //      upwards, special entries (undecided attempt 0: replay it with the a_1 term) from the last thread downwards ----
       const uint32_t qc = s_qctl[0];
-      const uint32_t qn = min(qc & 0xffffu, (uint32_t)QSTD);
+      const uint32_t qn = min(qc & 0xffffu, (uint32_t)QSTD), qu = min(qc >> 16, (uint32_t)(QCAP - QSTD));
       for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
         const bool has2 = idx + CTA_THREADS < qn;
         const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
@@ -451,41 +498,34 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         }
         if (om1 < 0.f) om1 = 0.25f * (float)PG_T;
         if (om2 < 0.f) om2 = 0.25f * (float)PG_T;
-        if (!b1) s_om[p1 * Jp + j1] = om1;
-        if (has2 && !b2) s_om[p2 * Jp + j2] = om2;
-        if (b1 || (has2 && b2)) {  // rare: forward to the special queue (or finish here when it is full)
-          if (b1) {
-            const uint32_t s = atomicAdd(&s_qctl[0], 0x10000u) >> 16;
-            if (s < (uint32_t)(QCAP - QSTD)) s_queue[QSTD + s] = e1;
-            else s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, g1, k + 1, j1, z1, false);
-          }
-          if (has2 && b2) {
-            const uint32_t s = atomicAdd(&s_qctl[0], 0x10000u) >> 16;
-            if (s < (uint32_t)(QCAP - QSTD)) s_queue[QSTD + s] = e2;
-            else s_om[p2 * Jp + j2] = pg_resolve_f32(A.key, g2, k + 1, j2, z2, false);
-          }
-        }
+        if (b1) om1 = pg_resolve_f32(A.key, g1, k + 1, j1, z1, false);  // rare: Method-B regime (or NaN state)
+        if (has2 && b2) om2 = pg_resolve_f32(A.key, g2, k + 1, j2, z2, false);
+        s_om[p1 * Jp + j1] = om1;
+        if (has2) s_om[p2 * Jp + j2] = om2;
       }
-    }
-    __syncthreads();
-    {
-      // ---- special queue: undecided attempt 0 (bit 31: replay it with the a_1 term) and Method-B cells ----
-      const uint32_t qn = min(s_qctl[0] >> 16, (uint32_t)(QCAP - QSTD));
-      for (uint32_t idx = tid; idx < qn; idx += CTA_THREADS) {
+      for (uint32_t idx = (uint32_t)(CTA_THREADS - 1 - tid); idx < qu; idx += CTA_THREADS) {
         const uint32_t e1 = s_queue[QSTD + idx];
         const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
-        s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, (e1 >> 31) != 0u);
+        s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, true);
       }
     }
+    PF_TICK(9);  // drain
     __syncthreads();
+    if (tid == 0) s_qctl[0] = 0;  // next written by the push of the next tile, two barriers from here
+    PF_TICK(10);  // barrier
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
     if (e_active) {
-      for (int pp = er; pp < P; pp += Rc) {
-        const R tp = s_u[pp * Dgp + F + 1], zp = s_u[pp * Dgp + F + 2];
-        const float4 om = *reinterpret_cast<const float4*>(s_om + pp * Jp + 4 * eg);
-        const uint32_t yw = *reinterpret_cast<const uint32_t*>(s_y + pp * Jp + 4 * eg);
+      const R* r_om = s_om + er * Jp + 4 * eg;
+      const uint8_t* r_y = s_y + er * Jp + 4 * eg;
+      const R* r_u = s_u + er * Dgp + F + 1;
+      const int step = Rc * Jp, ustep = Rc * Dgp;
+      const R* r_lt = s_lt + er * Jp + 4 * eg;
+      for (int pp = er; pp < P; pp += Rc, r_om += step, r_lt += step, r_y += step, r_u += ustep) {
+        const R tp = r_u[0];
+        const float4 om = *reinterpret_cast<const float4*>(r_om);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(r_y);
         const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w), T1 = bc2(tp), T2 = bc2(tp * tp);
         a0l = fadd2(a0l, o01);
         a0h = fadd2(a0h, o23);
@@ -494,29 +534,32 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         a2l = ffma2(T2, o01, a2l);
         a2h = ffma2(T2, o23, a2h);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) ay[e] += ((yw >> (8 * e)) & 0xffu) ? tp : R(0);
+        for (int e = 0; e < 4; ++e)
+          if (yw & (1u << (8 * e))) ay[e] += tp;
         if (has_rt) {
-          const float4 lt = *reinterpret_cast<const float4*>(s_lt + pp * Jp + 4 * eg);
-          const u64 Z = bc2(zp);
+          const u64 Z = bc2(r_u[1]);
+          const float4 lt = *reinterpret_cast<const float4*>(r_lt);
           acl = ffma2(pk2(lt.x, lt.y), Z, acl);
           ach = ffma2(pk2(lt.z, lt.w), Z, ach);
         }
       }
     }
-    if ((tiles_done % STAT_FLUSH_TILES) == STAT_FLUSH_TILES - 1) flush_item_stats();
+    PF_TICK(11);  // statistics pass
+    if ((tiles_done % FAST_FLUSH_TILES) == FAST_FLUSH_TILES - 1) flush_item_stats();
     // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin: entry t is shared by the 4 lanes of a quad (persons
     // pp = lane mod 4 (mod 4)), so that all four warps of the CTA take part instead of one
     for (int t0 = 0; t0 < L.ntri; t0 += CTA_THREADS / 4) {
       const int t = t0 + (tid >> 2);
-      double g0 = 0.0, g1 = 0.0;
+      float g0 = 0.f, g1 = 0.f;  // f32 over the <= 32 persons of a lane, f64 across tiles
       if (t < L.ntri) {
         int r = 0, rem = t;
         while (rem >= Dg - r) { rem -= Dg - r; ++r; }
         const int c = r + rem;
-        for (int pp = tid & 3; pp < P; pp += 4) {
-          const double ur = (double)s_u[pp * Dgp + r], uc = (double)s_u[pp * Dgp + c];
-          g0 += ur * uc;
-          if (qr) g1 += ur * uc * (double)s_u[pp * Dgp + F + 4];
+        const R* u = s_u + (tid & 3) * Dgp;
+        for (int pp = tid & 3; pp < P; pp += 4, u += 4 * Dgp) {
+          const float pr = u[r] * u[c];
+          g0 += pr;
+          if (qr) g1 = fmaf(pr, u[F + 4], g1);
         }
       }
       g0 += __shfl_xor_sync(0xffffffffu, g0, 1);
@@ -526,21 +569,23 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         g1 += __shfl_xor_sync(0xffffffffu, g1, 2);
       }
       if (t < L.ntri && (tid & 3) == 0) {
-        s_acc_gram[t] += g0;
-        if (qr) s_acc_gram[L.ntri + t] += g1;
+        s_acc_gram[t] += (double)g0;
+        if (qr) s_acc_gram[L.ntri + t] += (double)g1;
       }
     }
+    PF_TICK(12);  // flush + Gram
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
   }
+  PF_TICK_FLUSH();
   flush_item_stats();
 
   // ---- flush CTA accumulators ----
   atomicAdd(&s_scal[SC_LL_BERN], acc_ll_bern);
-  if (tid < P) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
+  if (q == 0) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
   atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
-  if (tid < P) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
+  if (q == 0) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
   __syncthreads();
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
     const int j = t % Jp;

@@ -5,8 +5,8 @@ os.environ["ERIRT_B200_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.p
 import numpy as np, torch
 import erirt_b200 as E
 import bench
-names = ["issue+person part1", "mbar wait (TMA)", "row sums", "barrier 1", "person part 2 + u rows", "barrier 2", "PG main pass",
-         "queue push", "barrier 3", "retry drain (+barrier 4)", "statistics pass", "flush + Gram", "barrier 5 + store issue", "-", "-", "-"]
+names = ["issue+person part1+logT sums", "mbar wait (TMA)", "row sums", "barrier 1", "person part 2 + u rows", "barrier 2", "PG main pass",
+         "queue push", "barrier 3", "drain", "barrier 4", "statistics pass", "flush + Gram", "fence+barrier 5+store issue", "-", "-"]
 tp = bench.true_params()
 dev = torch.device("cuda", 0)
 dY, dT, dX, off, n = bench.gen_shard_torch(tp, 0, 1, dev)
@@ -25,7 +25,7 @@ L.erirt_diag_ticks(buf, 0)
 t = np.array(list(buf), dtype=np.float64)
 st = eng.stats()
 print("ms per sweep", st["last_sample_ms"] / K)
-warps = 444 * 4
+warps = int(os.environ.get("ERIRT_TICK_CTAS", "444")) * 4
 print("per-warp mean cycles per sweep and share:")
 tot = t.sum()
 for nm, v in zip(names, t):
