@@ -433,6 +433,11 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   const char* env_occ = getenv("ERIRT_CTAS_PER_SM");
   if (env_occ && atoi(env_occ) > 0 && atoi(env_occ) < occ) occ = atoi(env_occ);
   h->grid = std::min(n_tiles, h->sm_count * occ);
+  {  // the global kernel stages the statistics in dynamic shared memory on top of its ~42 KB of static scratch
+    const size_t gsm = (size_t)(h->L.s_count + 2 + (h->L.F + 1) * (h->L.F + 1) + 5 * h->L.Jp) * sizeof(double);
+    ce = cudaFuncSetAttribute((const void*)global_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+    if (ce != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "cudaFuncSetAttribute(global_draw_kernel, %zu bytes): %s", gsm, cudaGetErrorString(ce)); }
+  }
   {
     int occ_gen = 0;
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen, person_kernel_for(h, 1), CTA_THREADS, h->S_gen.total);
@@ -727,7 +732,8 @@ static int launch_person(erirt_handle* h, int stage) {
 static int launch_global(erirt_handle* h, int stage) {
   if (h->comm) NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
   GlobalArgs G = make_global_args(h, stage);
-  global_draw_kernel<<<1, G_THREADS, 0, h->stream>>>(G);
+  const size_t gsm = (size_t)(h->L.s_count + 2 + (h->L.F + 1) * (h->L.F + 1) + 5 * h->L.Jp) * sizeof(double);  // staged statistics, X'X, raw variates
+  global_draw_kernel<<<1, G_THREADS, gsm, h->stream>>>(G);
   CU(cudaGetLastError());
   return 0;
 }

@@ -199,6 +199,12 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         l2_prefetch(A.Y + rown * Jp, (uint32_t)A.S.tile_y_bytes);
       }
     }
+    if (tid >= 32 && tid < 32 + 3 + F && tile + (int)gridDim.x < A.n_tiles) {  // ... and its person vectors (theta, zeta, nu, X columns)
+      const int a = tid - 32;
+      const int64_t rown = row0 + (int64_t)gridDim.x * P;
+      const R* src = a == 0 ? A.theta : (a == 1 ? A.zeta : (a == 2 ? A.nu : A.X + (int64_t)(a - 3) * A.n_pad));
+      l2_prefetch(src + rown, (uint32_t)(P * sizeof(R)));
+    }
     // ---- person phase, part 1 (the first of the TPP lanes of a person): state k-1, regression means, the person's variates.
     //      Every warp serves its own persons, so nothing up to the work queues needs a CTA barrier ----
     const bool lead = q == 0;

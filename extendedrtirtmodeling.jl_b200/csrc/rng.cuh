@@ -128,25 +128,26 @@ template <>
 __device__ __forceinline__ float normal2r<float>(uint32_t w0, uint32_t w1) { return normal2f(w0, w1); }
 
 // ---- item/global-site variates, always f64 (J + O(F) draws per sweep) ----
-__device__ inline double site_normal(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site) {
+__device__ __noinline__ double site_normal(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site) {
   uint4 w = philox(key, unit, sweep, site, 0);
   return normal2(w.x, w.y);
 }
 
 // N(mu, sd^2) truncated to (0, inf): rejection from the parent when the standardised bound alpha = -mu/sd <= 0.5,
 // Robert's (1995) translated-exponential proposal otherwise.
-__device__ inline double site_tnorm_pos(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double mu, double sd) {
+__device__ __noinline__ double site_tnorm_pos(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double mu, double sd,
+                                               uint32_t att0 = 0) {
   double alpha = -mu / sd;
   if (!(alpha == alpha)) return alpha;  // NaN parameters: propagate instead of spinning
   if (alpha <= 0.5) {
-    for (uint32_t att = 0;; ++att) {
+    for (uint32_t att = att0;; ++att) {
       uint4 w = philox(key, unit, sweep, site, att);
       double z = normal2(w.x, w.y);
       if (z >= alpha || att > 10000u) return mu + sd * z;
     }
   }
   double lam = 0.5 * (alpha + sqrt(alpha * alpha + 4.0));
-  for (uint32_t att = 0;; ++att) {
+  for (uint32_t att = att0;; ++att) {
     uint4 w = philox(key, unit, sweep, site, att);
     double x = alpha - log(u01d(w.x)) / lam;
     double d = x - lam;
@@ -155,7 +156,7 @@ __device__ inline double site_tnorm_pos(PhiloxKey key, uint32_t unit, uint32_t s
 }
 
 // Gamma(shape, 1) by Marsaglia-Tsang (2000); shape >= 1 here (delta + N/2, (N+3)/2, ...)
-__device__ inline double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double shape) {
+__device__ __noinline__ double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double shape, uint32_t att0 = 0) {
   if (!(shape > 0.0)) return shape * 0.0 / 0.0;  // NaN / non-positive shape
   double boost = 1.0;
   if (shape < 1.0) {
@@ -164,7 +165,7 @@ __device__ inline double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep
     shape += 1.0;
   }
   double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-  for (uint32_t att = 0;; ++att) {
+  for (uint32_t att = att0;; ++att) {
     uint4 w = philox(key, unit, sweep, site, att);
     double x = normal2(w.x, w.y);
     double v = 1.0 + c * x;
@@ -173,6 +174,28 @@ __device__ inline double site_gamma(PhiloxKey key, uint32_t unit, uint32_t sweep
     double u = u01d(w.z);
     if (log(u) < 0.5 * x * x + d - d * v + d * log(v) || att > 10000u) return boost * d * v;
   }
+}
+
+// ---- the same variates from the raw material of attempt 0 (z0 = normal2(w.x, w.y), u0 = u01d(w.z) of the site's attempt-0
+//      block), which the global kernel computes for all items at once on separate lanes before the parameters are known.
+//      Decision-identical to the functions above: attempt 0 is judged from the raw values, later attempts fall back to them. ----
+__device__ inline double tnorm_pos_from_raw(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double mu, double sd, double z0) {
+  const double alpha = -mu / sd;
+  if (!(alpha == alpha)) return alpha;
+  if (alpha <= 0.5) return z0 >= alpha ? mu + sd * z0 : site_tnorm_pos(key, unit, sweep, site, mu, sd, 1u);
+  return site_tnorm_pos(key, unit, sweep, site, mu, sd, 0u);  // Robert's exponential proposal reads the words differently (rare)
+}
+__device__ inline double gamma_from_raw(PhiloxKey key, uint32_t unit, uint32_t sweep, uint32_t site, double shape, double x0, double u0) {
+  if (!(shape >= 1.0)) return site_gamma(key, unit, sweep, site, shape, 0u);  // boost path / NaN
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  double v = 1.0 + c * x0;
+  if (v > 0.0) {
+    v = v * v * v;
+    const double x2 = x0 * x0;
+    // Marsaglia-Tsang's squeeze u < 1 - 0.0331 x^4 implies the exact test, so it never changes a decision; it skips two logs
+    if (u0 < 1.0 - 0.0331 * x2 * x2 || log(u0) < 0.5 * x2 + d - d * v + d * log(v)) return d * v;
+  }
+  return site_gamma(key, unit, sweep, site, shape, 1u);
 }
 
 // Inverse Gaussian by Michael-Schucany-Haas (1976) from a normal z and a uniform u; the smaller root is

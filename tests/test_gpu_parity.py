@@ -210,7 +210,7 @@ def test_loglik_at_given_state_matches_oracle(E, oracle, model):
     eng.set_state(**st)
     got = eng.loglik_current()
     assert abs(got - want) < 1e-11 * abs(want)
-    assert eng.loglik_current() == got  # idempotent: nothing was modified
+    assert abs(eng.loglik_current() - got) <= 1e-13 * abs(got)  # idempotent: nothing was modified (f64 atomics reorder the sums)
     eng.close()
 
 

@@ -31,3 +31,7 @@ tot = t.sum()
 for nm, v in zip(names, t):
     print(f"  {nm:28s} {v / warps / K:12.0f} cyc  {100 * v / tot:5.1f} %")
 print("sum per warp per sweep", tot / warps / K, "cycles =", tot / warps / K / 1.965e6, "ms")
+gb = (ctypes.c_longlong * 16)()
+L.erirt_diag_gticks(gb)
+print("global_draw_kernel, cycles since kernel start (last sweep): staging %d, loglik %d, structural lane %d, item lane 32 %d, barrier %d, end %d, raw variates %d | structural (Latent*): XX built %d, solve done %d, ss %d, scale %d, gamma %d"
+      % tuple(gb[i] for i in range(12)))

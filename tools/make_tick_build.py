@@ -12,6 +12,10 @@ extern "C" int erirt_diag_ticks(unsigned long long* out, int reset) {
   if (reset) { unsigned long long z[PF_NTICK] = {0}; cudaMemcpyToSymbol(erirt::g_ticks, z, sizeof(z)); }
   return PF_NTICK;
 }
+extern "C" int erirt_diag_gticks(long long* out) {
+  cudaMemcpyFromSymbol(out, erirt::g_gticks, 16 * sizeof(long long));
+  return 16;
+}
 """
 tmp = os.path.join(CSRC, "_tick_build.cu")
 open(tmp, "w").write(src)
