@@ -269,6 +269,8 @@ def main():
         if world > 1:
             sh, _ = D.make_shard(N_SUBJ)  # a fresh NCCL id per communicator
             eng.comm_init(sh[0], sh[1], sh[2])
+            if os.environ.get("ERIRT_EXCHANGE", "peer") == "peer":
+                D.attach_peers(eng)  # one-shot exchange over NVLink peer memory fused into the global draw kernel
         return eng
 
     def barrier():

@@ -214,6 +214,13 @@ struct erirt_handle {
   // NCCL
   nccl::comm_t comm = nullptr;
   int rank = 0, world = 1;
+  // one-shot peer exchange (NVLink peer memory, CUDA IPC between the per-GPU processes)
+  double* xbuf = nullptr;             // this GPU's exchange buffer
+  double** dPeerBufs = nullptr;       // device array [world] of every GPU's exchange buffer
+  std::vector<void*> peer_opened;     // mappings opened with cudaIpcOpenMemHandle
+  uint32_t* dXseq = nullptr;
+  int xstride = 0;
+  bool peer_ready = false;
   // graph
   cudaGraphExec_t graph_exec = nullptr;
 };
@@ -300,6 +307,10 @@ static int free_handle(erirt_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->comm && nccl::comm_destroy) nccl::comm_destroy(h->comm);
+  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+  if (h->xbuf) cudaFree(h->xbuf);
+  if (h->dPeerBufs) cudaFree(h->dPeerBufs);
+  if (h->dXseq) cudaFree(h->dXseq);
   void* ptrs[] = {h->dNuCell, h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
                   h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut};
   for (void* p : ptrs)
@@ -713,6 +724,11 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   A.k1 = (1.0 - 2.0 * q) / (q * (1.0 - q));
   A.k2 = 2.0 / (q * (1.0 - q));
   A.key = make_key(h->cfg.seed, h->cfg.chain);
+  A.peer_bufs = h->peer_ready ? h->dPeerBufs : nullptr;
+  A.xseq = h->dXseq;
+  A.world = h->world;
+  A.rank = h->rank;
+  A.xstride = h->xstride;
   return A;
 }
 
@@ -730,7 +746,8 @@ static int launch_person(erirt_handle* h, int stage) {
   return 0;
 }
 static int launch_global(erirt_handle* h, int stage) {
-  if (h->comm) NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
+  if (h->comm && !h->peer_ready)  // fallback: the exchange is otherwise fused into the kernel below
+    NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
   GlobalArgs G = make_global_args(h, stage);
   const size_t gsm = (size_t)(h->L.s_count + 2 + (h->L.F + 1) * (h->L.F + 1) + 5 * h->L.Jp) * sizeof(double);  // staged statistics, X'X, raw variates
   global_draw_kernel<<<1, G_THREADS, gsm, h->stream>>>(G);
@@ -977,6 +994,48 @@ extern "C" int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, con
   h->rank = rank;
   h->world = world;
   h->consts_final = false;
+  return 0;
+}
+
+extern "C" int erirt_peer_export(erirt_handle* h, void* ipc_handle64) {
+  if (!h || !ipc_handle64) return fail(ERIRT_E_ARG, "null argument");
+  if (h->world < 2) return fail(ERIRT_E_STATE, "erirt_peer_export needs erirt_comm_init with world >= 2 first");
+  if (h->prologue_done) return fail(ERIRT_E_STATE, "erirt_peer_export must precede erirt_sample");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->xbuf) {
+    h->xstride = (int)align_up((size_t)h->L.s_count, 16);
+    const size_t bytes = (size_t)2 * h->world * h->xstride * sizeof(double) + (size_t)2 * h->world * sizeof(uint32_t) + 256;
+    CU(cudaMalloc((void**)&h->xbuf, bytes));
+    CU(cudaMemset(h->xbuf, 0, bytes));
+    CU(cudaMalloc((void**)&h->dPeerBufs, h->world * sizeof(double*)));
+    CU(cudaMalloc((void**)&h->dXseq, sizeof(uint32_t)));
+    CU(cudaMemset(h->dXseq, 0, sizeof(uint32_t)));
+    CU(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hd;
+  CU(cudaIpcGetMemHandle(&hd, h->xbuf));
+  memcpy(ipc_handle64, &hd, 64);
+  return 0;
+}
+extern "C" int erirt_peer_attach(erirt_handle* h, const void* ipc_handles) {
+  if (!h || !ipc_handles) return fail(ERIRT_E_ARG, "null argument");
+  if (!h->xbuf) return fail(ERIRT_E_STATE, "erirt_peer_export has not been called");
+  if (h->prologue_done) return fail(ERIRT_E_STATE, "erirt_peer_attach must precede erirt_sample");
+  CU(cudaSetDevice(h->cfg.device));
+  std::vector<double*> ptrs(h->world, nullptr);
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) { ptrs[r] = h->xbuf; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)ipc_handles + (size_t)64 * r, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (the GPUs must be peers on one node, one process each)", r, cudaGetErrorString(e));
+    h->peer_opened.push_back(p);
+    ptrs[r] = (double*)p;
+  }
+  CU(cudaMemcpy(h->dPeerBufs, ptrs.data(), h->world * sizeof(double*), cudaMemcpyHostToDevice));
+  h->peer_ready = true;
   return 0;
 }
 

@@ -1,7 +1,9 @@
 // global.cuh -- item and structural draws from the reduced sufficient statistics (K3/K4/K6/K7 of SURVEY.md 2c).
 //
-// One CTA, launched after the person kernel P(k) (and after the NCCL all-reduce when persons are sharded;
-// every GPU runs it redundantly with the same Philox key, so the new parameters need no broadcast).
+// One CTA, launched after the person kernel P(k).  When persons are sharded over GPUs the all-reduce of the statistics is
+// fused into this kernel (one-shot exchange over NVLink peer memory, see the top of global_draw_kernel; an ncclAllReduce
+// in front of the launch is the fallback when no peer buffers are attached); every GPU then runs the draws redundantly
+// with the same Philox key, so the new parameters need no broadcast.
 //   1. log-likelihood of state k: Bernoulli + structural parts arrive in the statistics, the response-time
 //      part is evaluated from sufficient statistics (getLogLikelihood*, GibbsRtIrt.pl.jl:262-272)
 //   2. parameters of sweep k+1 in the reference's order, every sum over persons expanded into
@@ -331,7 +333,45 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   double* sXtX = g_dyn + L.s_count + 2;   // [(F+1)^2]
   double* sRaw = sXtX + (F + 1) * (F + 1);  // [5][Jp] attempt-0 raw material of the item sites: z_b, z_a, z_lambda, x_sigma2, u_sigma2
   const int Jp = L.Jp;
-  for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats[t];
+  if (A.peer_bufs) {
+    // ---- fused one-shot all-reduce over NVLink peer memory: push this GPU's statistics into slot [parity][rank] of every
+    //      GPU's exchange buffer, publish the sequence stamp, wait for the peers' stamps, sum the slots in rank order.
+    //      Two parities suffice: a GPU can only be two exchanges ahead of a slot it overwrites after the owner has published
+    //      the stamp of the exchange in between, i.e. after the owner has finished reading that slot. ----
+    const int world = A.world, rank = A.rank, S = A.xstride;
+    const uint32_t seq = *A.xseq + 1u;
+    const int par = (int)(seq & 1u);
+    for (int r = 0; r < world; ++r) {
+      double* dst = A.peer_bufs[r] + ((size_t)par * world + rank) * S;
+      for (int t = tid; t < L.s_count; t += G_THREADS) dst[t] = A.stats[t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+      uint32_t* theirs = reinterpret_cast<uint32_t*>(A.peer_bufs[tid] + (size_t)2 * world * S) + par * world + rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
+      const uint32_t* mine = reinterpret_cast<const uint32_t*>(A.peer_bufs[rank] + (size_t)2 * world * S) + par * world + tid;
+      uint32_t got;
+      const long long t_start = clock64();
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+        if (got != seq && clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
+          atomicExch(A.status, -1000 - tid);
+          break;
+        }
+      } while (got != seq);
+    }
+    __syncthreads();
+    const double* slots = A.peer_bufs[rank] + (size_t)par * world * S;
+    for (int t = tid; t < L.s_count; t += G_THREADS) {
+      double acc = 0.0;
+      for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * S + t);
+      st[t] = acc;
+    }
+    if (tid == 0) *A.xseq = seq;
+  } else {
+    for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats[t];
+  }
   for (int t = tid; t < (F + 1) * (F + 1); t += G_THREADS) sXtX[t] = A.XtX[t];
   if (tid < MAXD) w.beta[tid] = par[L.p_beta + tid];  // one lane each: a single lane copying global -> shared pays a round trip per element
   if (tid >= 64 && tid < 68) w.Sigma[tid - 64] = par[L.p_Sigma + tid - 64];

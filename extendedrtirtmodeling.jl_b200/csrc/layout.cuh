@@ -132,6 +132,10 @@ struct GlobalArgs {
   int stage;  // 0/2: full draw + trace + counter; 1 (Cross family): lambda, sigma2 only
   double k1, k2;
   PhiloxKey key;
+  // one-shot peer exchange of the statistics (person-sharded chains, NVLink peer memory); peer_bufs == nullptr: not used
+  double* const* peer_bufs;  // [world] base of every GPU's exchange buffer: data [2][world][xstride] doubles, then stamps [2][world] u32
+  uint32_t* xseq;            // exchanges completed so far (identical on every GPU)
+  int world, rank, xstride;
 };
 
 }  // namespace erirt

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing, one process per GPU (torchrun): person sharding of one chain and independent chains.
 
-torch.distributed is used only as the bootstrap (rendezvous, broadcasting the 128-byte NCCL id, gathering
-results); the per-sweep exchange of item statistics is an ncclAllReduce issued by the library itself on its own
-stream (csrc/erirt_b200.cu, enqueue_step).  SURVEY.md 8e."""
+torch.distributed is used only as the bootstrap (rendezvous, broadcasting the 128-byte NCCL id, all-gathering the
+CUDA IPC handles of the exchange buffers, gathering results).  The per-sweep exchange of item statistics runs inside
+the library: a one-shot all-reduce over NVLink peer memory fused into the global draw kernel (attach_peers), or an
+ncclAllReduce on the library's stream when no peer buffers are attached (csrc/erirt_b200.cu, launch_global).  SURVEY.md 8e."""
 import numpy as np
 
 
@@ -41,6 +42,23 @@ def make_shard(n_total, group=None):
     uid = broadcast_bytes(uid, 0, group)
     offset, count = shard_bounds(n_total, world, rank)
     return (rank, world, uid, offset, n_total), count
+
+
+def allgather_bytes(payload, group=None):
+    """All-gather equal-length byte strings; returns their concatenation in rank order."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    outs = [torch.zeros_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(outs, mine, group=group)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in outs)
+
+
+def attach_peers(engine, group=None):
+    """Switch a person-sharded engine (after comm_init) to the fused peer-memory exchange: export this GPU's buffer,
+    all-gather the IPC handles, map the peers.  One process per GPU on one node (NVLink / NVSwitch peers)."""
+    engine.peer_attach(allgather_bytes(engine.peer_export(), group))
 
 
 def gather_person_vector(local, n_total, group=None):

@@ -125,6 +125,17 @@ class Engine:
         buf = C.create_string_buffer(unique_id, 128)
         check(self.lib.erirt_comm_init(self.h, rank, world, buf))
 
+    def peer_export(self) -> bytes:
+        """Allocate this GPU's exchange buffer of the fused one-shot all-reduce and return its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        check(self.lib.erirt_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles: bytes):
+        """Map the peers' exchange buffers (world x 64 bytes of IPC handles, in rank order)."""
+        buf = C.create_string_buffer(handles, len(handles))
+        check(self.lib.erirt_peer_attach(self.h, buf))
+
 
 def nccl_unique_id() -> bytes:
     L = _lib.load()

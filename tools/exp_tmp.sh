@@ -1,2 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -q -x -k "one_sweep or multi_sweep or variants or loglik" 2>&1 | tail -3
-python bench.py --short --steps 6 --warmup 3 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'person_sweep|global_draw' -c 24 --csv python bench.py --short --steps 6 --warmup 3 2>/dev/null | grep -o '"\(person_sweep[a-z_]*\|global_draw_kernel\)[^"]*".*' | awk -F'","' '{print $1, $NF}' | tail -8
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py 2>&1 | grep -v "^$\|Warning\|warn" | tail -12
+for mode in peer nccl; do
+echo "== exchange=$mode"
+ERIRT_EXCHANGE=$mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --short --steps 50 --warmup 5 2>&1 | grep -o '"ms_per_step": [0-9.]*\|"value": [0-9.]*\|rror.*' | head -4
+done
