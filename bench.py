@@ -8,8 +8,9 @@ One "step" = one Gibbs sweep of GibbsRtIrtQuantile (the LatentQr sampler, q = 0.
 synthetic BASELINE config 5: nSubj = 1,000,000 x nItem = 100, data from setDataRtIrtLatent(type="skew")
 (src/SimTools.jl:300-343), f32 storage / per-cell arithmetic, f64 statistics, log-likelihood and running
 person moments ON (the reference computes logLike and stores the trace every sweep).  With N > 1 the persons of
-the one chain are sharded over the N GPUs of the box and the item statistics are all-reduced with NCCL every
-sweep, so the total work is fixed: "scaling": "strong".
+the one chain are sharded over the N GPUs of the box and the item statistics are all-reduced every sweep (one-shot
+exchange over NVLink peer memory fused into the global draw kernel; ERIRT_EXCHANGE=nccl selects ncclAllReduce), so
+the total work is fixed: "scaling": "strong".
 
 Keys (see DESIGN.md "Measurement"):
   value       sweeps/s, data resident in HBM, CUDA events on the library's stream, max over ranks
@@ -325,7 +326,7 @@ def main():
         peak, which = measured_peak()
         bytes_launch = sk["bytes_per_sweep"]
         achieved = bytes_launch / (pk_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "person_sweep_kernel", "achieved": achieved, "peak": peak, "peak_source": which,
+        roofline = {"bound": "hbm", "kernel": "person_sweep_fast_kernel" if args.dtype == "f32" else "person_sweep_kernel", "achieved": achieved, "peak": peak, "peak_source": which,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": bytes_launch,
                     "kernel_ms": pk_ms, "launches_timed": kk, "pg_deferred_frac": sk["pg_deferred_frac"]}
         engk.close()
@@ -376,7 +377,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": f"persons sharded over {world} GPU(s), NCCL all-reduce of item statistics per sweep" if world > 1 else "single GPU",
+                "config": {"workload": WORKLOAD, "parallelism": (f"persons sharded over {world} GPUs, item statistics all-reduced per sweep by "
+                                           + ("a one-shot exchange over NVLink peer memory fused into the global draw kernel"
+                                              if os.environ.get("ERIRT_EXCHANGE", "peer") == "peer" else "ncclAllReduce")) if world > 1 else "single GPU",
                            "l2": "inputs (1.3 GB/sweep) larger than the 126 MB L2", "cuda_graph": True,
                            "loglik_and_moments": "on"},
                 "clocks": clk, "gpu_launches": 2 * K, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,

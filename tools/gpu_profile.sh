@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'person_sweep
     --log-file gpurun_out/launches_${TAG}.csv $SHORT > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
 $SHORT > gpurun_out/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:person_sweep -s 4 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:person_sweep -s 4 -c 1 \
     -o gpurun_out/prof_person_${TAG} $SHORT > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full rc=$?"
 ls -la gpurun_out
