@@ -11,3 +11,5 @@ from .simulate import (getBias, getRmse, setDataMlIrt, setDataRtIrt, setDataRtIr
                        setDataRtIrtNull, setTrueParaMlIrt, setTrueParaRtIrt, setTrueParaRtIrtCross,
                        setTrueParaRtIrtLatent)
 from .structs import InputData, InputData4R, InputPara, OutputDic, OutputPost, SimConditions, setCond  # noqa: F401
+from .simtools import checkConvergence, comparePara, getMetrics, getMetrics2, runSimulation  # noqa: F401
+from .ingest import readCsvData  # noqa: F401

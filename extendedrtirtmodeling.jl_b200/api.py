@@ -114,7 +114,9 @@ def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", 
 
     Extra keyword-only engine options: dtype ("f64" parity mode / "f32" fast mode), seed, chain (independent
     chain id), device, person_trace, compat (quirk switches, default = as written in the reference),
-    shard = (rank, world, nccl_unique_id_bytes, subj_offset, n_subj_total) for a person-sharded chain.
+    shard = (rank, world, nccl_unique_id_bytes, subj_offset, n_subj_total[, allgather]) for a person-sharded chain; the
+    optional sixth entry is a callable bytes -> concatenated bytes of all ranks (e.g. distributed.allgather_bytes), which
+    switches the per-sweep exchange from ncclAllReduce to the fused peer-memory all-reduce.
     Returns MCMC (mutated), like the reference."""
     if itemtype not in ("1pl", "2pl"):
         raise ValueError("Invalid input: the item type must be '1pl' or '2pl'.")  # src/GibbsRtIrt.pl.jl:212-214
@@ -135,6 +137,8 @@ def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", 
     MCMC.engine = eng
     if shard is not None:
         eng.comm_init(shard[0], shard[1], shard[2])
+        if len(shard) > 5 and shard[5] is not None:
+            eng.peer_attach(shard[5](eng.peer_export()))
     eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if F > 0 else None)
     init = dict(theta=P0.theta, a=P0.a, b=P0.b)
     if MCMC.has_rt:

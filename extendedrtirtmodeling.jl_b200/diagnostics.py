@@ -70,3 +70,61 @@ def summarize(arr, names=None):
         out.append(dict(name=names[c] if names else str(c), mean=float(x.mean()), std=float(x.std(ddof=1)), ess=e, rhat=r,
                         q025=float(np.quantile(x, 0.025)), q975=float(np.quantile(x, 0.975))))
     return out
+
+
+def ess_rhat_batched(arr, device=None):
+    """Bulk ESS and R-hat of many parameters at once: arr (draws, params, chains) -> (ess[params], rhat[params]).
+    Same estimator as ess_rhat (rank-normalised split chains, FFT autocovariance, Geyer's initial monotone sequence), written
+    with torch tensor operations so that the whole table of checkConvergence (src/SimTools.jl:419-443: every column of
+    Post.ra / Post.rt / Post.qr) is one batched computation; device="cuda" keeps it on the GPU next to the traces
+    (SURVEY 8f-2), device=None runs the identical code on the CPU."""
+    import torch
+    x = torch.as_tensor(np.asarray(arr, dtype=np.float64), device=device)
+    n0, P, m0 = x.shape
+    h = n0 // 2
+    if h > 0:
+        x = torch.cat([x[:h], x[n0 - h:]], dim=2)  # split chains
+    n, _, m = x.shape
+    const = (x.amax(dim=(0, 2)) - x.amin(dim=(0, 2))) == 0
+    bad = const | ~torch.isfinite(x).all(dim=0).all(dim=1)
+    xs = torch.nan_to_num(x)
+    # rank normalisation per parameter over all draws and chains (average ranks for ties)
+    flat = xs.permute(1, 0, 2).reshape(P, n * m)
+    order = flat.argsort(dim=1, stable=True)
+    ranks = torch.empty_like(flat)
+    ar = torch.arange(1, n * m + 1, dtype=torch.float64, device=x.device).expand(P, -1)
+    ranks.scatter_(1, order, ar)
+    srt = flat.gather(1, order)
+    # average the ranks of equal values: group boundaries in sorted order
+    newgrp = torch.ones_like(srt, dtype=torch.bool)
+    newgrp[:, 1:] = srt[:, 1:] != srt[:, :-1]
+    gid = newgrp.cumsum(dim=1) - 1
+    gsum = torch.zeros_like(srt).scatter_add_(1, gid, ar)
+    gcnt = torch.zeros_like(srt).scatter_add_(1, gid, torch.ones_like(srt))
+    avg_sorted = (gsum / gcnt.clamp(min=1)).gather(1, gid)
+    ranks.scatter_(1, order, avg_sorted)
+    z = torch.special.ndtri((ranks - 0.375) / (n * m + 0.25)).reshape(P, n, m).permute(1, 0, 2)  # (n, P, m)
+    # autocovariance by FFT
+    L = 1 << int(np.ceil(np.log2(2 * n)))
+    zc = z - z.mean(dim=0, keepdim=True)
+    f = torch.fft.rfft(zc, n=L, dim=0)
+    ac = torch.fft.irfft(f * f.conj(), n=L, dim=0)[:n] / n  # (n, P, m)
+    chain_var = ac[0] * n / (n - 1.0)
+    W = chain_var.mean(dim=1)
+    B = n * z.mean(dim=0).var(dim=1, unbiased=True) if m > 1 else torch.zeros_like(W)
+    var_plus = W * (n - 1.0) / n + B / n
+    rhat = torch.sqrt(var_plus / W)
+    rho = 1.0 - (W[None, :] - ac.mean(dim=2)) / var_plus[None, :]
+    rho[0] = 1.0
+    # Geyer: pair sums, cut at the first negative pair, running minimum
+    npairs = n // 2
+    pairs = rho[0:2 * npairs:2] + rho[1:2 * npairs:2]  # (npairs, P)
+    alive = (pairs >= 0).to(torch.float64).cumprod(dim=0)
+    mono = torch.cummin(torch.where(alive > 0, pairs, torch.full_like(pairs, float("inf"))), dim=0).values
+    tau = -1.0 + 2.0 * (torch.where(alive > 0, mono, torch.zeros_like(mono))).sum(dim=0)
+    tau = torch.clamp(tau, min=1.0 / np.log10(n * m))
+    ess = n * m / tau
+    nan = torch.full_like(ess, float("nan"))
+    ess = torch.where(bad | (n < 4), nan, ess)
+    rhat = torch.where(bad | (n < 4), nan, rhat)
+    return ess.cpu().numpy(), rhat.cpu().numpy()

@@ -359,3 +359,14 @@ def test_full_size_properties_c5(E):
     st = eng.stats()
     assert 0 < st["pg_deferred_frac"] < 0.25
     eng.close()
+
+
+def test_run_simulation_driver(E):
+    """runSimulation (src/SimTools.jl:457-495) on the GPU sampler: Dict layout, getMetrics on top of it."""
+    Cond = E.setCond(nSubj=400, nItem=8, nFeat=2, nIter=120, nChain=1, nRep=2)
+    tp = E.setTrueParaRtIrt(Cond, rng=5)
+    run = E.runSimulation(Cond, tp, Para=("a", "b", "λ", "σ²t"), funcData=E.setDataRtIrt, funcGibbs=E.GibbsRtIrt, dtype="f32")
+    assert set(run.keys()) == {"True", 1, 2}
+    assert run[1]["a"].shape == (8,) and np.isfinite(run[2]["Dic"][0]) and "essN" in run[1]["Diag"]
+    m = E.getMetrics(run, par="b")
+    assert m["Rmse"] < 0.5 and m["Corr"] > 0.8

@@ -94,3 +94,71 @@ def test_shard_bounds_partition_persons():
             assert o0 + c0 == o1
         assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
     assert distributed.chain_assignment(8, 4, 1) == [1, 5]
+
+
+def test_batched_ess_matches_scalar_estimator():
+    rng = np.random.default_rng(3)
+    n, P, m = 400, 6, 3
+    x = rng.standard_normal((n, P, m))
+    for p in range(1, P):
+        for t in range(1, n):
+            x[t, p] = 0.15 * p * x[t - 1, p] + x[t, p]
+    x[:, 2, 1] += 2.0            # a chain that sits elsewhere: R-hat > 1.1
+    x[:, 4] = np.round(x[:, 4], 1)  # ties
+    x[:, 5] = 1.0                # constant column -> NaN, skipped by checkConvergence (SimTools.jl:430-433)
+    e, r = diagnostics.ess_rhat_batched(x)
+    for p in range(P):
+        e0, r0 = diagnostics.ess_rhat(x[:, p, :])
+        assert (np.isnan(e0) and np.isnan(e[p])) or abs(e0 - e[p]) < 1e-9 * e0
+        assert (np.isnan(r0) and np.isnan(r[p])) or abs(r0 - r[p]) < 1e-12
+
+
+def test_simtools_metrics_and_convergence_table():
+    import erirt_b200 as E
+    true = np.array([1.0, 1.2, 0.8, 1.1])
+    rng = np.random.default_rng(1)
+    obj = {"True": {"a": true}}
+    for r in range(1, 6):
+        obj[r] = {"a": true + 0.01 * rng.standard_normal(4) + 0.02}
+    m = E.getMetrics(obj, par="a")
+    assert abs(m["Bias"] - 0.02) < 0.01 and m["Rmse"] < 0.04 and m["Corr"] > 0.99
+    m2 = E.getMetrics2(obj, par="a")
+    assert abs(m2["relativeBias"] - 0.02) < 0.015
+
+    class Fake:
+        pass
+    M = Fake()
+    M.Cond = E.setCond(nSubj=5, nItem=3, nIter=1000, nChain=2)
+    M.Post = E.OutputPost()
+    M.Post.ra = rng.standard_normal((1000, 11, 2))
+    M.Post.ra[:, :5] = np.nan            # person columns absent (person_trace=False)
+    M.Post.rt = rng.standard_normal((1000, 11, 2))
+    M.Post.qr = np.ones((1000, 4, 2))   # constant columns are not counted
+    conv = E.checkConvergence(M)
+    assert conv["essN"].endswith("/ 17") and conv["ess"] == 100.0 and conv["rhat"] == 100.0
+
+
+def test_csv_ingest_timss_shaped(tmp_path):
+    """A TIMSS-2019-shaped table (item scores, *_S response times in seconds, covariates, ids, a missing cell) -> InputData."""
+    import erirt_b200 as E
+    rng = np.random.default_rng(2)
+    n, J = 40, 5
+    items = [f"ME62{100 + j}" for j in range(J)]
+    hdr = ["IDSTUD"] + items + [i + "_S" for i in items] + ["BSBG01", "BSBGHER_Z"]
+    Y = (rng.random((n, J)) < 0.7).astype(int)
+    T = np.exp(rng.normal(3.7, 0.6, (n, J)))
+    X = np.column_stack([rng.integers(1, 3, n), rng.standard_normal(n)])
+    lines = [",".join(hdr)]
+    for i in range(n):
+        lines.append(",".join([str(1000 + i)] + [str(v) for v in Y[i]] + [f"{v:.3f}" for v in T[i]] + [str(X[i, 0]), f"{X[i, 1]:.6f}"]))
+    bad = lines[7].split(",")
+    bad[8] = ""  # a missing response time
+    lines[7] = ",".join(bad)
+    p = tmp_path / "toy.csv"
+    p.write_text("\n".join(lines) + "\n")
+    D = E.readCsvData(str(p), y_cols=items, t_cols=[i + "_S" for i in items], x_cols=["BSBG01", "BSBGHER_Z"])
+    assert D.Y.shape == (n - 1, J) and D.T.shape == (n - 1, J) and D.X.shape == (n - 1, 2) and D.dropped_rows == [8]
+    keep = [i for i in range(n) if i != 6]
+    assert np.array_equal(D.Y, Y[keep]) and np.allclose(D.logT, np.log(np.round(T[keep], 3)))
+    with pytest.raises(ValueError):
+        E.readCsvData(str(p), y_cols=items, t_cols=[i + "_S" for i in items], drop_missing=False)
