@@ -163,8 +163,30 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   const int eg = tid % G, er = tid / G;
   u64 a0l = 0ull, a0h = 0ull, a1l = 0ull, a1h = 0ull, a2l = 0ull, a2h = 0ull, acl = 0ull, ach = 0ull;  // {items 0,1} / {items 2,3}
   R ay[4] = {0, 0, 0, 0};
-  auto flush_item_stats = [&]() {
-    if (e_active) {
+  // Folding the f32 register sums into the CTA's f64 accumulators: the Rc person classes of an item group would collide on the
+  // same 500 addresses (f64 shared atomics are CAS loops), so each class writes its 20 sums into its own slab of a staging area
+  // -- the logT tile, dead between the statistics pass and the next tile's load -- and the slabs are added without atomics.
+  const bool stage_flush = has_rt && (size_t)Rc * 5 * Jp * sizeof(R) <= (size_t)A.S.tile_real_bytes;
+  auto flush_item_stats = [&]() {  // called by all threads of the CTA at the same point
+    if (stage_flush) {
+      R* stg = s_lt;
+      __syncthreads();  // every warp is done reading logT in the statistics pass
+      if (e_active) {
+        R* d = stg + (size_t)er * 5 * Jp + 4 * eg;
+        *reinterpret_cast<float4*>(d + 0 * Jp) = make_float4(lo2(a0l), hi2(a0l), lo2(a0h), hi2(a0h));
+        *reinterpret_cast<float4*>(d + 1 * Jp) = make_float4(lo2(a1l), hi2(a1l), lo2(a1h), hi2(a1h));
+        *reinterpret_cast<float4*>(d + 2 * Jp) = make_float4(lo2(a2l), hi2(a2l), lo2(a2h), hi2(a2h));
+        *reinterpret_cast<float4*>(d + 3 * Jp) = make_float4(ay[0], ay[1], ay[2], ay[3]);
+        *reinterpret_cast<float4*>(d + 4 * Jp) = make_float4(lo2(acl), hi2(acl), lo2(ach), hi2(ach));
+      }
+      __syncthreads();
+      for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
+        double acc = 0.0;
+        for (int r = 0; r < Rc; ++r) acc += (double)stg[(size_t)r * 5 * Jp + t];
+        s_acc_item[t] += acc;
+      }
+      __syncthreads();  // the staging area is a tile buffer again after this point
+    } else if (e_active) {
       const R v0[4] = {lo2(a0l), hi2(a0l), lo2(a0h), hi2(a0h)}, v1[4] = {lo2(a1l), hi2(a1l), lo2(a1h), hi2(a1h)};
       const R v2[4] = {lo2(a2l), hi2(a2l), lo2(a2h), hi2(a2h)}, vc[4] = {lo2(acl), hi2(acl), lo2(ach), hi2(ach)};
 #pragma unroll
@@ -175,10 +197,10 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         atomicAdd(&s_acc_item[2 * Jp + j], (double)v2[e]);
         atomicAdd(&s_acc_item[3 * Jp + j], (double)ay[e]);
         atomicAdd(&s_acc_item[4 * Jp + j], (double)vc[e]);
-        ay[e] = R(0);
       }
-      a0l = a0h = a1l = a1h = a2l = a2h = acl = ach = 0ull;
     }
+    ay[0] = ay[1] = ay[2] = ay[3] = R(0);
+    a0l = a0h = a1l = a1h = a2l = a2h = acl = ach = 0ull;
   };
 
   int tiles_done = 0;
@@ -214,26 +236,42 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     R th = R(0), ze = R(0), nu = R(1), xb1 = R(0), xb2 = R(0);
     R zn_theta = R(0), zn_zeta = R(0), zn_nu = R(0), un_nu = R(0);
     if (lead) {
+      // global loads first (independent, all in flight together), the variates while they travel
+      th = A.theta[pi];
+      if (has_rt) ze = A.zeta[pi];
+      if (qr) nu = A.nu[pi];
+      R xs[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < F) xs[i] = A.X[(int64_t)i * A.n_pad + pi];
       if (do_draws) {
-        const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
+        const uint4 w = philox(A.sched, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
         zn_theta = normal2f(w.x, w.y);
         zn_zeta = normal2f(w.z, w.w);
       }
       if (qr) {
-        const uint4 w = philox(A.key, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+        const uint4 w = philox(A.sched, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
         zn_nu = normal2f(w.x, w.y);
         un_nu = u01f(w.z);
       }
-      th = A.theta[pi];
-      if (has_rt) ze = A.zeta[pi];
-      if (qr) nu = A.nu[pi];
       if (reg_x) xb1 = s_beta[0];
       if (model == M_RTIRT) xb2 = s_beta[pb];
-      for (int f = 0; f < F; ++f) {
-        const R x = A.X[(int64_t)f * A.n_pad + pi];
-        s_u[p * Dgp + 1 + f] = pvalid ? x : R(0);
-        if (reg_x) xb1 = fmaf(x, s_beta[1 + f], xb1);
-        if (model == M_RTIRT) xb2 = fmaf(x, s_beta[pb + 1 + f], xb2);
+      for (int f0 = 0; f0 < F; f0 += 4) {
+        if (f0 > 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (f0 + i < F) xs[i] = A.X[(int64_t)(f0 + i) * A.n_pad + pi];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = f0 + i;
+          if (f < F) {
+            const R x = xs[i];
+            s_u[p * Dgp + 1 + f] = pvalid ? x : R(0);
+            if (reg_x) xb1 = fmaf(x, s_beta[1 + f], xb1);
+            if (model == M_RTIRT) xb2 = fmaf(x, s_beta[pb + 1 + f], xb2);
+          }
+        }
       }
     }
     PF_TICK(0);  // TMA issue, person part 1
