@@ -423,41 +423,59 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       const u64 TH = bc2(thp);
       u64 prod = bc2(1.0f);
       R sabs = R(0), skz = R(0);
-      constexpr int U = TPP <= 2 ? 2 : 1;  // groups per iteration: group_of(q, kk + 1) == group_of(q, kk) + 1 for even kk when 8/TPP is even
-      for (int kk = 0; kk < nk; kk += U) {
-        const int g0 = group_of<TPP>(q, kk);
-        if (g0 >= G) continue;
-        const R* r_par = s_par + 4 * g0;
-        const R* r_ta = s_ta + g0 * TAB_PITCH;
-        uint32_t dm = 0, rm = 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (g0 + u < G) {
-            const float4 pA = *reinterpret_cast<const float4*>(r_par + PAR_A * Jp + 4 * u);
-            const float4 pN = *reinterpret_cast<const float4*>(r_par + PAR_AB * Jp + 4 * u);
-            const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * (g0 + u)));
-            skz += fmaf(thp, r_ta[u * TAB_PITCH + yb], r_ta[G * TAB_PITCH + u * TAB_PITCH + yb]);  // sum_e kappa_e z_e of this group
-            const u64 z01 = ffma2(pk2(pA.x, pA.y), TH, pk2(pN.x, pN.y)), z23 = ffma2(pk2(pA.z, pA.w), TH, pk2(pN.z, pN.w));
-            const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * (g0 + u))), 0);
-            const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * (g0 + u) + 1)), 0);
-            float4 out;
-            uint32_t dmu = 0, rmu = 0;
-            pg_fast_pair<0>(z01, wA.x, wA.y, wA.z, wA.w, out.x, out.y, dmu, rmu, prod, sabs);
-            pg_fast_pair<2>(z23, wB.x, wB.y, wB.z, wB.w, out.z, out.w, dmu, rmu, prod, sabs);
-            if (wide) {  // attempt 0 does not exist beyond |z| = 16: straight to the retry blocks
-              const R zs[4] = {lo2(z01), hi2(z01), lo2(z23), hi2(z23)};
-              R* o = &out.x;
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (!(fabsf(zs[e]) <= PG_Z0MAX)) { o[e] = -2.0f; dmu |= 1u << e; rmu |= 1u << e; }
-            }
-            *reinterpret_cast<float4*>(my_om + 4 * (g0 + u)) = out;
-            dm |= dmu << (4 * u);
-            rm |= rmu << (4 * u);
+      // one 4-item group: straight-line code (no branch inside), so that the groups of an iteration interleave when scheduled
+      auto do_group = [&](const int g, uint32_t& dmu, uint32_t& rmu) {
+        const float4 pA = *reinterpret_cast<const float4*>(s_par + PAR_A * Jp + 4 * g);
+        const float4 pN = *reinterpret_cast<const float4*>(s_par + PAR_AB * Jp + 4 * g);
+        const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * g));
+        skz += fmaf(thp, s_ta[g * TAB_PITCH + yb], s_tb[g * TAB_PITCH + yb]);  // sum_e kappa_e z_e of this group
+        const u64 z01 = ffma2(pk2(pA.x, pA.y), TH, pk2(pN.x, pN.y)), z23 = ffma2(pk2(pA.z, pA.w), TH, pk2(pN.z, pN.w));
+        const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
+        const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
+        float4 out;
+        pg_fast_pair<0>(z01, wA.x, wA.y, wA.z, wA.w, out.x, out.y, dmu, rmu, prod, sabs);
+        pg_fast_pair<2>(z23, wB.x, wB.y, wB.z, wB.w, out.z, out.w, dmu, rmu, prod, sabs);
+        *reinterpret_cast<float4*>(my_om + 4 * g) = out;
+      };
+      if (!wide) {
+        constexpr bool PAIRS = TPP <= 2;  // group_of(q, kk + 1) == group_of(q, kk) + 1 for even kk when 8/TPP is even
+        for (int kk = 0; kk < nk; kk += PAIRS ? 2 : 1) {
+          const int g0 = group_of<TPP>(q, kk);
+          if (g0 >= G) continue;
+          uint32_t dm0 = 0, rm0 = 0, dm1 = 0, rm1 = 0;
+          if (PAIRS && g0 + 1 < G) {
+            do_group(g0, dm0, rm0);
+            do_group(g0 + 1, dm1, rm1);
+          } else {
+            do_group(g0, dm0, rm0);
           }
+          dmask |= (u64)(dm0 | (dm1 << 4)) << (4 * kk);
+          rmask |= (u64)(rm0 | (rm1 << 4)) << (4 * kk);
         }
-        dmask |= (u64)dm << (4 * kk);
-        rmask |= (u64)rm << (4 * kk);
+      } else {
+        // |theta| so large that some |z| may leave the range in which attempt 0 is defined (PG_Z0MAX): no fast evaluation for
+        // this row -- every cell goes to the work queues, with the attempt-0 replay where attempt 0 exists.  Never taken with
+        // sane parameters; kept exact for parity with the oracle.
+        for (int kk = 0; kk < nk; ++kk) {
+          const int g = group_of<TPP>(q, kk);
+          if (g >= G) continue;
+          const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * g));
+          skz += fmaf(thp, s_ta[g * TAB_PITCH + yb], s_tb[g * TAB_PITCH + yb]);
+          uint32_t dm = 0, rm = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const R z = fmaf(s_par[PAR_A * Jp + 4 * g + e], thp, s_par[PAR_AB * Jp + 4 * g + e]);
+            const R az = fabsf(z);
+            if (e & 1) prod = ffma2(prod, pk2(0.f, fast_ex2(-PGF_LOG2E * az)), prod);
+            else prod = ffma2(prod, pk2(fast_ex2(-PGF_LOG2E * az), 0.f), prod);
+            sabs += az;
+            my_om[4 * g + e] = -2.0f;
+            dm |= 1u << e;
+            if (!(az <= PG_Z0MAX)) rm |= 1u << e;
+          }
+          dmask |= (u64)dm << (4 * kk);
+          rmask |= (u64)rm << (4 * kk);
+        }
       }
       // kappa z - |z|/2 - ln(1 + e^{-|z|}); a padding cell has z = 0 and contributed -ln 2
       const R ll_row = skz - R(0.5) * sabs - PGF_LN2 * (fast_lg2(lo2(prod)) + fast_lg2(hi2(prod)) - (R)n_pad_cells);
