@@ -168,6 +168,21 @@ __device__ inline bool mvn_draw(const GlobalArgs& A, uint32_t s, int d, GScratch
   return true;
 }
 
+// w.XX = x'x and w.rhs = x'y of the Latent family (x = [1 X θ]), one element per lane
+__device__ inline void latent_prebuild(const GlobalArgs& A, const double* XtX, const GramView& Gm, GScratch& w, int tid, int nthreads) {
+  const int F = A.L.F, pb = F + 1, d = F + 2;
+  const bool qrm = A.model == M_LATENTQR;
+  for (int t = tid; t < d * d + d; t += nthreads) {
+    if (t < d * d) {
+      const int r = t % d, q = t / d;
+      w.XX[r + d * q] = (r < pb && q < pb) ? XtX[r + pb * q] : Gm.at(r, q);
+    } else {
+      const int r = t - d * d;
+      w.rhs[r] = Gm.at(r, Gm.ze()) - (qrm ? A.k1 * Gm.at(r, Gm.nu()) : 0.0);
+    }
+  }
+}
+
 __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, uint32_t s, const GramView& Gm, const GramView& Gw, GScratch& w) {
   const Layout& L = A.L;
   const int F = L.F, pb = F + 1, model = A.model;
@@ -242,15 +257,9 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
   } else if (model == M_LATENT || model == M_LATENTQR) {
     const int d = F + 2;
     const bool qrm = model == M_LATENTQR;
-    // x = [1 X θ]: x'x = ingest constant (f64) bordered by the θ column of the Gram
-    #pragma unroll 1
-    for (int r = 0; r < d; ++r)
-      #pragma unroll 1
-      for (int q = 0; q < d; ++q) w.XX[r + d * q] = (r < pb && q < pb) ? XtX[r + pb * q] : Gm.at(r, q);
+    // x = [1 X θ]: x'x (ingest constant bordered by the θ column of the Gram) and x'y, y = ζ (Latent) or ζ - k1 ν (LatentQr),
+    // were built by all lanes in latent_prebuild
     S_TICK(7);
-    // y = ζ (Latent) or ζ - k1 ν (LatentQr)
-    #pragma unroll 1
-    for (int r = 0; r < d; ++r) w.rhs[r] = Gm.at(r, ZE) - (qrm ? A.k1 * Gm.at(r, NU) : 0.0);
     double yy = Sze2;
     if (qrm) yy += -2.0 * A.k1 * Gm.at(ZE, NU) + A.k1 * A.k1 * Gm.at(NU, NU);
     if (!qrm) {  // drawSubjCoefficientsLatent
@@ -478,6 +487,7 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
       w.graw[2 * u + 1] = u01d(wd.z);
     }
   }
+  if (model == M_LATENT || model == M_LATENTQR) latent_prebuild(A, sXtX, Gm, w, tid, G_THREADS);
   __syncthreads();
   G_TICK(6, 0);  // raw variates done
   // ---- 2a. structural draws (thread 0), 2b. item draws (warps 1..) ----
@@ -485,28 +495,31 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     if (!structural_draws(A, sXtX, s, Gm, Gw, w)) atomicExch(A.status, (int)s);
     G_TICK(2, 0);  // structural block done
   }
-  // item draws on warps 1..: the structural lane of warp 0 runs concurrently instead of serialising with 31 item lanes
-  for (int j = tid - 32; j >= 0 && j < J; j += G_THREADS - 32) {
-    const double S0 = st[L.s_S0 + j], S1 = st[L.s_S1 + j], S2 = st[L.s_S2 + j];
-    const double K0 = A.K0[j], K1 = st[L.s_Ky + j] - 0.5 * Sth;  // Σκ, Σκθ
-    double a = par[L.p_a + j], b = par[L.p_b + j];
-    auto draw_b = [&]() {  // drawItemDifficulty
-      const double parV = 1.0 / (1.0 + a * a * S0);
-      const double parM = parV * (0.0 - (a * K0 - a * a * S1));
-      double v = parM + sqrt(parV) * sRaw[0 * Jp + j];
-      b = v < -4.0 ? -4.0 : (v > 4.0 ? 4.0 : v);
-    };
-    auto draw_a = [&]() {  // drawItemDiscrimination
-      const double parV = 1.0 / (1.0 + (S2 - 2.0 * b * S1 + b * b * S0));
-      const double parM = parV * (1.0 + (K1 - b * K0));
-      a = tnorm_pos_from_raw(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_A), parM, sqrt(parV), sRaw[1 * Jp + j]);
-      if (A.onepl) a = 1.0;
-    };
-    if (model == M_MLIRT) { draw_a(); draw_b(); }  // GibbsRtIrt.pl.jl:233-237 (quirk Q8)
-    else { draw_b(); draw_a(); }
-    par[L.p_a + j] = a;
-    par[L.p_b + j] = b;
-    if (cross) {  // drawSubjCorrCross, Draw.pl.jl:463-469 (state k: theta_k, zeta_k, lambda_k, sigma2_k)
+  // item draws on warps 1..: the structural lane of warp 0 runs concurrently.  Two tasks per item, dealt so that a warp holds one
+  // kind: (b, a) [MlIrt: (a, b)] and the response-time pair (lambda, sigma2) [Cross family: rho], which do not depend on each other
+  for (int t = tid - 32; t >= 0 && t < 2 * J; t += G_THREADS - 32) {
+    const int part = t / J, j = t - part * J;
+    if (part == 0) {
+      const double S0 = st[L.s_S0 + j], S1 = st[L.s_S1 + j], S2 = st[L.s_S2 + j];
+      const double K0 = A.K0[j], K1 = st[L.s_Ky + j] - 0.5 * Sth;  // Σκ, Σκθ
+      double a = par[L.p_a + j], b = par[L.p_b + j];
+      auto draw_b = [&]() {  // drawItemDifficulty
+        const double parV = 1.0 / (1.0 + a * a * S0);
+        const double parM = parV * (0.0 - (a * K0 - a * a * S1));
+        double v = parM + sqrt(parV) * sRaw[0 * Jp + j];
+        b = v < -4.0 ? -4.0 : (v > 4.0 ? 4.0 : v);
+      };
+      auto draw_a = [&]() {  // drawItemDiscrimination
+        const double parV = 1.0 / (1.0 + (S2 - 2.0 * b * S1 + b * b * S0));
+        const double parM = parV * (1.0 + (K1 - b * K0));
+        a = tnorm_pos_from_raw(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_A), parM, sqrt(parV), sRaw[1 * Jp + j]);
+        if (A.onepl) a = 1.0;
+      };
+      if (model == M_MLIRT) { draw_a(); draw_b(); }  // GibbsRtIrt.pl.jl:233-237 (quirk Q8)
+      else { draw_b(); draw_a(); }
+      par[L.p_a + j] = a;
+      par[L.p_b + j] = b;
+    } else if (cross) {  // drawSubjCorrCross, Draw.pl.jl:463-469 (state k: theta_k, zeta_k, lambda_k, sigma2_k)
       const double s2 = par[L.p_sigma2 + j], lam = par[L.p_lambda + j];
       double parV, parM;
       if (model == M_CROSS) {

@@ -82,20 +82,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     s_par[PAR_A2B * Jp + j] = (R)(a * a * b);
     s_par[PAR_IS2 * Jp + j] = (R)is2;
   }
-  for (int t = tid; t < G * 16; t += CTA_THREADS) {
-    const int g = t >> 4, yb = t & 15;
-    double ta = 0, tb = 0;
-    for (int e = 0; e < 4; ++e) {
-      const int j = 4 * g + e;
-      if (j < J) {
-        const double kap = ((yb >> e) & 1) ? 0.5 : -0.5, a = par[L.p_a + j];
-        ta += kap * a;
-        tb -= kap * a * par[L.p_b + j];
-      }
-    }
-    s_ta[g * TAB_PITCH + yb] = (R)ta;
-    s_tb[g * TAB_PITCH + yb] = (R)tb;
-  }
   if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
   if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
@@ -128,6 +114,16 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       s_qctl[0] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+  }
+  __syncthreads();
+  // response tables from the staged parameters (shared memory): T_a[g][y] = sum_e kappa_e a_e, T_b[g][y] = -sum_e kappa_e a_e b_e
+  for (int t = tid; t < G * 16; t += CTA_THREADS) {
+    const int g = t >> 4, yb = t & 15;
+    const float4 a4 = *reinterpret_cast<const float4*>(s_par + PAR_A * Jp + 4 * g);
+    const float4 n4 = *reinterpret_cast<const float4*>(s_par + PAR_AB * Jp + 4 * g);
+    const R k0 = (yb & 1) ? R(0.5) : R(-0.5), k1y = (yb & 2) ? R(0.5) : R(-0.5), k2y = (yb & 4) ? R(0.5) : R(-0.5), k3 = (yb & 8) ? R(0.5) : R(-0.5);
+    s_ta[g * TAB_PITCH + yb] = fmaf(k0, a4.x, fmaf(k1y, a4.y, fmaf(k2y, a4.z, k3 * a4.w)));
+    s_tb[g * TAB_PITCH + yb] = fmaf(k0, n4.x, fmaf(k1y, n4.y, fmaf(k2y, n4.z, k3 * n4.w)));
   }
   __syncthreads();
 
