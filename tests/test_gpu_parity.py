@@ -370,3 +370,25 @@ def test_run_simulation_driver(E):
     assert run[1]["a"].shape == (8,) and np.isfinite(run[2]["Dic"][0]) and "essN" in run[1]["Diag"]
     m = E.getMetrics(run, par="b")
     assert m["Rmse"] < 0.5 and m["Corr"] > 0.8
+
+
+def test_f64_engine_matches_committed_fixture(E):
+    """The f64 engine against tests/golden/oracle_v2.npz (outputs of the CPU oracle, committed): every model, three sweeps, and
+    the PG grid including the Method switch (|z| = 3.125) and the attempt-0 limit (|z| = 16)."""
+    import os
+    from helpers import MODELS, make_problem, run_engine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
+    out = E.k_pg(g["pg_z"], seed=5, chain=2, sweep=3, row0=10, dtype="f64")
+    assert relerr(out, g["pg_omega"]).max() < 1e-12
+    for model in MODELS:
+        pb = make_problem(model, 96, 9, 2, seed=41)
+        eng = run_engine(E, pb, 3, dtype="f64")
+        N = pb["N"]
+        tol = 1e-7 if model == "RtIrtCrossQr" else 1e-9
+        assert relerr(eng.get_trace("ra")[:3, N:, 0], g[f"{model}_ra"][:, N:], atol=1e-3).max() < tol, model
+        if model != "MlIrt":
+            assert relerr(eng.get_trace("rt")[:3, N:, 0], g[f"{model}_rt"][:, N:], atol=1e-3).max() < tol, model
+        qw = g[f"{model}_qr"].shape[1] - (N if model == "RtIrtLatentQr" else 0)
+        assert relerr(eng.get_trace("qr")[:3, :qw, 0], g[f"{model}_qr"][:, :qw], atol=1e-3).max() < tol, model
+        assert relerr(eng.get_trace("logLike")[:3, 0, 0], g[f"{model}_ll"]).max() < tol, model
+        eng.close()

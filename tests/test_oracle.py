@@ -159,3 +159,21 @@ def test_oracle_recovers_item_parameters(oracle):
     b_true = rng.normal(0, 0.5, pb["J"])
     assert np.sqrt(np.mean((a_hat - a_true) ** 2)) < 0.15
     assert np.sqrt(np.mean((b_hat - b_true) ** 2)) < 0.15
+
+
+def test_oracle_reproduces_committed_fixture(oracle):
+    """tests/golden/oracle_v2.npz (made by tests/golden/make_golden.py) pins the oracle's own stream layout and formulas; it is
+    not reference-pinned (the Julia package cannot run here and ships no vectors)."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = np.load(mg.GOLDEN)
+    got = mg.compute()
+    assert set(got.keys()) == set(want.files)
+    for k in want.files:
+        w, g = np.asarray(want[k], dtype=np.float64), np.asarray(got[k], dtype=np.float64)
+        assert w.shape == g.shape, k
+        assert np.allclose(g, w, rtol=1e-11, atol=1e-12), (k, float(np.max(np.abs(g - w))))
