@@ -24,7 +24,9 @@ def main():
     for model, dtype, tol, mode in (("RtIrtLatentQr", "f64", 1e-9, "peer"), ("RtIrtLatentQr", "f64", 1e-9, "nccl"), ("RtIrt", "f64", 1e-9, "peer"),
                                     ("RtIrtNull", "f32", 2e-4, "peer"), ("MlIrt", "f64", 1e-9, "peer"), ("RtIrtCross", "f64", 1e-9, "peer"),
                                     ("RtIrtCrossQr", "f64", 1e-7, "nccl")):
-        N, J, F, ns = 5003, 21, 3, 10
+        # CrossQr amplifies rounding differences by ~30x per sweep (weights 1/nu_ij, nu clamped to [1e-10, 1e10], Draw.pl.jl:318;
+        # the single-GPU engine itself is 7e-12 from the oracle after 4 sweeps), so it is compared over 3 sweeps
+        N, J, F, ns = 5003, 21, 3, (3 if model == "RtIrtCrossQr" else 10)
         pb = make_problem(model, N, J, F, seed=31)
         shard, cnt = D.make_shard(N)
         off = shard[3]
@@ -63,9 +65,7 @@ def main():
             e1 = np.max(np.abs(items_s - items_w) / (np.abs(items_w) + 1e-3))
             e2 = np.quantile(np.abs(theta_s - theta_w) / (np.abs(theta_w) + 1e-1), 0.995)
             e3 = np.max(np.abs(ll_s - ll_w) / np.abs(ll_w))
-            # CrossQr: the per-cell response-time log-likelihood of a sharded chain differs from the single-GPU one at the 1e-3
-            # level (known gap); its draws (items, theta) are checked, the log-likelihood is only reported
-            good = e1 < tol and e2 < tol and (e3 < tol or model == "RtIrtCrossQr")
+            good = e1 < tol and e2 < tol and e3 < tol
             ok &= bool(good)
             print(f"{model} {dtype} world={world} exchange={mode}: items {e1:.2e} theta(q99.5) {e2:.2e} loglik {e3:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
         dist.barrier()
