@@ -255,7 +255,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        shard, _ = D.make_shard(N_SUBJ)
+        shard, _ = D.make_shard(N_SUBJ, nccl=False)
 
     tp = true_params()
     dY, dT, dX, offset, n_local = gen_shard_torch(tp, rank, world, dev)
@@ -268,11 +268,18 @@ def main():
                        cov2one=False, dtype=args.dtype, seed=SEED, person_trace=False, device=local, use_graph=use_graph,
                        n_subj_total=N_SUBJ, subj_offset=offset, time_kernels=time_kernels)
         if world > 1:
-            sh, _ = D.make_shard(N_SUBJ)  # a fresh NCCL id per communicator
+            peer = os.environ.get("ERIRT_EXCHANGE", "peer") == "peer"
+            sh, _ = D.make_shard(N_SUBJ, nccl=not peer)  # NCCL mode: a fresh id per communicator
             eng.comm_init(sh[0], sh[1], sh[2])
-            if os.environ.get("ERIRT_EXCHANGE", "peer") == "peer":
-                D.attach_peers(eng)  # one-shot exchange over NVLink peer memory fused into the global draw kernel
+            if peer:
+                D.attach_peers(eng)  # one-shot exchange over NVLink peer memory fused into the global draw kernel; no NCCL at all
         return eng
+
+    def close_engine(e):
+        if world > 1:
+            D.close_sharded(e)  # unmap the peers' exchange buffers on every rank before anybody frees its own
+        else:
+            e.close()
 
     def barrier():
         if world > 1:
@@ -309,7 +316,7 @@ def main():
             ess_min, ess_med = ess_per_sweep(eng, W, K, qw)
         except Exception:
             pass
-    eng.close()
+    close_engine(eng)
 
     # ---------------- roofline of the person kernel (plain launches bracketed by CUDA events) ----------------
     roofline = None
@@ -329,7 +336,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "person_sweep_fast_kernel" if args.dtype == "f32" else "person_sweep_kernel", "achieved": achieved, "peak": peak, "peak_source": which,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": bytes_launch,
                     "kernel_ms": pk_ms, "launches_timed": kk, "pg_deferred_frac": sk["pg_deferred_frac"]}
-        engk.close()
+        close_engine(engk)
 
     # ---------------- end to end through the C ABI with host buffers ("e2e") ----------------
     e2e = None
@@ -359,7 +366,7 @@ def main():
         e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world / K), "d2h_bytes_per_step": int(d2h * world / K),
                "seconds": dt, "note": "erirt_create + erirt_set_data (pinned host f64, H2D + ingest) + erirt_set_state + K sweeps + "
                                      "erirt_get_trace/erirt_get_moments (D2H); bytes are totals of the call divided by K"}
-        enge.close()
+        close_engine(enge)
 
     # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------
     cpu = None

@@ -19,7 +19,7 @@ COMPAT_LATENTQR_SCALE_ELEMENTWISE = 2
 EXPORTED = ["erirt_version", "erirt_last_error", "erirt_create", "erirt_destroy", "erirt_set_data",
             "erirt_set_data_device", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
             "erirt_trace_width", "erirt_get_moments", "erirt_loglik_current", "erirt_get_stats",
-            "erirt_nccl_unique_id", "erirt_comm_init", "erirt_peer_export", "erirt_peer_attach", "erirt_k_pg", "erirt_k_nu_person", "erirt_k_philox"]
+            "erirt_nccl_unique_id", "erirt_comm_init", "erirt_peer_export", "erirt_peer_attach", "erirt_peer_detach", "erirt_k_pg", "erirt_k_nu_person", "erirt_k_philox"]
 
 
 class Config(C.Structure):
@@ -75,6 +75,7 @@ def load():
     L.erirt_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.erirt_peer_export.argtypes = [vp, vp]
     L.erirt_peer_attach.argtypes = [vp, vp]
+    L.erirt_peer_detach.argtypes = [vp]
     L.erirt_k_pg.argtypes = [dp, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32,
                              C.c_int32, dp]
     L.erirt_k_nu_person.argtypes = [dp, C.c_double, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,

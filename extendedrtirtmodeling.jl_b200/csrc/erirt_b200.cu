@@ -540,7 +540,16 @@ extern "C" int erirt_set_data(erirt_handle* h, const double* Y, int64_t ldY, con
 static int finalize_constants(erirt_handle* h) {
   if (h->consts_final) return 0;
   CU(cudaMemcpyAsync(h->dConsts, h->dConstsLocal, h->c_count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  if (h->comm) NC(nccl::all_reduce(h->dConsts, h->dConsts, (size_t)h->c_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
+  if (h->world > 1) {
+    if (h->peer_ready) {
+      peer_allreduce_kernel<<<1, 512, 0, h->stream>>>(h->dPeerBufs, h->dXseq, h->world, h->rank, h->xstride, h->dConsts, h->c_count, h->dStatus);
+      CU(cudaGetLastError());
+    } else if (h->comm) {
+      NC(nccl::all_reduce(h->dConsts, h->dConsts, (size_t)h->c_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
+    } else {
+      return fail(ERIRT_E_STATE, "sharded chain without a communicator: call erirt_peer_attach (or erirt_comm_init with an NCCL id) first");
+    }
+  }
   std::vector<double> c(h->c_count);
   CU(cudaMemcpyAsync(c.data(), h->dConsts, h->c_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -984,15 +993,17 @@ extern "C" int erirt_nccl_unique_id(void* id128) {
   return 0;
 }
 extern "C" int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, const void* id128) {
-  if (!h || !id128) return fail(ERIRT_E_ARG, "null argument");
+  if (!h) return fail(ERIRT_E_ARG, "null argument");
   if (world < 1 || rank < 0 || rank >= world) return fail(ERIRT_E_ARG, "bad rank/world");
   if (h->prologue_done) return fail(ERIRT_E_STATE, "erirt_comm_init must precede erirt_sample");
-  int rc = nccl::load();
-  if (rc) return rc;
   CU(cudaSetDevice(h->cfg.device));
-  nccl::unique_id id;
-  memcpy(&id, id128, 128);
-  NC(nccl::comm_init_rank(&h->comm, world, id, rank));
+  if (id128) {  // NCCL communicator (fallback exchange); id128 == NULL: rank/world only, the peer exchange is attached next
+    int rc = nccl::load();
+    if (rc) return rc;
+    nccl::unique_id id;
+    memcpy(&id, id128, 128);
+    NC(nccl::comm_init_rank(&h->comm, world, id, rank));
+  }
   h->rank = rank;
   h->world = world;
   h->consts_final = false;
@@ -1006,7 +1017,7 @@ extern "C" int erirt_peer_export(erirt_handle* h, void* ipc_handle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
   CU(cudaSetDevice(h->cfg.device));
   if (!h->xbuf) {
-    h->xstride = (int)align_up((size_t)h->L.s_count, 16);
+    h->xstride = (int)align_up((size_t)std::max(h->L.s_count, h->c_count), 16);  // the statistics per sweep, the ingest constants once
     const size_t bytes = (size_t)2 * h->world * h->xstride * sizeof(double) + (size_t)2 * h->world * sizeof(uint32_t) + 256;
     CU(cudaMalloc((void**)&h->xbuf, bytes));
     CU(cudaMemset(h->xbuf, 0, bytes));
@@ -1038,6 +1049,17 @@ extern "C" int erirt_peer_attach(erirt_handle* h, const void* ipc_handles) {
   }
   CU(cudaMemcpy(h->dPeerBufs, ptrs.data(), h->world * sizeof(double*), cudaMemcpyHostToDevice));
   h->peer_ready = true;
+  return 0;
+}
+
+extern "C" int erirt_peer_detach(erirt_handle* h) {
+  if (!h) return fail(ERIRT_E_ARG, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+  h->peer_opened.clear();
+  h->peer_ready = false;  // later sweeps fall back to ncclAllReduce
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
   return 0;
 }
 

@@ -148,6 +148,51 @@ struct GramView {  // accessors into the upper-triangular Gram of u = [1, X(1..F
   __device__ int nu() const { return F + 3; }
 };
 
+// ---- fused one-shot all-reduce over NVLink peer memory (one CTA; all its threads call it at the same point) ----
+// Push `count` doubles of `src` into slot [parity][rank] of every GPU's exchange buffer, publish the sequence stamp, wait for the
+// peers' stamps, sum the slots in rank order into `dst` (shared or global; bitwise the same result on every GPU).
+// Two parities suffice: a GPU can only be two exchanges ahead of a slot it overwrites after the owner has published the stamp of
+// the exchange in between, i.e. after the owner has finished reading that slot.
+__device__ inline void peer_allreduce_sum(double* const* peer_bufs, uint32_t* xseq, int world, int rank, int S, const double* src,
+                                          int count, double* dst, int* status, int tid, int nthreads) {
+  const uint32_t seq = *xseq + 1u;
+  const int par = (int)(seq & 1u);
+  for (int r = 0; r < world; ++r) {
+    double* slot = peer_bufs[r] + ((size_t)par * world + rank) * S;
+    for (int t = tid; t < count; t += nthreads) slot[t] = src[t];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world) {
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(peer_bufs[tid] + (size_t)2 * world * S) + par * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_bufs[rank] + (size_t)2 * world * S) + par * world + tid;
+    uint32_t got;
+    const long long t_start = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+      if (got != seq && clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
+        atomicExch(status, -1000 - tid);
+        break;
+      }
+    } while (got != seq);
+  }
+  __syncthreads();
+  const double* slots = peer_bufs[rank] + (size_t)par * world * S;
+  for (int t = tid; t < count; t += nthreads) {
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * S + t);
+    dst[t] = acc;
+  }
+  __syncthreads();  // every thread has read *xseq and the slots
+  if (tid == 0) *xseq = seq;
+}
+// the same exchange on its own, for the one-time ingest constants
+__global__ void __launch_bounds__(512) peer_allreduce_kernel(double* const* peer_bufs, uint32_t* xseq, int world, int rank, int S,
+                                                             double* buf, int count, int* status) {
+  peer_allreduce_sum(peer_bufs, xseq, world, rank, S, buf, count, buf, status, (int)threadIdx.x, (int)blockDim.x);
+}
+
 struct GScratch {
   double M[MAXD * MAXD], V[MAXD * MAXD], Lc[MAXD * MAXD], T[MAXD * MAXD], XX[MAXD * MAXD];
   double rhs[MAXD], mean[MAXD], z[MAXD], beta[MAXD], Sigma[4];
@@ -343,41 +388,7 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   double* sRaw = sXtX + (F + 1) * (F + 1);  // [5][Jp] attempt-0 raw material of the item sites: z_b, z_a, z_lambda, x_sigma2, u_sigma2
   const int Jp = L.Jp;
   if (A.peer_bufs) {
-    // ---- fused one-shot all-reduce over NVLink peer memory: push this GPU's statistics into slot [parity][rank] of every
-    //      GPU's exchange buffer, publish the sequence stamp, wait for the peers' stamps, sum the slots in rank order.
-    //      Two parities suffice: a GPU can only be two exchanges ahead of a slot it overwrites after the owner has published
-    //      the stamp of the exchange in between, i.e. after the owner has finished reading that slot. ----
-    const int world = A.world, rank = A.rank, S = A.xstride;
-    const uint32_t seq = *A.xseq + 1u;
-    const int par = (int)(seq & 1u);
-    for (int r = 0; r < world; ++r) {
-      double* dst = A.peer_bufs[r] + ((size_t)par * world + rank) * S;
-      for (int t = tid; t < L.s_count; t += G_THREADS) dst[t] = A.stats[t];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) {
-      uint32_t* theirs = reinterpret_cast<uint32_t*>(A.peer_bufs[tid] + (size_t)2 * world * S) + par * world + rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
-      const uint32_t* mine = reinterpret_cast<const uint32_t*>(A.peer_bufs[rank] + (size_t)2 * world * S) + par * world + tid;
-      uint32_t got;
-      const long long t_start = clock64();
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
-        if (got != seq && clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
-          atomicExch(A.status, -1000 - tid);
-          break;
-        }
-      } while (got != seq);
-    }
-    __syncthreads();
-    const double* slots = A.peer_bufs[rank] + (size_t)par * world * S;
-    for (int t = tid; t < L.s_count; t += G_THREADS) {
-      double acc = 0.0;
-      for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * S + t);
-      st[t] = acc;
-    }
-    if (tid == 0) *A.xseq = seq;
+    peer_allreduce_sum(A.peer_bufs, A.xseq, A.world, A.rank, A.xstride, A.stats, L.s_count, st, A.status, tid, G_THREADS);
   } else {
     for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats[t];
   }

@@ -32,14 +32,17 @@ def broadcast_bytes(payload, src=0, group=None, nbytes=128):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def make_shard(n_total, group=None):
+def make_shard(n_total, group=None, nccl=True):
     """Returns the `shard` tuple accepted by api.sample / Engine.comm_init for this rank:
-    (rank, world, nccl_unique_id, subj_offset, n_subj_total) plus the local person count."""
+    (rank, world, nccl_unique_id, subj_offset, n_subj_total) plus the local person count.  nccl=False: no NCCL
+    communicator (unique id None); the caller attaches the peer exchange (attach_peers)."""
     import torch.distributed as dist
     from .engine import nccl_unique_id
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    uid = nccl_unique_id() if rank == 0 else b"\0" * 128
-    uid = broadcast_bytes(uid, 0, group)
+    uid = None
+    if nccl:
+        uid = nccl_unique_id() if rank == 0 else b"\0" * 128
+        uid = broadcast_bytes(uid, 0, group)
     offset, count = shard_bounds(n_total, world, rank)
     return (rank, world, uid, offset, n_total), count
 
@@ -59,6 +62,14 @@ def attach_peers(engine, group=None):
     """Switch a person-sharded engine (after comm_init) to the fused peer-memory exchange: export this GPU's buffer,
     all-gather the IPC handles, map the peers.  One process per GPU on one node (NVLink / NVSwitch peers)."""
     engine.peer_attach(allgather_bytes(engine.peer_export(), group))
+
+
+def close_sharded(engine, group=None):
+    """Tear a person-sharded engine down in the order the peer mappings need: unmap on every rank, barrier, free."""
+    import torch.distributed as dist
+    engine.peer_detach()
+    dist.barrier(group=group)
+    engine.close()
 
 
 def gather_person_vector(local, n_total, group=None):

@@ -121,8 +121,9 @@ class Engine:
         return {f[0]: getattr(s, f[0]) for f in _lib.Stats._fields_}
 
     # ---- multi-GPU ----
-    def comm_init(self, rank, world, unique_id: bytes):
-        buf = C.create_string_buffer(unique_id, 128)
+    def comm_init(self, rank, world, unique_id=None):
+        """unique_id: 128 bytes of an NCCL id (ncclAllReduce exchange), or None when the peer exchange is attached next."""
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         check(self.lib.erirt_comm_init(self.h, rank, world, buf))
 
     def peer_export(self) -> bytes:
@@ -130,6 +131,10 @@ class Engine:
         buf = C.create_string_buffer(64)
         check(self.lib.erirt_peer_export(self.h, buf))
         return buf.raw
+
+    def peer_detach(self):
+        """Unmap the peers' exchange buffers (all ranks, then a host barrier, then close())."""
+        check(self.lib.erirt_peer_detach(self.h))
 
     def peer_attach(self, handles: bytes):
         """Map the peers' exchange buffers (world x 64 bytes of IPC handles, in rank order)."""

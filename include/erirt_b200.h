@@ -124,15 +124,20 @@ int erirt_get_stats(erirt_handle* h, erirt_stats* out);
 
 /* ---- person-sharded chains: one handle per GPU/process, item statistics all-reduced with NCCL ---- */
 int erirt_nccl_unique_id(void* id128);                 /* rank 0 creates 128 bytes, caller broadcasts them */
-int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, const void* id128);
+int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, const void* id128);  /* id128 == NULL: no NCCL communicator,
+                                                                the peer exchange below must be attached before erirt_sample */
 /* One-shot exchange over NVLink peer memory, fused into the global draw kernel (replaces the per-sweep ncclAllReduce):
  * every GPU stores its statistics vector into a slot of every peer's exchange buffer, publishes a sequence stamp, waits
  * for the peers' stamps and sums the slots in rank order (bitwise identical on every GPU).  One process per GPU on one
  * node: erirt_peer_export allocates this GPU's exchange buffer and returns its 64-byte CUDA IPC handle; the caller
  * all-gathers the handles (any transport) and passes the world*64 bytes, in rank order, to erirt_peer_attach.
- * erirt_comm_init must have been called first (it fixes rank/world and still serves the one-time ingest constants). */
+ * erirt_comm_init must have been called first (it fixes rank/world; with a NULL id no NCCL communicator is created and the
+ * one-time ingest constants go through the same exchange). */
 int erirt_peer_export(erirt_handle* h, void* ipc_handle64);
 int erirt_peer_attach(erirt_handle* h, const void* ipc_handles /* world x 64 bytes */);
+/* Unmap the peers' buffers.  Call it on every rank, then synchronise the ranks (host barrier), then erirt_destroy: an
+ * exchange buffer must not be freed by its owner while a peer still has it mapped. */
+int erirt_peer_detach(erirt_handle* h);
 
 /* ---- parity entry points: one conditional kernel at a time on explicit inputs (tests only) ---- */
 /* PG(1, z) on a rows x cols row-major grid; cell (i,j) uses the sampler's counters for person row0+i, item j. */

@@ -28,7 +28,7 @@ def main():
         # the single-GPU engine itself is 7e-12 from the oracle after 4 sweeps), so it is compared over 3 sweeps
         N, J, F, ns = 5003, 21, 3, (3 if model == "RtIrtCrossQr" else 10)
         pb = make_problem(model, N, J, F, seed=31)
-        shard, cnt = D.make_shard(N)
+        shard, cnt = D.make_shard(N, nccl=(mode == "nccl"))  # peer mode runs without any NCCL communicator
         off = shard[3]
         cov2one = model not in ("RtIrtLatent", "RtIrtLatentQr")
 
@@ -68,7 +68,7 @@ def main():
             good = e1 < tol and e2 < tol and e3 < tol
             ok &= bool(good)
             print(f"{model} {dtype} world={world} exchange={mode}: items {e1:.2e} theta(q99.5) {e2:.2e} loglik {e3:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
-        dist.barrier()
+        D.close_sharded(sharded)
     dist.destroy_process_group()
     if rank == 0:
         print("SHARDING_OK" if ok else "SHARDING_FAIL")
