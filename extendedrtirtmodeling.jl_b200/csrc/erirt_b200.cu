@@ -266,16 +266,26 @@ static const void* person_kernel_ptr(int tpp) {
   }
 }
 // fam 0: the specialised kernel of the one-launch models; fam 1: Cross family and the evaluation stage
-static const void* person_fast_kernel_ptr(int tpp) {
+template <int MODEL>
+static const void* person_fast_kernel_ptr_m(int tpp) {
   switch (tpp) {
-    case 1: return (const void*)person_sweep_fast_kernel<1>;
-    case 2: return (const void*)person_sweep_fast_kernel<2>;
-    case 4: return (const void*)person_sweep_fast_kernel<4>;
-    default: return (const void*)person_sweep_fast_kernel<8>;
+    case 1: return (const void*)person_sweep_fast_kernel<1, MODEL>;
+    case 2: return (const void*)person_sweep_fast_kernel<2, MODEL>;
+    case 4: return (const void*)person_sweep_fast_kernel<4, MODEL>;
+    default: return (const void*)person_sweep_fast_kernel<8, MODEL>;
+  }
+}
+static const void* person_fast_kernel_ptr(int tpp, int model) {
+  switch (model) {
+    case M_MLIRT: return person_fast_kernel_ptr_m<M_MLIRT>(tpp);
+    case M_RTIRT: return person_fast_kernel_ptr_m<M_RTIRT>(tpp);
+    case M_NULL: return person_fast_kernel_ptr_m<M_NULL>(tpp);
+    case M_LATENT: return person_fast_kernel_ptr_m<M_LATENT>(tpp);
+    default: return person_fast_kernel_ptr_m<M_LATENTQR>(tpp);
   }
 }
 static const void* person_kernel_for(const erirt_handle* h, int fam) {
-  if (fam == 0) return h->cfg.dtype == ERIRT_F32 ? person_fast_kernel_ptr(h->tpp) : person_kernel_ptr<double, 0>(h->tpp);
+  if (fam == 0) return h->cfg.dtype == ERIRT_F32 ? person_fast_kernel_ptr(h->tpp, h->cfg.model) : person_kernel_ptr<double, 0>(h->tpp);
   return h->cfg.dtype == ERIRT_F32 ? person_kernel_ptr<float, 1>(h->tpp_gen) : person_kernel_ptr<double, 1>(h->tpp_gen);
 }
 

@@ -34,18 +34,19 @@ __device__ unsigned long long g_ticks[PF_NTICK];
 
 __device__ __forceinline__ uint32_t y_nibble(uint32_t yw) { return (yw * 0x01020408u) >> 24; }  // bytes 0/1 -> 4-bit index
 
-template <int TPP>
+// MODEL is a template parameter: each instantiation carries the code of one model only (less code to fetch, no model branches)
+template <int TPP, int MODEL>
 __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sweep_fast_kernel(const PersonArgs<float> A) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int P = CTA_THREADS / TPP;
   typedef float R;
   const Layout& L = A.L;
   const int J = L.J, Jp = L.Jp, F = L.F, Dg = L.Dg, Dgp = A.S.Dgp, G = Jp / 4;
-  const int model = A.model;
-  const bool has_rt = model != M_MLIRT;
-  const bool latent = model == M_LATENT || model == M_LATENTQR;
-  const bool qr = model == M_LATENTQR;
-  const bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
+  constexpr int model = MODEL;
+  constexpr bool has_rt = model != M_MLIRT;
+  constexpr bool latent = model == M_LATENT || model == M_LATENTQR;
+  constexpr bool qr = model == M_LATENTQR;
+  constexpr bool reg_x = model == M_MLIRT || model == M_RTIRT || latent;  // models with a regression on [1 X]
 
   R* s_om = reinterpret_cast<R*>(smem + A.S.off_omega);
   R* s_lt = reinterpret_cast<R*>(smem + A.S.off_logt);
