@@ -118,7 +118,7 @@ class ClockSampler:
                 pass
             if self.stop_flag:
                 break
-            time.sleep(0.003)
+            time.sleep(0.02)  # 50 Hz: NVML calls take driver locks, a tighter loop was seen to perturb 8-GPU runs
 
     def start(self):
         try:
