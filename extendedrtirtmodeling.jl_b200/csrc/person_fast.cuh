@@ -15,6 +15,10 @@
 
 namespace erirt {
 
+// slots of the f64 misc block as this kernel uses them (person.cuh's MiscD names the generic kernel's use of the same four doubles)
+enum FastMiscD { FMD_SUM_IS2 = 0, FMD_SUM_LAM_IS2 = 1, FMD_AMAX = 2, FMD_ABMAX = 3 };
+static_assert(FMD_ABMAX < MD_COUNT, "misc block too small");
+
 constexpr int TAB_PITCH = 20;  // floats per item group in the response tables: groups g and g+4 fall on disjoint banks
 constexpr int FAST_FLUSH_TILES = 16;  // item statistics live in f32 registers and are folded into the f64 accumulators every 16 tiles
 constexpr int QSTD = 768;      // work-queue split: [0, QSTD) certainly-rejected cells, [QSTD, QCAP) undecided / Method-B cells
@@ -107,10 +111,10 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       abmax = fmax(abmax, __shfl_xor_sync(0xffffffffu, abmax, o));
     }
     if (tid == 0) {
-      s_miscd[MD_SUM_IS2] = s1;
-      s_miscd[MD_SUM_RHO_IS2] = s2;  // this kernel: sum_j lambda_j / sigma2_j
-      s_miscd[MD_SUM_LOGS2K] = amax;
-      s_miscd[MD_SUM_LOGS2K + 1] = abmax;
+      s_miscd[FMD_SUM_IS2] = s1;
+      s_miscd[FMD_SUM_LAM_IS2] = s2;
+      s_miscd[FMD_AMAX] = amax;
+      s_miscd[FMD_ABMAX] = abmax;
       mbar_init(s_bar, 1);
       s_qctl[0] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -128,8 +132,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   }
   __syncthreads();
 
-  const R sum_is2 = (R)s_miscd[MD_SUM_IS2], sum_lam_is2 = (R)s_miscd[MD_SUM_RHO_IS2];
-  const R z_amax = (R)s_miscd[MD_SUM_LOGS2K], z_abmax = (R)s_miscd[MD_SUM_LOGS2K + 1];
+  const R sum_is2 = (R)s_miscd[FMD_SUM_IS2], sum_lam_is2 = (R)s_miscd[FMD_SUM_LAM_IS2];
+  const R z_amax = (R)s_miscd[FMD_AMAX], z_abmax = (R)s_miscd[FMD_ABMAX];
   const R S11 = s_beta[MAXD + 0], S12 = s_beta[MAXD + 2], S22 = s_beta[MAXD + 3];
   const R k1 = (R)A.k1, k2 = (R)A.k2;
   const int pb = F + 1;  // length of one regression block [1 X]

@@ -19,7 +19,12 @@ def _worker(rank, world, port, ret):
     off, cnt = D.shard_bounds(n_total, world, rank)
     local = np.arange(off, off + cnt, dtype=np.float64) * 2
     full = D.gather_person_vector(local, n_total)
-    ret[rank] = (got == bytes(range(128)), full.tolist(), (off, cnt))
+    # the transport of the 64-byte CUDA IPC handles of the fused peer exchange (attach_peers): rank order, equal lengths
+    handles = D.allgather_bytes(bytes([rank + 1]) * 64)
+    # runSimulation deals replication r to rank (r-1) mod world; chains c to GPU c mod world
+    reps = [r for r in range(1, 8) if (r - 1) % world == rank]
+    ret[rank] = (got == bytes(range(128)) and handles == b"\x01" * 64 + b"\x02" * 64 and D.make_shard(n_total, nccl=False)[0][2] is None,
+                 full.tolist(), (off, cnt), reps, D.chain_assignment(5, world, rank))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -30,7 +35,9 @@ def test_two_rank_plumbing():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, 29531, ret), nprocs=world, join=True)
     for r in range(world):
-        ok, full, _ = ret[r]
+        ok, full = ret[r][0], ret[r][1]
         assert ok
         assert full == [2.0 * i for i in range(11)]
     assert ret[0][2] == (0, 6) and ret[1][2] == (6, 5)
+    assert ret[0][3] == [1, 3, 5, 7] and ret[1][3] == [2, 4, 6]
+    assert ret[0][4] == [0, 2, 4] and ret[1][4] == [1, 3]

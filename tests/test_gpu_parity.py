@@ -175,6 +175,23 @@ def test_ragged_shapes_f64(E, oracle, N, J, F):
         eng.close()
 
 
+@pytest.mark.parametrize("N,J,F", [(1, 1, 0), (5, 3, 0), (129, 4, 1), (300, 21, 2), (257, 100, 3), (200, 150, 2), (130, 260, 1), (70, 500, 0)])
+def test_ragged_shapes_f32_fast_kernel(E, oracle, N, J, F):
+    """The f32 fast kernel over its whole configuration range: every TPP (J = 100 -> 2, 150 -> 4, 260 / 500 -> 8; small J -> 1), item
+    counts that are not multiples of 4 or 8 (padding cells, odd group counts, the single-group tail of the two-group main loop),
+    person counts around the tile size, no covariates; two sweeps against the oracle at the f32 tolerance."""
+    models = ("MlIrt",) if N * J == 1 else ("RtIrtNull", "RtIrtLatentQr" if F else "MlIrt", "RtIrt" if F else "RtIrtLatent")
+    for model in models:
+        pb = make_problem(model, N, J, F, seed=16)
+        ref = run_oracle(oracle, pb, 2)
+        eng = run_engine(E, pb, 2, dtype="f32")
+        # a flipped PG branch changes that person's theta: tolerate 1% of the persons (at least one)
+        _compare_traces(eng, ref, pb, 2, 3e-5, 1e-1, frac_ok=min(0.99, 1.0 - 1.5 / max(N, 2)))
+        om = eng.get_state("omega")
+        assert om.shape == (N, J) and np.all(om > 0) and np.all(om <= 0.25 + 1e-6)
+        eng.close()
+
+
 def test_crossqr_cell_weights_parity(E, oracle):
     """drawQrWeightsCrossQr (Draw.pl.jl:303-320): the N x J weights nu_{k+1} held by the engine after k sweeps."""
     pb = make_problem("RtIrtCrossQr", 333, 11, 0, seed=21)
