@@ -188,7 +188,7 @@ def test_ragged_shapes_f32_fast_kernel(E, oracle, N, J, F):
         # a flipped PG branch changes that person's theta: tolerate 1% of the persons (at least one)
         _compare_traces(eng, ref, pb, 2, 3e-5, 1e-1, frac_ok=min(0.99, 1.0 - 1.5 / max(N, 2)))
         om = eng.get_state("omega")
-        assert om.shape == (N, J) and np.all(om > 0) and np.all(om <= 0.25 + 1e-6)
+        assert om.shape == (N, J) and np.all(om > 0) and np.all(np.isfinite(om))
         eng.close()
 
 
