@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--impl", default="erirt_b200", choices=["erirt_b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-y", choices=["u8", "f64"], default="u8", help="host type of Y in the end-to-end pass (Julia Matrix{Bool} or Float64)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--short", action="store_true", help="profiling run: timed sweeps only, no e2e / cpu / roofline passes")
     args = ap.parse_args()
@@ -384,31 +385,43 @@ def main():
     # ---------------- end to end through the C ABI with host buffers ("e2e") ----------------
     e2e = None
     if not args.no_e2e and not args.short:
-        hY = torch.empty(dY.shape, dtype=torch.float64, pin_memory=True).copy_(dY)
+        # the host holds what the reference's InputData holds: Y as Julia's Matrix{Bool} (one byte per response, `rand.(BernoulliLogit…)`
+        # src/SimTools.jl:165; --e2e-y f64 passes a Float64 Y instead), logT and X as Float64; all column-major, pinned
+        y8 = args.e2e_y == "u8"
+        hY = torch.empty(dY.shape, dtype=torch.uint8 if y8 else torch.float64, pin_memory=True).copy_(dY)
         hT = torch.empty(dT.shape, dtype=torch.float64, pin_memory=True).copy_(dT)
         hX = torch.empty(dX.shape, dtype=torch.float64, pin_memory=True).copy_(dX)
+        hM = torch.empty((3, 2, n_local), dtype=torch.float64, pin_memory=True)  # Post.mean / SD of theta, zeta, nu land here
+        hMn = hM.numpy()
         del dY, dT, dX
         torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         enge = make_engine()
+        t1 = time.perf_counter()
         from erirt_b200._lib import check
-        check(enge.lib.erirt_set_data(enge.h, hY.data_ptr(), n_local, hT.data_ptr(), n_local, hX.data_ptr(), n_local))
+        set_data = enge.lib.erirt_set_data_y8 if y8 else enge.lib.erirt_set_data
+        check(set_data(enge.h, hY.data_ptr(), n_local, hT.data_ptr(), n_local, hX.data_ptr(), n_local))
         enge.set_state(theta=theta0, zeta=zeta0, beta=beta0)
+        t2 = time.perf_counter()
         enge.sample(K)
+        t3 = time.perf_counter()
         tr_a = enge.get_trace("ra", n_local, 2 * N_ITEM)
         tr_t = enge.get_trace("rt", n_local, 2 * N_ITEM)
         tr_q = enge.get_trace("qr", 0, qw)
         tr_l = enge.get_trace("logLike")
-        moms = [enge.get_moments(f) for f in ("theta", "zeta", "nu")]
+        moms = [enge.get_moments(f, out=(hMn[k, 0], hMn[k, 1])) for k, f in enumerate(("theta", "zeta", "nu"))]
+        t4 = time.perf_counter()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        h2d = (hY.numel() + hT.numel() + hX.numel()) * 8 + (2 * n_local + N_FEAT + 2) * 8
+        h2d = hY.numel() * hY.element_size() + (hT.numel() + hX.numel()) * 8 + (2 * n_local + N_FEAT + 2) * 8
         d2h = K * (tr_a.shape[1] + tr_t.shape[1] + tr_q.shape[1] + 1) * 8 + 3 * 2 * n_local * 8
         assert np.all(np.isfinite(tr_l[:K])) and np.all(np.isfinite(moms[0][0]))
         e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world / K), "d2h_bytes_per_step": int(d2h * world / K),
-               "seconds": dt, "note": "erirt_create + erirt_set_data (pinned host f64, H2D + ingest) + erirt_set_state + K sweeps + "
-                                     "erirt_get_trace/erirt_get_moments (D2H); bytes are totals of the call divided by K"}
+               "seconds": dt, "parts_ms_rank0": {"create": (t1 - t0) * 1e3, "set_data_and_state": (t2 - t1) * 1e3, "sample": (t3 - t2) * 1e3, "read_back": (t4 - t3) * 1e3},
+               "note": "erirt_create + " + ("erirt_set_data_y8 (pinned host: Y as Matrix{Bool} bytes, logT/X f64" if y8 else "erirt_set_data (pinned host f64")
+                                     + "; chunked H2D + ingest) + erirt_set_state + K sweeps + "
+                                     "erirt_get_trace/erirt_get_moments (D2H into pinned buffers); bytes are totals of the call divided by K"}
         close_engine(enge)
 
     # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------

@@ -17,7 +17,7 @@ COMPAT_BETA_PRIOR_DIAG = 1
 COMPAT_LATENTQR_SCALE_ELEMENTWISE = 2
 
 EXPORTED = ["erirt_version", "erirt_last_error", "erirt_create", "erirt_destroy", "erirt_set_data",
-            "erirt_set_data_device", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
+            "erirt_set_data_device", "erirt_set_data_y8", "erirt_checkpoint_size", "erirt_checkpoint_save", "erirt_checkpoint_load", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
             "erirt_trace_width", "erirt_get_moments", "erirt_loglik_current", "erirt_get_stats",
             "erirt_nccl_unique_id", "erirt_comm_init", "erirt_peer_export", "erirt_peer_attach", "erirt_peer_detach", "erirt_k_pg", "erirt_k_nu_person", "erirt_k_philox"]
 
@@ -62,6 +62,11 @@ def load():
     L.erirt_destroy.argtypes = [vp]
     L.erirt_set_data.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
     L.erirt_set_data_device.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
+    L.erirt_set_data_y8.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
+    L.erirt_checkpoint_size.argtypes = [vp]
+    L.erirt_checkpoint_size.restype = C.c_int64
+    L.erirt_checkpoint_save.argtypes = [vp, vp, C.c_int64]
+    L.erirt_checkpoint_load.argtypes = [vp, vp, C.c_int64]
     L.erirt_set_state.argtypes = [vp, C.c_int32, dp, C.c_int64]
     L.erirt_get_state.argtypes = [vp, C.c_int32, dp, C.c_int64]
     L.erirt_sample.argtypes = [vp, C.c_int64]
@@ -82,7 +87,7 @@ def load():
                                     C.c_int32, C.c_int32, dp]
     L.erirt_k_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_uint32)]
     for name in EXPORTED:
-        if name not in ("erirt_last_error", "erirt_trace_width", "erirt_version"):
+        if name not in ("erirt_last_error", "erirt_trace_width", "erirt_version", "erirt_checkpoint_size"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

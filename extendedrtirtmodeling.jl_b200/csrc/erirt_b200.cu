@@ -95,15 +95,15 @@ static int load() {
 // ------------------------------------------------------------------------------------------------
 // ingest kernels (K8): Julia column-major float64 -> person-major tiles
 // ------------------------------------------------------------------------------------------------
-template <typename OutT, bool AS_U8>
-__global__ void pack_transpose_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int J, OutT* __restrict__ dst, int Jp) {
+template <typename SrcT, typename OutT, bool AS_U8>
+__global__ void pack_transpose_kernel(const SrcT* __restrict__ src, int64_t ld, int64_t n, int J, OutT* __restrict__ dst, int Jp) {
   __shared__ double tile[32][33];
   const int64_t i0 = (int64_t)blockIdx.x * 32;
   const int j0 = blockIdx.y * 32;
   for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
     const int64_t i = i0 + threadIdx.x;
     const int j = j0 + jj;
-    tile[jj][threadIdx.x] = (i < n && j < J) ? src[i + ld * j] : 0.0;
+    tile[jj][threadIdx.x] = (i < n && j < J) ? (double)src[i + ld * j] : 0.0;
   }
   __syncthreads();
   for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
@@ -143,13 +143,18 @@ __global__ void colmajor_to_tile_kernel(const double* __restrict__ src, int64_t 
     dst[i * Jp + j] = (R)src[t];
   }
 }
-// column sums over persons: out[j] = sum_i f(src[i + ld*j]);  mode 0: v, 1: v^2, 2: v - 0.5
-__global__ void colsum_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int mode, double* __restrict__ out) {
+// column sums over persons in two deterministic stages (the grouping depends only on n, not on how the columns were chunked):
+// part[(j)*COLSUM_PARTS + p] = sum over the p-th contiguous slice of rows of f(src[i + ld*j]);  mode 0: v, 1: v^2, 2: (v > 0.5) - 0.5
+#define COLSUM_PARTS 32
+template <typename SrcT>
+__global__ void colsum_part_kernel(const SrcT* __restrict__ src, int64_t ld, int64_t n, int mode, double* __restrict__ part) {
   __shared__ double red[256];
-  const int j = blockIdx.x;
+  const int j = blockIdx.x, p = blockIdx.y;
+  const int64_t per = (n + COLSUM_PARTS - 1) / COLSUM_PARTS;
+  const int64_t lo = p * per, hi = lo + per < n ? lo + per : n;
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double v = src[i + ld * j];
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double v = (double)src[i + ld * j];
     acc += mode == 0 ? v : (mode == 1 ? v * v : ((v > 0.5 ? 1.0 : 0.0) - 0.5));
   }
   red[threadIdx.x] = acc;
@@ -158,7 +163,24 @@ __global__ void colsum_kernel(const double* __restrict__ src, int64_t ld, int64_
     if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[j] = red[0];
+  if (threadIdx.x == 0) part[(int64_t)j * COLSUM_PARTS + p] = red[0];
+}
+__global__ void colsum_finish_kernel(const double* __restrict__ part, int J, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  double acc = 0.0;
+  for (int p = 0; p < COLSUM_PARTS; ++p) acc += part[(int64_t)j * COLSUM_PARTS + p];
+  out[j] = acc;
+}
+// post-burn-in mean and SD of a person vector from its running sums (erirt_get_moments)
+__global__ void moments_finish_kernel(const double* __restrict__ s1, const double* __restrict__ s2, int64_t n, double cnt,
+                                      double* __restrict__ mean, double* __restrict__ sd) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (cnt <= 0.0) { mean[i] = sd[i] = __longlong_as_double(0x7ff8000000000000LL); continue; }
+    const double m = s1[i] / cnt;
+    mean[i] = m;
+    sd[i] = cnt > 1.0 ? sqrt(fmax(0.0, __dsub_rn(s2[i], __dmul_rn(__dmul_rn(cnt, m), m)) / (cnt - 1.0))) : 0.0;  // no FMA contraction: same bits as the host formula
+  }
 }
 // XtX[r + pb*c] = sum_i x_ir x_ic, x = [1 X]
 __global__ void xtx_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int pb, double* __restrict__ out) {
@@ -201,6 +223,7 @@ struct erirt_handle {
   void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
   double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
   double* dLlOut = nullptr;
+  double* dColPart = nullptr;  // [3][Jp][COLSUM_PARTS] partial column sums of the ingest
   double *dTrRa = nullptr, *dTrRt = nullptr, *dTrQr = nullptr, *dTrLl = nullptr;
   uint32_t* dSweep = nullptr;
   int* dStatus = nullptr;
@@ -322,7 +345,7 @@ static int free_handle(erirt_handle* h) {
   if (h->dPeerBufs) cudaFree(h->dPeerBufs);
   if (h->dXseq) cudaFree(h->dXseq);
   void* ptrs[] = {h->dNuCell, h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
-                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut};
+                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut, h->dColPart};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
@@ -365,6 +388,13 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   CU(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major < 10) return fail(ERIRT_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
+  {  // staging buffers are stream-ordered allocations: keep up to 256 MB in the pool instead of returning it to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+      uint64_t thr = (uint64_t)256 << 20;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   erirt_handle* h = new erirt_handle();
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
@@ -427,6 +457,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   TRY(dalloc(&h->dConstsLocal, (size_t)h->c_count));
   TRY(dalloc(&h->dConsts, (size_t)h->c_count));
   TRY(dalloc(&h->dDerived, 4));
+  TRY(dalloc(&h->dColPart, (size_t)3 * h->L.Jp * COLSUM_PARTS));
   TRY(dalloc(&h->dTrRa, (size_t)h->cap * 2 * cfg->n_item));
   TRY(dalloc(&h->dTrRt, (size_t)h->cap * 2 * cfg->n_item));
   TRY(dalloc(&h->dTrQr, (size_t)h->cap * h->qw));
@@ -474,76 +505,97 @@ extern "C" int erirt_destroy(erirt_handle* h) { return free_handle(h); }
 // ------------------------------------------------------------------------------------------------
 // data
 // ------------------------------------------------------------------------------------------------
-template <typename R>
-static void launch_pack(erirt_handle* h, const double* dYc, int64_t ldY, const double* dTc, int64_t ldT, const double* dXc, int64_t ldX) {
+// Pack columns [c0, c0+nc) of Y / logT (column-major, on the device) into the person-major tiles and add their partial column sums.
+template <typename R, typename YT>
+static void pack_columns(erirt_handle* h, const YT* dYc, int64_t ldY, const double* dTc, int64_t ldT, int c0, int nc) {
   const int64_t n = h->cfg.n_subj;
-  const int J = h->cfg.n_item, Jp = h->L.Jp, F = h->cfg.n_feat;
-  dim3 blk(32, 8), grd((unsigned)((n + 31) / 32), (unsigned)((J + 31) / 32));
-  pack_transpose_kernel<uint8_t, true><<<grd, blk, 0, h->stream>>>(dYc, ldY, n, J, h->dY, Jp);
-  if (dTc) pack_transpose_kernel<R, false><<<grd, blk, 0, h->stream>>>(dTc, ldT, n, J, (R*)h->dLogT, Jp);
-  for (int f = 0; f < F; ++f)
-    pack_vec_kernel<R><<<256, 256, 0, h->stream>>>(dXc + ldX * f, n, (R*)h->dX + (int64_t)f * h->n_pad);
+  const int Jp = h->L.Jp;
+  dim3 blk(32, 8), grd((unsigned)((n + 31) / 32), (unsigned)((nc + 31) / 32));
+  dim3 cg((unsigned)nc, COLSUM_PARTS);
+  pack_transpose_kernel<YT, uint8_t, true><<<grd, blk, 0, h->stream>>>(dYc, ldY, n, nc, h->dY + c0, Jp);
+  colsum_part_kernel<YT><<<cg, 256, 0, h->stream>>>(dYc, ldY, n, 2, h->dColPart + (size_t)(2 * Jp + c0) * COLSUM_PARTS);
+  if (dTc) {
+    pack_transpose_kernel<double, R, false><<<grd, blk, 0, h->stream>>>(dTc, ldT, n, nc, (R*)h->dLogT + c0, Jp);
+    colsum_part_kernel<double><<<cg, 256, 0, h->stream>>>(dTc, ldT, n, 0, h->dColPart + (size_t)(0 * Jp + c0) * COLSUM_PARTS);
+    colsum_part_kernel<double><<<cg, 256, 0, h->stream>>>(dTc, ldT, n, 1, h->dColPart + (size_t)(1 * Jp + c0) * COLSUM_PARTS);
+  }
 }
 
-extern "C" int erirt_set_data_device(erirt_handle* h, const double* dYc, int64_t ldY, const double* dTc, int64_t ldT,
-                                     const double* dXc, int64_t ldX) {
-  if (!h || !dYc) return fail(ERIRT_E_ARG, "null argument");
+// Ingest (K8).  on_device: the three matrices are device buffers and are packed in place.  Otherwise they are host buffers and are
+// streamed through one bounded staging buffer in chunks of whole columns (H2D copy, pack, next chunk: the staging memory stays at
+// <= 64 MB instead of a second copy of the data set, and the packed tiles are the only full-size device copy).
+template <typename YT>
+static int ingest(erirt_handle* h, const YT* Y, int64_t ldY, const double* T, int64_t ldT, const double* X, int64_t ldX, bool on_device) {
+  if (!h || !Y) return fail(ERIRT_E_ARG, "null argument");
   const bool has_rt = h->cfg.model != ERIRT_MLIRT;
-  if (has_rt && !dTc) return fail(ERIRT_E_ARG, "logT is required for this model");
-  if (h->cfg.n_feat > 0 && !dXc) return fail(ERIRT_E_ARG, "X is required when n_feat > 0");
+  if (has_rt && !T) return fail(ERIRT_E_ARG, "logT is required for this model");
+  if (h->cfg.n_feat > 0 && !X) return fail(ERIRT_E_ARG, "X is required when n_feat > 0");
   CU(cudaSetDevice(h->cfg.device));
   const int64_t n = h->cfg.n_subj;
-  const int J = h->cfg.n_item, pb = h->cfg.n_feat + 1;
-  if (ldY < n || (has_rt && ldT < n) || (h->cfg.n_feat > 0 && ldX < n)) return fail(ERIRT_E_ARG, "leading dimension smaller than n_subj");
-  const size_t cells = (size_t)h->n_pad * h->L.Jp;
+  const int J = h->cfg.n_item, Jp = h->L.Jp, F = h->cfg.n_feat, pb = F + 1;
+  const bool f32 = h->cfg.dtype == ERIRT_F32;
+  if (ldY < n || (has_rt && ldT < n) || (F > 0 && ldX < n)) return fail(ERIRT_E_ARG, "leading dimension smaller than n_subj");
+  if (!has_rt) T = nullptr;
+  const size_t cells = (size_t)h->n_pad * Jp;
   CU(cudaMemsetAsync(h->dY, 0, cells, h->stream));
   if (has_rt) CU(cudaMemsetAsync(h->dLogT, 0, cells * h->rsz, h->stream));
-  if (h->cfg.dtype == ERIRT_F32) launch_pack<float>(h, dYc, ldY, has_rt ? dTc : nullptr, ldT, dXc, ldX);
-  else launch_pack<double>(h, dYc, ldY, has_rt ? dTc : nullptr, ldT, dXc, ldX);
-  // constants: column sums in f64 straight from the caller's float64 data
   CU(cudaMemsetAsync(h->dConstsLocal, 0, h->c_count * sizeof(double), h->stream));
-  colsum_kernel<<<J, 256, 0, h->stream>>>(dYc, ldY, n, 2, h->dConstsLocal + h->c_K0);
-  if (has_rt) {
-    colsum_kernel<<<J, 256, 0, h->stream>>>(dTc, ldT, n, 0, h->dConstsLocal + h->c_T1);
-    colsum_kernel<<<J, 256, 0, h->stream>>>(dTc, ldT, n, 1, h->dConstsLocal + h->c_T2);
+  CU(cudaMemsetAsync(h->dColPart, 0, (size_t)3 * Jp * COLSUM_PARTS * sizeof(double), h->stream));
+  char* stage = nullptr;
+  double* dXc = nullptr;
+  auto cleanup = [&]() { if (stage) cudaFreeAsync(stage, h->stream); if (dXc && !on_device) cudaFreeAsync(dXc, h->stream); };
+#define CUX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(ERIRT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+  if (on_device) {
+    if (f32) pack_columns<float, YT>(h, Y, ldY, T, ldT, 0, J);
+    else pack_columns<double, YT>(h, Y, ldY, T, ldT, 0, J);
+    dXc = const_cast<double*>(X);
+  } else {
+    // stream-ordered allocations: cudaFree of large blocks is a device-wide synchronisation (measured up to 0.9 s for GB-sized blocks)
+    const size_t col_bytes = (size_t)n * (sizeof(YT) + (has_rt ? sizeof(double) : 0));
+    int cc = (int)std::max<size_t>(1, std::min<size_t>((size_t)J, ((size_t)64 << 20) / col_bytes));
+    const size_t y_bytes = align_up((size_t)n * cc * sizeof(YT), 256);
+    CUX(cudaMallocAsync((void**)&stage, y_bytes + (has_rt ? (size_t)n * cc * sizeof(double) : 0), h->stream));
+    YT* sY = (YT*)stage;
+    double* sT = has_rt ? (double*)(stage + y_bytes) : nullptr;
+    for (int c0 = 0; c0 < J; c0 += cc) {
+      const int nc = std::min(cc, J - c0);
+      CUX(cudaMemcpy2DAsync(sY, n * sizeof(YT), Y + ldY * c0, ldY * sizeof(YT), n * sizeof(YT), nc, cudaMemcpyHostToDevice, h->stream));
+      if (has_rt) CUX(cudaMemcpy2DAsync(sT, n * sizeof(double), T + ldT * c0, ldT * sizeof(double), n * sizeof(double), nc, cudaMemcpyHostToDevice, h->stream));
+      if (f32) pack_columns<float, YT>(h, sY, n, sT, n, c0, nc);
+      else pack_columns<double, YT>(h, sY, n, sT, n, c0, nc);
+    }
+    if (F > 0) {
+      CUX(cudaMallocAsync((void**)&dXc, (size_t)n * F * sizeof(double), h->stream));
+      CUX(cudaMemcpy2DAsync(dXc, n * sizeof(double), X, ldX * sizeof(double), n * sizeof(double), F, cudaMemcpyHostToDevice, h->stream));
+      ldX = n;
+    }
   }
+  for (int f = 0; f < F; ++f) {
+    if (f32) pack_vec_kernel<float><<<256, 256, 0, h->stream>>>(dXc + ldX * f, n, (float*)h->dX + (int64_t)f * h->n_pad);
+    else pack_vec_kernel<double><<<256, 256, 0, h->stream>>>(dXc + ldX * f, n, (double*)h->dX + (int64_t)f * h->n_pad);
+  }
+  // constants in f64 straight from the caller's data: T1, T2, K0 are consecutive Jp-blocks of the consts vector
+  colsum_finish_kernel<<<(3 * Jp + 127) / 128, 128, 0, h->stream>>>(h->dColPart, 3 * Jp, h->dConstsLocal + h->c_T1);
   xtx_kernel<<<pb * pb, 256, 0, h->stream>>>(dXc, ldX, n, pb, h->dConstsLocal + h->c_XtX);
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(h->stream));
+  CUX(cudaGetLastError());
+  cleanup();
+  stage = nullptr; dXc = nullptr;
+  CUX(cudaStreamSynchronize(h->stream));
+#undef CUX
   h->data_set = true;
   h->consts_final = false;
   return 0;
 }
 
+extern "C" int erirt_set_data_device(erirt_handle* h, const double* dYc, int64_t ldY, const double* dTc, int64_t ldT,
+                                     const double* dXc, int64_t ldX) {
+  return ingest<double>(h, dYc, ldY, dTc, ldT, dXc, ldX, true);
+}
 extern "C" int erirt_set_data(erirt_handle* h, const double* Y, int64_t ldY, const double* logT, int64_t ldT, const double* X, int64_t ldX) {
-  if (!h || !Y) return fail(ERIRT_E_ARG, "null argument");
-  const bool has_rt = h->cfg.model != ERIRT_MLIRT;
-  if (has_rt && !logT) return fail(ERIRT_E_ARG, "logT is required for this model");
-  if (h->cfg.n_feat > 0 && !X) return fail(ERIRT_E_ARG, "X is required when n_feat > 0");
-  CU(cudaSetDevice(h->cfg.device));
-  const int64_t n = h->cfg.n_subj;
-  const int J = h->cfg.n_item, F = h->cfg.n_feat;
-  if (ldY < n || (has_rt && ldT < n) || (F > 0 && ldX < n)) return fail(ERIRT_E_ARG, "leading dimension smaller than n_subj");
-  double *dYc = nullptr, *dTc = nullptr, *dXc = nullptr;
-  int rc = 0;
-  // staging copies of the caller's column-major f64 matrices: stream-ordered allocations (cudaFree of GB-sized blocks is a
-  // device-wide synchronisation that was measured to take up to 0.9 s)
-  auto cleanup = [&]() { if (dYc) cudaFreeAsync(dYc, h->stream); if (dTc) cudaFreeAsync(dTc, h->stream); if (dXc) cudaFreeAsync(dXc, h->stream); };
-#define CUX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(ERIRT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
-  CUX(cudaMallocAsync((void**)&dYc, (size_t)n * J * sizeof(double), h->stream));
-  CUX(cudaMemcpy2DAsync(dYc, n * sizeof(double), Y, ldY * sizeof(double), n * sizeof(double), J, cudaMemcpyHostToDevice, h->stream));
-  if (has_rt) {
-    CUX(cudaMallocAsync((void**)&dTc, (size_t)n * J * sizeof(double), h->stream));
-    CUX(cudaMemcpy2DAsync(dTc, n * sizeof(double), logT, ldT * sizeof(double), n * sizeof(double), J, cudaMemcpyHostToDevice, h->stream));
-  }
-  if (F > 0) {
-    CUX(cudaMallocAsync((void**)&dXc, (size_t)n * F * sizeof(double), h->stream));
-    CUX(cudaMemcpy2DAsync(dXc, n * sizeof(double), X, ldX * sizeof(double), n * sizeof(double), F, cudaMemcpyHostToDevice, h->stream));
-  }
-#undef CUX
-  rc = erirt_set_data_device(h, dYc, n, dTc, n, dXc, n);
-  cleanup();
-  return rc;
+  return ingest<double>(h, Y, ldY, logT, ldT, X, ldX, false);
+}
+extern "C" int erirt_set_data_y8(erirt_handle* h, const uint8_t* Y, int64_t ldY, const double* logT, int64_t ldT, const double* X, int64_t ldX) {
+  return ingest<uint8_t>(h, Y, ldY, logT, ldT, X, ldX, false);
 }
 
 // all-reduce the ingest constants over shards once, derive mean/std of logT
@@ -612,12 +664,12 @@ extern "C" int erirt_set_state(erirt_handle* h, int32_t field, const double* v, 
   if (person_vec(h, field, &pv) == 0) {
     if (n != h->cfg.n_subj) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)h->cfg.n_subj, (long long)n);
     double* tmp;
-    CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    CU(cudaMallocAsync((void**)&tmp, n * sizeof(double), h->stream));
     cudaMemcpyAsync(tmp, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (h->cfg.dtype == ERIRT_F32) pack_vec_kernel<float><<<256, 256, 0, h->stream>>>(tmp, n, (float*)pv);
     else pack_vec_kernel<double><<<256, 256, 0, h->stream>>>(tmp, n, (double*)pv);
+    cudaFreeAsync(tmp, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "set_state: %s", cudaGetErrorString(e));
     return 0;
   }
@@ -625,12 +677,12 @@ extern "C" int erirt_set_state(erirt_handle* h, int32_t field, const double* v, 
     const int64_t want = h->cfg.n_subj * h->cfg.n_item;
     if (n != want) return fail(ERIRT_E_ARG, "omega expects %lld values", (long long)want);
     double* tmp;
-    CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    CU(cudaMallocAsync((void**)&tmp, n * sizeof(double), h->stream));
     cudaMemcpyAsync(tmp, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (h->cfg.dtype == ERIRT_F32) colmajor_to_tile_kernel<float><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (float*)h->dOmega);
     else colmajor_to_tile_kernel<double><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (double*)h->dOmega);
+    cudaFreeAsync(tmp, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "set_state: %s", cudaGetErrorString(e));
     return 0;
   }
@@ -654,7 +706,7 @@ extern "C" int erirt_get_state(erirt_handle* h, int32_t field, double* out, int6
     const int64_t want = om ? h->cfg.n_subj * h->cfg.n_item : h->cfg.n_subj;
     if (n != want) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)want, (long long)n);
     double* tmp;
-    CU(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    CU(cudaMallocAsync((void**)&tmp, n * sizeof(double), h->stream));
     if (om) {
       if (h->cfg.dtype == ERIRT_F32) tile_to_colmajor_kernel<float><<<1024, 256, 0, h->stream>>>((const float*)tile_src, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
       else tile_to_colmajor_kernel<double><<<1024, 256, 0, h->stream>>>((const double*)tile_src, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, tmp);
@@ -663,8 +715,8 @@ extern "C" int erirt_get_state(erirt_handle* h, int32_t field, double* out, int6
       else unpack_vec_kernel<double><<<256, 256, 0, h->stream>>>((const double*)pv, n, tmp);
     }
     cudaMemcpyAsync(out, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaFreeAsync(tmp, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_state: %s", cudaGetErrorString(e));
     return 0;
   }
@@ -937,15 +989,15 @@ extern "C" int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, d
   const int64_t nChain = h->cfg.n_chain;
   const int64_t first = (int64_t)h->cfg.n_burnin * nChain;  // sweeps with m > n_burnin
   const int64_t cnt = h->sweeps_done > first ? h->sweeps_done - first : 0;
-  std::vector<double> s1(n), s2(n);
-  CU(cudaMemcpy(s1.data(), h->dMom + (size_t)(2 * slot) * h->n_pad, n * sizeof(double), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(s2.data(), h->dMom + (size_t)(2 * slot + 1) * h->n_pad, n * sizeof(double), cudaMemcpyDeviceToHost));
-  for (int64_t i = 0; i < n; ++i) {
-    if (cnt == 0) { mean[i] = std::numeric_limits<double>::quiet_NaN(); if (sd) sd[i] = mean[i]; continue; }
-    const double m = s1[i] / cnt;
-    mean[i] = m;
-    if (sd) sd[i] = cnt > 1 ? std::sqrt(std::max(0.0, (s2[i] - cnt * m * m) / (cnt - 1))) : 0.0;
-  }
+  // mean and SD are finished on the device and copied straight into the caller's buffers (pinned buffers make this a plain DMA)
+  double* tmp = nullptr;
+  CU(cudaMallocAsync((void**)&tmp, (size_t)2 * n * sizeof(double), h->stream));
+  moments_finish_kernel<<<592, 256, 0, h->stream>>>(h->dMom + (size_t)(2 * slot) * h->n_pad, h->dMom + (size_t)(2 * slot + 1) * h->n_pad, n, (double)cnt, tmp, tmp + n);
+  cudaError_t e = cudaMemcpyAsync(mean, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && sd) e = cudaMemcpyAsync(sd, tmp + n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaFreeAsync(tmp, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_moments: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -987,6 +1039,97 @@ extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(d, h->dStats + h->L.s_count, sizeof(d), cudaMemcpyDeviceToHost));
   out->pg_deferred_frac = d[1] > 0 ? d[0] / d[1] : 0.0;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// checkpoint / resume: every mutable device buffer of the chain (state, auxiliaries, Philox sweep counter, running moments,
+// traces) behind a header that pins the configuration it belongs to.  The data (Y, logT, X) is not part of it.
+// ------------------------------------------------------------------------------------------------
+struct CkHeader {
+  char magic[8];
+  int32_t abi, model, dtype, n_item, n_feat, n_iter, n_chain, n_burnin, person_trace, prologue_done;
+  int64_t n_subj, n_subj_total, subj_offset, sweeps_done, payload_bytes;
+  uint64_t seed;
+  uint32_t chain, pad;
+};
+struct CkSeg { void* p; size_t bytes; };
+static std::vector<CkSeg> ck_segments(erirt_handle* h) {
+  const size_t cells = (size_t)h->n_pad * h->L.Jp, vec = (size_t)h->n_pad * h->rsz, J = (size_t)h->cfg.n_item, cap = (size_t)h->cap;
+  std::vector<CkSeg> v;
+  v.push_back({h->dOmega, cells * h->rsz});
+  if (h->dNuCell) v.push_back({h->dNuCell, cells * h->rsz});
+  v.push_back({h->dTheta, vec});
+  v.push_back({h->dZeta, vec});
+  v.push_back({h->dNu, vec});
+  v.push_back({h->dMom, (size_t)6 * h->n_pad * sizeof(double)});
+  v.push_back({h->dParams, (size_t)h->L.p_count * sizeof(double)});
+  v.push_back({h->dStats, (size_t)(h->L.s_count + 2) * sizeof(double)});
+  v.push_back({h->dSweep, sizeof(uint32_t)});
+  v.push_back({h->dStatus, sizeof(int)});
+  v.push_back({h->dTrRa, cap * 2 * J * sizeof(double)});
+  v.push_back({h->dTrRt, cap * 2 * J * sizeof(double)});
+  v.push_back({h->dTrQr, cap * (size_t)h->qw * sizeof(double)});
+  v.push_back({h->dTrLl, cap * sizeof(double)});
+  if (h->dPtrace) v.push_back({h->dPtrace, cap * 3 * vec});
+  return v;
+}
+static CkHeader ck_header(erirt_handle* h) {
+  CkHeader H{};
+  memcpy(H.magic, "ERIRTCK1", 8);
+  const erirt_config& c = h->cfg;
+  H.abi = ERIRT_ABI_VERSION; H.model = c.model; H.dtype = c.dtype; H.n_item = c.n_item; H.n_feat = c.n_feat; H.n_iter = c.n_iter;
+  H.n_chain = c.n_chain; H.n_burnin = c.n_burnin; H.person_trace = c.person_trace ? 1 : 0; H.prologue_done = h->prologue_done ? 1 : 0;
+  H.n_subj = c.n_subj; H.n_subj_total = c.n_subj_total; H.subj_offset = c.subj_offset; H.sweeps_done = h->sweeps_done;
+  H.seed = c.seed; H.chain = c.chain;
+  for (const CkSeg& sg : ck_segments(h)) H.payload_bytes += (int64_t)sg.bytes;
+  return H;
+}
+extern "C" int64_t erirt_checkpoint_size(erirt_handle* h) {
+  if (!h) { fail(ERIRT_E_ARG, "null handle"); return -1; }
+  return (int64_t)sizeof(CkHeader) + ck_header(h).payload_bytes;
+}
+extern "C" int erirt_checkpoint_save(erirt_handle* h, void* buf, int64_t size) {
+  if (!h || !buf) return fail(ERIRT_E_ARG, "null argument");
+  const CkHeader H = ck_header(h);
+  const int64_t need = (int64_t)sizeof(CkHeader) + H.payload_bytes;
+  if (size < need) return fail(ERIRT_E_ARG, "checkpoint buffer of %lld bytes, %lld needed", (long long)size, (long long)need);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(buf, &H, sizeof(H));
+  char* dst = (char*)buf + sizeof(H);
+  for (const CkSeg& sg : ck_segments(h)) {
+    CU(cudaMemcpyAsync(dst, sg.p, sg.bytes, cudaMemcpyDeviceToHost, h->stream));
+    dst += sg.bytes;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int erirt_checkpoint_load(erirt_handle* h, const void* buf, int64_t size) {
+  if (!h || !buf) return fail(ERIRT_E_ARG, "null argument");
+  if (size < (int64_t)sizeof(CkHeader)) return fail(ERIRT_E_ARG, "checkpoint shorter than its header");
+  CkHeader H;
+  memcpy(&H, buf, sizeof(H));
+  if (memcmp(H.magic, "ERIRTCK1", 8) != 0) return fail(ERIRT_E_ARG, "not an erirt checkpoint (bad magic)");
+  CkHeader W = ck_header(h);
+  // everything but the progress fields must match the handle: a checkpoint continues THE SAME chain on the same shard
+  W.sweeps_done = H.sweeps_done; W.prologue_done = H.prologue_done;
+  if (memcmp(&H, &W, sizeof(H)) != 0)
+    return fail(ERIRT_E_ARG, "checkpoint belongs to another configuration (model %d dtype %d %lld x %d, F=%d, nIter=%d nChain=%d, shard %lld+%lld, seed %llu chain %u)",
+                H.model, H.dtype, (long long)H.n_subj, H.n_item, H.n_feat, H.n_iter, H.n_chain, (long long)H.subj_offset, (long long)H.n_subj,
+                (unsigned long long)H.seed, H.chain);
+  if (size < (int64_t)sizeof(CkHeader) + H.payload_bytes) return fail(ERIRT_E_ARG, "checkpoint truncated: %lld of %lld bytes", (long long)size, (long long)(sizeof(CkHeader) + H.payload_bytes));
+  if (H.sweeps_done < 0 || H.sweeps_done > h->cap) return fail(ERIRT_E_ARG, "checkpoint holds %lld sweeps, capacity is %d", (long long)H.sweeps_done, h->cap);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const char* src = (const char*)buf + sizeof(H);
+  for (const CkSeg& sg : ck_segments(h)) {
+    CU(cudaMemcpyAsync(sg.p, src, sg.bytes, cudaMemcpyHostToDevice, h->stream));
+    src += sg.bytes;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  h->sweeps_done = H.sweeps_done;
+  h->prologue_done = H.prologue_done != 0;
   return 0;
 }
 

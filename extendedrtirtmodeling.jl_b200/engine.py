@@ -55,13 +55,18 @@ class Engine:
 
     # ---- data / state ----
     def set_data(self, Y, logT=None, X=None):
-        Y = np.asfortranarray(Y, dtype=np.float64)
+        """Host matrices as Julia holds them.  A bool / uint8 Y (Julia's Matrix{Bool}) goes through erirt_set_data_y8 as it
+        lies in memory; anything else is passed as column-major float64."""
+        Y = np.asarray(Y)
+        y8 = Y.dtype in (np.bool_, np.uint8)
+        Y = np.asfortranarray(Y, dtype=np.uint8 if y8 else np.float64)
         assert Y.shape == (self.N, self.J), Y.shape
         T = np.asfortranarray(logT, dtype=np.float64) if logT is not None else None
         Xf = np.asfortranarray(X, dtype=np.float64) if (X is not None and self.F > 0) else None
-        check(self.lib.erirt_set_data(self.h, Y.ctypes.data, Y.shape[0], T.ctypes.data if T is not None else None,
-                                      T.shape[0] if T is not None else 0, Xf.ctypes.data if Xf is not None else None,
-                                      Xf.shape[0] if Xf is not None else 0))
+        fn = self.lib.erirt_set_data_y8 if y8 else self.lib.erirt_set_data
+        check(fn(self.h, Y.ctypes.data, Y.shape[0], T.ctypes.data if T is not None else None,
+                 T.shape[0] if T is not None else 0, Xf.ctypes.data if Xf is not None else None,
+                 Xf.shape[0] if Xf is not None else 0))
 
     def set_data_device(self, dY_ptr, ldY, dlogT_ptr, ldT, dX_ptr, ldX):
         """Column-major float64 buffers already on this engine's device (e.g. torch tensors' data_ptr())."""
@@ -109,11 +114,27 @@ class Engine:
         check(self.lib.erirt_get_trace(self.h, _lib.TRACES[which], first_col, n_cols, _dp(out)))
         return out
 
-    def get_moments(self, name):
-        mean = np.empty(self.N)
-        sd = np.empty(self.N)
+    def get_moments(self, name, out=None):
+        """Post-burn-in mean and SD of theta / zeta / nu.  out: optional (mean, sd) float64 arrays to fill (e.g. views of pinned memory)."""
+        mean, sd = out if out is not None else (np.empty(self.N), np.empty(self.N))
+        assert mean.dtype == np.float64 and sd.dtype == np.float64 and mean.size == self.N and sd.size == self.N
         check(self.lib.erirt_get_moments(self.h, _lib.FIELDS[name], _dp(mean), _dp(sd), self.N))
         return mean, sd
+
+    # ---- checkpoint / resume ----
+    def checkpoint(self) -> np.ndarray:
+        """State, auxiliaries, Philox sweep counter, running moments and traces of the chain as one byte array."""
+        n = int(self.lib.erirt_checkpoint_size(self.h))
+        if n < 0:
+            check(-1)
+        buf = np.empty(n, dtype=np.uint8)
+        check(self.lib.erirt_checkpoint_save(self.h, buf.ctypes.data, n))
+        return buf
+
+    def restore(self, buf):
+        """Continue the chain a checkpoint() was taken from (same configuration; call set_data first)."""
+        buf = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf)
+        check(self.lib.erirt_checkpoint_load(self.h, buf.ctypes.data, buf.size))
 
     def stats(self):
         s = _lib.Stats()

@@ -93,6 +93,11 @@ int erirt_destroy(erirt_handle* h);
  * full matrix with the full leading dimension.  logT may be NULL for GibbsMlIrt; X may be NULL if n_feat=0. */
 int erirt_set_data(erirt_handle* h, const double* Y, int64_t ldY, const double* logT, int64_t ldT,
                    const double* X, int64_t ldX);
+/* Same contract with Y as one byte per response (0/1): a Julia Matrix{Bool} -- what `rand.(BernoulliLogit...)` in
+ * src/SimTools.jl:165 produces and InputData stores -- is passed as it lies in memory, without widening it to Float64 first
+ * (an eighth of the host->device bytes of Y). */
+int erirt_set_data_y8(erirt_handle* h, const uint8_t* Y, int64_t ldY, const double* logT, int64_t ldT,
+                      const double* X, int64_t ldX);
 /* Same contract with the buffers already on this handle's device (cudaMalloc'ed by the caller). */
 int erirt_set_data_device(erirt_handle* h, const double* dY, int64_t ldY, const double* dlogT, int64_t ldT,
                           const double* dX, int64_t ldX);
@@ -121,6 +126,16 @@ int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, 
 int erirt_loglik_current(erirt_handle* h, double* out);
 
 int erirt_get_stats(erirt_handle* h, erirt_stats* out);
+
+/* ---- checkpoint / resume: state, auxiliaries, Philox sweep counter, running moments and traces of the chain ----
+ * erirt_checkpoint_save writes erirt_checkpoint_size(h) bytes into the caller's buffer (the caller persists them).
+ * erirt_checkpoint_load restores them into a handle created with the SAME erirt_config (model, dimensions, dtype, n_iter,
+ * n_chain, n_burnin, person_trace, shard, seed, chain -- checked, ERIRT_E_ARG otherwise) after erirt_set_data; the data is not
+ * part of the checkpoint.  The resumed chain continues bit for bit as if it had never stopped.  Sharded chains: every rank
+ * saves and loads its own shard. */
+int64_t erirt_checkpoint_size(erirt_handle* h);
+int erirt_checkpoint_save(erirt_handle* h, void* buf, int64_t size);
+int erirt_checkpoint_load(erirt_handle* h, const void* buf, int64_t size);
 
 /* ---- person-sharded chains: one handle per GPU/process, item statistics all-reduced with NCCL ---- */
 int erirt_nccl_unique_id(void* id128);                 /* rank 0 creates 128 bytes, caller broadcasts them */

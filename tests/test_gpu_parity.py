@@ -409,3 +409,78 @@ def test_f64_engine_matches_committed_fixture(E):
         assert relerr(eng.get_trace("qr")[:3, :qw, 0], g[f"{model}_qr"][:, :qw], atol=1e-3).max() < tol, model
         assert relerr(eng.get_trace("logLike")[:3, 0, 0], g[f"{model}_ll"]).max() < tol, model
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,dtype", [("RtIrtLatentQr", "f32"), ("RtIrt", "f64"), ("RtIrtCrossQr", "f32"), ("MlIrt", "f32")])
+def test_checkpoint_resume_is_bit_exact(E, model, dtype):
+    """A chain restored from erirt_checkpoint_save into a FRESH handle continues the uninterrupted one: same Philox counters, same
+    state, same traces (up to the summation order of the f64 atomics that combine the item statistics, as between any two runs)."""
+    pb = make_problem(model, 100, 7, 2, seed=31)
+    tol = 1e-10 if dtype == "f64" else 1e-5
+    full = run_engine(E, pb, 6, dtype=dtype, person_trace=True)
+    # the same chain, stopped after 3 sweeps, checkpointed, destroyed, restored into a new handle and run for 3 more
+    first = E.Engine(model, 100, 7, 2, n_iter=6, n_chain=1, n_burnin=0, q_rt=pb["q"], cov2one=model not in ("RtIrtLatent", "RtIrtLatentQr"),
+                     dtype=dtype, seed=99, person_trace=True, use_graph=False)
+    first.set_data(pb["Y"], None if model == "MlIrt" else pb["logT"], pb["X"])
+    i = pb["init"]
+    st = dict(theta=i["theta"], a=i["a"], b=i["b"])
+    if model != "MlIrt":
+        st.update(zeta=i["zeta"], lambda_=i["lambda_"], sigma2=i["sigma2"], Sigma=i["Sigma"])
+    if pb["nb"]:
+        st["beta"] = i["beta"][: pb["nb"]]
+    if "Cross" in model:
+        st["rho"] = i["rho"]
+    first.set_state(**st)
+    first.sample(3)
+    ck = first.checkpoint()
+    first.close()
+    second = E.Engine(model, 100, 7, 2, n_iter=6, n_chain=1, n_burnin=0, q_rt=pb["q"], cov2one=model not in ("RtIrtLatent", "RtIrtLatentQr"),
+                      dtype=dtype, seed=99, person_trace=True, use_graph=False)
+    second.set_data(pb["Y"], None if model == "MlIrt" else pb["logT"], pb["X"])
+    second.restore(ck)
+    assert second.stats()["sweeps_done"] == 3
+    second.sample(3)
+    for which in ("ra", "qr", "logLike") + (() if model == "MlIrt" else ("rt",)):
+        a, b = full.get_trace(which), second.get_trace(which)
+        assert np.allclose(a, b, rtol=tol, atol=tol * 1e-3, equal_nan=True), which
+    for f in ("theta",) + (() if model == "MlIrt" else ("zeta",)):
+        assert np.allclose(full.get_state(f), second.get_state(f), rtol=tol, atol=tol * 1e-3)
+        for k in (0, 1):  # running mean and SD cover sweeps from before AND after the checkpoint
+            assert np.allclose(full.get_moments(f)[k], second.get_moments(f)[k], rtol=tol, atol=tol * 1e-3)
+    # a checkpoint of another configuration is refused, and so is a truncated one
+    other = E.Engine(model, 100, 7, 2, n_iter=6, n_chain=1, n_burnin=0, q_rt=pb["q"], dtype=dtype, seed=100, person_trace=True)
+    with pytest.raises(E.ErirtError) as ei:
+        other.restore(ck)
+    assert ei.value.code == -1 and "another configuration" in str(ei.value)
+    with pytest.raises(E.ErirtError):
+        second.restore(ck[: ck.size // 2])
+    with pytest.raises(E.ErirtError):
+        second.restore(np.zeros(ck.size, np.uint8))
+    for e in (full, second, other):
+        e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,J", [(300, 21), (1000, 100), (70000, 9)])
+def test_set_data_y8_equals_float64_ingest(E, N, J):
+    """erirt_set_data_y8 (Julia Matrix{Bool}) and erirt_set_data (Float64 Y) build the same device data set; the chunked host ingest
+    (whole columns through a bounded staging buffer; (70000, 9) needs more than one chunk) equals the one-pass device ingest."""
+    import torch
+    pb = make_problem("RtIrtLatentQr", N, J, 2, seed=32)
+    tr = []
+    for mode in ("f64", "u8", "device"):
+        eng = E.Engine("RtIrtLatentQr", N, J, 2, n_iter=3, n_burnin=0, q_rt=0.85, cov2one=False, dtype="f32", seed=5, use_graph=False)
+        if mode == "device":
+            dY, dT, dX = (torch.tensor(np.asfortranarray(pb[k]).T.copy(), device="cuda") for k in ("Y", "logT", "X"))  # column-major on the device
+            eng.set_data_device(dY.data_ptr(), N, dT.data_ptr(), N, dX.data_ptr(), N)
+        else:
+            eng.set_data(pb["Y"].astype(bool) if mode == "u8" else pb["Y"], pb["logT"], pb["X"])
+        i = pb["init"]
+        eng.set_state(theta=i["theta"], zeta=i["zeta"], beta=i["beta"][:4])
+        eng.sample(3)
+        tr.append((eng.get_trace("ra", N, 2 * J), eng.get_trace("qr", 0, 8), eng.get_state("theta")))
+        eng.close()
+    for other in tr[1:]:
+        assert np.array_equal(tr[0][2], other[2])  # the person draws only see the packed tiles
+        assert np.allclose(tr[0][0], other[0], rtol=1e-6, atol=1e-9) and np.allclose(tr[0][1], other[1], rtol=1e-6, atol=1e-9)
