@@ -28,7 +28,7 @@ class Config(C.Structure):
                 ("n_chain", C.c_int32), ("n_burnin", C.c_int32), ("q_rt", C.c_double), ("intercept", C.c_int32),
                 ("itemtype_1pl", C.c_int32), ("cov2one", C.c_int32), ("dtype", C.c_int32), ("seed", C.c_uint64),
                 ("chain", C.c_uint32), ("compat", C.c_int32), ("person_trace", C.c_int32), ("device", C.c_int32),
-                ("use_graph", C.c_int32), ("time_kernels", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("use_graph", C.c_int32), ("time_kernels", C.c_int32), ("nu_cell_moments", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class Stats(C.Structure):

@@ -109,7 +109,7 @@ def _qr_layout(MCMC):
 
 
 def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", seed=1234, chain=0, device=0,
-           person_trace=None, compat=0, use_graph=True, shard=None, progress=None, chunk=None):
+           person_trace=None, compat=0, use_graph=True, shard=None, progress=None, chunk=None, nu_cell_moments=None):
     """sample!(MCMC; intercept, itemtype, cov2one) for every Gibbs* type.
 
     Extra keyword-only engine options: dtype ("f64" parity mode / "f32" fast mode), seed, chain (independent
@@ -117,6 +117,8 @@ def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", 
     shard = (rank, world, nccl_unique_id_bytes, subj_offset, n_subj_total[, allgather]) for a person-sharded chain; the
     optional sixth entry is a callable bytes -> concatenated bytes of all ranks (e.g. distributed.allgather_bytes), which
     switches the per-sweep exchange from ncclAllReduce to the fused peer-memory all-reduce.
+    nu_cell_moments (CrossQr): keep the running mean / SD of the N x J weights on the device so that Post.mean.ν exists
+    (src/GibbsRtIrtCross.pl.jl:310) without the reference's nIter x N*J trace; default: on while 16 N J bytes fit the budget.
     Returns MCMC (mutated), like the reference."""
     if itemtype not in ("1pl", "2pl"):
         raise ValueError("Invalid input: the item type must be '1pl' or '2pl'.")  # src/GibbsRtIrt.pl.jl:212-214
@@ -130,10 +132,13 @@ def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", 
     n_total, offset = N, 0
     if shard is not None:
         offset, n_total = shard[3], shard[4]
+    if nu_cell_moments is None:
+        nu_cell_moments = MCMC.model == "RtIrtCrossQr" and 16 * N * J <= PERSON_TRACE_BUDGET
     eng = Engine(MCMC.model, N, J, F, n_iter=C.nIter, n_chain=C.nChain, n_burnin=C.nBurnin, q_rt=C.qRt,
                  intercept=intercept, itemtype=itemtype, cov2one=cov2one, dtype=dtype, seed=seed, chain=chain,
                  compat=compat, person_trace=person_trace, device=device, use_graph=use_graph,
-                 n_subj_total=n_total, subj_offset=offset)
+                 n_subj_total=n_total, subj_offset=offset, nu_cell_moments=nu_cell_moments and MCMC.model == "RtIrtCrossQr")
+    MCMC.nu_cell_moments = bool(nu_cell_moments and MCMC.model == "RtIrtCrossQr")
     MCMC.engine = eng
     if shard is not None:
         eng.comm_init(shard[0], shard[1], shard[2])
@@ -208,6 +213,8 @@ def _collect(MCMC, eng, person_trace):
         sd.nu = s
         if not person_trace:
             mean.nu = m
+    if MCMC.model == "RtIrtCrossQr" and getattr(MCMC, "nu_cell_moments", False):
+        mean.nu, sd.nu = eng.get_moments("nu")  # N x J, src/GibbsRtIrtCross.pl.jl:310
     Post.mean, Post.sd = mean, sd
     # the reference leaves the last state in MCMC.Para
     Para = MCMC.Para
@@ -234,7 +241,9 @@ def getLogLikelihood(MCMC, P, dtype="f64", device=0):
             st["beta"] = P.beta
         if P.rho.size:
             st["rho"] = P.rho
-        if MCMC.model == "RtIrtLatentQr":
+        if MCMC.model in ("RtIrtLatentQr", "RtIrtCrossQr"):
+            if np.size(P.nu) == 0:
+                raise ValueError("the log-likelihood of a quantile model needs the weights ν (sample CrossQr with nu_cell_moments=True)")
             st["nu"] = P.nu
         eng.set_state(**st)
         return eng.loglik_current()
@@ -306,7 +315,7 @@ def coef(MCMC, file=None):
         print("2) Covariance of Person Parameters.", np.asarray(m.Sigma_p).reshape(2, 2).round(3).tolist(), file=file)
     if m.beta.size:
         print("3) Regression Coefficients.", np.round(m.beta, 3).tolist(), file=file)
-    dic = getDic(MCMC) if MCMC.model != "RtIrtCrossQr" else None
+    dic = getDic(MCMC) if (MCMC.model != "RtIrtCrossQr" or np.size(MCMC.Post.mean.nu)) else None
     if dic is not None:
         print(f"4) Criterion. Deviance {dic.DIC - dic.pD:.3f}  DIC {dic.DIC:.3f}", file=file)
     return dic

@@ -172,6 +172,19 @@ __global__ void colsum_finish_kernel(const double* __restrict__ part, int J, dou
   for (int p = 0; p < COLSUM_PARTS; ++p) acc += part[(int64_t)j * COLSUM_PARTS + p];
   out[j] = acc;
 }
+// the same for the N x J cell weights of CrossQr: sums tiled [n_pad][Jp], results column-major [n][J]
+__global__ void tile_moments_kernel(const double* __restrict__ s1, const double* __restrict__ s2, int64_t n, int J, int Jp, double cnt,
+                                    double* __restrict__ mean, double* __restrict__ sd) {
+  const int64_t total = n * J;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t % n;
+    const int j = (int)(t / n);
+    if (cnt <= 0.0) { mean[t] = sd[t] = __longlong_as_double(0x7ff8000000000000LL); continue; }
+    const double a = s1[i * Jp + j], b = s2[i * Jp + j], m = a / cnt;
+    mean[t] = m;
+    sd[t] = cnt > 1.0 ? sqrt(fmax(0.0, __dsub_rn(b, __dmul_rn(__dmul_rn(cnt, m), m)) / (cnt - 1.0))) : 0.0;
+  }
+}
 // post-burn-in mean and SD of a person vector from its running sums (erirt_get_moments)
 __global__ void moments_finish_kernel(const double* __restrict__ s1, const double* __restrict__ s2, int64_t n, double cnt,
                                       double* __restrict__ mean, double* __restrict__ sd) {
@@ -223,6 +236,7 @@ struct erirt_handle {
   void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
   double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
   double* dLlOut = nullptr;
+  double* dNuMom = nullptr;    // CrossQr with cfg.nu_cell_moments: [2][n_pad][Jp] running sum / sum of squares of the cell weights
   double* dColPart = nullptr;  // [3][Jp][COLSUM_PARTS] partial column sums of the ingest
   double *dTrRa = nullptr, *dTrRt = nullptr, *dTrQr = nullptr, *dTrLl = nullptr;
   uint32_t* dSweep = nullptr;
@@ -345,7 +359,7 @@ static int free_handle(erirt_handle* h) {
   if (h->dPeerBufs) cudaFree(h->dPeerBufs);
   if (h->dXseq) cudaFree(h->dXseq);
   void* ptrs[] = {h->dNuCell, h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
-                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut, h->dColPart};
+                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut, h->dColPart, h->dNuMom};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
@@ -444,6 +458,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dOmega = p; }
   if (has_rt) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dLogT = p; }
   if (cfg->model == ERIRT_RTIRT_CROSSQR) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dNuCell = p; }
+  if (cfg->model == ERIRT_RTIRT_CROSSQR && cfg->nu_cell_moments) TRY(dalloc(&h->dNuMom, 2 * cells));
   { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dTheta = p; }
   { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dZeta = p; }
   { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dNu = p; }
@@ -660,8 +675,10 @@ extern "C" int erirt_set_state(erirt_handle* h, int32_t field, const double* v, 
   CU(cudaSetDevice(h->cfg.device));
   void* pv;
   int off, len;
-  if (field == ERIRT_NU && h->cfg.model == ERIRT_RTIRT_CROSSQR) return fail(ERIRT_E_ARG, "CrossQr draws nu before it is read; no initial value is needed");
-  if (person_vec(h, field, &pv) == 0) {
+  // CrossQr: nu is N x J.  The sampler draws it before reading it (no initial value is needed); setting it serves
+  // erirt_loglik_current (D-hat at Post.mean, GibbsRtIrtCross.pl.jl:344-352)
+  const bool nu_cell = field == ERIRT_NU && h->cfg.model == ERIRT_RTIRT_CROSSQR;
+  if (!nu_cell && person_vec(h, field, &pv) == 0) {
     if (n != h->cfg.n_subj) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)h->cfg.n_subj, (long long)n);
     double* tmp;
     CU(cudaMallocAsync((void**)&tmp, n * sizeof(double), h->stream));
@@ -673,14 +690,15 @@ extern "C" int erirt_set_state(erirt_handle* h, int32_t field, const double* v, 
     if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "set_state: %s", cudaGetErrorString(e));
     return 0;
   }
-  if (field == ERIRT_OMEGA) {
+  if (field == ERIRT_OMEGA || nu_cell) {
     const int64_t want = h->cfg.n_subj * h->cfg.n_item;
-    if (n != want) return fail(ERIRT_E_ARG, "omega expects %lld values", (long long)want);
+    if (n != want) return fail(ERIRT_E_ARG, "field %d expects %lld values, got %lld", field, (long long)want, (long long)n);
+    void* dst = nu_cell ? h->dNuCell : h->dOmega;
     double* tmp;
     CU(cudaMallocAsync((void**)&tmp, n * sizeof(double), h->stream));
     cudaMemcpyAsync(tmp, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (h->cfg.dtype == ERIRT_F32) colmajor_to_tile_kernel<float><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (float*)h->dOmega);
-    else colmajor_to_tile_kernel<double><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (double*)h->dOmega);
+    if (h->cfg.dtype == ERIRT_F32) colmajor_to_tile_kernel<float><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (float*)dst);
+    else colmajor_to_tile_kernel<double><<<1024, 256, 0, h->stream>>>(tmp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (double*)dst);
     cudaFreeAsync(tmp, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "set_state: %s", cudaGetErrorString(e));
@@ -746,6 +764,7 @@ static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   A.X = (const R*)h->dX;
   A.mom = h->dMom;
   A.ptrace = (R*)h->dPtrace;
+  A.nu_mom = h->dNuMom;
   A.params = h->dParams;
   A.stats = h->dStats;
   A.sweep_ctr = h->dSweep;
@@ -983,12 +1002,25 @@ extern "C" int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, d
   if (!h || !mean) return fail(ERIRT_E_ARG, "null argument");
   int slot = field == ERIRT_THETA ? 0 : (field == ERIRT_ZETA ? 1 : (field == ERIRT_NU ? 2 : -1));
   if (slot < 0) return fail(ERIRT_E_ARG, "moments exist for THETA, ZETA and NU only");
-  if (n != h->cfg.n_subj) return fail(ERIRT_E_ARG, "expects n_subj values");
+  const bool nu_cell = field == ERIRT_NU && h->cfg.model == ERIRT_RTIRT_CROSSQR;
+  if (nu_cell && !h->dNuMom) return fail(ERIRT_E_STATE, "the running moments of the N x J weights of CrossQr need erirt_config.nu_cell_moments = 1");
+  if (n != (nu_cell ? h->cfg.n_subj * h->cfg.n_item : h->cfg.n_subj)) return fail(ERIRT_E_ARG, nu_cell ? "expects n_subj * n_item values" : "expects n_subj values");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->stream));
   const int64_t nChain = h->cfg.n_chain;
   const int64_t first = (int64_t)h->cfg.n_burnin * nChain;  // sweeps with m > n_burnin
   const int64_t cnt = h->sweeps_done > first ? h->sweeps_done - first : 0;
+  if (nu_cell) {  // column-major N x J out of the tiled sums
+    double* tmp = nullptr;
+    CU(cudaMallocAsync((void**)&tmp, (size_t)2 * n * sizeof(double), h->stream));
+    tile_moments_kernel<<<1024, 256, 0, h->stream>>>(h->dNuMom, h->dNuMom + (size_t)h->n_pad * h->L.Jp, h->cfg.n_subj, h->cfg.n_item, h->L.Jp, (double)cnt, tmp, tmp + n);
+    cudaError_t e = cudaMemcpyAsync(mean, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && sd) e = cudaMemcpyAsync(sd, tmp + n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaFreeAsync(tmp, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_moments: %s", cudaGetErrorString(e));
+    return 0;
+  }
   // mean and SD are finished on the device and copied straight into the caller's buffers (pinned buffers make this a plain DMA)
   double* tmp = nullptr;
   CU(cudaMallocAsync((void**)&tmp, (size_t)2 * n * sizeof(double), h->stream));
@@ -1004,8 +1036,6 @@ extern "C" int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, d
 extern "C" int erirt_loglik_current(erirt_handle* h, double* out) {
   if (!h || !out) return fail(ERIRT_E_ARG, "null argument");
   if (!h->data_set) return fail(ERIRT_E_STATE, "erirt_set_data has not been called");
-  if (h->cfg.model == ERIRT_RTIRT_CROSSQR)
-    return fail(ERIRT_E_UNSUPPORTED, "the log-likelihood at a given state needs the N x J weights nu, which CrossQr does not take as input");
   CU(cudaSetDevice(h->cfg.device));
   int rc = finalize_constants(h);
   if (rc) return rc;
@@ -1072,6 +1102,7 @@ static std::vector<CkSeg> ck_segments(erirt_handle* h) {
   v.push_back({h->dTrQr, cap * (size_t)h->qw * sizeof(double)});
   v.push_back({h->dTrLl, cap * sizeof(double)});
   if (h->dPtrace) v.push_back({h->dPtrace, cap * 3 * vec});
+  if (h->dNuMom) v.push_back({h->dNuMom, 2 * cells * sizeof(double)});
   return v;
 }
 static CkHeader ck_header(erirt_handle* h) {

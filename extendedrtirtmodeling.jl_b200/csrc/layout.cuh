@@ -93,6 +93,7 @@ struct PersonArgs {
   const R* X;
   double* mom;    // [6][n_pad] running sum / sum of squares of theta, zeta, nu (post burn-in)
   R* ptrace;      // optional [cap][3][n_pad] person trace (theta, zeta, nu) or nullptr
+  double* nu_mom; // optional (CrossQr, cfg.nu_cell_moments) [2][n_pad][Jp] post-burn-in sum / sum of squares of the cell weights, or nullptr
   const double* params;
   double* stats;
   const uint32_t* sweep_ctr;  // k: this launch draws theta_k, zeta_k (k >= 1) and omega_{k+1}, nu_{k+1}

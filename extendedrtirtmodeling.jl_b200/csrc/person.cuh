@@ -467,14 +467,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
     __syncthreads();
 
-    if (cqr && do_pg) {
+    if (cqr && (do_pg || eval)) {
       // ---- CrossQr cell pass (thread per person row): response-time log-likelihood of state k with nu_k
       //      (getLogLikelihoodRtIrtCrossQr, GibbsRtIrtCross.pl.jl:240-258), then nu_{k+1} | state k
-      //      (drawQrWeightsCrossQr, Draw.pl.jl:303-320), written in place ----
+      //      (drawQrWeightsCrossQr, Draw.pl.jl:303-320), written in place.  Evaluation stage: the log-likelihood only ----
       const bool cvalid = (row0 + p) < A.n_local;
       const uint32_t cgid = A.person_offset + (uint32_t)(row0 + p);
       const R thc = s_u[p * Dgp + F + 1], zec = s_u[p * Dgp + F + 2];
       const R cB = rsqrt_of(R(2) * k2 + k1 * k1);
+      const bool nu_acc = A.nu_mom != nullptr && post_burnin && !eval;  // Post.mean.nu of GibbsRtIrtCross.pl.jl:310 as a running sum
       R llrt = R(0);
       for (int kk = 0; kk < nk; ++kk) {
         const int g = group_of<TPP>(q, kk);
@@ -486,12 +487,25 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         const Quad<R> pR = ld4(s_par + PAR_RHO * Jp + 4 * g);
         const Quad<R> pC = ld4(s_par + PAR_ISC * Jp + 4 * g);
         const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
-        const uint4 wA = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g)), 0);
-        const uint4 wB = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g + 1)), 0);
-        R zn[4];
-        normal_pair(wA.x, wA.y, zn[0], zn[1]);
-        normal_pair(wB.x, wB.y, zn[2], zn[3]);
-        const R un[4] = {u01<R>(wA.z), u01<R>(wA.w), u01<R>(wB.z), u01<R>(wB.w)};
+        R zn[4] = {R(0), R(0), R(0), R(0)}, un[4] = {R(0.5), R(0.5), R(0.5), R(0.5)};
+        if (!eval) {
+          const uint4 wA = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g)), 0);
+          const uint4 wB = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g + 1)), 0);
+          normal_pair(wA.x, wA.y, zn[0], zn[1]);
+          normal_pair(wB.x, wB.y, zn[2], zn[3]);
+          un[0] = u01<R>(wA.z); un[1] = u01<R>(wA.w); un[2] = u01<R>(wB.z); un[3] = u01<R>(wB.w);
+        }
+        if (nu_acc && cvalid) {  // every cell is owned by exactly one thread of one CTA: plain read-modify-write
+          double* m1 = A.nu_mom + (row0 + p) * (int64_t)Jp + 4 * g;
+          double* m2 = m1 + A.n_pad * (int64_t)Jp;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (4 * g + e < J) {
+              const double v = (double)nc.v[e];
+              m1[e] += v;
+              m2[e] += v * v;
+            }
+        }
         Quad<R> out;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -503,17 +517,19 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
               const R res = resid - k1 * nu0;
               llrt += R(-0.5) * (rlog(nu0) + res * res * rdiv(pI.v[e], nu0));
             }
-            const R parA = fabs(resid) * pC.v[e];
-            const R parB = cB * pC.v[e];
-            R mu = rdiv(parB, parA);
-            if (!(mu >= R(1e-10))) mu = R(1e-10);
-            const R ig = ig_msh<R>(mu, parB * parB, zn[e], un[e]);
-            nun = rdiv(R(1), ig);
-            nun = nun < R(1e-10) ? R(1e-10) : (nun > R(1e10) ? R(1e10) : nun);
+            if (!eval) {
+              const R parA = fabs(resid) * pC.v[e];
+              const R parB = cB * pC.v[e];
+              R mu = rdiv(parB, parA);
+              if (!(mu >= R(1e-10))) mu = R(1e-10);
+              const R ig = ig_msh<R>(mu, parB * parB, zn[e], un[e]);
+              nun = rdiv(R(1), ig);
+              nun = nun < R(1e-10) ? R(1e-10) : (nun > R(1e10) ? R(1e10) : nun);
+            }
           }
           out.v[e] = nun;
         }
-        st4(s_nc + p * Jp + 4 * g, out);
+        if (!eval) st4(s_nc + p * Jp + 4 * g, out);
       }
 #pragma unroll
       for (int o = 1; o < TPP; o <<= 1) llrt += __shfl_xor_sync(0xffffffffu, llrt, o);

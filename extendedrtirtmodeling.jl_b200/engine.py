@@ -14,7 +14,8 @@ def _dp(a):
 class Engine:
     def __init__(self, model, n_subj, n_item, n_feat=0, *, n_iter=5000, n_chain=1, n_burnin=None, q_rt=0.5,
                  intercept=False, itemtype="2pl", cov2one=True, dtype="f32", seed=1234, chain=0, compat=0,
-                 person_trace=False, device=0, use_graph=True, n_subj_total=None, subj_offset=0, time_kernels=False):
+                 person_trace=False, device=0, use_graph=True, n_subj_total=None, subj_offset=0, time_kernels=False,
+                 nu_cell_moments=False):
         if itemtype not in ("1pl", "2pl"):
             # same text as the reference's sample! (src/GibbsRtIrt.pl.jl:212-214)
             raise ValueError("Invalid input: the item type must be '1pl' or '2pl'.")
@@ -36,6 +37,7 @@ class Engine:
         cfg.seed, cfg.chain, cfg.compat = seed, chain, compat
         cfg.person_trace, cfg.device, cfg.use_graph = int(person_trace), device, int(use_graph)
         cfg.time_kernels = int(time_kernels)
+        cfg.nu_cell_moments = int(nu_cell_moments)
         self.cfg = cfg
         self.model = mid
         self.N, self.J, self.F = n_subj, n_item, n_feat
@@ -116,9 +118,13 @@ class Engine:
 
     def get_moments(self, name, out=None):
         """Post-burn-in mean and SD of theta / zeta / nu.  out: optional (mean, sd) float64 arrays to fill (e.g. views of pinned memory)."""
-        mean, sd = out if out is not None else (np.empty(self.N), np.empty(self.N))
-        assert mean.dtype == np.float64 and sd.dtype == np.float64 and mean.size == self.N and sd.size == self.N
-        check(self.lib.erirt_get_moments(self.h, _lib.FIELDS[name], _dp(mean), _dp(sd), self.N))
+        cell = name == "nu" and self.model == 4  # CrossQr: N x J weights (needs nu_cell_moments=True)
+        n = self.N * self.J if cell else self.N
+        mean, sd = out if out is not None else (np.empty(n), np.empty(n))
+        assert mean.dtype == np.float64 and sd.dtype == np.float64 and mean.size == n and sd.size == n
+        check(self.lib.erirt_get_moments(self.h, _lib.FIELDS[name], _dp(mean), _dp(sd), n))
+        if cell and out is None:
+            return mean.reshape((self.N, self.J), order="F"), sd.reshape((self.N, self.J), order="F")
         return mean, sd
 
     # ---- checkpoint / resume ----

@@ -69,7 +69,10 @@ typedef struct erirt_config {
   int32_t device;         /* CUDA device ordinal */
   int32_t use_graph;      /* 1: replay sweeps from a captured CUDA graph */
   int32_t time_kernels;   /* 1: bracket every person-sweep launch with CUDA events (forces plain launches) */
-  int32_t reserved[7];
+  int32_t nu_cell_moments; /* CrossQr only, 1: keep the post-burn-in running sum / sum of squares of the N x J weights nu on the
+                              device (16 bytes per cell, +32 bytes of HBM traffic per cell and sweep): Post.mean.nu of
+                              src/GibbsRtIrtCross.pl.jl:310 without the reference's nIter x N*J trace; read with erirt_get_moments(ERIRT_NU) */
+  int32_t reserved[6];
 } erirt_config;
 
 typedef struct erirt_stats {
@@ -103,7 +106,8 @@ int erirt_set_data_device(erirt_handle* h, const double* dY, int64_t ldY, const 
                           const double* dX, int64_t ldX);
 
 /* Initial / current values of one InputPara field (float64, Julia layout: beta is vec(β) column-major,
- * SIGMA_P is vec(Σp), NU is n_subj (LatentQr) or n_subj x n_item column-major (CrossQr), OMEGA n_subj x n_item). */
+ * SIGMA_P is vec(Σp), NU is n_subj (LatentQr) or n_subj x n_item column-major (CrossQr), OMEGA n_subj x n_item).
+ * CrossQr draws NU before reading it, so setting it only matters for erirt_loglik_current. */
 int erirt_set_state(erirt_handle* h, int32_t field, const double* v, int64_t n);
 int erirt_get_state(erirt_handle* h, int32_t field, double* out, int64_t n);
 
@@ -117,12 +121,14 @@ int erirt_sample(erirt_handle* h, int64_t n_sweeps);
 int erirt_get_trace(erirt_handle* h, int32_t which, int64_t first_col, int64_t n_cols, double* out);
 int64_t erirt_trace_width(erirt_handle* h, int32_t which);
 
-/* Post-burn-in running mean and SD (over sweeps with m > n_burnin) of THETA, ZETA or NU (person-level). */
+/* Post-burn-in running mean and SD (over sweeps with m > n_burnin) of THETA, ZETA or NU (n = n_subj values; CrossQr's NU is
+ * n_subj x n_item column-major and needs erirt_config.nu_cell_moments). */
 int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n);
 
 /* getLogLikelihood*(Cond, Data; P) of the state currently held by the handle (every InputPara field as last set
  * with erirt_set_state, or as left by erirt_sample): used for DIC's D-hat at Post.mean,
- * src/GibbsRtIrt.pl.jl:432-472.  No draw is made and nothing is modified.  CrossQr: ERIRT_E_UNSUPPORTED. */
+ * src/GibbsRtIrt.pl.jl:432-472.  No draw is made and nothing is modified.  CrossQr (getLogLikelihoodRtIrtCrossQr,
+ * src/GibbsRtIrtCross.pl.jl:240-258) reads the N x J weights last set with erirt_set_state(ERIRT_NU) or left by erirt_sample. */
 int erirt_loglik_current(erirt_handle* h, double* out);
 
 int erirt_get_stats(erirt_handle* h, erirt_stats* out);

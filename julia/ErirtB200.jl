@@ -9,7 +9,8 @@
 module ErirtB200
 
 using ExtendedRtIrtModeling
-import ExtendedRtIrtModeling: sample!, InputPara, GibbsMlIrt, GibbsRtIrt, GibbsRtIrtNull, GibbsRtIrtLatent, GibbsRtIrtLatentQr
+import ExtendedRtIrtModeling: sample!, InputPara, GibbsMlIrt, GibbsRtIrt, GibbsRtIrtNull, GibbsRtIrtCross, GibbsRtIrtCrossQr,
+                               GibbsRtIrtLatent, GibbsRtIrtLatentQr
 
 export GibbsRtIrtQuantile
 
@@ -39,10 +40,12 @@ struct ErirtConfig
     device::Int32
     use_graph::Int32
     time_kernels::Int32
-    reserved::NTuple{7,Int32}
+    nu_cell_moments::Int32
+    reserved::NTuple{6,Int32}
 end
 
-const MODEL_ID = Dict(GibbsMlIrt => 0, GibbsRtIrt => 1, GibbsRtIrtNull => 2, GibbsRtIrtLatent => 5, GibbsRtIrtLatentQr => 6)
+const MODEL_ID = Dict(GibbsMlIrt => 0, GibbsRtIrt => 1, GibbsRtIrtNull => 2, GibbsRtIrtCross => 3, GibbsRtIrtCrossQr => 4,
+                      GibbsRtIrtLatent => 5, GibbsRtIrtLatentQr => 6)
 const F_THETA, F_ZETA, F_A, F_B, F_LAMBDA, F_SIGMA2, F_BETA, F_RHO, F_SIGMA_P, F_NU = Int32.(0:9)
 const T_RA, T_RT, T_QR, T_LL = Int32.(0:3)
 
@@ -70,34 +73,55 @@ function _sample_gpu!(MCMC; intercept=false, itemtype="2pl", cov2one=true, dtype
     Cond, Data, Para, Post = MCMC.Cond, MCMC.Data, MCMC.Para, MCMC.Post
     N, J, F = Cond.nSubj, Cond.nItem, Cond.nFeat
     has_rt = !(MCMC isa GibbsMlIrt)
+    cqr = MCMC isa GibbsRtIrtCrossQr
     cfg = ErirtConfig(1, MODEL_ID[typeof(MCMC)], N, N, 0, J, F, Cond.nIter, Cond.nChain, Cond.nBurnin, Cond.qRt,
-                      intercept, itemtype == "1pl", cov2one, dtype, seed, 0, 0, 1, device, 1, 0, ntuple(_ -> Int32(0), 7))
+                      intercept, itemtype == "1pl", cov2one, dtype, seed, 0, 0, 1, device, 1, 0, cqr, ntuple(_ -> Int32(0), 6))
+    νmean = Float64[]   # CrossQr: post-burn-in mean of the N*J weights
     href = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:erirt_create, LIB), Cint, (Ref{ErirtConfig}, Ref{Ptr{Cvoid}}), cfg, href))
     h = href[]
     try
-        Y = Matrix{Float64}(Data.Y)
         logT = has_rt ? Matrix{Float64}(Data.logT) : zeros(0, 0)
         X = F > 0 ? Matrix{Float64}(Data.X) : zeros(0, 0)
-        GC.@preserve Y logT X check(ccall((:erirt_set_data, LIB), Cint,
-            (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
-            h, Y, N, has_rt ? pointer(logT) : C_NULL, N, F > 0 ? pointer(X) : C_NULL, N))
+        if Data.Y isa Matrix{Bool}   # rand.(BernoulliLogit…) of src/SimTools.jl:165: one byte per response, passed as it lies in memory
+            Y8 = Data.Y
+            GC.@preserve Y8 logT X check(ccall((:erirt_set_data_y8, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Bool}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+                h, Y8, N, has_rt ? pointer(logT) : C_NULL, N, F > 0 ? pointer(X) : C_NULL, N))
+        else                         # Int from CSV (src/Base.pl.jl:84-95) or Float64
+            Y = Matrix{Float64}(Data.Y)
+            GC.@preserve Y logT X check(ccall((:erirt_set_data, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+                h, Y, N, has_rt ? pointer(logT) : C_NULL, N, F > 0 ? pointer(X) : C_NULL, N))
+        end
         _set_state(h, F_THETA, Para.θ); _set_state(h, F_A, Para.a); _set_state(h, F_B, Para.b)
         if has_rt
             _set_state(h, F_ZETA, Para.ζ); _set_state(h, F_LAMBDA, Para.λ); _set_state(h, F_SIGMA2, Para.σ²t)
             _set_state(h, F_SIGMA_P, Matrix{Float64}(Para.Σp))
         end
         _set_state(h, F_BETA, Para.β)
+        (MCMC isa GibbsRtIrtCross || cqr) && _set_state(h, F_RHO, Para.ρ)
         check(ccall((:erirt_sample, LIB), Cint, (Ptr{Cvoid}, Int64), h, Cond.nIter * Cond.nChain))
         # fill the pre-allocated Post arrays (same layouts, src/GibbsRtIrt.pl.jl:63-69)
         _trace!(h, T_RA, Post.ra, 0)
         has_rt && _trace!(h, T_RT, Post.rt, 0)
-        _trace!(h, T_QR, Post.qr, 0)
+        if cqr
+            # the reference traces all N*J weights per sweep (src/GibbsRtIrtCross.pl.jl:65, :297); the engine keeps their running
+            # mean instead, so only the [ρ; vec Σp] columns of Post.qr are filled and Post.mean.ν comes from erirt_get_moments
+            small = Array{Float64}(undef, Cond.nIter, J + 4, Cond.nChain)
+            _trace!(h, T_QR, small, 0)
+            Post.qr[:, 1:(J + 4), :] .= small
+            νmean = Vector{Float64}(undef, N * J)
+            GC.@preserve νmean check(ccall((:erirt_get_moments, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64),
+                                           h, F_NU, νmean, C_NULL, N * J))
+        else
+            _trace!(h, T_QR, Post.qr, 0)
+        end
         _trace!(h, T_LL, Post.logLike, 0)
     finally
         ccall((:erirt_destroy, LIB), Cint, (Ptr{Cvoid},), h)
     end
-    return MCMC
+    return νmean
 end
 
 _pm(A, r, nb) = vec(ExtendedRtIrtModeling.mean(A[(nb + 1):end, r, :], dims=(1, 3)))
@@ -127,11 +151,36 @@ end
 function sample!(MCMC::GibbsRtIrtNull; itemtype::Union{String}="2pl", cov2one=true)
     _sample_gpu!(MCMC; itemtype, cov2one); _rt_mean!(MCMC, 2 * (MCMC.Cond.nFeat + 1))
 end
+function _cross_mean!(MCMC; ν=Float64[])
+    C, P = MCMC.Cond, MCMC.Post
+    nb, N, J = C.nBurnin, C.nSubj, C.nItem
+    P.mean = InputPara(ρ=_pm(P.qr, 1:J, nb), Σp=_pm(P.qr, (J + 1):(J + 4), nb), ν=ν,
+                       θ=_pm(P.ra, 1:N, nb), a=_pm(P.ra, (N + 1):(N + J), nb), b=_pm(P.ra, (N + J + 1):(N + 2J), nb),
+                       ζ=_pm(P.rt, 1:N, nb), λ=_pm(P.rt, (N + 1):(N + J), nb), σ²t=_pm(P.rt, (N + J + 1):(N + 2J), nb))
+    return MCMC
+end
+function sample!(MCMC::GibbsRtIrtCross; itemtype::Union{String}="2pl", cov2one=true)      # src/GibbsRtIrtCross.pl.jl:176
+    _sample_gpu!(MCMC; itemtype, cov2one); _cross_mean!(MCMC)
+end
+function sample!(MCMC::GibbsRtIrtCrossQr; itemtype::Union{String}="2pl", cov2one=true)    # src/GibbsRtIrtCross.pl.jl:265
+    ν = _sample_gpu!(MCMC; itemtype, cov2one); _cross_mean!(MCMC; ν=ν)                     # Post.mean.ν, :310
+end
 function sample!(MCMC::GibbsRtIrtLatent; intercept=false, itemtype::Union{String}="2pl", cov2one=false)
     _sample_gpu!(MCMC; intercept, itemtype, cov2one); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2)
 end
 function sample!(MCMC::GibbsRtIrtLatentQr; intercept=false, itemtype::Union{String}="2pl", cov2one=false)
     _sample_gpu!(MCMC; intercept, itemtype, cov2one); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2; with_ν=true)
 end
+
+# ---- checkpoint / resume of a running chain (erirt_checkpoint_*): `h` is the handle of a chain driven in chunks ----
+function checkpoint(h)::Vector{UInt8}
+    n = ccall((:erirt_checkpoint_size, LIB), Int64, (Ptr{Cvoid},), h)
+    n < 0 && error("erirt_b200: " * lasterror())
+    buf = Vector{UInt8}(undef, n)
+    GC.@preserve buf check(ccall((:erirt_checkpoint_save, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h, buf, n))
+    return buf      # write(io, buf) to persist it
+end
+restore!(h, buf::Vector{UInt8}) =
+    GC.@preserve buf check(ccall((:erirt_checkpoint_load, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h, buf, length(buf)))
 
 end # module

@@ -38,7 +38,7 @@ def test_config_struct_matches_header(lib):
     from erirt_b200 import _lib
     # field order and sizes of erirt_config as laid out by the C compiler
     assert ctypes.sizeof(_lib.Config) == 144 and ctypes.sizeof(_lib.Stats) == 48
-    assert _lib.Config.q_rt.offset == 56 and _lib.Config.seed.offset == 80 and _lib.Config.reserved.offset == 112
+    assert _lib.Config.q_rt.offset == 56 and _lib.Config.seed.offset == 80 and _lib.Config.nu_cell_moments.offset == 112 and _lib.Config.reserved.offset == 116
 
 
 def test_no_cpu_fallback(lib):

@@ -204,7 +204,7 @@ def test_crossqr_cell_weights_parity(E, oracle):
     eng32.close()
 
 
-@pytest.mark.parametrize("model", [m for m in MODELS if m != "RtIrtCrossQr"])
+@pytest.mark.parametrize("model", MODELS)
 def test_loglik_at_given_state_matches_oracle(E, oracle, model):
     """erirt_loglik_current == getLogLikelihood*(P) of the reference (DIC's D-hat), f64, no state is modified."""
     pb = make_problem(model, 500, 9, 2, seed=23)
@@ -222,8 +222,8 @@ def test_loglik_at_given_state_matches_oracle(E, oracle, model):
         st["beta"] = ref["beta"][: pb["nb"]]
     if "Cross" in model:
         st["rho"] = ref["rho"]
-    if model == "RtIrtLatentQr":
-        st["nu"] = ref["nu"]
+    if model in ("RtIrtLatentQr", "RtIrtCrossQr"):
+        st["nu"] = ref["nu"]  # CrossQr: the N x J weights (getLogLikelihoodRtIrtCrossQr, GibbsRtIrtCross.pl.jl:240-258)
     eng.set_state(**st)
     got = eng.loglik_current()
     assert abs(got - want) < 1e-11 * abs(want)
@@ -484,3 +484,39 @@ def test_set_data_y8_equals_float64_ingest(E, N, J):
     for other in tr[1:]:
         assert np.array_equal(tr[0][2], other[2])  # the person draws only see the packed tiles
         assert np.allclose(tr[0][0], other[0], rtol=1e-6, atol=1e-9) and np.allclose(tr[0][1], other[1], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_crossqr_weight_moments_and_dic(E, oracle):
+    """Post.mean.ν of GibbsRtIrtCrossQr (GibbsRtIrtCross.pl.jl:310: mean of the traced N x J weights over m > nBurnin) as a running
+    mean on the device, against the oracle's full trace; getDic through the API mirror (GibbsRtIrtCross.pl.jl:344-352)."""
+    pb = make_problem("RtIrtCrossQr", 150, 13, 0, seed=33)
+    N, J, n_iter, nb = 150, 13, 5, 2
+    ref = run_oracle(oracle, pb, n_iter)
+    nu_tr = ref["qr"][:, J + 4:].reshape(n_iter, N, J, order="F")  # vec(ν) column-major per sweep
+    eng = E.Engine("RtIrtCrossQr", N, J, 0, n_iter=n_iter, n_chain=1, n_burnin=nb, q_rt=pb["q"], cov2one=True, dtype="f64", seed=99,
+                   person_trace=True, use_graph=False, nu_cell_moments=True)
+    eng.set_data(pb["Y"], pb["logT"], None)
+    i = pb["init"]
+    eng.set_state(theta=i["theta"], zeta=i["zeta"], a=i["a"], b=i["b"], lambda_=i["lambda_"], sigma2=i["sigma2"], Sigma=i["Sigma"], rho=i["rho"])
+    eng.sample(n_iter)
+    mean, sd = eng.get_moments("nu")
+    assert mean.shape == (N, J)
+    # CrossQr amplifies rounding differences ~30x per sweep (DESIGN.md), so five sweeps agree to ~1e-9, not 1e-12
+    assert np.quantile(relerr(mean, nu_tr[nb:].mean(axis=0)), 0.99) < 1e-6
+    assert np.quantile(relerr(sd, nu_tr[nb:].std(axis=0, ddof=1), atol=1e-9), 0.99) < 1e-5
+    eng.close()
+    plain = E.Engine("RtIrtCrossQr", N, J, 0, n_iter=2, dtype="f64")
+    with pytest.raises(E.ErirtError) as ei:
+        plain.get_moments("nu")
+    assert ei.value.code == -3 and "nu_cell_moments" in str(ei.value)
+    plain.close()
+    # API mirror: Post.mean.ν and getDic for GibbsRtIrtCrossQr
+    Cond = E.setCond(nSubj=300, nItem=8, nFeat=0, nIter=120, nChain=1, qRt=0.85)
+    tp = E.setTrueParaRtIrtCross(Cond, rng=5)
+    Data = E.setDataRtIrtCross(Cond, tp, rng=5)
+    MCMC = E.GibbsRtIrtCrossQr(Cond, Data=Data, rng=5)
+    E.sample(MCMC, dtype="f32")
+    assert MCMC.Post.mean.nu.shape == (300, 8) and np.all(MCMC.Post.mean.nu > 0)
+    dic = E.getDic(MCMC)
+    assert np.isfinite(dic.DIC) and np.isfinite(dic.pD)
