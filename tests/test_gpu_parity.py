@@ -520,3 +520,55 @@ def test_crossqr_weight_moments_and_dic(E, oracle):
     assert MCMC.Post.mean.nu.shape == (300, 8) and np.all(MCMC.Post.mean.nu > 0)
     dic = E.getDic(MCMC)
     assert np.isfinite(dic.DIC) and np.isfinite(dic.pD)
+
+
+# ---- the BASELINE.json configurations at their own sizes (configs[1..3]; configs[0] is test_readme_flow_*, configs[4] the C5 tests) ----
+@pytest.mark.gpu
+def test_baseline_config2_rtirt_10k_x_30_three_chains(E, oracle):
+    """configs[1]: GibbsRtIrt, nSubj=10k, nItem=30, F=3, nChain=3 (interleaved pseudo-chains, GibbsRtIrt.pl.jl:289): two iterations of
+    the three chains = six sweeps against the oracle, f64 1e-8 over the window, and one f32 sweep at 1e-5."""
+    pb = make_problem("RtIrt", 10_000, 30, 3, seed=41)
+    ref = run_oracle(oracle, pb, 6)
+    eng = run_engine(E, pb, 6, dtype="f64", n_chain=3, use_graph=True, person_trace=True)
+    ra = eng.get_trace("ra")
+    assert ra.shape == (2, 10_000 + 60, 3)
+    for s in range(6):
+        assert relerr(ra[s // 3, 10_000:, s % 3], ref["ra"][s][10_000:], atol=1e-3).max() < 1e-8
+        assert np.quantile(relerr(ra[s // 3, :10_000, s % 3], ref["ra"][s][:10_000], atol=1e-3), 0.999) < 1e-8
+    assert relerr(eng.get_trace("logLike").transpose(0, 2, 1).reshape(6), ref["ll"][:6]).max() < 1e-9
+    eng.close()
+    eng32 = run_engine(E, pb, 1, dtype="f32")
+    _compare_traces(eng32, ref, pb, 1, 1e-5, 1e-1, frac_ok=0.995)
+    eng32.close()
+
+
+@pytest.mark.gpu
+def test_baseline_config3_quantile_timss_shaped(E, oracle):
+    """configs[2]: GibbsRtIrtQuantile (qRt=0.85) on TIMSS-shaped data: 631 persons, 14 items, all 10 covariates (README.md:87)."""
+    pb = make_problem("RtIrtLatentQr", 631, 14, 10, seed=42, q=0.85)
+    ref = run_oracle(oracle, pb, 6)
+    eng = run_engine(E, pb, 6, dtype="f64", use_graph=True)
+    _compare_traces(eng, ref, pb, 6, 1e-8, 1e-3)
+    eng.close()
+    eng32 = run_engine(E, pb, 1, dtype="f32")
+    _compare_traces(eng32, ref, pb, 1, 1e-5, 1e-1, frac_ok=0.995)
+    eng32.close()
+
+
+@pytest.mark.gpu
+def test_baseline_config4_null_model_independent_chains(E, oracle):
+    """configs[3]: GibbsRtIrtNull, 100k x 40, independent chains with distinct Philox keys (one per GPU in production; here two of the
+    eight chain ids on one GPU): each chain equals the oracle run with the same chain id, and the chains differ from each other."""
+    pb = make_problem("RtIrtNull", 100_000, 40, 0, seed=43)
+    last = {}
+    for chain in (0, 7):
+        ref = run_oracle(oracle, pb, 2, chain=chain)
+        eng = run_engine(E, pb, 2, dtype="f64", chain=chain, person_trace=False, use_graph=True)
+        a = eng.get_trace("ra", 100_000, 80)[:, :, 0]
+        for s in range(2):
+            assert relerr(a[s], ref["ra"][s][100_000:], atol=1e-3).max() < 1e-9
+        assert relerr(eng.get_trace("logLike")[:2, 0, 0], ref["ll"][:2]).max() < 1e-10
+        assert relerr(eng.get_state("theta"), ref["theta"], atol=1e-3).max() < 1e-8
+        last[chain] = a[-1]
+        eng.close()
+    assert np.abs(last[0] - last[7]).max() > 1e-6
