@@ -412,17 +412,18 @@ def main():
         tr_l = enge.get_trace("logLike")
         moms = [enge.get_moments(f, out=(hMn[k, 0], hMn[k, 1])) for k, f in enumerate(("theta", "zeta", "nu"))]
         t4 = time.perf_counter()
+        close_engine(enge)  # erirt_destroy is part of the call a user makes (the Julia shim destroys the handle inside sample!)
+        t5 = time.perf_counter()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         h2d = hY.numel() * hY.element_size() + (hT.numel() + hX.numel()) * 8 + (2 * n_local + N_FEAT + 2) * 8
         d2h = K * (tr_a.shape[1] + tr_t.shape[1] + tr_q.shape[1] + 1) * 8 + 3 * 2 * n_local * 8
         assert np.all(np.isfinite(tr_l[:K])) and np.all(np.isfinite(moms[0][0]))
         e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world / K), "d2h_bytes_per_step": int(d2h * world / K),
-               "seconds": dt, "parts_ms_rank0": {"create": (t1 - t0) * 1e3, "set_data_and_state": (t2 - t1) * 1e3, "sample": (t3 - t2) * 1e3, "read_back": (t4 - t3) * 1e3},
+               "seconds": dt, "parts_ms_rank0": {"create": (t1 - t0) * 1e3, "set_data_and_state": (t2 - t1) * 1e3, "sample": (t3 - t2) * 1e3, "read_back": (t4 - t3) * 1e3, "destroy": (t5 - t4) * 1e3},
                "note": "erirt_create + " + ("erirt_set_data_y8 (pinned host: Y as Matrix{Bool} bytes, logT/X f64" if y8 else "erirt_set_data (pinned host f64")
                                      + "; chunked H2D + ingest) + erirt_set_state + K sweeps + "
-                                     "erirt_get_trace/erirt_get_moments (D2H into pinned buffers); bytes are totals of the call divided by K"}
-        close_engine(enge)
+                                     "erirt_get_trace/erirt_get_moments (D2H into pinned buffers) + erirt_destroy; bytes are totals of the call divided by K"}
 
     # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------
     cpu = None

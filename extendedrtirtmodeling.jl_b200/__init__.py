@@ -6,7 +6,7 @@ from . import _lib  # noqa: F401
 from .api import (GibbsMlIrt, GibbsRtIrt, GibbsRtIrtCross, GibbsRtIrtCrossQr, GibbsRtIrtLatent,  # noqa: F401
                   GibbsRtIrtLatentQr, GibbsRtIrtNull, GibbsRtIrtQuantile, coef, getDic, getLogLikelihood, precis, sample,
                   sample_bang)
-from .engine import Engine, ErirtError, k_nu_person, k_pg, k_philox, nccl_unique_id  # noqa: F401
+from .engine import Engine, ErirtError, k_nu_person, k_pg, k_philox, nccl_unique_id, trim_pool  # noqa: F401
 from .simulate import (getBias, getRmse, setDataMlIrt, setDataRtIrt, setDataRtIrtCross, setDataRtIrtLatent,  # noqa: F401
                        setDataRtIrtNull, setTrueParaMlIrt, setTrueParaRtIrt, setTrueParaRtIrtCross,
                        setTrueParaRtIrtLatent)

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -28,6 +29,17 @@ using namespace erirt;
 // errors
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+// ERIRT_TIMING=1: host-side wall-clock marks of the set-up calls on stderr (diagnostic)
+struct HostTimer {
+  bool on = getenv("ERIRT_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[erirt timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 static int fail(int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -232,6 +244,7 @@ struct erirt_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // device buffers
+  char* arena = nullptr;  // the one device allocation every pointer below is a slice of
   uint8_t* dY = nullptr;
   void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
   double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
@@ -358,10 +371,10 @@ static int free_handle(erirt_handle* h) {
   if (h->xbuf) cudaFree(h->xbuf);
   if (h->dPeerBufs) cudaFree(h->dPeerBufs);
   if (h->dXseq) cudaFree(h->dXseq);
-  void* ptrs[] = {h->dNuCell, h->dY, h->dLogT, h->dOmega, h->dTheta, h->dZeta, h->dNu, h->dX, h->dPtrace, h->dMom, h->dParams,
-                  h->dStats, h->dConstsLocal, h->dConsts, h->dDerived, h->dTrRa, h->dTrRt, h->dTrQr, h->dTrLl, h->dSweep, h->dStatus, h->dLlOut, h->dColPart, h->dNuMom};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  if (h->arena && h->stream) {  // all device buffers of the handle: back to the pool
+    cudaFreeAsync(h->arena, h->stream);
+    cudaStreamSynchronize(h->stream);
+  } else if (h->arena) cudaFree(h->arena);
   for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -393,19 +406,27 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   if (cfg->dtype != ERIRT_F32 && cfg->dtype != ERIRT_F64) return fail(ERIRT_E_ARG, "dtype must be ERIRT_F32 or ERIRT_F64");
   if (!(cfg->q_rt > 0.0 && cfg->q_rt < 1.0)) return fail(ERIRT_E_ARG, "qRt must be between 0 and 1");  // Draw.pl.jl:476
 
+  HostTimer tm;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(ERIRT_E_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(e));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(ERIRT_E_ARG, "device %d out of range [0,%d)", cfg->device, ndev);
   CU(cudaSetDevice(cfg->device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  // three attributes, not cudaGetDeviceProperties: that call was measured at 3-260 ms per erirt_create on this box
+  struct { int major, minor, multiProcessorCount; } prop;
+  CU(cudaDeviceGetAttribute(&prop.major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+  CU(cudaDeviceGetAttribute(&prop.minor, cudaDevAttrComputeCapabilityMinor, cfg->device));
+  CU(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, cfg->device));
+  tm.mark("create: device properties");
   if (prop.major < 10) return fail(ERIRT_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
-  {  // staging buffers are stream-ordered allocations: keep up to 256 MB in the pool instead of returning it to the driver at every sync
+  {  // staging buffers and the full-size buffers of a handle are stream-ordered allocations: keep up to ERIRT_POOL_KEEP_MB (default
+     // 4096) of freed memory in the device's default pool instead of returning it to the driver at every synchronisation, so that the
+     // next sample! of the process does not pay for mapping its gigabyte again.  erirt_trim_pool() gives it back.
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
-      uint64_t thr = (uint64_t)256 << 20;
+      const char* env = getenv("ERIRT_POOL_KEEP_MB");
+      uint64_t thr = (uint64_t)(env ? atoll(env) : 4096) << 20;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
   }
@@ -448,47 +469,69 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
 
 #define TRY(x) do { int _r = (x); if (_r) { free_handle(h); return _r; } } while (0)
   {
+    tm.mark("create: pool attr, plans");
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
   }
+  // Every device buffer of the handle is a slice of ONE zero-initialised block from the device's stream-ordered pool: one allocation
+  // and one memset at create, one free at destroy (dozens of cudaMalloc / cudaFree calls, each a driver round trip and, for cudaFree,
+  // a device-wide synchronisation, made create and destroy take 10-250 ms), and the next handle of the process finds the memory in
+  // the pool again.
   const size_t cells = (size_t)h->n_pad * h->L.Jp;
-  TRY(dalloc(&h->dY, cells));
-  { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dOmega = p; }
-  if (has_rt) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dLogT = p; }
-  if (cfg->model == ERIRT_RTIRT_CROSSQR) { char* p; TRY(dalloc(&p, cells * h->rsz)); h->dNuCell = p; }
-  if (cfg->model == ERIRT_RTIRT_CROSSQR && cfg->nu_cell_moments) TRY(dalloc(&h->dNuMom, 2 * cells));
-  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dTheta = p; }
-  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dZeta = p; }
-  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz)); h->dNu = p; }
-  { char* p; TRY(dalloc(&p, (size_t)h->n_pad * h->rsz * (cfg->n_feat > 0 ? cfg->n_feat : 1))); h->dX = p; }
-  TRY(dalloc(&h->dMom, (size_t)6 * h->n_pad));
-  if (cfg->person_trace) { char* p; TRY(dalloc(&p, (size_t)h->cap * 3 * h->n_pad * h->rsz)); h->dPtrace = p; }
-  TRY(dalloc(&h->dParams, (size_t)h->L.p_count));
-  TRY(dalloc(&h->dStats, (size_t)h->L.s_count + 2));
   h->c_T1 = 0; h->c_T2 = h->L.Jp; h->c_K0 = 2 * h->L.Jp; h->c_XtX = 3 * h->L.Jp; h->c_sums = h->c_XtX + MAXD * MAXD / 4;
   h->c_count = h->c_sums + 2;
-  TRY(dalloc(&h->dConstsLocal, (size_t)h->c_count));
-  TRY(dalloc(&h->dConsts, (size_t)h->c_count));
-  TRY(dalloc(&h->dDerived, 4));
-  TRY(dalloc(&h->dColPart, (size_t)3 * h->L.Jp * COLSUM_PARTS));
-  TRY(dalloc(&h->dTrRa, (size_t)h->cap * 2 * cfg->n_item));
-  TRY(dalloc(&h->dTrRt, (size_t)h->cap * 2 * cfg->n_item));
-  TRY(dalloc(&h->dTrQr, (size_t)h->cap * h->qw));
-  TRY(dalloc(&h->dTrLl, (size_t)h->cap));
-  TRY(dalloc(&h->dSweep, 1));
-  TRY(dalloc(&h->dStatus, 1));
-  TRY(dalloc(&h->dLlOut, 1));
+  {
+    struct Req { void** p; size_t bytes; };
+    std::vector<Req> reqs;
+    auto want = [&](void** p, size_t bytes) { reqs.push_back({p, align_up(bytes > 0 ? bytes : 16, 256)}); };
+    const size_t vec = (size_t)h->n_pad * h->rsz, D = sizeof(double);
+    want((void**)&h->dY, cells);
+    want(&h->dOmega, cells * h->rsz);
+    if (has_rt) want(&h->dLogT, cells * h->rsz);
+    if (cfg->model == ERIRT_RTIRT_CROSSQR) want(&h->dNuCell, cells * h->rsz);
+    if (cfg->model == ERIRT_RTIRT_CROSSQR && cfg->nu_cell_moments) want((void**)&h->dNuMom, 2 * cells * D);
+    want(&h->dTheta, vec);
+    want(&h->dZeta, vec);
+    want(&h->dNu, vec);
+    want(&h->dX, vec * (cfg->n_feat > 0 ? cfg->n_feat : 1));
+    want((void**)&h->dMom, (size_t)6 * h->n_pad * D);
+    if (cfg->person_trace) want(&h->dPtrace, (size_t)h->cap * 3 * vec);
+    want((void**)&h->dParams, (size_t)h->L.p_count * D);
+    want((void**)&h->dStats, (size_t)(h->L.s_count + 2) * D);
+    want((void**)&h->dConstsLocal, (size_t)h->c_count * D);
+    want((void**)&h->dConsts, (size_t)h->c_count * D);
+    want((void**)&h->dDerived, 4 * D);
+    want((void**)&h->dColPart, (size_t)3 * h->L.Jp * COLSUM_PARTS * D);
+    want((void**)&h->dTrRa, (size_t)h->cap * 2 * cfg->n_item * D);
+    want((void**)&h->dTrRt, (size_t)h->cap * 2 * cfg->n_item * D);
+    want((void**)&h->dTrQr, (size_t)h->cap * h->qw * D);
+    want((void**)&h->dTrLl, (size_t)h->cap * D);
+    want((void**)&h->dSweep, sizeof(uint32_t));
+    want((void**)&h->dStatus, sizeof(int));
+    want((void**)&h->dLlOut, D);
+    size_t total = 0;
+    for (const Req& r : reqs) total += r.bytes;
+    tm.mark("create: stream, events");
+    cudaError_t ae = cudaMallocAsync((void**)&h->arena, total, h->stream);
+    tm.mark("create: cudaMallocAsync");
+    if (ae == cudaSuccess) ae = cudaMemsetAsync(h->arena, 0, total, h->stream);
+    if (ae != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "allocating %zu bytes of device memory: %s", total, cudaGetErrorString(ae)); }
+    size_t off = 0;
+    for (const Req& r : reqs) { *r.p = h->arena + off; off += r.bytes; }
+  }
 #undef TRY
   // default parameters == setInitialValues (a = 1, sigma2 = 1, Sigma = I; src/GibbsRtIrt.pl.jl:122-133)
   {
     std::vector<double> p(h->L.p_count, 0.0);
     for (int j = 0; j < cfg->n_item; ++j) { p[h->L.p_a + j] = 1.0; p[h->L.p_sigma2 + j] = 1.0; }
     p[h->L.p_Sigma + 0] = 1.0; p[h->L.p_Sigma + 3] = 1.0;
-    cudaMemcpy(h->dParams, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpyAsync(h->dParams, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);  // p is a local; also orders the zero-fill before any default-stream access below
   }
   // kernel attributes / occupancy-sized persistent grid
+  tm.mark("create: memset, params, sync");
   const void* kfn = person_kernel_for(h, is_cross ? 1 : 0);
   cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->S.total);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(person_kernel_for(h, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, h->S_gen.total);
@@ -511,11 +554,20 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
     if (ce != cudaSuccess || occ_gen < 1) { free_handle(h); return fail(ERIRT_E_CUDA, "generic person kernel does not fit on an SM: %s", cudaGetErrorString(ce)); }
     h->grid_gen = std::min((int)(h->n_pad / h->S_gen.P), h->sm_count * occ_gen);
   }
+  tm.mark("create: func attrs, occupancy");
   *out = h;
   return 0;
 }
 
 extern "C" int erirt_destroy(erirt_handle* h) { return free_handle(h); }
+extern "C" int erirt_trim_pool(int32_t device) {
+  CU(cudaSetDevice(device));
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemPoolTrimTo(pool, 0));
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // data

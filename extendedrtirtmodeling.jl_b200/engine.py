@@ -169,6 +169,11 @@ class Engine:
         check(self.lib.erirt_peer_attach(self.h, buf))
 
 
+def trim_pool(device=0):
+    """Return the device memory the library's stream-ordered pool kept from destroyed engines to the driver."""
+    check(_lib.load().erirt_trim_pool(device))
+
+
 def nccl_unique_id() -> bytes:
     L = _lib.load()
     buf = C.create_string_buffer(128)

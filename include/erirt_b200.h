@@ -90,6 +90,10 @@ const char* erirt_last_error(void);
 
 int erirt_create(const erirt_config* cfg, erirt_handle** out);
 int erirt_destroy(erirt_handle* h);
+/* The full-size device buffers of a handle and the ingest staging come from the device's stream-ordered memory pool, which keeps up to
+ * ERIRT_POOL_KEEP_MB (environment, default 4096) of freed memory for the next handle of the process.  erirt_trim_pool returns all of
+ * it to the driver (call it after erirt_destroy when the GPU memory is needed elsewhere). */
+int erirt_trim_pool(int32_t device);
 
 /* Host, column-major float64 as Julia stores them: Y[i + ldY*j] in {0,1}, logT[i + ldT*j] = log(T),
  * X[i + ldX*k].  i runs over this handle's n_subj persons, so a shard passes a pointer offset into the
