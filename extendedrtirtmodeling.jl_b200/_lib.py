@@ -13,11 +13,12 @@ F32, F64 = 0, 1
 FIELDS = {"theta": 0, "zeta": 1, "a": 2, "b": 3, "lambda": 4, "sigma2": 5, "beta": 6, "rho": 7, "Sigma": 8, "nu": 9,
           "omega": 10}
 TRACES = {"ra": 0, "rt": 1, "qr": 2, "logLike": 3}
+ERROR_TYPES = {"tnorm": 0, "unit": 1, "norm": 2, "tail": 3, "skew": 4}
 COMPAT_BETA_PRIOR_DIAG = 1
 COMPAT_LATENTQR_SCALE_ELEMENTWISE = 2
 
 EXPORTED = ["erirt_version", "erirt_last_error", "erirt_create", "erirt_destroy", "erirt_set_data",
-            "erirt_set_data_device", "erirt_trim_pool", "erirt_set_data_y8", "erirt_checkpoint_size", "erirt_checkpoint_save", "erirt_checkpoint_load", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
+            "erirt_set_data_device", "erirt_trim_pool", "erirt_generate_data", "erirt_get_data", "erirt_set_data_y8", "erirt_checkpoint_size", "erirt_checkpoint_save", "erirt_checkpoint_load", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
             "erirt_trace_width", "erirt_get_moments", "erirt_loglik_current", "erirt_get_stats",
             "erirt_nccl_unique_id", "erirt_comm_init", "erirt_peer_export", "erirt_peer_attach", "erirt_peer_detach", "erirt_k_pg", "erirt_k_nu_person", "erirt_k_philox"]
 
@@ -64,6 +65,8 @@ def load():
     L.erirt_set_data.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
     L.erirt_set_data_device.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
     L.erirt_set_data_y8.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64]
+    L.erirt_generate_data.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp, C.c_int64, C.c_int32, C.c_uint64]
+    L.erirt_get_data.argtypes = [vp, dp, C.c_int64, dp, C.c_int64]
     L.erirt_checkpoint_size.argtypes = [vp]
     L.erirt_checkpoint_size.restype = C.c_int64
     L.erirt_checkpoint_save.argtypes = [vp, vp, C.c_int64]

@@ -207,6 +207,95 @@ __global__ void moments_finish_kernel(const double* __restrict__ s1, const doubl
     sd[i] = cnt > 1.0 ? sqrt(fmax(0.0, __dsub_rn(s2[i], __dmul_rn(__dmul_rn(cnt, m), m)) / (cnt - 1.0))) : 0.0;  // no FMA contraction: same bits as the host formula
   }
 }
+// column sums of the packed tiles (erirt_generate_data: the data never existed in column-major form), same two-stage scheme
+template <typename R>
+__global__ void tile_colsum_part_kernel(const uint8_t* __restrict__ Y, const R* __restrict__ T, int64_t n, int Jp, double* __restrict__ part) {
+  const int j = threadIdx.x, p = blockIdx.x;
+  if (j >= Jp) return;
+  const int64_t per = (n + COLSUM_PARTS - 1) / COLSUM_PARTS;
+  const int64_t lo = p * per, hi = lo + per < n ? lo + per : n;
+  double t1 = 0.0, t2 = 0.0, k0 = 0.0;
+  for (int64_t i = lo; i < hi; ++i) {
+    k0 += Y[i * Jp + j] ? 0.5 : -0.5;
+    if (T) { const double v = (double)T[i * Jp + j]; t1 += v; t2 += v * v; }
+  }
+  part[((int64_t)(0 * Jp + j)) * COLSUM_PARTS + p] = t1;
+  part[((int64_t)(1 * Jp + j)) * COLSUM_PARTS + p] = t2;
+  part[((int64_t)(2 * Jp + j)) * COLSUM_PARTS + p] = k0;
+}
+
+// ---- device-side data generator: the N x J part of setData* (src/SimTools.jl:117-368) straight into the packed tiles ----
+//   Y_ij ~ Bernoulli(logistic(a_j (theta_i - b_j)))                                   (:131, :165, :241, :329, :363)
+//   logT_ij = lambda_j - zeta_i - theta_i rho_j + e_ij,  e_ij by `err`:
+//     0: N(0, sigma2_j) with logT truncated to (0, inf)  (Null / RtIrt, :136-139, :170-173)
+//     1: N(0, 1)                                         (Latent*, :336)
+//     2: N(0, 0.3)  3: t(5)  4: Gamma(0.5, 1) - 1        (Cross "norm" / "tail" / "skew", :236-247)
+struct GenArgs {
+  uint8_t* Y;
+  void* logT;
+  const double *theta, *zeta, *a, *b, *lam, *sd, *rho;  // person vectors [n], item vectors [Jp]
+  int64_t n;
+  int J, Jp, err, has_rt;
+  uint32_t person_offset;
+  PhiloxKey key;
+};
+__device__ __forceinline__ void bm_pair(uint32_t w0, uint32_t w1, double& c, double& s) {
+  const double r = sqrt(-2.0 * log(u01d(w0)));
+  double sn, cs;
+  sincospi(2.0 * u01d(w1), &sn, &cs);
+  c = r * cs;
+  s = r * sn;
+}
+template <typename R>
+__global__ void generate_data_kernel(const GenArgs A) {
+  const int G = A.Jp / 4;
+  const int64_t total = A.n * G;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / G;
+    const int g = (int)(t % G);
+    const uint32_t gid = A.person_offset + (uint32_t)i;
+    const double th = A.theta[i], ze = A.zeta ? A.zeta[i] : 0.0;
+    const uint4 wy = philox(A.key, gid, 0u, make_site(DOM_DATA, DK_Y, (uint32_t)g), 0u);
+    const uint32_t wys[4] = {wy.x, wy.y, wy.z, wy.w};
+    uint32_t ypack = 0u;
+    R lt[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * g + e;
+      if (j >= A.J) break;
+      const double eta = A.a[j] * (th - A.b[j]);
+      if (u01d(wys[e]) < 1.0 / (1.0 + exp(-eta))) ypack |= 1u << (8 * e);
+      if (!A.has_rt) continue;
+      const double mu = A.lam[j] - ze - th * A.rho[j];
+      const uint32_t site = make_site(DOM_DATA, DK_LOGT, (uint32_t)j);
+      double x;
+      if (A.err == 0) {
+        x = site_tnorm_pos(A.key, gid, 0u, site, mu, A.sd[j]);
+      } else {
+        const uint4 wa = philox(A.key, gid, 0u, site, 0u);
+        const double z = normal2(wa.x, wa.y);
+        if (A.err == 1) x = mu + z;
+        else if (A.err == 2) x = mu + 0.3 * z;
+        else if (A.err == 4) x = mu + (0.5 * z * z - 1.0);
+        else {  // t(5) = Z / sqrt(chi2_5 / 5)
+          const uint4 wb = philox(A.key, gid, 0u, make_site(DOM_DATA, DK_AUX, (uint32_t)j), 0u);
+          double n1, n2, n3, n4;
+          bm_pair(wb.x, wb.y, n1, n2);
+          bm_pair(wb.z, wb.w, n3, n4);
+          const double n5 = normal2(wa.z, wa.w);
+          x = mu + z / sqrt((n1 * n1 + n2 * n2 + n3 * n3 + n4 * n4 + n5 * n5) / 5.0);
+        }
+      }
+      lt[e] = (R)x;
+    }
+    *reinterpret_cast<uint32_t*>(A.Y + i * A.Jp + 4 * g) = ypack;
+    if (A.has_rt) {
+      R* d = (R*)A.logT + i * A.Jp + 4 * g;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[e] = lt[e];
+    }
+  }
+}
 // XtX[r + pb*c] = sum_i x_ir x_ic, x = [1 X]
 __global__ void xtx_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int pb, double* __restrict__ out) {
   __shared__ double red[256];
@@ -651,6 +740,102 @@ static int ingest(erirt_handle* h, const YT* Y, int64_t ldY, const double* T, in
 #undef CUX
   h->data_set = true;
   h->consts_final = false;
+  return 0;
+}
+
+// ---- data generated on the device ----
+extern "C" int erirt_generate_data(erirt_handle* h, const double* theta, const double* zeta, const double* a, const double* b,
+                                   const double* lambda, const double* sigma2, const double* rho, const double* X, int64_t ldX,
+                                   int32_t error_type, uint64_t seed) {
+  if (!h || !theta || !a || !b) return fail(ERIRT_E_ARG, "null argument");
+  const bool has_rt = h->cfg.model != ERIRT_MLIRT;
+  if (has_rt && (!zeta || !lambda)) return fail(ERIRT_E_ARG, "zeta and lambda are required for a response-time model");
+  if (error_type < 0 || error_type > 4) return fail(ERIRT_E_ARG, "error_type must be 0 (truncated normal), 1 (unit normal), 2 (norm), 3 (tail) or 4 (skew)");
+  if (has_rt && error_type == 0 && !sigma2) return fail(ERIRT_E_ARG, "sigma2 is required for error_type 0");
+  const int64_t n = h->cfg.n_subj;
+  const int J = h->cfg.n_item, Jp = h->L.Jp, F = h->cfg.n_feat, pb = F + 1;
+  if (F > 0 && (!X || ldX < n)) return fail(ERIRT_E_ARG, "X (leading dimension >= n_subj) is required when n_feat > 0");
+  CU(cudaSetDevice(h->cfg.device));
+  const bool f32 = h->cfg.dtype == ERIRT_F32;
+  // host staging of the small inputs: [theta n][zeta n][a Jp][b Jp][lambda Jp][sd Jp][rho Jp]
+  std::vector<double> hbuf((size_t)2 * n + 5 * Jp, 0.0);
+  memcpy(hbuf.data(), theta, n * sizeof(double));
+  if (has_rt) memcpy(hbuf.data() + n, zeta, n * sizeof(double));
+  double* it = hbuf.data() + 2 * n;
+  for (int j = 0; j < J; ++j) {
+    it[j] = a[j];
+    it[Jp + j] = b[j];
+    it[2 * Jp + j] = has_rt ? lambda[j] : 0.0;
+    it[3 * Jp + j] = sigma2 ? std::sqrt(sigma2[j]) : 1.0;
+    it[4 * Jp + j] = rho ? rho[j] : 0.0;
+  }
+  double *dbuf = nullptr, *dXc = nullptr;
+  auto cleanup = [&]() { if (dbuf) cudaFreeAsync(dbuf, h->stream); if (dXc) cudaFreeAsync(dXc, h->stream); };
+#define CUX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(ERIRT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+  CUX(cudaMallocAsync((void**)&dbuf, hbuf.size() * sizeof(double), h->stream));
+  CUX(cudaMemcpyAsync(dbuf, hbuf.data(), hbuf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const size_t cells = (size_t)h->n_pad * Jp;
+  CUX(cudaMemsetAsync(h->dY, 0, cells, h->stream));
+  if (has_rt) CUX(cudaMemsetAsync(h->dLogT, 0, cells * h->rsz, h->stream));
+  CUX(cudaMemsetAsync(h->dConstsLocal, 0, h->c_count * sizeof(double), h->stream));
+  CUX(cudaMemsetAsync(h->dColPart, 0, (size_t)3 * Jp * COLSUM_PARTS * sizeof(double), h->stream));
+  GenArgs A{};
+  A.Y = h->dY; A.logT = h->dLogT;
+  A.theta = dbuf; A.zeta = has_rt ? dbuf + n : nullptr;
+  A.a = dbuf + 2 * n; A.b = A.a + Jp; A.lam = A.a + 2 * Jp; A.sd = A.a + 3 * Jp; A.rho = A.a + 4 * Jp;
+  A.n = n; A.J = J; A.Jp = Jp; A.err = error_type; A.has_rt = has_rt ? 1 : 0;
+  A.person_offset = (uint32_t)h->cfg.subj_offset;
+  A.key = make_key(seed, 0xDA7Au);
+  const int grid = h->sm_count * 8;
+  if (f32) generate_data_kernel<float><<<grid, 256, 0, h->stream>>>(A);
+  else generate_data_kernel<double><<<grid, 256, 0, h->stream>>>(A);
+  if (f32) tile_colsum_part_kernel<float><<<COLSUM_PARTS, Jp, 0, h->stream>>>(h->dY, has_rt ? (const float*)h->dLogT : nullptr, n, Jp, h->dColPart);
+  else tile_colsum_part_kernel<double><<<COLSUM_PARTS, Jp, 0, h->stream>>>(h->dY, has_rt ? (const double*)h->dLogT : nullptr, n, Jp, h->dColPart);
+  if (F > 0) {
+    CUX(cudaMallocAsync((void**)&dXc, (size_t)n * F * sizeof(double), h->stream));
+    CUX(cudaMemcpy2DAsync(dXc, n * sizeof(double), X, ldX * sizeof(double), n * sizeof(double), F, cudaMemcpyHostToDevice, h->stream));
+  }
+  for (int f = 0; f < F; ++f) {
+    if (f32) pack_vec_kernel<float><<<256, 256, 0, h->stream>>>(dXc + (int64_t)n * f, n, (float*)h->dX + (int64_t)f * h->n_pad);
+    else pack_vec_kernel<double><<<256, 256, 0, h->stream>>>(dXc + (int64_t)n * f, n, (double*)h->dX + (int64_t)f * h->n_pad);
+  }
+  colsum_finish_kernel<<<(3 * Jp + 127) / 128, 128, 0, h->stream>>>(h->dColPart, 3 * Jp, h->dConstsLocal + h->c_T1);
+  xtx_kernel<<<pb * pb, 256, 0, h->stream>>>(dXc, n, n, pb, h->dConstsLocal + h->c_XtX);
+  CUX(cudaGetLastError());
+  cleanup();
+  dbuf = dXc = nullptr;
+  CUX(cudaStreamSynchronize(h->stream));
+#undef CUX
+  h->data_set = true;
+  h->consts_final = false;
+  return 0;
+}
+
+// The data set held by the handle (ingested or generated), back in Julia's column-major Float64 (logT as stored: f32-rounded in f32 mode)
+extern "C" int erirt_get_data(erirt_handle* h, double* Y, int64_t ldY, double* logT, int64_t ldT) {
+  if (!h || (!Y && !logT)) return fail(ERIRT_E_ARG, "null argument");
+  if (!h->data_set) return fail(ERIRT_E_STATE, "no data set: call erirt_set_data or erirt_generate_data first");
+  const int64_t n = h->cfg.n_subj;
+  const int J = h->cfg.n_item, Jp = h->L.Jp;
+  if ((Y && ldY < n) || (logT && ldT < n)) return fail(ERIRT_E_ARG, "leading dimension smaller than n_subj");
+  if (logT && h->cfg.model == ERIRT_MLIRT) return fail(ERIRT_E_ARG, "GibbsMlIrt has no response times");
+  CU(cudaSetDevice(h->cfg.device));
+  double* tmp = nullptr;
+  CU(cudaMallocAsync((void**)&tmp, (size_t)n * J * sizeof(double), h->stream));
+  cudaError_t e = cudaSuccess;
+  if (Y) {
+    tile_to_colmajor_kernel<uint8_t><<<1024, 256, 0, h->stream>>>(h->dY, n, J, Jp, tmp);
+    e = cudaMemcpy2DAsync(Y, ldY * sizeof(double), tmp, n * sizeof(double), n * sizeof(double), J, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  }
+  if (logT && e == cudaSuccess) {
+    if (h->cfg.dtype == ERIRT_F32) tile_to_colmajor_kernel<float><<<1024, 256, 0, h->stream>>>((const float*)h->dLogT, n, J, Jp, tmp);
+    else tile_to_colmajor_kernel<double><<<1024, 256, 0, h->stream>>>((const double*)h->dLogT, n, J, Jp, tmp);
+    e = cudaMemcpy2DAsync(logT, ldT * sizeof(double), tmp, n * sizeof(double), n * sizeof(double), J, cudaMemcpyDeviceToHost, h->stream);
+  }
+  cudaFreeAsync(tmp, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_data: %s", cudaGetErrorString(e));
   return 0;
 }
 

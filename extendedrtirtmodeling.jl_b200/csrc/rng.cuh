@@ -24,6 +24,11 @@ constexpr uint32_t PK_NU_CELL = 4;   // CrossQr nu_ij, idx = j/2: words 0,1 -> B
 constexpr uint32_t IK_B = 0, IK_A = 1, IK_LAMBDA = 2, IK_SIGMA2 = 3, IK_RHO = 4;
 // global-domain kinds (unit = component)
 constexpr uint32_t GK_BETA = 0, GK_SIGMAP = 1;
+// data domain (erirt_generate_data, sweep = 0, unit = global person id): DK_Y idx = j/4, word j%4 -> uniform of Y_ij;
+// DK_LOGT idx = j -> words 0,1 normal of the logT error (truncated normal: attempts in ctr.w), words 2,3 a spare normal;
+// DK_AUX idx = j -> two Box-Muller pairs (the chi-square of the t5 errors)
+constexpr uint32_t DOM_DATA = 4u;
+constexpr uint32_t DK_Y = 0, DK_LOGT = 1, DK_AUX = 2;
 
 __host__ __device__ constexpr uint32_t make_site(uint32_t dom, uint32_t kind, uint32_t idx = 0) {
   return (dom << 28) | (kind << 20) | idx;

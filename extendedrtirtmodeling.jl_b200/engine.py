@@ -70,6 +70,29 @@ class Engine:
                  T.shape[0] if T is not None else 0, Xf.ctypes.data if Xf is not None else None,
                  Xf.shape[0] if Xf is not None else 0))
 
+    def generate_data(self, theta, a, b, zeta=None, lambda_=None, sigma2=None, rho=None, X=None, error="unit", seed=1234):
+        """The N x J part of setData* (src/SimTools.jl:117-368) on the device, straight into the packed layout (erirt_generate_data).
+        error: "tnorm" (Null / RtIrt), "unit" (Latent*), "norm" / "tail" / "skew" (Cross)."""
+        def vec(v, n):
+            if v is None:
+                return None
+            v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+            assert v.size == n, (v.size, n)
+            return v
+        th, ze = vec(theta, self.N), vec(zeta, self.N)
+        av, bv, lv, sv, rv = (vec(v, self.J) for v in (a, b, lambda_, sigma2, rho))
+        Xf = np.asfortranarray(X, dtype=np.float64) if (X is not None and self.F > 0) else None
+        p = lambda v: _dp(v) if v is not None else None  # noqa: E731
+        check(self.lib.erirt_generate_data(self.h, p(th), p(ze), p(av), p(bv), p(lv), p(sv), p(rv), p(Xf), Xf.shape[0] if Xf is not None else 0,
+                                           _lib.ERROR_TYPES[error], seed))
+
+    def get_data(self):
+        """(Y, logT) held by the engine, column-major float64 (logT is None for MlIrt)."""
+        Y = np.empty((self.N, self.J), dtype=np.float64, order="F")
+        T = np.empty((self.N, self.J), dtype=np.float64, order="F") if self.model != 0 else None
+        check(self.lib.erirt_get_data(self.h, _dp(Y), self.N, _dp(T) if T is not None else None, self.N))
+        return Y, T
+
     def set_data_device(self, dY_ptr, ldY, dlogT_ptr, ldT, dX_ptr, ldX):
         """Column-major float64 buffers already on this engine's device (e.g. torch tensors' data_ptr())."""
         check(self.lib.erirt_set_data_device(self.h, dY_ptr, ldY, dlogT_ptr, ldT, dX_ptr, ldX))

@@ -109,6 +109,22 @@ int erirt_set_data_y8(erirt_handle* h, const uint8_t* Y, int64_t ldY, const doub
 int erirt_set_data_device(erirt_handle* h, const double* dY, int64_t ldY, const double* dlogT, int64_t ldT,
                           const double* dX, int64_t ldX);
 
+/* Data generated on the device instead of ingested: the N x J part of the reference's simulators,
+ *   Y_ij ~ Bernoulli(logistic(a_j (theta_i - b_j))),   logT_ij = lambda_j - zeta_i - theta_i rho_j + e_ij,
+ * written straight into the handle's packed layout (replaces erirt_set_data; nothing of size N x J crosses PCIe).  The person-level
+ * part of setData* (theta, zeta, X: O(N) values) stays with the caller and is passed in.  error_type selects e_ij:
+ *   0  N(0, sigma2_j), logT truncated to (0, inf)   setDataRtIrtNull / setDataRtIrt      src/SimTools.jl:117-178
+ *   1  N(0, 1)                                       setDataRtIrtLatent                   src/SimTools.jl:300-343
+ *   2  N(0, 0.3)   3  t(5)   4  Gamma(0.5, 1) - 1    setDataRtIrtCross "norm"/"tail"/"skew" src/SimTools.jl:220-255
+ * GibbsMlIrt (setDataMlIrt, :349-368): zeta, lambda, sigma2, rho are ignored.  sigma2 == NULL means 1, rho == NULL means 0.
+ * The variates come from a Philox stream keyed by `seed` and counted by GLOBAL person id and item, so a sharded chain generates
+ * exactly the shards of the one data set.  erirt_get_data copies the data set held by the handle back to the host (column-major
+ * Float64; either pointer may be NULL). */
+int erirt_generate_data(erirt_handle* h, const double* theta, const double* zeta, const double* a, const double* b,
+                        const double* lambda, const double* sigma2, const double* rho, const double* X, int64_t ldX,
+                        int32_t error_type, uint64_t seed);
+int erirt_get_data(erirt_handle* h, double* Y, int64_t ldY, double* logT, int64_t ldT);
+
 /* Initial / current values of one InputPara field (float64, Julia layout: beta is vec(β) column-major,
  * SIGMA_P is vec(Σp), NU is n_subj (LatentQr) or n_subj x n_item column-major (CrossQr), OMEGA n_subj x n_item).
  * CrossQr draws NU before reading it, so setting it only matters for erirt_loglik_current. */

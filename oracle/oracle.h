@@ -84,6 +84,10 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 void orc_pg_grid(const double* z, int64_t rows, int32_t cols, int64_t row0, uint64_t seed, uint32_t chain,
                  uint32_t sweep, double* out, int32_t* attempts);
 /* 1/IG draws for the person-level nu site: nu_i = clamp(1/IG(mu_i, lam),1e-10,1e10) */
+/* gen.c: restatement of erirt_generate_data (the N x J part of setData*, src/SimTools.jl:117-368) */
+void orc_generate_data(int64_t n, int32_t J, int64_t person_offset, uint64_t seed, int32_t has_rt, int32_t err, const double* theta,
+                       const double* zeta, const double* a, const double* b, const double* lambda, const double* sigma2,
+                       const double* rho, double* Y, double* logT);
 void orc_nu_person(const double* mu, double lam, int64_t n, int64_t row0, uint64_t seed, uint32_t chain,
                    uint32_t sweep, double* out);
 double orc_inv_normal_tail(double y);    /* Phic^{-1}(y) */

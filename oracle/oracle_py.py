@@ -31,7 +31,7 @@ class State(C.Structure):
 
 def build(force=False):
     """Compile the oracle if the shared object is missing (gcc is in the image)."""
-    srcs = [os.path.join(_HERE, f) for f in ("rng.c", "pg.c", "sampler.c", "oracle.h", "rng.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("rng.c", "pg.c", "sampler.c", "gen.c", "oracle.h", "rng.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs if os.path.exists(s))
     if force or stale:
@@ -65,6 +65,7 @@ def lib():
         L.orc_inv_normal_tail.argtypes = [C.c_double]
         L.orc_variates.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int64, C.c_uint64, dp]
         L.orc_inv_wishart2.argtypes = [C.c_double, dp, C.c_uint64, C.c_uint32, dp]
+        L.orc_generate_data.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int32] + [dp] * 9
         _lib = L
     return _lib
 
@@ -184,3 +185,24 @@ def loglik(cfg, Y, logT, X, state):
     Xf = np.asfortranarray(X, dtype=np.float64) if X is not None and cfg.nFeat > 0 else None
     st = OracleState(cfg, state)
     return lib().orc_loglik(C.byref(cfg), _dp(Yf), _dp(Tf), _dp(Xf), C.byref(st.c))
+
+
+ERROR_TYPES = {"tnorm": 0, "unit": 1, "norm": 2, "tail": 3, "skew": 4}
+
+
+def generate_data(N, J, theta, a, b, zeta=None, lambda_=None, sigma2=None, rho=None, error="unit", seed=1234, person_offset=0):
+    """CPU restatement of erirt_generate_data (oracle/gen.c): returns (Y, logT) column-major float64; logT is None without zeta."""
+    def vec(v, n):
+        if v is None:
+            return None
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+        assert v.size == n
+        return v
+    has_rt = zeta is not None
+    th, ze = vec(theta, N), vec(zeta, N)
+    av, bv, lv, sv, rv = (vec(v, J) for v in (a, b, lambda_, sigma2, rho))
+    Y = np.empty((N, J), dtype=np.float64, order="F")
+    T = np.empty((N, J), dtype=np.float64, order="F") if has_rt else None
+    p = lambda v: _dp(v) if v is not None else None  # noqa: E731
+    lib().orc_generate_data(N, J, person_offset, seed, int(has_rt), ERROR_TYPES[error], p(th), p(ze), p(av), p(bv), p(lv), p(sv), p(rv), p(Y), p(T))
+    return Y, T

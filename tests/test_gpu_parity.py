@@ -572,3 +572,73 @@ def test_baseline_config4_null_model_independent_chains(E, oracle):
         last[chain] = a[-1]
         eng.close()
     assert np.abs(last[0] - last[7]).max() > 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,error", [("RtIrtNull", "tnorm"), ("RtIrtLatentQr", "unit"), ("RtIrtCross", "norm"), ("RtIrtCrossQr", "tail"),
+                                         ("RtIrtCrossQr", "skew"), ("MlIrt", "unit")])
+def test_generate_data_matches_oracle(E, oracle, model, error):
+    """erirt_generate_data (the N x J part of setData*, src/SimTools.jl:117-368, on the device) against oracle/gen.c: responses bit-exact,
+    logT to 1e-12 (f64) / f32 rounding; a shard generates its rows of the one data set; sampling on the generated data equals the oracle
+    sampling on the oracle's data (i.e. the ingest constants computed from the tiles are right)."""
+    N, J, F = 1500, 13, (2 if model in ("MlIrt", "RtIrtLatentQr") else 0)
+    pb = make_problem(model, N, J, F, seed=51)
+    rng = np.random.default_rng(51)
+    th, ze = rng.normal(size=N), 0.4 * rng.normal(size=N)
+    a, b, lam, s2 = rng.uniform(0.7, 1.4, J), rng.normal(0, 0.5, J), rng.uniform(2.5, 3.5, J), rng.uniform(0.2, 0.4, J)
+    rho = rng.normal(0, 0.2, J) if "Cross" in model else None
+    rt = model != "MlIrt"
+    Yo, To = oracle.generate_data(N, J, th, a, b, ze if rt else None, lam, s2, rho, error=error, seed=77)
+    kw = dict(n_iter=2, n_burnin=0, q_rt=pb["q"], cov2one=model not in ("RtIrtLatent", "RtIrtLatentQr"), seed=99, person_trace=True, use_graph=False)
+    for dtype in ("f64", "f32"):
+        eng = E.Engine(model, N, J, F, dtype=dtype, **kw)
+        eng.generate_data(th, a, b, ze if rt else None, lam if rt else None, s2, rho, pb["X"] if F else None, error=error, seed=77)
+        Y, T = eng.get_data()
+        assert np.array_equal(Y, Yo)
+        if rt:
+            assert relerr(T, To).max() < (1e-12 if dtype == "f64" else 1e-6)
+        if dtype == "f64":
+            pb2 = dict(pb, Y=Yo, logT=To)
+            ref = run_oracle(oracle, pb2, 2)
+            i = pb["init"]
+            st = dict(theta=i["theta"], a=i["a"], b=i["b"])
+            if rt:
+                st.update(zeta=i["zeta"], lambda_=i["lambda_"], sigma2=i["sigma2"], Sigma=i["Sigma"])
+            if pb["nb"]:
+                st["beta"] = i["beta"][: pb["nb"]]
+            if "Cross" in model:
+                st["rho"] = i["rho"]
+            eng.set_state(**st)
+            eng.sample(2)
+            _compare_traces(eng, ref, pb2, 2, 1e-9, 1e-3)
+        eng.close()
+    # shard [500, 1100) of the same data set
+    sh = E.Engine(model, 600, J, F, dtype="f64", n_subj_total=N, subj_offset=500, **kw)
+    sh.generate_data(th[500:1100], a, b, ze[500:1100] if rt else None, lam if rt else None, s2, rho, pb["X"][500:1100] if F else None, error=error, seed=77)
+    Ys, Ts = sh.get_data()
+    assert np.array_equal(Ys, Yo[500:1100]) and (not rt or relerr(Ts, To[500:1100]).max() < 1e-12)
+    sh.close()
+
+
+@pytest.mark.gpu
+def test_generate_data_full_size_c5(E):
+    """configs[4] size: 1M x 100 generated on the device (no N x J host buffer at all), then sampled; size-independent checks."""
+    N, J, F = 1_000_000, 100, 3
+    rng = np.random.default_rng(52)
+    th = rng.standard_normal(N)
+    X = rng.standard_normal((N, F))
+    ze = X @ np.array([0.3, -0.2, 0.1]) + 0.4 * th + (0.5 * rng.standard_normal(N) ** 2 - 1.0)  # setDataRtIrtLatent(type="skew")
+    a, b, lam = rng.uniform(0.8, 1.3, J), rng.normal(0, 0.5, J), rng.uniform(2.8, 3.2, J)
+    eng = E.Engine("RtIrtQuantile", N, J, F, n_iter=6, n_burnin=0, q_rt=0.85, cov2one=False, dtype="f32", seed=7)
+    eng.generate_data(th, a, b, ze, lam, None, None, X, error="unit", seed=3)
+    eng.set_state(theta=rng.standard_normal(N), zeta=rng.standard_normal(N), beta=rng.standard_normal(F + 2))
+    eng.sample(6)
+    bt = eng.get_trace("ra", N, 2 * J)[:, J:, 0]
+    assert np.all(np.isfinite(eng.get_trace("logLike")[:6]))
+    assert np.sqrt(np.mean((bt[-1] - b) ** 2)) < np.sqrt(np.mean((bt[0] - b) ** 2)) + 1e-3
+    Y, T = eng.get_data()
+    p = 1 / (1 + np.exp(-a[None, :] * (th[:20000, None] - b[None, :])))
+    assert abs(Y[:20000].mean() - p.mean()) < 5 * np.sqrt(0.25 / p.size)
+    r = T[:20000] - (lam[None, :] - ze[:20000, None])
+    assert abs(r.mean()) < 5 / np.sqrt(r.size) and abs(r.var() - 1.0) < 0.01
+    eng.close()

@@ -177,3 +177,30 @@ def test_oracle_reproduces_committed_fixture(oracle):
         w, g = np.asarray(want[k], dtype=np.float64), np.asarray(got[k], dtype=np.float64)
         assert w.shape == g.shape, k
         assert np.allclose(g, w, rtol=1e-11, atol=1e-12), (k, float(np.max(np.abs(g - w))))
+
+
+@pytest.mark.parametrize("error,mean,var", [("tnorm", 0.0, 0.3), ("unit", 0.0, 1.0), ("norm", 0.0, 0.09), ("tail", 0.0, 5.0 / 3.0), ("skew", -0.5, 0.5)])
+def test_generator_error_laws(oracle, error, mean, var):
+    """oracle/gen.c (restatement of erirt_generate_data): Bernoulli-logit responses and the five error laws of the reference's
+    simulators (src/SimTools.jl:117-368): N(0, sigma2_j) truncated, N(0,1), N(0,0.3), t(5), Gamma(0.5,1)-1."""
+    rng = np.random.default_rng(1)
+    N, J = 100_000, 6
+    th, ze = rng.normal(size=N), 0.3 * rng.normal(size=N)
+    a, b, lam = rng.uniform(0.7, 1.4, J), rng.normal(0, 0.5, J), np.full(J, 3.0)
+    rho = rng.normal(0, 0.2, J) if error in ("norm", "tail", "skew") else None
+    Y, T = oracle.generate_data(N, J, th, a, b, ze, lam, np.full(J, 0.3), rho, error=error, seed=11)
+    p = 1 / (1 + np.exp(-a * (th[:, None] - b)))
+    assert set(np.unique(Y)) == {0.0, 1.0} and abs(Y.mean() - p.mean()) < 4 * np.sqrt(0.25 / Y.size)
+    e = (T - (lam[None, :] - ze[:, None] - (np.outer(th, rho) if rho is not None else 0.0))).ravel()
+    assert abs(e.mean() - mean) < 5 * np.sqrt(var / e.size)
+    assert abs(e.var() - var) < (0.15 if error == "tail" else 0.03) * var + 1e-3
+    if error == "skew":
+        assert e.min() >= -1.0 and abs(np.mean(((e - e.mean()) / e.std()) ** 3) - np.sqrt(8.0)) < 0.15
+    if error == "tnorm":
+        assert T.min() > 0.0
+    # counters are global person ids: a shard generates exactly its rows of the one data set
+    Y2, T2 = oracle.generate_data(1000, J, th[5000:6000], a, b, ze[5000:6000], lam, np.full(J, 0.3), rho, error=error, seed=11, person_offset=5000)
+    assert np.array_equal(Y2, Y[5000:6000]) and np.array_equal(T2, T[5000:6000])
+    # MlIrt: responses only
+    Y3, T3 = oracle.generate_data(1000, J, th[:1000], a, b, seed=11)
+    assert T3 is None and np.array_equal(Y3, Y[:1000])
