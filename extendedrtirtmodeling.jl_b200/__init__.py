@@ -7,7 +7,7 @@ from .api import (GibbsMlIrt, GibbsRtIrt, GibbsRtIrtCross, GibbsRtIrtCrossQr, Gi
                   GibbsRtIrtLatentQr, GibbsRtIrtNull, GibbsRtIrtQuantile, coef, getDic, getLogLikelihood, precis, sample,
                   sample_bang)
 from .engine import Engine, ErirtError, k_nu_person, k_pg, k_philox, nccl_unique_id, trim_pool  # noqa: F401
-from .simulate import (getBias, getRmse, setDataMlIrt, setDataRtIrt, setDataRtIrtCross, setDataRtIrtLatent,  # noqa: F401
+from .simulate import (DeviceData, getBias, getRmse, setDataOnDevice, setDataMlIrt, setDataRtIrt, setDataRtIrtCross, setDataRtIrtLatent,  # noqa: F401
                        setDataRtIrtNull, setTrueParaMlIrt, setTrueParaRtIrt, setTrueParaRtIrtCross,
                        setTrueParaRtIrtLatent)
 from .structs import InputData, InputData4R, InputPara, OutputDic, OutputPost, SimConditions, setCond  # noqa: F401

@@ -14,6 +14,7 @@ import numpy as np
 
 from . import _lib
 from .engine import Engine
+from .simulate import DeviceData
 from .structs import InputPara, OutputDic, OutputPost
 
 # budget for keeping the full person-level trace on the device/host (bytes); beyond it Post.ra / Post.rt hold
@@ -144,7 +145,11 @@ def sample(MCMC, intercept=False, itemtype="2pl", cov2one=None, *, dtype="f64", 
         eng.comm_init(shard[0], shard[1], shard[2])
         if len(shard) > 5 and shard[5] is not None:
             eng.peer_attach(shard[5](eng.peer_export()))
-    eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if F > 0 else None)
+    if isinstance(D, DeviceData):  # the N x J part is generated on the device (a shard generates its rows of the one data set)
+        D.generate_into(eng, MCMC.has_rt, offset, offset + N) if shard is not None and len(D.truePara.theta) == n_total \
+            else D.generate_into(eng, MCMC.has_rt)
+    else:
+        eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if F > 0 else None)
     init = dict(theta=P0.theta, a=P0.a, b=P0.b)
     if MCMC.has_rt:
         init.update(zeta=P0.zeta, lambda_=P0.lambda_, sigma2=P0.sigma2t, Sigma=P0.Sigma_p)
@@ -233,7 +238,10 @@ def getLogLikelihood(MCMC, P, dtype="f64", device=0):
     eng = Engine(MCMC.model, C.nSubj, C.nItem, C.nFeat, n_iter=1, n_chain=1, q_rt=C.qRt, dtype=dtype, device=device,
                  person_trace=False, use_graph=False)
     try:
-        eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if C.nFeat > 0 else None)
+        if isinstance(D, DeviceData):
+            D.generate_into(eng, MCMC.has_rt)
+        else:
+            eng.set_data(D.Y, D.logT if MCMC.has_rt else None, D.X if C.nFeat > 0 else None)
         st = dict(theta=P.theta, a=P.a, b=P.b)
         if MCMC.has_rt:
             st.update(zeta=P.zeta, lambda_=P.lambda_, sigma2=P.sigma2t, Sigma=np.asarray(P.Sigma_p).reshape(4))

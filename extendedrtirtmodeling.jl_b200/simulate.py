@@ -152,6 +152,58 @@ def setDataRtIrtLatent(Cond, truePara, type="norm", rng=None, dtype=np.float64):
     return InputData(Y=Y, T=np.exp(logT), X=X)
 
 
+class DeviceData:
+    """Stand-in for InputData whose N x J part (Y, logT) is generated ON THE DEVICE by erirt_generate_data when `sample` creates
+    the engine: only the person-level part of setData* (theta, zeta, X: O(N) values) is drawn on the host.  SURVEY.md 8f-1."""
+
+    def __init__(self, truePara, X=None, error="unit", seed=1234):
+        self.truePara, self.X, self.error, self.seed = truePara, X, error, int(seed)
+        self.Y = self.T = self.logT = self.kappa = None  # never materialised on the host (engine.get_data() copies them back on request)
+
+    def generate_into(self, eng, has_rt, lo=0, hi=None):
+        """Fill the engine (a whole chain, or the shard [lo, hi) of one) from the person-level draws held here."""
+        p = self.truePara
+        sl = slice(lo, hi)
+        eng.generate_data(p.theta[sl], p.a, p.b, p.zeta[sl] if has_rt else None, p.lambda_ if has_rt else None,
+                          p.sigma2t if (has_rt and np.size(p.sigma2t)) else None, p.rho if np.size(p.rho) else None,
+                          None if self.X is None else self.X[sl], error=self.error, seed=self.seed)
+
+
+def setDataOnDevice(Cond, truePara, model, type="norm", rng=None, seed=None):
+    """setData* of src/SimTools.jl:117-368 with the N x J part left to the device.  model: "MlIrt", "RtIrtNull", "RtIrt", "RtIrtCross",
+    "RtIrtLatent" (also for the *Qr samplers).  The person-level draws follow the reference line by line; returns a DeviceData."""
+    rng = _rng(rng)
+    N, F = Cond.nSubj, Cond.nFeat
+    seed = int(rng.integers(1, 2 ** 62)) if seed is None else seed
+    if model == "MlIrt":            # :349-368
+        X = np.empty((N, F))
+        X[:, 0] = rng.random(N) < 0.5
+        X[:, 1:] = rng.normal(0.0, 1.0, (N, F - 1))
+        truePara.theta = rng.normal((X @ truePara.beta).ravel(), 1.0)
+        return DeviceData(truePara, X, "unit", seed)
+    if model == "RtIrtNull":        # :117-144
+        noise = _mvn2(rng, truePara.Sigma_p, N)
+        truePara.theta, truePara.zeta = noise[:, 0].copy(), noise[:, 1].copy()
+        return DeviceData(truePara, None, "tnorm", seed)
+    if model == "RtIrt":            # :149-178
+        X = rng.normal(0.0, 1.0, (N, F))
+        subj = X @ truePara.beta + _mvn2(rng, truePara.Sigma_p, N)
+        truePara.theta, truePara.zeta = subj[:, 0].copy(), subj[:, 1].copy()
+        return DeviceData(truePara, X, "tnorm", seed)
+    if model in ("RtIrtCross", "RtIrtCrossQr"):   # :220-255, cell-level errors of the given type
+        if type not in ("norm", "tail", "skew"):
+            raise ValueError("type must be 'norm', 'tail' or 'skew'")
+        noise = _mvn2(rng, truePara.Sigma_p, N)
+        truePara.theta, truePara.zeta = noise[:, 0].copy(), noise[:, 1].copy()
+        return DeviceData(truePara, None, type, seed)
+    if model in ("RtIrtLatent", "RtIrtLatentQr", "RtIrtQuantile"):  # :300-343, person-level errors of the given type, N(0,1) cells
+        truePara.theta = rng.standard_normal(N)
+        X = rng.normal(0.0, 1.0, (N, F))
+        truePara.zeta = np.column_stack([X, truePara.theta]) @ truePara.beta + _errors(rng, type, N)
+        return DeviceData(truePara, X, "unit", seed)
+    raise ValueError(f"unknown model {model!r}")
+
+
 def getRmse(a, b):
     """src/SimTools.jl:42"""
     return float(np.sqrt(np.mean((np.asarray(a) - np.asarray(b)) ** 2)))

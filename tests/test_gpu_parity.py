@@ -642,3 +642,26 @@ def test_generate_data_full_size_c5(E):
     r = T[:20000] - (lam[None, :] - ze[:20000, None])
     assert abs(r.mean()) < 5 / np.sqrt(r.size) and abs(r.var() - 1.0) < 0.01
     eng.close()
+
+
+@pytest.mark.gpu
+def test_api_flow_with_device_generated_data(E):
+    """README flow with setDataOnDevice: the N x J part of setData* never exists on the host; item parameters are recovered, the
+    DIC evaluation regenerates the same data set from the same seed, and get_data returns what was sampled on."""
+    Cond = E.setCond(nSubj=3000, nItem=12, nFeat=0, nIter=300, nChain=1)
+    tp = E.setTrueParaRtIrt(Cond, rng=6)
+    Data = E.setDataOnDevice(Cond, tp, "RtIrtNull", rng=6)
+    assert isinstance(Data, E.DeviceData) and Data.Y is None
+    MCMC = E.GibbsRtIrtNull(Cond, Data=Data, truePara=tp, rng=6)
+    E.sample(MCMC, dtype="f32")
+    assert E.getRmse(tp.b, MCMC.Post.mean.b) < 0.12 and E.getRmse(tp.lambda_, MCMC.Post.mean.lambda_) < 0.05
+    Y, logT = MCMC.engine.get_data()
+    assert Y.shape == (3000, 12) and set(np.unique(Y)) == {0.0, 1.0} and logT.min() > 0.0
+    dic = E.getDic(MCMC)
+    assert np.isfinite(dic.DIC) and dic.pD > 0
+    # Cross family with heavy-tailed cell errors, quantile sampler
+    Cond = E.setCond(nSubj=800, nItem=8, nFeat=0, nIter=60, nChain=1, qRt=0.5)
+    tp = E.setTrueParaRtIrtCross(Cond, rng=7)
+    MCMC = E.GibbsRtIrtCrossQr(Cond, Data=E.setDataOnDevice(Cond, tp, "RtIrtCross", type="tail", rng=7), truePara=tp, rng=7)
+    E.sample(MCMC, dtype="f64")
+    assert np.all(np.isfinite(MCMC.Post.logLike)) and MCMC.Post.mean.nu.shape == (800, 8)
