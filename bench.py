@@ -425,6 +425,31 @@ def main():
                                      + "; chunked H2D + ingest) + erirt_set_state + K sweeps + "
                                      "erirt_get_trace/erirt_get_moments (D2H into pinned buffers) + erirt_destroy; bytes are totals of the call divided by K"}
 
+    # ---------------- the same call with the N x J data generated on the device (informational: no N x J upload) ----------------
+    e2e_gen = None
+    if not args.no_e2e and not args.short:
+        rng = np.random.default_rng(SEED + 11)
+        th_all = rng.standard_normal(N_SUBJ)
+        X_all = rng.standard_normal((N_SUBJ, N_FEAT))
+        ze_all = np.column_stack([X_all, th_all]) @ tp.beta + (0.5 * rng.standard_normal(N_SUBJ) ** 2 - 1.0)  # setDataRtIrtLatent(type="skew")
+        sl = slice(offset, offset + n_local)
+        th_g, ze_g, X_g = th_all[sl].copy(), ze_all[sl].copy(), np.asfortranarray(X_all[sl])
+        barrier()
+        t0 = time.perf_counter()
+        engg = make_engine()
+        engg.generate_data(th_g, tp.a, tp.b, ze_g, tp.lambda_, None, None, X_g, error="unit", seed=SEED)
+        engg.set_state(theta=theta0, zeta=zeta0, beta=beta0)
+        engg.sample(K)
+        tr_g = [engg.get_trace("ra", n_local, 2 * N_ITEM), engg.get_trace("rt", n_local, 2 * N_ITEM), engg.get_trace("qr", 0, qw), engg.get_trace("logLike")]
+        moms_g = [engg.get_moments(f, out=(hMn[k, 0], hMn[k, 1])) for k, f in enumerate(("theta", "zeta", "nu"))]
+        close_engine(engg)
+        barrier()
+        dtg = max_over_ranks(time.perf_counter() - t0)
+        assert np.all(np.isfinite(tr_g[3][:K])) and np.all(np.isfinite(moms_g[0][0]))
+        e2e_gen = {"value": K / dtg, "unit": UNIT, "seconds": dtg, "h2d_bytes_per_step": int((2 + N_FEAT) * n_local * 8 * world / K),
+                   "note": "erirt_create + erirt_generate_data (person-level theta, zeta, X from the host; responses and log-times generated "
+                           "on the device) + erirt_set_state + K sweeps + read-back + erirt_destroy"}
+
     # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and not args.short:
@@ -446,7 +471,7 @@ def main():
                                               if os.environ.get("ERIRT_EXCHANGE", "peer") == "peer" else "ncclAllReduce")) if world > 1 else "single GPU",
                            "l2": "inputs (1.3 GB/sweep) larger than the 126 MB L2", "cuda_graph": True,
                            "loglik_and_moments": "on"},
-                "clocks": clk, "gpu_launches": 2 * K, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clk, "gpu_launches": 2 * K, "e2e": e2e, "e2e_device_generated_data": e2e_gen, "roofline": roofline, "cpu_baseline": cpu,
                 "ess_per_sweep": {"min": ess_min, "median": ess_med, "estimator": "rank-normalised bulk ESS over the K timed sweeps (a, b, lambda, sigma2, beta, Sigma)"},
                 "ess_per_sec": {"min": None if ess_min is None else ess_min * value, "median": None if ess_med is None else ess_med * value},
                 "bytes_per_sweep": st["bytes_per_sweep"] * world}
