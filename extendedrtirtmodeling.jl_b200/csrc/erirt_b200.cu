@@ -177,11 +177,11 @@ __global__ void colsum_part_kernel(const SrcT* __restrict__ src, int64_t ld, int
   }
   if (threadIdx.x == 0) part[(int64_t)j * COLSUM_PARTS + p] = red[0];
 }
-__global__ void colsum_finish_kernel(const double* __restrict__ part, int J, double* __restrict__ out) {
+__global__ void colsum_finish_kernel(const double* __restrict__ part, int J, double* __restrict__ out, int parts = COLSUM_PARTS) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= J) return;
   double acc = 0.0;
-  for (int p = 0; p < COLSUM_PARTS; ++p) acc += part[(int64_t)j * COLSUM_PARTS + p];
+  for (int p = 0; p < parts; ++p) acc += part[(int64_t)j * parts + p];
   out[j] = acc;
 }
 // the same for the N x J cell weights of CrossQr: sums tiled [n_pad][Jp], results column-major [n][J]
@@ -207,21 +207,24 @@ __global__ void moments_finish_kernel(const double* __restrict__ s1, const doubl
     sd[i] = cnt > 1.0 ? sqrt(fmax(0.0, __dsub_rn(s2[i], __dmul_rn(__dmul_rn(cnt, m), m)) / (cnt - 1.0))) : 0.0;  // no FMA contraction: same bits as the host formula
   }
 }
-// column sums of the packed tiles (erirt_generate_data: the data never existed in column-major form), same two-stage scheme
+// column sums of the packed tiles (erirt_generate_data: the data never existed in column-major form), same two-stage scheme with
+// TILE_COLSUM_PARTS row slices (one block each, thread per column: a warp reads a contiguous piece of a row)
+#define TILE_COLSUM_PARTS 1024
 template <typename R>
 __global__ void tile_colsum_part_kernel(const uint8_t* __restrict__ Y, const R* __restrict__ T, int64_t n, int Jp, double* __restrict__ part) {
   const int j = threadIdx.x, p = blockIdx.x;
   if (j >= Jp) return;
-  const int64_t per = (n + COLSUM_PARTS - 1) / COLSUM_PARTS;
+  const int64_t per = (n + TILE_COLSUM_PARTS - 1) / TILE_COLSUM_PARTS;
   const int64_t lo = p * per, hi = lo + per < n ? lo + per : n;
   double t1 = 0.0, t2 = 0.0, k0 = 0.0;
+#pragma unroll 4
   for (int64_t i = lo; i < hi; ++i) {
     k0 += Y[i * Jp + j] ? 0.5 : -0.5;
     if (T) { const double v = (double)T[i * Jp + j]; t1 += v; t2 += v * v; }
   }
-  part[((int64_t)(0 * Jp + j)) * COLSUM_PARTS + p] = t1;
-  part[((int64_t)(1 * Jp + j)) * COLSUM_PARTS + p] = t2;
-  part[((int64_t)(2 * Jp + j)) * COLSUM_PARTS + p] = k0;
+  part[((int64_t)(0 * Jp + j)) * TILE_COLSUM_PARTS + p] = t1;
+  part[((int64_t)(1 * Jp + j)) * TILE_COLSUM_PARTS + p] = t2;
+  part[((int64_t)(2 * Jp + j)) * TILE_COLSUM_PARTS + p] = k0;
 }
 
 // ---- device-side data generator: the N x J part of setData* (src/SimTools.jl:117-368) straight into the packed tiles ----
@@ -757,11 +760,11 @@ extern "C" int erirt_generate_data(erirt_handle* h, const double* theta, const d
   if (F > 0 && (!X || ldX < n)) return fail(ERIRT_E_ARG, "X (leading dimension >= n_subj) is required when n_feat > 0");
   CU(cudaSetDevice(h->cfg.device));
   const bool f32 = h->cfg.dtype == ERIRT_F32;
-  // host staging of the small inputs: [theta n][zeta n][a Jp][b Jp][lambda Jp][sd Jp][rho Jp]
-  std::vector<double> hbuf((size_t)2 * n + 5 * Jp, 0.0);
-  memcpy(hbuf.data(), theta, n * sizeof(double));
-  if (has_rt) memcpy(hbuf.data() + n, zeta, n * sizeof(double));
-  double* it = hbuf.data() + 2 * n;
+  HostTimer tm;
+  // device copy of the small inputs: [theta n][zeta n][a Jp][b Jp][lambda Jp][sd Jp][rho Jp]; the person vectors go straight from
+  // the caller's buffers, the item vectors through a small host block
+  std::vector<double> hit((size_t)5 * Jp, 0.0);
+  double* it = hit.data();
   for (int j = 0; j < J; ++j) {
     it[j] = a[j];
     it[Jp + j] = b[j];
@@ -769,16 +772,19 @@ extern "C" int erirt_generate_data(erirt_handle* h, const double* theta, const d
     it[3 * Jp + j] = sigma2 ? std::sqrt(sigma2[j]) : 1.0;
     it[4 * Jp + j] = rho ? rho[j] : 0.0;
   }
-  double *dbuf = nullptr, *dXc = nullptr;
-  auto cleanup = [&]() { if (dbuf) cudaFreeAsync(dbuf, h->stream); if (dXc) cudaFreeAsync(dXc, h->stream); };
+  double *dbuf = nullptr, *dXc = nullptr, *dpart_alloc = nullptr;
+  auto cleanup = [&]() { if (dbuf) cudaFreeAsync(dbuf, h->stream); if (dXc) cudaFreeAsync(dXc, h->stream); if (dpart_alloc) cudaFreeAsync(dpart_alloc, h->stream); };
 #define CUX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(ERIRT_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
-  CUX(cudaMallocAsync((void**)&dbuf, hbuf.size() * sizeof(double), h->stream));
-  CUX(cudaMemcpyAsync(dbuf, hbuf.data(), hbuf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMallocAsync((void**)&dbuf, ((size_t)2 * n + 5 * Jp) * sizeof(double), h->stream));
+  CUX(cudaMemcpyAsync(dbuf, theta, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (has_rt) CUX(cudaMemcpyAsync(dbuf + n, zeta, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUX(cudaMemcpyAsync(dbuf + 2 * n, hit.data(), hit.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  tm.mark("generate: host staging, H2D");
   const size_t cells = (size_t)h->n_pad * Jp;
   CUX(cudaMemsetAsync(h->dY, 0, cells, h->stream));
   if (has_rt) CUX(cudaMemsetAsync(h->dLogT, 0, cells * h->rsz, h->stream));
   CUX(cudaMemsetAsync(h->dConstsLocal, 0, h->c_count * sizeof(double), h->stream));
-  CUX(cudaMemsetAsync(h->dColPart, 0, (size_t)3 * Jp * COLSUM_PARTS * sizeof(double), h->stream));
+  double* dpart = nullptr;  // [3][Jp][TILE_COLSUM_PARTS]
   GenArgs A{};
   A.Y = h->dY; A.logT = h->dLogT;
   A.theta = dbuf; A.zeta = has_rt ? dbuf + n : nullptr;
@@ -789,8 +795,10 @@ extern "C" int erirt_generate_data(erirt_handle* h, const double* theta, const d
   const int grid = h->sm_count * 8;
   if (f32) generate_data_kernel<float><<<grid, 256, 0, h->stream>>>(A);
   else generate_data_kernel<double><<<grid, 256, 0, h->stream>>>(A);
-  if (f32) tile_colsum_part_kernel<float><<<COLSUM_PARTS, Jp, 0, h->stream>>>(h->dY, has_rt ? (const float*)h->dLogT : nullptr, n, Jp, h->dColPart);
-  else tile_colsum_part_kernel<double><<<COLSUM_PARTS, Jp, 0, h->stream>>>(h->dY, has_rt ? (const double*)h->dLogT : nullptr, n, Jp, h->dColPart);
+  CUX(cudaMallocAsync((void**)&dpart_alloc, (size_t)3 * Jp * TILE_COLSUM_PARTS * sizeof(double), h->stream));
+  dpart = dpart_alloc;
+  if (f32) tile_colsum_part_kernel<float><<<TILE_COLSUM_PARTS, Jp, 0, h->stream>>>(h->dY, has_rt ? (const float*)h->dLogT : nullptr, n, Jp, dpart);
+  else tile_colsum_part_kernel<double><<<TILE_COLSUM_PARTS, Jp, 0, h->stream>>>(h->dY, has_rt ? (const double*)h->dLogT : nullptr, n, Jp, dpart);
   if (F > 0) {
     CUX(cudaMallocAsync((void**)&dXc, (size_t)n * F * sizeof(double), h->stream));
     CUX(cudaMemcpy2DAsync(dXc, n * sizeof(double), X, ldX * sizeof(double), n * sizeof(double), F, cudaMemcpyHostToDevice, h->stream));
@@ -799,12 +807,14 @@ extern "C" int erirt_generate_data(erirt_handle* h, const double* theta, const d
     if (f32) pack_vec_kernel<float><<<256, 256, 0, h->stream>>>(dXc + (int64_t)n * f, n, (float*)h->dX + (int64_t)f * h->n_pad);
     else pack_vec_kernel<double><<<256, 256, 0, h->stream>>>(dXc + (int64_t)n * f, n, (double*)h->dX + (int64_t)f * h->n_pad);
   }
-  colsum_finish_kernel<<<(3 * Jp + 127) / 128, 128, 0, h->stream>>>(h->dColPart, 3 * Jp, h->dConstsLocal + h->c_T1);
+  colsum_finish_kernel<<<(3 * Jp + 127) / 128, 128, 0, h->stream>>>(dpart, 3 * Jp, h->dConstsLocal + h->c_T1, TILE_COLSUM_PARTS);
   xtx_kernel<<<pb * pb, 256, 0, h->stream>>>(dXc, n, n, pb, h->dConstsLocal + h->c_XtX);
   CUX(cudaGetLastError());
   cleanup();
-  dbuf = dXc = nullptr;
+  dbuf = dXc = dpart_alloc = nullptr;
+  tm.mark("generate: launches, X H2D");
   CUX(cudaStreamSynchronize(h->stream));
+  tm.mark("generate: device work");
 #undef CUX
   h->data_set = true;
   h->consts_final = false;

@@ -17,7 +17,11 @@ for rep in range(int(os.environ.get("REPS", "4"))):
     t = [time.perf_counter()]
     eng = E.Engine("RtIrtQuantile", n, bench.N_ITEM, bench.N_FEAT, n_iter=K + 31, n_chain=1, n_burnin=0, q_rt=bench.Q_RT, cov2one=False, dtype="f32", seed=1, person_trace=False, use_graph=True)
     t.append(time.perf_counter())
-    check(eng.lib.erirt_set_data_y8(eng.h, hY.data_ptr(), n, hT.data_ptr(), n, hX.data_ptr(), n)); t.append(time.perf_counter())
+    if os.environ.get("GEN"):  # data generated on the device instead of uploaded
+        eng.generate_data(th, tp.a, tp.b, ze, tp.lambda_, None, None, hX.numpy().T, error="unit", seed=5)
+    else:
+        check(eng.lib.erirt_set_data_y8(eng.h, hY.data_ptr(), n, hT.data_ptr(), n, hX.data_ptr(), n))
+    t.append(time.perf_counter())
     eng.set_state(theta=th, zeta=ze, beta=be); t.append(time.perf_counter())
     eng.sample(K); t.append(time.perf_counter())
     a = eng.get_trace("ra", n, 200); b = eng.get_trace("rt", n, 200); c = eng.get_trace("qr", 0, 9); d = eng.get_trace("logLike"); t.append(time.perf_counter())
