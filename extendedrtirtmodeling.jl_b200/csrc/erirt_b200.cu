@@ -1194,54 +1194,64 @@ static int64_t full_width(const erirt_handle* h, int which) {
 }
 extern "C" int64_t erirt_trace_width(erirt_handle* h, int32_t which) { return h ? full_width(h, which) : -1; }
 
+// Post.<which>[:, first_col + c0 .. first_col + c0 + nc, l] in Julia's layout (iteration fastest), assembled on the device:
+// dst[m + n_iter * c];  sweep s = m * n_chain + l;  NaN for sweeps not yet run.  Small (item / structural) columns come from the
+// sweep-major trace [s][small_w], person columns from the person trace [s][3][n_pad].
+template <typename R>
+__global__ void trace_gather_kernel(double* __restrict__ dst, int64_t n_iter, int64_t nc, int64_t col0, int64_t l, int64_t n_chain, int64_t done,
+                                    const double* __restrict__ small, int64_t small0, int64_t small_w,
+                                    const R* __restrict__ ptrace, int pfield, int64_t pcol0, int64_t n_subj, int64_t n_pad) {
+  const int64_t total = n_iter * nc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t % n_iter, col = col0 + t / n_iter, s = m * n_chain + l;
+    double v = __longlong_as_double(0x7ff8000000000000LL);
+    if (s < done) {
+      if (col >= small0 && col < small0 + small_w) v = small[s * small_w + (col - small0)];
+      else if (ptrace && col >= pcol0 && col < pcol0 + n_subj) v = (double)ptrace[(s * 3 + pfield) * n_pad + (col - pcol0)];
+    }
+    dst[t] = v;
+  }
+}
+
 extern "C" int erirt_get_trace(erirt_handle* h, int32_t which, int64_t first_col, int64_t n_cols, double* out) {
   if (!h || !out) return fail(ERIRT_E_ARG, "null argument");
   const int64_t W = full_width(h, which);
   if (W <= 0) return fail(ERIRT_E_ARG, "trace %d does not exist for this model", which);
   if (first_col < 0 || n_cols < 0 || first_col + n_cols > W) return fail(ERIRT_E_ARG, "columns [%lld,%lld) outside [0,%lld)", (long long)first_col, (long long)(first_col + n_cols), (long long)W);
   CU(cudaSetDevice(h->cfg.device));
-  CU(cudaStreamSynchronize(h->stream));
   const int64_t N = h->cfg.n_subj, J = h->cfg.n_item, nIter = h->cfg.n_iter, nChain = h->cfg.n_chain;
   const int64_t done = h->sweeps_done;
-  const double nan = std::numeric_limits<double>::quiet_NaN();
-  for (int64_t t = 0; t < nIter * n_cols * nChain; ++t) out[t] = nan;
   // column ranges: person block [0,N) for ra/rt, trailing nu block for LatentQr qr
-  auto put = [&](int64_t s, int64_t col, double v) {  // sweep s (0-based), absolute column
-    const int64_t c = col - first_col;
-    if (c < 0 || c >= n_cols) return;
-    const int64_t m = s / nChain, l = s % nChain;
-    out[m + nIter * (c + n_cols * l)] = v;
-  };
   int pfield = -1;
-  int64_t pcol0 = 0, small0 = 0;
+  int64_t pcol0 = 0, small0 = 0, small_w = 0;
   const double* dsmall = nullptr;
-  int64_t small_w = 0;
-  if (which == ERIRT_TRACE_RA) { pfield = 0; pcol0 = 0; small0 = N; dsmall = h->dTrRa; small_w = 2 * J; }
-  else if (which == ERIRT_TRACE_RT) { pfield = 1; pcol0 = 0; small0 = N; dsmall = h->dTrRt; small_w = 2 * J; }
-  else if (which == ERIRT_TRACE_QR) { small0 = 0; dsmall = h->dTrQr; small_w = h->qw; if (h->cfg.model == ERIRT_RTIRT_LATENTQR) { pfield = 2; pcol0 = h->qw; } }
-  else { small0 = 0; dsmall = h->dTrLl; small_w = 1; }
-  // small (item / structural) columns
-  if (first_col < small0 + small_w && first_col + n_cols > small0 && done > 0) {
-    std::vector<double> buf((size_t)done * small_w);
-    CU(cudaMemcpy(buf.data(), dsmall, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int64_t s = 0; s < done; ++s)
-      for (int64_t c = 0; c < small_w; ++c) put(s, small0 + c, buf[(size_t)s * small_w + c]);
-  }
-  // person columns
-  if (pfield >= 0 && first_col < pcol0 + N && first_col + n_cols > pcol0 && done > 0) {
-    if (!h->dPtrace) return fail(ERIRT_E_STATE, "person columns requested but person_trace = 0 (use erirt_get_moments)");
-    std::vector<double> row(N);
-    const size_t rb = (size_t)h->n_pad * h->rsz;
-    std::vector<char> raw(rb);
-    for (int64_t s = 0; s < done; ++s) {
-      const char* src = (const char*)h->dPtrace + ((size_t)s * 3 + pfield) * rb;
-      CU(cudaMemcpy(raw.data(), src, rb, cudaMemcpyDeviceToHost));
-      for (int64_t i = 0; i < N; ++i) {
-        const double v = h->rsz == 4 ? (double)((const float*)raw.data())[i] : ((const double*)raw.data())[i];
-        put(s, pcol0 + i, v);
-      }
+  if (which == ERIRT_TRACE_RA) { pfield = 0; small0 = N; dsmall = h->dTrRa; small_w = 2 * J; }
+  else if (which == ERIRT_TRACE_RT) { pfield = 1; small0 = N; dsmall = h->dTrRt; small_w = 2 * J; }
+  else if (which == ERIRT_TRACE_QR) { dsmall = h->dTrQr; small_w = h->qw; if (h->cfg.model == ERIRT_RTIRT_LATENTQR) { pfield = 2; pcol0 = h->qw; } }
+  else { dsmall = h->dTrLl; small_w = 1; }
+  if (pfield >= 0 && first_col < pcol0 + N && first_col + n_cols > pcol0 && done > 0 && !h->dPtrace)
+    return fail(ERIRT_E_STATE, "person columns requested but person_trace = 0 (use erirt_get_moments)");
+  if (n_cols == 0) return 0;
+  // assembled on the device in column chunks of <= 64 MB per chain (Julia's layout makes such a chunk contiguous in `out`), one D2H copy each
+  const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(n_cols, ((int64_t)64 << 20) / (nIter * (int64_t)sizeof(double))));
+  double* tmp = nullptr;
+  CU(cudaMallocAsync((void**)&tmp, (size_t)nIter * chunk_cols * sizeof(double), h->stream));
+  cudaError_t e = cudaSuccess;
+  for (int64_t l = 0; l < nChain && e == cudaSuccess; ++l)
+    for (int64_t c0 = 0; c0 < n_cols && e == cudaSuccess; c0 += chunk_cols) {
+      const int64_t nc = std::min(chunk_cols, n_cols - c0);
+      const int grid = (int)std::min<int64_t>((nIter * nc + 255) / 256, (int64_t)h->sm_count * 16);
+      if (h->rsz == 4)
+        trace_gather_kernel<float><<<grid, 256, 0, h->stream>>>(tmp, nIter, nc, first_col + c0, l, nChain, done, dsmall, small0, small_w,
+                                                                (const float*)h->dPtrace, pfield < 0 ? 0 : pfield, pfield < 0 ? -1 : pcol0, pfield < 0 ? 0 : N, h->n_pad);
+      else
+        trace_gather_kernel<double><<<grid, 256, 0, h->stream>>>(tmp, nIter, nc, first_col + c0, l, nChain, done, dsmall, small0, small_w,
+                                                                 (const double*)h->dPtrace, pfield < 0 ? 0 : pfield, pfield < 0 ? -1 : pcol0, pfield < 0 ? 0 : N, h->n_pad);
+      e = cudaMemcpyAsync(out + nIter * (c0 + n_cols * l), tmp, (size_t)nIter * nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // tmp is reused by the next chunk
     }
-  }
+  cudaFreeAsync(tmp, h->stream);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_trace: %s", cudaGetErrorString(e));
   return 0;
 }
 
