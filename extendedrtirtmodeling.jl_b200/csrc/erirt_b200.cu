@@ -475,13 +475,6 @@ static int free_handle(erirt_handle* h) {
   return 0;
 }
 
-template <typename T>
-static int dalloc(T** p, size_t count, bool zero = true) {
-  CU(cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
-  if (zero) CU(cudaMemset(*p, 0, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
-  return 0;
-}
-
 extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   if (!cfg || !out) return fail(ERIRT_E_ARG, "null argument");
   *out = nullptr;
@@ -559,7 +552,6 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   h->cap = cfg->n_iter * cfg->n_chain;
   h->qw = qr_small_width(cfg->model, cfg->n_item, cfg->n_feat);
 
-#define TRY(x) do { int _r = (x); if (_r) { free_handle(h); return _r; } } while (0)
   {
     tm.mark("create: pool attr, plans");
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -613,7 +605,6 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
     size_t off = 0;
     for (const Req& r : reqs) { *r.p = h->arena + off; off += r.bytes; }
   }
-#undef TRY
   // default parameters == setInitialValues (a = 1, sigma2 = 1, Sigma = I; src/GibbsRtIrt.pl.jl:122-133)
   {
     std::vector<double> p(h->L.p_count, 0.0);
