@@ -36,9 +36,6 @@ constexpr float PGF_EA_B = -0.7550282017651118f;     // (pi^2/8) t log2(e) + log
 constexpr float PGF_LOG2E = 1.4426950408889634f;
 constexpr float PGF_LN2 = 0.6931471805599453f;
 constexpr float PGF_PI2LOG2E = 14.238829324987504f;  // pi^2 log2(e)
-#ifndef ERIRT_R1SCALE
-#define ERIRT_R1SCALE 1.0  // timing experiments only (tools): shrinks the undecided band of attempt 0; any value but 1 breaks exactness
-#endif
 constexpr float PG_Z0MAX = 16.0f;                    // attempt 0 is evaluated only for |z| <= 16 (finite in f32), see pg.cuh
 
 // 0.5 * s/Z as a polynomial in r (coefficients of xq_poly halved, so that (r * p)^2 = X/4 = omega)
@@ -91,7 +88,7 @@ __device__ __forceinline__ float pg_decide(float v, float xr4, float xl4, float 
       "@pj or.b32 %2, %2, %9;\n"
       "}"
       : "=f"(out), "+r"(dmask), "+r"(rmask)
-      : "f"(v), "f"(xr4), "f"(xl4), "f"(thl), "f"(thj), "f"(1.0f - (float)(PG_R1MAX_RIGHT * ERIRT_R1SCALE)), "n"(1u << BIT));
+      : "f"(v), "f"(xr4), "f"(xl4), "f"(thl), "f"(thj), "f"(1.0f - (float)PG_R1MAX_RIGHT), "n"(1u << BIT));
   return out;
 }
 
@@ -110,7 +107,7 @@ __device__ __forceinline__ void pg_fast_pair(u64 z2, uint32_t wa0, uint32_t wb0,
   const u64 K = ffma2(zz, bc2(0.125f), bc2(PGF_PI2_8));
   const u64 Rm1 = fmul2(K, ex2_2(ffma2(zz, bc2(PGF_EA_K), bc2(PGF_EA_B))));         // q0/p = (2 q0/pi) K e^{Kt}
   const PgPair a = pg_pair_core(zz, K, Rm1, rcp_2(K), wa0, wb0, wa1, wb1);
-  const u64 thl = ffma2(a.fm, bc2(1.0f - (float)(PG_R1MAX_LEFT * ERIRT_R1SCALE)), bc2(1.0f));         // left: v < 1 + fm (1 - max a_1/a_0)
+  const u64 thl = ffma2(a.fm, bc2(1.0f - (float)PG_R1MAX_LEFT), bc2(1.0f));         // left: v < 1 + fm (1 - max a_1/a_0)
   const u64 thj = fadd2(a.fm, bc2(1.0f));                                           // v >= 1 + fm: certainly rejected
   out0 = pg_decide<BIT>(lo2(a.v), lo2(a.Xr4), lo2(a.Xl4), lo2(thl), lo2(thj), dmask, rmask);
   out1 = pg_decide<BIT + 1>(hi2(a.v), hi2(a.Xr4), hi2(a.Xl4), hi2(thl), hi2(thj), dmask, rmask);
