@@ -162,3 +162,26 @@ def test_csv_ingest_timss_shaped(tmp_path):
     assert np.array_equal(D.Y, Y[keep]) and np.allclose(D.logT, np.log(np.round(T[keep], 3)))
     with pytest.raises(ValueError):
         E.readCsvData(str(p), y_cols=items, t_cols=[i + "_S" for i in items], drop_missing=False)
+
+
+def test_set_data_on_device_draws_only_the_person_level_part():
+    """setDataOnDevice (the N x J part of setData* is left to erirt_generate_data): person-level draws per model as in
+    src/SimTools.jl:117-368, the error law handed to the device, nothing of size N x J on the host."""
+    C = E.setCond(nSubj=4000, nItem=7, nFeat=3, nIter=10, nChain=1)
+    cases = [("MlIrt", E.setTrueParaMlIrt, "norm", "unit", True, False), ("RtIrtNull", E.setTrueParaRtIrt, "norm", "tnorm", False, True),
+             ("RtIrt", E.setTrueParaRtIrt, "norm", "tnorm", True, True), ("RtIrtCross", E.setTrueParaRtIrtCross, "tail", "tail", False, True),
+             ("RtIrtLatent", E.setTrueParaRtIrtLatent, "skew", "unit", True, True)]
+    for model, mk, typ, err, has_x, has_zeta in cases:
+        tp = mk(C, rng=3)
+        D = E.setDataOnDevice(C, tp, model, type=typ, rng=3)
+        assert isinstance(D, E.DeviceData) and D.error == err and D.Y is None and D.logT is None
+        assert tp.theta.shape == (4000,) and (np.size(tp.zeta) == 4000) == has_zeta
+        assert (D.X is not None and D.X.shape == (4000, 3)) == has_x
+        assert abs(tp.theta.std() - (np.sqrt(1 + np.sum(tp.beta[:, 0] ** 2)) if model == "RtIrt" else tp.theta.std())) < 0.1
+    # same seed -> same data-domain seed: the DIC evaluation regenerates the data set the chain was sampled on
+    tp1, tp2 = E.setTrueParaRtIrt(C, rng=3), E.setTrueParaRtIrt(C, rng=3)
+    assert E.setDataOnDevice(C, tp1, "RtIrt", rng=9).seed == E.setDataOnDevice(C, tp2, "RtIrt", rng=9).seed
+    with pytest.raises(ValueError):
+        E.setDataOnDevice(C, E.setTrueParaRtIrtCross(C, rng=3), "RtIrtCross", type="cauchy", rng=3)
+    with pytest.raises(ValueError):
+        E.setDataOnDevice(C, tp1, "NoSuchModel", rng=3)
