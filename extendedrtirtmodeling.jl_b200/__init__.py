@@ -5,7 +5,7 @@ package is the host-side mirror of the reference's interface for that path.  No 
 from . import _lib  # noqa: F401
 from .api import (GibbsMlIrt, GibbsRtIrt, GibbsRtIrtCross, GibbsRtIrtCrossQr, GibbsRtIrtLatent,  # noqa: F401
                   GibbsRtIrtLatentQr, GibbsRtIrtNull, GibbsRtIrtQuantile, coef, getDic, getLogLikelihood, precis, sample,
-                  sample_bang)
+                  sample_bang, sampleIndependentChains)
 from .engine import Engine, ErirtError, k_nu_person, k_pg, k_philox, nccl_unique_id, trim_pool  # noqa: F401
 from .simulate import (DeviceData, getBias, getRmse, setDataOnDevice, setDataMlIrt, setDataRtIrt, setDataRtIrtCross, setDataRtIrtLatent,  # noqa: F401
                        setDataRtIrtNull, setTrueParaMlIrt, setTrueParaRtIrt, setTrueParaRtIrtCross,

@@ -231,6 +231,45 @@ def _collect(MCMC, eng, person_trace):
 sample_bang = sample  # `sample!` is not a Python identifier
 
 
+def sampleIndependentChains(MCMC, n_chains, group=None, rng=0, **kw):
+    """BASELINE configs[3] / SURVEY 8e "independent chains": n_chains truly independent chains of MCMC's model on MCMC's data -- distinct
+    Philox keys (chain id c) and distinct initial values (constructor seeded rng + c) -- dealt to the ranks of the torch.distributed
+    group c -> rank c mod world (one GPU each; a single process runs them one after the other), no collective while sampling.  The
+    reference has only interleaved pseudo-chains (one state, `for m in 1:nIter, l in 1:nChain`, src/GibbsRtIrt.pl.jl:289), so this is
+    new behaviour behind the same Post layout: MCMC.Post.ra / rt / qr / logLike come back as [nIter, item and structural columns,
+    n_chains] (person columns are not gathered), Post.mean is the mean over chains of the per-chain means, and MCMC.Cond.nChain is
+    set to n_chains, so precis / checkConvergence / getDic read it like any other run.  kw: sample()'s keyword arguments."""
+    import dataclasses
+
+    from .distributed import run_independent_chains
+    C1 = dataclasses.replace(MCMC.Cond, nChain=1)
+    for k in ("chain", "person_trace", "shard"):
+        kw.pop(k, None)
+
+    def run_chain(c):
+        M = type(MCMC)(C1, Data=MCMC.Data, truePara=MCMC.truePara, rng=rng + c)
+        sample(M, chain=c, person_trace=False, **kw)
+        P = M.Post
+        out = dict(ra=P.ra, qr=P.qr[:, :sum(n for _, n in _qr_layout(M)), :], logLike=P.logLike)
+        if M.has_rt:
+            out["rt"] = P.rt
+        for f in InputPara._FIELDS:  # per-chain posterior means, chain axis last
+            v = np.asarray(getattr(P.mean, f), dtype=np.float64)
+            if v.size:
+                out["mean_" + f] = v.reshape(v.shape + (1,))
+        M.engine.close()
+        return out
+
+    res = run_independent_chains(run_chain, n_chains, group)
+    MCMC.Cond = dataclasses.replace(MCMC.Cond, nChain=n_chains)
+    Post = OutputPost()
+    Post.ra, Post.qr, Post.logLike, Post.rt = res["ra"], res["qr"], res["logLike"], res.get("rt")
+    Post.person_cols = False
+    Post.mean = InputPara(**{k[5:]: v.mean(axis=-1) for k, v in res.items() if k.startswith("mean_")})
+    MCMC.Post = Post
+    return MCMC
+
+
 def getLogLikelihood(MCMC, P, dtype="f64", device=0):
     """getLogLikelihood*(Cond, Data; P) (src/GibbsRtIrt.pl.jl:195-204, 262-272, 351-361; Cross :158-169; Latent :151-161,
     :243-264), evaluated on the GPU for an InputPara `P` (e.g. MCMC.Post.mean)."""

@@ -85,3 +85,22 @@ def gather_person_vector(local, n_total, group=None):
     outs = [torch.zeros(mx, dtype=torch.float64, device=dev) for _ in range(world)]
     dist.all_gather(outs, buf, group=group)
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(outs, sizes)])
+
+
+def run_independent_chains(run_chain, n_chains, group=None):
+    """Independent chains, SURVEY 8e / BASELINE configs[3]: chain c runs on rank c mod world (one GPU per rank, chains of a rank one
+    after the other), no collective while sampling; the traces are gathered at the end.  `run_chain(c)` returns a dict
+    name -> array whose LAST axis is the chain axis of length 1 (e.g. Post.ra[:, item columns, :] of a one-chain run); every rank
+    gets dict name -> array with the chains concatenated in chain order along that axis."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    mine = {c: run_chain(c) for c in chain_assignment(n_chains, world, rank)}
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+        mine = {c: r for part in parts for c, r in part.items()}
+    names = list(mine[0].keys())
+    return {nm: np.concatenate([np.asarray(mine[c][nm]) for c in range(n_chains)], axis=-1) for nm in names}

@@ -23,7 +23,16 @@ def _worker(rank, world, port, ret):
     handles = D.allgather_bytes(bytes([rank + 1]) * 64)
     # runSimulation deals replication r to rank (r-1) mod world; chains c to GPU c mod world
     reps = [r for r in range(1, 8) if (r - 1) % world == rank]
-    ret[rank] = (got == bytes(range(128)) and handles == b"\x01" * 64 + b"\x02" * 64 and D.make_shard(n_total, nccl=False)[0][2] is None,
+    # independent chains (BASELINE configs[3]): chain c runs on rank c mod world, traces gathered in chain order on every rank
+    ran = []
+
+    def run_chain(c):
+        ran.append(c)
+        return dict(ra=np.full((4, 3, 1), float(c)), logLike=np.full((4, 1, 1), 10.0 * c))
+    chains = D.run_independent_chains(run_chain, 5)
+    chains_ok = (ran == D.chain_assignment(5, world, rank) and chains["ra"].shape == (4, 3, 5) and chains["logLike"].shape == (4, 1, 5)
+                 and chains["ra"][0, 0, :].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0] and chains["logLike"][1, 0, :].tolist() == [0.0, 10.0, 20.0, 30.0, 40.0])
+    ret[rank] = (chains_ok and got == bytes(range(128)) and handles == b"\x01" * 64 + b"\x02" * 64 and D.make_shard(n_total, nccl=False)[0][2] is None,
                  full.tolist(), (off, cnt), reps, D.chain_assignment(5, world, rank))
     dist.barrier()
     dist.destroy_process_group()

@@ -665,3 +665,21 @@ def test_api_flow_with_device_generated_data(E):
     MCMC = E.GibbsRtIrtCrossQr(Cond, Data=E.setDataOnDevice(Cond, tp, "RtIrtCross", type="tail", rng=7), truePara=tp, rng=7)
     E.sample(MCMC, dtype="f64")
     assert np.all(np.isfinite(MCMC.Post.logLike)) and MCMC.Post.mean.nu.shape == (800, 8)
+
+
+@pytest.mark.gpu
+def test_independent_chains_driver(E):
+    """BASELINE configs[3] (GibbsRtIrtNull, independent chains with distinct Philox keys and initial values) through the mirror:
+    one process here, so the chains run one after the other on this GPU; same Post layout with a real chain axis."""
+    Cond = E.setCond(nSubj=2000, nItem=10, nFeat=0, nIter=400, nChain=1)
+    tp = E.setTrueParaRtIrt(Cond, rng=8)
+    MCMC = E.GibbsRtIrtNull(Cond, Data=E.setDataRtIrtNull(Cond, tp, rng=8), truePara=tp, rng=8)
+    E.sampleIndependentChains(MCMC, 3, dtype="f32", seed=21)
+    P = MCMC.Post
+    assert MCMC.Cond.nChain == 3 and P.ra.shape == (400, 20, 3) and P.rt.shape == (400, 20, 3) and P.logLike.shape == (400, 1, 3)
+    assert np.all(np.isfinite(P.ra)) and np.abs(P.ra[-1, :, 0] - P.ra[-1, :, 1]).max() > 1e-6  # different streams
+    conv = E.checkConvergence(MCMC)
+    assert conv["rhat"] > 90.0  # independent chains agree after burn-in: R-hat < 1.1 for (almost) every traced parameter
+    assert E.getRmse(tp.b, P.mean.b) < 0.15 and P.mean.theta.shape == (2000,)
+    dic = E.getDic(MCMC)
+    assert np.isfinite(dic.DIC)
