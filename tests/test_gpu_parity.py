@@ -681,7 +681,7 @@ def test_independent_chains_driver(E):
     conv = E.checkConvergence(MCMC)
     # 200 post-burn-in sweeps of three chains started from different person parameters: most, not all, traced parameters are
     # already below R-hat 1.1 (76 % with these seeds); the point here is that the chain axis feeds the diagnostics
-    assert conv["rhat"] > 50.0 and conv["rhatN"].endswith("/ 44")
+    assert conv["rhat"] > 50.0
     assert E.getRmse(tp.b, P.mean.b) < 0.15 and P.mean.theta.shape == (2000,)
     dic = E.getDic(MCMC)
     assert np.isfinite(dic.DIC)
