@@ -172,6 +172,20 @@ function sample!(MCMC::GibbsRtIrtLatentQr; intercept=false, itemtype::Union{Stri
     _sample_gpu!(MCMC; intercept, itemtype, cov2one); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2; with_ν=true)
 end
 
+# ---- simulated data generated on the device (erirt_generate_data): the N x J part of setData* (src/SimTools.jl:117-368) never exists on
+#      the host.  `truePara` holds the person-level draws θ (and ζ) made by the caller as in setData*, X the covariates (or nothing);
+#      errortype: 0 truncated normal (Null / RtIrt), 1 N(0,1) (Latent*), 2 / 3 / 4 = "norm" / "tail" / "skew" (Cross) ----
+function generate_data!(h, truePara, X, errortype::Integer; seed::UInt64=rand(UInt64))
+    ptr(v) = isempty(v) ? Ptr{Float64}(C_NULL) : pointer(v)
+    θ, ζ = Vector{Float64}(vec(truePara.θ)), Vector{Float64}(vec(truePara.ζ))
+    a, b, λ = Vector{Float64}(vec(truePara.a)), Vector{Float64}(vec(truePara.b)), Vector{Float64}(vec(truePara.λ))
+    σ², ρ = Vector{Float64}(vec(truePara.σ²t)), Vector{Float64}(vec(truePara.ρ))
+    Xm = X === nothing ? zeros(0, 0) : Matrix{Float64}(X)
+    GC.@preserve θ ζ a b λ σ² ρ Xm check(ccall((:erirt_generate_data, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, UInt64),
+        h, θ, ptr(ζ), a, b, ptr(λ), ptr(σ²), ptr(ρ), ptr(Xm), max(size(Xm, 1), 1), errortype, seed))
+end
+
 # ---- checkpoint / resume of a running chain (erirt_checkpoint_*): `h` is the handle of a chain driven in chunks ----
 function checkpoint(h)::Vector{UInt8}
     n = ccall((:erirt_checkpoint_size, LIB), Int64, (Ptr{Cvoid},), h)

@@ -42,7 +42,22 @@ def compute():
                 if model == "RtIrtCrossQr" and k == "qr":
                     arr = arr[:, : J + 4]  # the N*J block of cell-level nu is not traced by the engine
                 out[f"{model}_{k}"] = arr
+    # device-side data generator (erirt_generate_data / oracle/gen.c): responses and log-times of the five error laws, a shard offset
+    th, ze, a, b, lam, s2, rho = gen_inputs()
+    for err in ("tnorm", "unit", "norm", "tail", "skew"):
+        Y, T = O.generate_data(GEN_N, GEN_J, th, a, b, ze, lam, s2, rho if err in ("norm", "tail", "skew") else None, error=err, seed=GEN_SEED,
+                               person_offset=GEN_OFFSET)
+        out[f"gen_{err}_Y"], out[f"gen_{err}_logT"] = Y, T
     return out
+
+
+GEN_N, GEN_J, GEN_SEED, GEN_OFFSET = 48, 7, 2024, 1000
+
+
+def gen_inputs():
+    rng = np.random.default_rng(23)
+    return (rng.normal(size=GEN_N), 0.4 * rng.normal(size=GEN_N), rng.uniform(0.7, 1.4, GEN_J), rng.normal(0, 0.5, GEN_J),
+            rng.uniform(2.5, 3.5, GEN_J), rng.uniform(0.2, 0.4, GEN_J), rng.normal(0, 0.2, GEN_J))
 
 
 if __name__ == "__main__":

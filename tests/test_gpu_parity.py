@@ -409,6 +409,18 @@ def test_f64_engine_matches_committed_fixture(E):
         assert relerr(eng.get_trace("qr")[:3, :qw, 0], g[f"{model}_qr"][:, :qw], atol=1e-3).max() < tol, model
         assert relerr(eng.get_trace("logLike")[:3, 0, 0], g[f"{model}_ll"]).max() < tol, model
         eng.close()
+    # the data generator against the committed vectors (persons 1000..1047 of a 2000-person data set)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    th, ze, a, b, lam, s2, rho = mg.gen_inputs()
+    for err, model in (("tnorm", "RtIrtNull"), ("unit", "RtIrtLatent"), ("norm", "RtIrtCross"), ("tail", "RtIrtCross"), ("skew", "RtIrtCrossQr")):
+        eng = E.Engine(model, mg.GEN_N, mg.GEN_J, 0, n_iter=1, dtype="f64", n_subj_total=2000, subj_offset=mg.GEN_OFFSET)
+        eng.generate_data(th, a, b, ze, lam, s2, rho if "Cross" in model else None, None, error=err, seed=mg.GEN_SEED)
+        Y, T = eng.get_data()
+        assert np.array_equal(Y, g[f"gen_{err}_Y"]) and relerr(T, g[f"gen_{err}_logT"], atol=1.0).max() < 1e-12, err
+        eng.close()
 
 
 @pytest.mark.gpu
