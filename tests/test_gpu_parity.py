@@ -697,3 +697,21 @@ def test_independent_chains_driver(E):
     assert E.getRmse(tp.b, P.mean.b) < 0.15 and P.mean.theta.shape == (2000,)
     dic = E.getDic(MCMC)
     assert np.isfinite(dic.DIC)
+
+
+@pytest.mark.gpu
+def test_sharded_chain_equals_single_gpu_chain(E):
+    """Sharding invariance on real GPUs: tools/check_sharded.py under torchrun with two ranks -- persons of one chain
+    split over two GPUs, item statistics exchanged every sweep (fused peer-memory exchange and ncclAllReduce) -- reproduces the
+    single-GPU chain up to f64 summation order for six of the models.  Needs two visible GPUs (gpurun --gpus 2); skipped otherwise."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "check_sharded.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0 and "SHARDING_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
