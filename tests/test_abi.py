@@ -76,3 +76,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in txt and "liberirt_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_julia_stub_matches_the_header(lib):
+    """julia/ErirtB200.jl cannot be executed here (no Julia): check statically that its ErirtConfig mirrors erirt_config field by field
+    (names, order, widths) and that every C symbol it ccalls is declared in include/erirt_b200.h."""
+    import re
+    from erirt_b200 import _lib
+    src = open(os.path.join(ROOT, "julia", "ErirtB200.jl"), encoding="utf-8").read()
+    body = src[src.index("struct ErirtConfig"):]
+    body = body[:body.index("\nend")]
+    fields = re.findall(r"^\s+(\w+)::([\w{},]+)\s*$", body, flags=re.M)
+    jl_size = {"Int32": 4, "UInt32": 4, "Int64": 8, "UInt64": 8, "Float64": 8}
+    assert [f for f, _ in fields] == [f[0] for f in _lib.Config._fields_]
+    for (name, jt), cf in zip(fields, _lib.Config._fields_):
+        m = re.fullmatch(r"NTuple\{(\d+),(\w+)\}", jt)
+        size = int(m.group(1)) * jl_size[m.group(2)] if m else jl_size[jt]
+        assert size == ctypes.sizeof(cf[1]), (name, jt)
+    called = set(re.findall(r"ccall\(\(:(\w+), LIB\)", src))
+    assert called and called <= set(_declared_symbols()), called - set(_declared_symbols())
+    assert {"erirt_create", "erirt_set_data", "erirt_set_data_y8", "erirt_set_state", "erirt_sample", "erirt_get_trace", "erirt_get_moments",
+            "erirt_destroy", "erirt_generate_data", "erirt_checkpoint_save", "erirt_checkpoint_load"} <= called
