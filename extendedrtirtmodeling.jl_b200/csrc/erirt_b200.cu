@@ -365,6 +365,8 @@ struct erirt_handle {
   bool peer_ready = false;
   // graph
   cudaGraphExec_t graph_exec = nullptr;
+  cudaGraphExec_t graph_multi = nullptr;  // ERIRT_GRAPH_SWEEPS sweeps in one graph (experimental)
+  int graph_multi_sweeps = 0;
 };
 
 static int launch_person(erirt_handle* h, int stage);
@@ -458,6 +460,7 @@ static int free_handle(erirt_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->graph_multi) cudaGraphExecDestroy(h->graph_multi);
   if (h->comm && nccl::comm_destroy) nccl::comm_destroy(h->comm);
   for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
   if (h->xbuf) cudaFree(h->xbuf);
@@ -1130,18 +1133,34 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
     }
   }
   if (h->cfg.use_graph && !h->cfg.time_kernels && n_sweeps > 0) {
-    if (!h->graph_exec) {
+    // one graph = one sweep (2 or 4 kernel nodes); ERIRT_GRAPH_SWEEPS=k additionally captures k sweeps into one graph, so that small
+    // problems, whose sweep is shorter than a graph launch, pay the launch once per k sweeps (experimental, default 1)
+    auto capture = [&](int sweeps, cudaGraphExec_t* exec) -> int {
       cudaGraph_t graph;
       CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      rc = enqueue_step(h, false);
+      int r = 0;
+      for (int t = 0; t < sweeps && !r; ++t) r = enqueue_step(h, false);
       cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-      if (rc) return rc;
+      if (r) return r;
       if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-      e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+      e = cudaGraphInstantiate(exec, graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+      return 0;
+    };
+    if (!h->graph_exec && (rc = capture(1, &h->graph_exec))) return rc;
+    const char* env_gs = getenv("ERIRT_GRAPH_SWEEPS");
+    const int gs = env_gs ? std::max(1, std::min(64, atoi(env_gs))) : 1;
+    int64_t left = n_sweeps;
+    if (gs > 1 && left >= gs) {
+      if (h->graph_multi && h->graph_multi_sweeps != gs) { cudaGraphExecDestroy(h->graph_multi); h->graph_multi = nullptr; }
+      if (!h->graph_multi) {
+        if ((rc = capture(gs, &h->graph_multi))) return rc;
+        h->graph_multi_sweeps = gs;
+      }
+      for (; left >= gs; left -= gs) CU(cudaGraphLaunch(h->graph_multi, h->stream));
     }
-    for (int64_t t = 0; t < n_sweeps; ++t) CU(cudaGraphLaunch(h->graph_exec, h->stream));
+    for (; left > 0; --left) CU(cudaGraphLaunch(h->graph_exec, h->stream));
   } else {
     for (int64_t t = 0; t < n_sweeps; ++t) {
       rc = enqueue_step(h, false);
