@@ -12,18 +12,26 @@ the one chain are sharded over the N GPUs of the box and the item statistics are
 exchange over NVLink peer memory fused into the global draw kernel; ERIRT_EXCHANGE=nccl selects ncclAllReduce), so
 the total work is fixed: "scaling": "strong".
 
-Keys (see DESIGN.md "Measurement"):
-  value       sweeps/s, data resident in HBM, CUDA events on the library's stream, max over ranks
-  e2e         sweeps/s through the public C-ABI calls with HOST (pinned) buffers: erirt_create + erirt_set_data
-              (H2D + ingest) + erirt_set_state + K sweeps + erirt_get_trace/erirt_get_moments (D2H), all timed
-  roofline    person-sweep kernel: algorithmic HBM bytes per launch / its mean CUDA-event duration, against the
-              measured HBM copy bandwidth of MEASURED_PEAKS.json
+Keys of the JSON line (DESIGN.md "Measurement"):
+  value         sweeps/s over EXACTLY K sweeps, data resident in HBM, CUDA events on the library's stream, max over
+                ranks; the timed region starts right after one throw-away sweep whose exchange lines the GPUs up
+  long_run      the same measurement over >= 0.5 s of sweeps (clocks are sampled over value + long_run)
+  e2e           sweeps/s through the public C-ABI calls with HOST (pinned) buffers: erirt_create + erirt_set_data
+                (H2D + ingest) + erirt_set_state + K sweeps + erirt_get_trace/erirt_get_moments (D2H), all timed
+  roofline      person-sweep kernel: algorithmic HBM bytes per launch / its mean CUDA-event duration, against the
+                measured HBM copy bandwidth of MEASURED_PEAKS.json
+  ess           bulk ESS per sweep of the item + structural parameters from a >= 3000-sweep run of the same chain
+                (second half), ESS/s on the GPU(s) and for the CPU baseline (same ESS per sweep x CPU sweeps/s)
+  sharding_check  logLike of sweeps 1..5 (f32 as benchmarked, and an f64 run): the same chain at every GPU count
+  f64, crossqr, configs, c4_chains   sub-records: Float64 mode, the cell-level quantile sampler (CrossQr) at the same
+                size, BASELINE configs 1-4 beside the CPU oracle, 8 independent RtIrtNull chains dealt over the GPUs
   cpu_baseline  the CPU oracle (a C restatement of the reference; Julia is not installed) on one host core, on a
-              bounded sample of the persons, extrapolated linearly in nSubj
+                bounded sample of the persons, extrapolated linearly in nSubj
 --impl reference times that same CPU restatement with all host threads (OpenMP over persons/items).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -41,6 +49,18 @@ SEED = 1234
 METRIC = "gibbs_sweeps_per_sec"
 UNIT = "sweeps/s"
 WORKLOAD = "GibbsRtIrtQuantile(LatentQr) synthetic nSubj=1M nItem=100 nFeat=3 qRt=0.85 (BASELINE config 5)"
+ESS_SWEEPS = 3000       # total length of the chain the ESS is taken from (second half used)
+LONG_RUN_SECONDS = 0.5  # minimum device time of the long timed region
+
+
+def make_config(world):
+    """The `config` object of the JSON line; identical for this arm and for --impl reference at the same --gpus."""
+    peer = os.environ.get("ERIRT_EXCHANGE", "peer") == "peer"
+    par = "single GPU" if world <= 1 else (
+        f"persons sharded over {world} GPUs, item statistics all-reduced per sweep by "
+        + ("a one-shot exchange over NVLink peer memory fused into the global draw kernel" if peer else "ncclAllReduce"))
+    return {"workload": WORKLOAD, "parallelism": par, "l2": "inputs (1.3 GB/sweep) larger than the 126 MB L2",
+            "cuda_graph": True, "loglik_and_moments": "on"}
 
 
 def true_params():
@@ -189,40 +209,47 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the person kernel from the last committed ncu --set full capture (or None)."""
+def ncu_traffic(key="dram_bytes_per_launch"):
+    """dram bytes per launch of the person kernel at N=1 from the last committed ncu --set full capture (or None)."""
     p = os.path.join(ROOT, "profiles", "person_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
 
 
-def ess_per_sweep(eng, first, n, qw):
-    """min / median bulk ESS per sweep over the traced item + structural parameters of sweeps [first, first+n)."""
+def bulk_ess(columns):
+    """min / median rank-normalised bulk ESS (Vehtari et al. 2021; diagnostics.ess_rhat) over the non-constant columns."""
     from erirt_b200.diagnostics import ess_rhat
-    N, J = eng.N, eng.J
-    cols = [eng.get_trace("ra", N, 2 * J)[first:first + n, :, 0], eng.get_trace("rt", N, 2 * J)[first:first + n, :, 0],
-            eng.get_trace("qr", 0, qw)[first:first + n, :, 0]]
     ess = []
-    for arr in cols:
+    for arr in columns:
         for c in range(arr.shape[1]):
             x = arr[:, c]
-            if np.ptp(x) > 0:
+            if np.ptp(x) > 0 and np.all(np.isfinite(x)):
                 ess.append(ess_rhat(x)[0])
     ess = np.asarray(ess)
-    return float(np.nanmin(ess) / n), float(np.nanmedian(ess) / n)
+    return float(np.nanmin(ess)), float(np.nanmedian(ess)), int(ess.size)
+
+
+def item_struct_traces(eng, first, n, qw):
+    N, J = eng.N, eng.J
+    has_rt = eng.model != 0
+    cols = [eng.get_trace("ra", N, 2 * J)[first:first + n, :, 0]]
+    if has_rt:
+        cols.append(eng.get_trace("rt", N, 2 * J)[first:first + n, :, 0])
+    cols.append(eng.get_trace("qr", 0, qw)[first:first + n, :, 0])
+    return cols
 
 
 def cpu_oracle_rate(tp, n_sample, n_sweeps, nthreads, warm=1):
     """sweeps/s of the CPU restatement on the first n_sample persons of block 0 (host-generated, same
     distributions), extrapolated linearly to N_SUBJ persons."""
+    import copy
     import erirt_b200 as E
     from oracle import oracle_py as O
     Cond = E.setCond(nSubj=n_sample, nItem=N_ITEM, nFeat=N_FEAT, qRt=Q_RT)
-    import copy
     tpc = copy.deepcopy(tp)
     D = E.setDataRtIrtLatent(Cond, tpc, type="skew", rng=SEED)
     cfg = O.make_cfg("RtIrtLatentQr", n_sample, N_ITEM, N_FEAT, qRt=Q_RT, seed=SEED, nthreads=nthreads)
@@ -260,10 +287,183 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
+            "config": make_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sub-records (single GPU only): Float64 mode, CrossQr at C5 size, BASELINE configs 1-4 beside the CPU oracle
+# ------------------------------------------------------------------------------------------------------------------
+def roofline_record(eng_stats, kernel_ms, kernel_name, launches):
+    peak, which = measured_peak()
+    b = eng_stats["bytes_per_sweep"]
+    achieved = b / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
+            "frac": achieved / peak, "algorithmic_bytes_per_launch": b, "kernel_ms": kernel_ms, "launches_timed": launches}
+
+
+def sub_f64(E, dY, dT, dX, n_local, theta0, zeta0, beta0, local):
+    """The benchmarked sampler in Float64 (the reference's precision): 25 B per cell."""
+    out = {}
+    for timed in (False, True):
+        eng = E.Engine("RtIrtQuantile", n_local, N_ITEM, N_FEAT, n_iter=64, n_chain=1, n_burnin=0, q_rt=Q_RT, cov2one=False, dtype="f64",
+                       seed=SEED, person_trace=False, device=local, use_graph=not timed, time_kernels=timed)
+        eng.set_data_device(dY.data_ptr(), n_local, dT.data_ptr(), n_local, dX.data_ptr(), n_local)
+        eng.set_state(theta=theta0, zeta=zeta0, beta=beta0)
+        eng.sample(4)
+        eng.sample(20)
+        st = eng.stats()
+        if not timed:
+            out.update(value=20 / (st["last_sample_ms"] / 1e3), unit=UNIT, ms_per_step=st["last_sample_ms"] / 20, sweeps=20, dtype="f64")
+        else:
+            out["roofline"] = roofline_record(st, st["person_kernel_ms"], "person_sweep_kernel<double>", 20)
+        eng.close()
+    return out
+
+
+def sub_crossqr(E, local):
+    """GibbsRtIrtCrossQr (cell-level quantile weights nu_ij, src/GibbsRtIrtCross.pl.jl:265-325) at 1M x 100, q = 0.85, data from
+    setDataRtIrtCross(type="skew") generated on the device; two person launches per sweep (K_a, K_b): 29 / 57 B per cell."""
+    Cond = E.setCond(nSubj=N_SUBJ, nItem=N_ITEM, nFeat=0, qRt=Q_RT)
+    tp = E.setTrueParaRtIrtCross(Cond, rng=SEED)
+    rng = np.random.default_rng(SEED + 21)
+    theta, zeta = rng.standard_normal(N_SUBJ), rng.standard_normal(N_SUBJ)
+    out = {"workload": "GibbsRtIrtCrossQr synthetic nSubj=1M nItem=100 qRt=0.85, setDataRtIrtCross(type=skew)"}
+    for dtype in ("f32", "f64"):
+        rec = {}
+        for timed in (False, True):
+            eng = E.Engine("RtIrtCrossQr", N_SUBJ, N_ITEM, 0, n_iter=64, n_chain=1, n_burnin=0, q_rt=Q_RT, cov2one=True, dtype=dtype,
+                           seed=SEED, person_trace=False, device=local, use_graph=not timed, time_kernels=timed)
+            eng.generate_data(theta, tp.a, tp.b, zeta, tp.lambda_, tp.sigma2t, tp.rho, None, error="skew", seed=SEED)
+            eng.set_state(theta=rng.standard_normal(N_SUBJ), zeta=rng.standard_normal(N_SUBJ), rho=np.zeros(N_ITEM))
+            n = 12
+            eng.sample(3)
+            eng.sample(n)
+            st = eng.stats()
+            if not timed:
+                b = st["bytes_per_sweep"]
+                peak, which = measured_peak()
+                ms = st["last_sample_ms"] / n
+                rec.update(value=1e3 / ms, unit=UNIT, ms_per_step=ms, sweeps=n,
+                           roofline={"bound": "hbm", "kernel": "person_sweep_kernel<FAM=1> K_a + K_b (whole sweep)", "achieved": b / (ms * 1e-3) / 1e9,
+                                     "peak": peak, "peak_source": which, "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / peak,
+                                     "algorithmic_bytes_per_sweep": b})
+            else:
+                rec["k_b_kernel_ms"] = st["person_kernel_ms"]
+            ll = eng.get_trace("logLike")[:n + 3, 0, 0]
+            assert np.all(np.isfinite(ll)), "CrossQr logLike not finite"
+            eng.close()
+        out[dtype] = rec
+    return out
+
+
+def _time_engine(E, model, Data, N, J, F, n_iter, n_chain, dtype, init, local, q_rt=0.5, cov2one=True, warm=50):
+    eng = E.Engine(model, N, J, F, n_iter=n_iter, n_chain=n_chain, n_burnin=0, q_rt=q_rt, cov2one=cov2one, dtype=dtype, seed=SEED,
+                   person_trace=False, device=local, use_graph=True)
+    eng.set_data(Data.Y, None if model == "MlIrt" else Data.logT, Data.X if F > 0 else None)
+    eng.set_state(**init)
+    total = n_iter * n_chain
+    eng.sample(warm)
+    eng.sample(total - warm)
+    ms = eng.stats()["last_sample_ms"] / (total - warm)
+    eng.close()
+    return 1e3 / ms
+
+
+def _time_oracle(model, Data, N, J, F, init, n_sweeps, q_rt=0.5, cov2one=None):
+    from oracle import oracle_py as O
+    cfg = O.make_cfg(model, N, J, F, qRt=q_rt, seed=SEED, nthreads=1, cov2one=cov2one)
+    logT = None if model == "MlIrt" else Data.logT
+    O.sample(cfg, Data.Y, logT, Data.X, init, 1, person_trace=False, qr_skip_nu=True)
+    t0 = time.perf_counter()
+    O.sample(cfg, Data.Y, logT, Data.X, init, n_sweeps, person_trace=False, qr_skip_nu=True)
+    return n_sweeps / (time.perf_counter() - t0)
+
+
+def sub_configs(E, local):
+    """BASELINE configs 1-4: sweeps/s on one GPU (f32 and f64, CUDA-graph replay, everything on) beside the CPU oracle on
+    one core.  These problems are launch / latency bound (their working set is L2- or SM-resident): no roofline fraction applies."""
+    rng = np.random.default_rng(SEED + 31)
+    out = {}
+
+    def rec(name, model, N, J, F, n_iter, n_chain, Data, init, cpu_sweeps, q_rt=0.5, cov2one=True):
+        r = {"workload": name, "n_subj": N, "n_item": J, "n_feat": F, "n_chain": n_chain}
+        for dt in ("f32", "f64"):
+            r[f"gpu_{dt}_sweeps_per_s"] = _time_engine(E, model, Data, N, J, F, n_iter, n_chain, dt, init, local, q_rt, cov2one)
+        oinit = dict(a=np.ones(J), b=np.zeros(J), lambda_=np.zeros(J), sigma2=np.ones(J), Sigma=np.eye(2).ravel())
+        oinit.update({k.rstrip("_"): v for k, v in init.items()})
+        r["cpu_oracle_sweeps_per_s"] = _time_oracle(model, Data, N, J, F, oinit, cpu_sweeps, q_rt, cov2one)
+        r["cpu_cores"] = 1
+        out[name.split(":")[0]] = r
+
+    # C1: GibbsMlIrt README simulation, 1000 x 15, single chain
+    Cond = E.setCond(nSubj=1000, nItem=15, nFeat=3, nIter=3000, nChain=1)
+    tp = E.setTrueParaMlIrt(Cond, rng=SEED)
+    D = E.setDataMlIrt(Cond, tp, rng=SEED)
+    rec("C1: GibbsMlIrt README simulation 1000x15 single chain", "MlIrt", 1000, 15, 3, 3000, 1, D,
+        dict(theta=rng.standard_normal(1000), beta=rng.standard_normal(4)), 300)
+    # C2: GibbsRtIrt 10k x 30, nChain = 3 (the reference's interleaved chains)
+    Cond = E.setCond(nSubj=10_000, nItem=30, nFeat=3, nIter=1000, nChain=3)
+    tp = E.setTrueParaRtIrt(Cond, rng=SEED)
+    D = E.setDataRtIrt(Cond, tp, rng=SEED)
+    rec("C2: GibbsRtIrt 10k x 30 nChain=3", "RtIrt", 10_000, 30, 3, 1000, 3, D,
+        dict(theta=rng.standard_normal(10_000), zeta=rng.standard_normal(10_000), beta=rng.standard_normal(8)), 20)
+    # C3: GibbsRtIrtQuantile q = 0.85 on TIMSS-shaped data 631 x 14, F = 10
+    Cond = E.setCond(nSubj=631, nItem=14, nFeat=10, nIter=1000, nChain=3, qRt=0.85)
+    tp = E.setTrueParaRtIrtLatent(Cond, rng=SEED)
+    D = E.setDataRtIrtLatent(Cond, tp, type="norm", rng=SEED)
+    rec("C3: GibbsRtIrtQuantile q=0.85 TIMSS-shaped 631x14 F=10 nChain=3", "RtIrtLatentQr", 631, 14, 10, 1000, 3, D,
+        dict(theta=rng.standard_normal(631), zeta=rng.standard_normal(631), beta=rng.standard_normal(12)), 300, q_rt=0.85, cov2one=False)
+    # C4: GibbsRtIrtNull 100k x 40, one of the 8 chains (the 8-chain run over the GPUs is the c4_chains record)
+    Cond = E.setCond(nSubj=100_000, nItem=40, nFeat=0, nIter=1000, nChain=1)
+    tp = E.setTrueParaRtIrt(Cond, rng=SEED)
+    D = E.setDataRtIrtNull(Cond, tp, rng=SEED)
+    rec("C4: GibbsRtIrtNull 100k x 40 one chain", "RtIrtNull", 100_000, 40, 0, 1000, 1, D,
+        dict(theta=rng.standard_normal(100_000), zeta=rng.standard_normal(100_000)), 3)
+    return out
+
+
+def c4_chains(E, rank, world, local, n_chains=8, n_iter=1000):
+    """BASELINE configs[3]: 8 independent GibbsRtIrtNull chains at 100k x 40 dealt over the ranks (chain c on rank c mod world, the
+    chains of a rank one after the other), no collective while sampling; chains x sweeps per second (max over ranks of the
+    device time) and the cross-chain split R-hat of the item parameters from the second half of the n_iter sweeps."""
+    import torch
+    from erirt_b200 import distributed as D
+    from erirt_b200.diagnostics import ess_rhat
+    N, J = 100_000, 40
+    Cond = E.setCond(nSubj=N, nItem=J, nFeat=0, nIter=n_iter, nChain=1)
+    tp = E.setTrueParaRtIrt(Cond, rng=SEED)
+    Data = E.setDataRtIrtNull(Cond, tp, rng=SEED)
+    mine = D.chain_assignment(n_chains, world, rank)
+    ms_total, traces = 0.0, {}
+    for c in mine:
+        rng = np.random.default_rng(SEED + 1000 + c)
+        eng = E.Engine("RtIrtNull", N, J, 0, n_iter=n_iter, n_chain=1, n_burnin=n_iter // 2, dtype="f32", seed=SEED, chain=c,
+                       person_trace=False, device=local, use_graph=True)
+        eng.set_data(Data.Y, Data.logT, None)
+        eng.set_state(theta=rng.standard_normal(N), zeta=rng.standard_normal(N))
+        eng.sample(n_iter)
+        ms_total += eng.stats()["last_sample_ms"]
+        traces[c] = np.concatenate([eng.get_trace("ra", N, 2 * J)[n_iter // 2:, :, 0], eng.get_trace("rt", N, 2 * J)[n_iter // 2:, :, 0]], axis=1)
+        eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        parts = [None] * world
+        dist.all_gather_object(parts, traces)
+        traces = {c: v for part in parts for c, v in part.items()}
+    if rank != 0:
+        return None
+    arr = np.stack([traces[c] for c in range(n_chains)], axis=2)  # [iter, param, chain]
+    rhat = [ess_rhat(arr[:, p, :])[1] for p in range(arr.shape[1])]
+    return {"workload": f"{n_chains} independent GibbsRtIrtNull chains 100k x 40, {n_iter} sweeps each, chain c on rank c mod {world}",
+            "value": n_chains * n_iter / (ms_total / 1e3), "unit": "chain-sweeps/s", "chains": n_chains, "sweeps_per_chain": n_iter,
+            "seconds_max_over_ranks": ms_total / 1e3, "rhat_max": float(np.nanmax(rhat)), "rhat_median": float(np.nanmedian(rhat)),
+            "rhat_params": "a, b, lambda, sigma2 (160 columns), split R-hat over the 8 chains, second half of each chain"}
 
 
 def main():
@@ -276,7 +476,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-y", choices=["u8", "f64"], default="u8", help="host type of Y in the end-to-end pass (Julia Matrix{Bool} or Float64)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--short", action="store_true", help="profiling run: timed sweeps only, no e2e / cpu / roofline passes")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (f64, crossqr, configs, c4_chains, ess)")
+    ap.add_argument("--short", action="store_true", help="profiling run: timed sweeps only, no e2e / cpu / roofline / sub-record passes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -295,21 +496,20 @@ def main():
     assert N_BLOCKS % world == 0, "GPU count must divide 8"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    shard = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        shard, _ = D.make_shard(N_SUBJ, nccl=False)
+    extras = not (args.short or args.no_extras)
 
     tp = true_params()
     dY, dT, dX, offset, n_local = gen_shard_torch(tp, rank, world, dev)
     theta0, zeta0, beta0 = init_state(offset, n_local)
     K, W = args.steps, args.warmup
-    n_iter = K + W + 8
+    qw = N_FEAT + 2 + 4
 
-    def make_engine(time_kernels=False, use_graph=True):
-        eng = E.Engine("RtIrtQuantile", n_local, N_ITEM, N_FEAT, n_iter=n_iter, n_chain=1, n_burnin=0, q_rt=Q_RT,
-                       cov2one=False, dtype=args.dtype, seed=SEED, person_trace=False, device=local, use_graph=use_graph,
+    def make_engine(time_kernels=False, use_graph=True, dtype=None, n_iter=None):
+        eng = E.Engine("RtIrtQuantile", n_local, N_ITEM, N_FEAT, n_iter=n_iter or (K + W + 8), n_chain=1, n_burnin=0, q_rt=Q_RT,
+                       cov2one=False, dtype=dtype or args.dtype, seed=SEED, person_trace=False, device=local, use_graph=use_graph,
                        n_subj_total=N_SUBJ, subj_offset=offset, time_kernels=time_kernels)
         if world > 1:
             peer = os.environ.get("ERIRT_EXCHANGE", "peer") == "peer"
@@ -339,28 +539,62 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident throughput ("value") ----------------
-    eng = make_engine()
+    # ---------------- device-resident throughput ("value"), the long run, the ESS chain ----------------
+    cap = max(ESS_SWEEPS, 2 * (K + W)) + 4096 if extras else K + W + 8
+    eng = make_engine(n_iter=cap)
     eng.set_data_device(dY.data_ptr(), n_local, dT.data_ptr(), n_local, dX.data_ptr(), n_local)
     eng.set_state(theta=theta0, zeta=zeta0, beta=beta0)
     eng.sample(W)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
+    eng.sample(1)  # throw-away sweep: its exchange is the device-side rendezvous of the ranks (the host barrier leaves them up to ~1 ms apart)
     eng.sample(K)
+    ms = max_over_ranks(eng.stats()["last_sample_ms"])
+    done = W + 1 + K
+    long_run = None
+    if not args.short:
+        n_long = int(min(cap - done - 8, max(K, math.ceil(LONG_RUN_SECONDS * 1e3 / (ms / K)))))
+        if world > 1:
+            eng.sample(1)
+            done += 1
+        eng.sample(n_long)
+        ms_long = max_over_ranks(eng.stats()["last_sample_ms"])
+        done += n_long
+        long_run = {"sweeps": n_long, "ms_per_step": ms_long / n_long, "value": n_long / (ms_long / 1e3), "unit": UNIT,
+                    "note": f"the same chain continued for >= {LONG_RUN_SECONDS} s of device time, CUDA events, max over ranks"}
     barrier()
     clk = clocks.stop()
-    ms = max_over_ranks(eng.stats()["last_sample_ms"])
     st = eng.stats()
     value = K / (ms / 1000.0)
-    qw = N_FEAT + 2 + 4
-    ess_min = ess_med = None
-    if rank == 0 and not args.short:
-        try:
-            ess_min, ess_med = ess_per_sweep(eng, W, K, qw)
-        except Exception:
-            pass
+    ll_first = [float(v) for v in eng.get_trace("logLike")[:5, 0, 0]] if rank == 0 else None
+    ess = None
+    if extras:
+        if done < ESS_SWEEPS:
+            eng.sample(ESS_SWEEPS - done)
+            done = ESS_SWEEPS
+        if rank == 0:
+            try:
+                half = done // 2
+                e_min, e_med, n_par = bulk_ess(item_struct_traces(eng, half, done - half, qw))
+                ess = {"chain_sweeps": done, "used_sweeps": done - half, "params": n_par, "min": e_min, "median": e_med,
+                       "per_sweep_min": e_min / (done - half), "per_sweep_median": e_med / (done - half),
+                       "per_sec_min": e_min / (done - half) * value, "per_sec_median": e_med / (done - half) * value,
+                       "estimator": "rank-normalised split bulk ESS (Vehtari et al. 2021) of a, b, lambda, sigma2, beta, Sigma_p over the second half of the chain"}
+            except Exception as ex:
+                ess = {"error": str(ex)}
     close_engine(eng)
+
+    # ---------------- sharding check in f64: logLike of sweeps 1..5 of the same chain at every GPU count ----------------
+    ll64 = None
+    if extras:
+        e64 = make_engine(dtype="f64", n_iter=8)
+        e64.set_data_device(dY.data_ptr(), n_local, dT.data_ptr(), n_local, dX.data_ptr(), n_local)
+        e64.set_state(theta=theta0, zeta=zeta0, beta=beta0)
+        e64.sample(5)
+        if rank == 0:
+            ll64 = [float(v) for v in e64.get_trace("logLike")[:5, 0, 0]]
+        close_engine(e64)
 
     # ---------------- roofline of the person kernel (plain launches bracketed by CUDA events) ----------------
     roofline = None
@@ -374,13 +608,22 @@ def main():
         engk.sample(kk)
         sk = engk.stats()
         pk_ms = max_over_ranks(sk["person_kernel_ms"])
-        peak, which = measured_peak()
-        bytes_launch = sk["bytes_per_sweep"]
-        achieved = bytes_launch / (pk_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "person_sweep_fast_kernel" if args.dtype == "f32" else "person_sweep_kernel", "achieved": achieved, "peak": peak, "peak_source": which,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": bytes_launch,
-                    "kernel_ms": pk_ms, "launches_timed": kk, "pg_deferred_frac": sk["pg_deferred_frac"]}
+        roofline = roofline_record(sk, pk_ms, "person_sweep_fast_kernel" if args.dtype == "f32" else "person_sweep_kernel", kk)
+        # dram bytes of one launch come from the committed ncu --set full capture at N = 1 (profiles/person_kernel_traffic.json): quoted
+        # for the single-GPU line only, where a launch processes the same 1M x 100 cells as the capture
+        roofline["traffic"] = ncu_traffic() if world == 1 else None
+        roofline["traffic_source"] = "profiles/person_kernel_traffic.json (ncu --set full of this kernel at N=1; not re-measured by this run)" if world == 1 else None
+        roofline["pg_deferred_frac"] = sk["pg_deferred_frac"]
+        roofline["ideal_kernel_ms_at_this_n"] = None
         close_engine(engk)
+
+    # ---------------- sub-records that only need one GPU ----------------
+    f64_rec = crossqr_rec = configs_rec = None
+    if extras and world == 1:
+        try:
+            f64_rec = sub_f64(E, dY, dT, dX, n_local, theta0, zeta0, beta0, local)
+        except Exception as ex:
+            f64_rec = {"error": str(ex)}
 
     # ---------------- end to end through the C ABI with host buffers ("e2e") ----------------
     e2e = None
@@ -424,6 +667,11 @@ def main():
                "note": "erirt_create + " + ("erirt_set_data_y8 (pinned host: Y as Matrix{Bool} bytes, logT/X f64" if y8 else "erirt_set_data (pinned host f64")
                                      + "; chunked H2D + ingest) + erirt_set_state + K sweeps + "
                                      "erirt_get_trace/erirt_get_moments (D2H into pinned buffers) + erirt_destroy; bytes are totals of the call divided by K"}
+        del hY, hT, hX
+    else:
+        del dY, dT, dX
+        torch.cuda.empty_cache()
+        hMn = np.empty((3, 2, n_local))
 
     # ---------------- the same call with the N x J data generated on the device (informational: no N x J upload) ----------------
     e2e_gen = None
@@ -450,31 +698,52 @@ def main():
                    "note": "erirt_create + erirt_generate_data (person-level theta, zeta, X from the host; responses and log-times generated "
                            "on the device) + erirt_set_state + K sweeps + read-back + erirt_destroy"}
 
+    if extras and world == 1:
+        try:
+            crossqr_rec = sub_crossqr(E, local)
+        except Exception as ex:
+            crossqr_rec = {"error": str(ex)}
+        try:
+            configs_rec = sub_configs(E, local)
+        except Exception as ex:
+            configs_rec = {"error": str(ex)}
+    chains_rec = None
+    if extras:
+        try:
+            chains_rec = c4_chains(E, rank, world, local)
+        except Exception as ex:
+            chains_rec = {"error": str(ex)}
+
     # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and not args.short:
         try:
-            n_sample = 20000
+            n_sample = 40000
             v, dtc = cpu_oracle_rate(tp, n_sample, 8, 1, warm=1)
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"oracle (C restatement of Draw.pl.jl; the Julia reference cannot run here) on 1 core of {os.cpu_count()}, "
                              f"first {n_sample} persons x {N_ITEM} items, 8 sweeps in {dtc:.1f} s, scaled by {n_sample}/{N_SUBJ}"}
+            if ess and "per_sweep_min" in ess:
+                cpu["ess_per_sec_min"] = ess["per_sweep_min"] * v
+                cpu["ess_per_sec_median"] = ess["per_sweep_median"] * v
+                cpu["ess_note"] = "ESS per sweep is a property of the scan (measured once, on the GPU chain) x CPU sweeps/s"
         except Exception as ex:  # the bench line must still be printed
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {ex}"}
 
     if rank == 0:
+        launches = 2 * K
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": (f"persons sharded over {world} GPUs, item statistics all-reduced per sweep by "
-                                           + ("a one-shot exchange over NVLink peer memory fused into the global draw kernel"
-                                              if os.environ.get("ERIRT_EXCHANGE", "peer") == "peer" else "ncclAllReduce")) if world > 1 else "single GPU",
-                           "l2": "inputs (1.3 GB/sweep) larger than the 126 MB L2", "cuda_graph": True,
-                           "loglik_and_moments": "on"},
-                "clocks": clk, "gpu_launches": 2 * K, "e2e": e2e, "e2e_device_generated_data": e2e_gen, "roofline": roofline, "cpu_baseline": cpu,
-                "ess_per_sweep": {"min": ess_min, "median": ess_med, "estimator": "rank-normalised bulk ESS over the K timed sweeps (a, b, lambda, sigma2, beta, Sigma)"},
-                "ess_per_sec": {"min": None if ess_min is None else ess_min * value, "median": None if ess_med is None else ess_med * value},
+                "dtype": args.dtype, "data": "synthetic", "config": make_config(world),
+                "clocks": clk, "gpu_launches": launches, "long_run": long_run, "e2e": e2e, "e2e_device_generated_data": e2e_gen,
+                "roofline": roofline, "cpu_baseline": cpu, "ess": ess,
+                "sharding_check": {"loglike_sweeps_1_5_" + args.dtype: ll_first, "loglike_sweeps_1_5_f64": ll64,
+                                   "note": "the same chain (seed, data, initial state) at every GPU count: Philox counters use global person ids, "
+                                           "so the values agree across N up to the summation order of the statistics"},
+                "f64": f64_rec, "crossqr": crossqr_rec, "configs": configs_rec, "c4_chains": chains_rec,
                 "bytes_per_sweep": st["bytes_per_sweep"] * world}
+        if roofline is not None:
+            roofline["ideal_kernel_ms_at_this_n"] = ncu_traffic("kernel_ms_n1") / world if ncu_traffic("kernel_ms_n1") else None
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -1009,6 +1009,7 @@ static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   A.params = h->dParams;
   A.stats = h->dStats;
   A.sweep_ctr = h->dSweep;
+  A.status = h->dStatus;
   A.n_local = h->cfg.n_subj;
   A.n_pad = h->n_pad;
   A.person_offset = (uint32_t)h->cfg.subj_offset;
@@ -1079,6 +1080,8 @@ static int launch_person(erirt_handle* h, int stage) {
   return 0;
 }
 static int launch_global(erirt_handle* h, int stage) {
+  if (h->world > 1 && !h->peer_ready && !h->comm)
+    return fail(ERIRT_E_STATE, "sharded chain (world %d) without an exchange: the peer buffers were detached and there is no NCCL communicator", h->world);
   if (h->comm && !h->peer_ready)  // fallback: the exchange is otherwise fused into the kernel below
     NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
   GlobalArgs G = make_global_args(h, stage);
@@ -1185,6 +1188,7 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
   h->sweeps_done += n_sweeps;
   int status = 0;
   CU(cudaMemcpy(&status, h->dStatus, sizeof(int), cudaMemcpyDeviceToHost));
+  if (status <= -1000) return fail(ERIRT_E_NCCL, "peer exchange timed out waiting for rank %d (a GPU of the sharded chain is gone); the chain is unusable", -1000 - status);
   if (status != 0) return fail(ERIRT_E_NUMERIC, "a posterior covariance was not positive definite at sweep %d (PosDefException in the reference)", status);
   return 0;
 }
@@ -1349,6 +1353,9 @@ struct CkHeader {
   int64_t n_subj, n_subj_total, subj_offset, sweeps_done, payload_bytes;
   uint64_t seed;
   uint32_t chain, pad;
+  // sampler flags: a checkpoint continues the SAME chain only under the same keyword arguments
+  int32_t intercept, itemtype_1pl, cov2one, compat, nu_cell_moments, pad2;
+  double q_rt;
 };
 struct CkSeg { void* p; size_t bytes; };
 static std::vector<CkSeg> ck_segments(erirt_handle* h) {
@@ -1374,12 +1381,14 @@ static std::vector<CkSeg> ck_segments(erirt_handle* h) {
 }
 static CkHeader ck_header(erirt_handle* h) {
   CkHeader H{};
-  memcpy(H.magic, "ERIRTCK1", 8);
+  memcpy(H.magic, "ERIRTCK2", 8);
   const erirt_config& c = h->cfg;
   H.abi = ERIRT_ABI_VERSION; H.model = c.model; H.dtype = c.dtype; H.n_item = c.n_item; H.n_feat = c.n_feat; H.n_iter = c.n_iter;
   H.n_chain = c.n_chain; H.n_burnin = c.n_burnin; H.person_trace = c.person_trace ? 1 : 0; H.prologue_done = h->prologue_done ? 1 : 0;
   H.n_subj = c.n_subj; H.n_subj_total = c.n_subj_total; H.subj_offset = c.subj_offset; H.sweeps_done = h->sweeps_done;
   H.seed = c.seed; H.chain = c.chain;
+  H.intercept = c.intercept; H.itemtype_1pl = c.itemtype_1pl; H.cov2one = c.cov2one; H.compat = c.compat;
+  H.nu_cell_moments = c.nu_cell_moments ? 1 : 0; H.q_rt = c.q_rt;
   for (const CkSeg& sg : ck_segments(h)) H.payload_bytes += (int64_t)sg.bytes;
   return H;
 }
@@ -1408,14 +1417,15 @@ extern "C" int erirt_checkpoint_load(erirt_handle* h, const void* buf, int64_t s
   if (size < (int64_t)sizeof(CkHeader)) return fail(ERIRT_E_ARG, "checkpoint shorter than its header");
   CkHeader H;
   memcpy(&H, buf, sizeof(H));
-  if (memcmp(H.magic, "ERIRTCK1", 8) != 0) return fail(ERIRT_E_ARG, "not an erirt checkpoint (bad magic)");
+  if (memcmp(H.magic, "ERIRTCK2", 8) != 0) return fail(ERIRT_E_ARG, "not an erirt checkpoint (bad magic)");
   CkHeader W = ck_header(h);
   // everything but the progress fields must match the handle: a checkpoint continues THE SAME chain on the same shard
   W.sweeps_done = H.sweeps_done; W.prologue_done = H.prologue_done;
   if (memcmp(&H, &W, sizeof(H)) != 0)
-    return fail(ERIRT_E_ARG, "checkpoint belongs to another configuration (model %d dtype %d %lld x %d, F=%d, nIter=%d nChain=%d, shard %lld+%lld, seed %llu chain %u)",
+    return fail(ERIRT_E_ARG, "checkpoint belongs to another configuration (model %d dtype %d %lld x %d, F=%d, nIter=%d nChain=%d, shard %lld+%lld, seed %llu chain %u, "
+                "intercept %d 1pl %d cov2one %d compat %d qRt %g)",
                 H.model, H.dtype, (long long)H.n_subj, H.n_item, H.n_feat, H.n_iter, H.n_chain, (long long)H.subj_offset, (long long)H.n_subj,
-                (unsigned long long)H.seed, H.chain);
+                (unsigned long long)H.seed, H.chain, H.intercept, H.itemtype_1pl, H.cov2one, H.compat, H.q_rt);
   if (size < (int64_t)sizeof(CkHeader) + H.payload_bytes) return fail(ERIRT_E_ARG, "checkpoint truncated: %lld of %lld bytes", (long long)size, (long long)(sizeof(CkHeader) + H.payload_bytes));
   if (H.sweeps_done < 0 || H.sweeps_done > h->cap) return fail(ERIRT_E_ARG, "checkpoint holds %lld sweeps, capacity is %d", (long long)H.sweeps_done, h->cap);
   CU(cudaSetDevice(h->cfg.device));
@@ -1509,8 +1519,13 @@ extern "C" int erirt_peer_detach(erirt_handle* h) {
   CU(cudaStreamSynchronize(h->stream));
   for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
   h->peer_opened.clear();
-  h->peer_ready = false;  // later sweeps fall back to ncclAllReduce
+  // Later sweeps go through ncclAllReduce when the chain has an NCCL communicator; a chain created with
+  // erirt_comm_init(..., NULL) has no exchange left and launch_global refuses to run (ERIRT_E_STATE) instead of drawing
+  // the item / structural parameters from the local shard's statistics only.
+  h->peer_ready = false;
+  // both captured graphs carry GlobalArgs.peer_bufs of the mappings just closed
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  if (h->graph_multi) { cudaGraphExecDestroy(h->graph_multi); h->graph_multi = nullptr; h->graph_multi_sweeps = 0; }
   return 0;
 }
 

@@ -190,6 +190,7 @@ __device__ inline void peer_allreduce_sum(double* const* peer_bufs, uint32_t* xs
 // the same exchange on its own, for the one-time ingest constants
 __global__ void __launch_bounds__(512) peer_allreduce_kernel(double* const* peer_bufs, uint32_t* xseq, int world, int rank, int S,
                                                              double* buf, int count, int* status) {
+  if (*status <= -1000) return;
   peer_allreduce_sum(peer_bufs, xseq, world, rank, S, buf, count, buf, status, (int)threadIdx.x, (int)blockDim.x);
 }
 
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   const int J = L.J, F = L.F, Dg = L.Dg, tid = threadIdx.x;
   const int model = A.model;
   const bool has_rt = model != M_MLIRT;
+  if (*A.status <= -1000) return;   // a peer timed out in an earlier exchange: no draws from partial sums, no further 10 s waits
   const uint32_t k = *A.sweep_ctr;  // person launch P(k) just finished
   const uint32_t s = k + 1;         // sweep whose parameters are drawn now
   const double N = (double)A.n_total;
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   const int Jp = L.Jp;
   if (A.peer_bufs) {
     peer_allreduce_sum(A.peer_bufs, A.xseq, A.world, A.rank, A.xstride, A.stats, L.s_count, st, A.status, tid, G_THREADS);
+    if (*reinterpret_cast<volatile int*>(A.status) <= -1000) return;  // timed out in this exchange (uniform: written before the CTA barrier)
   } else {
     for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats[t];
   }

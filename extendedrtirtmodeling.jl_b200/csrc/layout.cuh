@@ -97,6 +97,7 @@ struct PersonArgs {
   const double* params;
   double* stats;
   const uint32_t* sweep_ctr;  // k: this launch draws theta_k, zeta_k (k >= 1) and omega_{k+1}, nu_{k+1}
+  const int* status;          // sticky error flag of the chain; <= -1000: a peer of the sharded chain timed out, every launch returns at once
   int64_t n_local, n_pad;
   uint32_t person_offset;
   int n_tiles;

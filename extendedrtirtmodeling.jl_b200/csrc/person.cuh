@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);         // fast queue [0] count [1] head, exact queue [2] count [3] head
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  if (*A.status <= -1000) return;  // a peer of the sharded chain timed out: the chain is dead
   const uint32_t k = *A.sweep_ctr;
   const bool do_draws = k >= 1 || (FAM == 1 && A.stage == 3);
   const double* par = A.params;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const R iv0 = rdiv(R(1), var0);
           const R parV = rdiv(R(1), iv0 + d[0]);
           const R parM = parV * (mu0 * iv0 + d[2] + d[1]);
-          th = parM + rsqrt_of(parV) * zn_theta;
+          th = parM + sqrt_of(parV) * zn_theta;
         }
         R mu_z = R(0), var_z = R(1);
         if (has_rt) {
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const R num = cqr ? d[3] - th * d[1] + k1 * sum_is2 : (cross ? d[3] - th * sum_rho_is2 : d[3]);
           const R parV = rdiv(R(1), ivz + prec);
           const R parM = parV * (mu_z * ivz + num);
-          ze = parM + rsqrt_of(parV) * zn_zeta;
+          ze = parM + sqrt_of(parV) * zn_zeta;
         }
         if (pvalid && stage == 1) A.theta[pi] = th;  // K_a: theta_k only; everything else happens in K_b
         if (pvalid && stage != 1) {
@@ -447,9 +448,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
       if (qr && !eval) {
         const R xb = fma(th, s_beta[F + 1], xb1);
-        const R isc = rdiv(R(1), rsqrt_of(S22 * k2));
+        const R isc = rdiv(R(1), sqrt_of(S22 * k2));
         const R parA = fabs(ze - xb) * isc;
-        const R parB = rsqrt_of(R(2) * k2 + k1 * k1) * isc;
+        const R parB = sqrt_of(R(2) * k2 + k1 * k1) * isc;
         R mu = rdiv(parB, parA);
         if (!(mu >= R(1e-10))) mu = R(1e-10);
         const R ig = ig_msh<R>(mu, parB * parB, zn_nu, un_nu);
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       const bool cvalid = (row0 + p) < A.n_local;
       const uint32_t cgid = A.person_offset + (uint32_t)(row0 + p);
       const R thc = s_u[p * Dgp + F + 1], zec = s_u[p * Dgp + F + 2];
-      const R cB = rsqrt_of(R(2) * k2 + k1 * k1);
+      const R cB = sqrt_of(R(2) * k2 + k1 * k1);
       const bool nu_acc = A.nu_mom != nullptr && post_burnin && !eval;  // Post.mean.nu of GibbsRtIrtCross.pl.jl:310 as a running sum
       R llrt = R(0);
       for (int kk = 0; kk < nk; ++kk) {

@@ -21,7 +21,11 @@ static_assert(FMD_ABMAX < MD_COUNT, "misc block too small");
 
 constexpr int TAB_PITCH = 20;  // floats per item group in the response tables: groups g and g+4 fall on disjoint banks
 constexpr int FAST_FLUSH_TILES = 16;  // item statistics live in f32 registers and are folded into the f64 accumulators every 16 tiles
-constexpr int QSTD = 768;      // work-queue split: [0, QSTD) certainly-rejected cells, [QSTD, QCAP) undecided / Method-B cells
+// Work queues of the cells that leave the fast path are WARP-LOCAL: a warp serves its own persons from the row sums to the
+// drain, so nothing between the tile load and the transposed statistics pass needs a CTA barrier.  Region of a warp:
+// QW entries, [0, QSTDW) certainly-rejected cells (standard), [QSTDW, QW) undecided / Method-B cells (special).
+constexpr int QW = QCAP / (CTA_THREADS / 32);
+constexpr int QSTDW = (QW * 3) / 4;
 
 // Phase timers of the diagnostic build (tools/make_tick_build.py, -DERIRT_TICKS): clock64() per warp at the phase boundaries.
 #ifdef ERIRT_TICKS
@@ -66,9 +70,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   double* s_miscd = reinterpret_cast<double*>(smem + A.S.off_misc);  // MD_COUNT + SC_COUNT doubles
   double* s_scal = s_miscd + MD_COUNT;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scal + SC_COUNT);
-  uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);  // [0]: packed counts (low 16 bits standard, high 16 bits special)
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  if (*A.status <= -1000) return;  // a peer of the sharded chain timed out: the chain is dead, do not spin through queued sweeps
   const uint32_t k = *A.sweep_ctr;
   const bool do_draws = k >= 1;
   const double* par = A.params;
@@ -116,7 +120,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       s_miscd[FMD_AMAX] = amax;
       s_miscd[FMD_ABMAX] = abmax;
       mbar_init(s_bar, 1);
-      s_qctl[0] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         zn_theta = normal2f(w.x, w.y);
         zn_zeta = normal2f(w.z, w.w);
       }
-      if (qr) {
+      if (qr && TPP == 1) {
         const uint4 w = philox(A.sched, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
         zn_nu = normal2f(w.x, w.y);
         un_nu = u01f(w.z);
@@ -274,6 +277,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           }
         }
       }
+    }
+    if (qr && TPP >= 2) {  // the nu site's block is evaluated by the person's SECOND lane (idle otherwise) and handed to the first
+      if (q == 1) {
+        const uint4 w = philox(A.sched, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+        zn_nu = normal2f(w.x, w.y);
+        un_nu = u01f(w.z);
+      }
+      const R zn_o = __shfl_down_sync(0xffffffffu, zn_nu, 1), un_o = __shfl_down_sync(0xffffffffu, un_nu, 1);
+      if (lead) { zn_nu = zn_o; un_nu = un_o; }
     }
     PF_TICK(0);  // TMA issue, person part 1
     mbar_wait(s_bar, parity);
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const R iv0 = rdiv(R(1), var0);
           const R parV = rdiv(R(1), iv0 + d.x);
           const R parM = parV * (mu0 * iv0 + d.z + d.y);
-          th = parM + rsqrt_of(parV) * zn_theta;
+          th = parM + sqrt_of(parV) * zn_theta;
         }
         R mu_z = R(0), var_z = R(1);
         if (has_rt) {
@@ -348,7 +360,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const R ivz = rdiv(R(1), var_z);
           const R parV = rdiv(R(1), ivz + sum_is2);
           const R parM = parV * (mu_z * ivz + d.w);
-          ze = parM + rsqrt_of(parV) * zn_zeta;
+          ze = parM + sqrt_of(parV) * zn_zeta;
         }
         if (pvalid) {
           const R LOG2PI = R(1.8378770664093454835606594728112);
@@ -394,9 +406,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       // ---- nu_{k+1} (LatentQr), Draw.pl.jl:325-343 ----
       if (qr) {
         const R xb = fmaf(th, s_beta[F + 1], xb1);
-        const R isc = rdiv(R(1), rsqrt_of(S22 * k2));
+        const R isc = rdiv(R(1), sqrt_of(S22 * k2));
         const R parA = fabsf(ze - xb) * isc;
-        const R parB = rsqrt_of(R(2) * k2 + k1 * k1) * isc;
+        const R parB = sqrt_of(R(2) * k2 + k1 * k1) * isc;
         R mu = rdiv(parB, parA);
         if (!(mu >= R(1e-10))) mu = R(1e-10);
         const R ig = ig_msh<R>(mu, parB * parB, zn_nu, un_nu);
@@ -494,9 +506,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       }
     }
     PF_TICK(6);  // PG main pass
+    uint32_t wq_counts;  // packed entry counts of this warp's queues (low 16 bits standard, high 16 bits special)
+    uint32_t* const wq = s_queue + (tid >> 5) * QW;
     {
-      // ---- hand the cells that left the fast path to the tile's work queues: one shared-memory atomic per WARP reserves the
-      //      slots of all its lanes in both queues (packed counts, warp prefix sum), then every lane writes its entries ----
+      // ---- hand the cells that left the fast path to the WARP's work queues: a warp prefix sum over the packed counts gives every
+      //      lane its slots in both queues (no atomic, no CTA barrier), then every lane writes its entries ----
       const u64 smask = dmask & rmask, umask = dmask & ~rmask;  // standard (certainly rejected) / special (undecided)
       const uint32_t n_std = (uint32_t)__popcll(smask), n_spc = (uint32_t)__popcll(umask);
       acc_defer += n_std + n_spc;
@@ -506,12 +520,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
         if ((tid & 31) >= o) pre += t;
       }
-      const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
-      uint32_t wbase = 0;
-      if ((tid & 31) == 31 && wtotal) wbase = atomicAdd(&s_qctl[0], wtotal);
-      wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      uint32_t slot_s = (wbase & 0xffffu) + (pre & 0xffffu) - n_std;
-      uint32_t slot_u = (wbase >> 16) + (pre >> 16) - n_spc;
+      wq_counts = __shfl_sync(0xffffffffu, pre, 31);
+      uint32_t slot_s = (pre & 0xffffu) - n_std;
+      uint32_t slot_u = (pre >> 16) - n_spc;
       // bit 4*kk+e of a mask -> item index: the thread owns 32/TPP consecutive items in every block of 32
       constexpr int BPB = 32 / TPP;
       auto push = [&](uint32_t m, int bit0, uint32_t& slot, const uint32_t cap, const uint32_t qbase, const uint32_t flag) {
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const int bit = bit0 + __ffs((int)m) - 1;
           m &= m - 1u;
           const int j = ((bit / BPB) << 5) + q * BPB + (bit % BPB);
-          if (slot < cap) s_queue[qbase + slot] = ((uint32_t)p << 16) | (uint32_t)j | flag;
+          if (slot < cap) wq[qbase + slot] = ((uint32_t)p << 16) | (uint32_t)j | flag;
           else {  // queue overflow: finish the cell here
             const float z = fmaf(s_par[PAR_A * Jp + j], thp, s_par[PAR_AB * Jp + j]);
             my_om[j] = pg_resolve_f32(A.key, gid, k + 1, j, z, flag != 0u);
@@ -527,23 +538,25 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           ++slot;
         }
       };
-      push((uint32_t)smask, 0, slot_s, (uint32_t)QSTD, 0u, 0u);
-      push((uint32_t)(smask >> 32), 32, slot_s, (uint32_t)QSTD, 0u, 0u);
-      push((uint32_t)umask, 0, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
-      push((uint32_t)(umask >> 32), 32, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
+      if (wq_counts) {
+        push((uint32_t)smask, 0, slot_s, (uint32_t)QSTDW, 0u, 0u);
+        push((uint32_t)(smask >> 32), 32, slot_s, (uint32_t)QSTDW, 0u, 0u);
+        push((uint32_t)umask, 0, slot_u, (uint32_t)(QW - QSTDW), (uint32_t)QSTDW, 0x80000000u);
+        push((uint32_t)(umask >> 32), 32, slot_u, (uint32_t)(QW - QSTDW), (uint32_t)QSTDW, 0x80000000u);
+      }
     }
     PF_TICK(7);  // queue push
-    __syncthreads();
-    PF_TICK(8);  // barrier
+    __syncwarp();  // the warp's queue entries and the theta_k of its persons (s_u) are visible to its lanes
+    PF_TICK(8);
 
-    {
-      // ---- drain, one phase: standard entries (Method-A retry rounds, two cells in flight per thread) are dealt from thread 0
-      //      upwards, special entries (undecided attempt 0: replay it with the a_1 term) from the last thread downwards ----
-      const uint32_t qc = s_qctl[0];
-      const uint32_t qn = min(qc & 0xffffu, (uint32_t)QSTD), qu = min(qc >> 16, (uint32_t)(QCAP - QSTD));
-      for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
-        const bool has2 = idx + CTA_THREADS < qn;
-        const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
+    if (wq_counts) {
+      // ---- drain, one phase per warp: standard entries (Method-A retry rounds, two cells in flight per lane) are dealt from lane 0
+      //      upwards, special entries (undecided attempt 0: replay it with the a_1 term) from the last lane downwards ----
+      const int lane = tid & 31;
+      const uint32_t qn = min(wq_counts & 0xffffu, (uint32_t)QSTDW), qu = min(wq_counts >> 16, (uint32_t)(QW - QSTDW));
+      for (uint32_t idx = lane; idx < qn; idx += 64) {
+        const bool has2 = idx + 32 < qn;
+        const uint32_t e1 = wq[idx], e2 = wq[has2 ? idx + 32 : idx];
         const int j1 = (int)(e1 & 0xffffu), p1 = (int)(e1 >> 16), j2 = (int)(e2 & 0xffffu), p2 = (int)(e2 >> 16);
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
         const float z2 = fmaf(s_par[PAR_A * Jp + j2], s_u[p2 * Dgp + F + 1], s_par[PAR_AB * Jp + j2]);
@@ -566,16 +579,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         s_om[p1 * Jp + j1] = om1;
         if (has2) s_om[p2 * Jp + j2] = om2;
       }
-      for (uint32_t idx = (uint32_t)(CTA_THREADS - 1 - tid); idx < qu; idx += CTA_THREADS) {
-        const uint32_t e1 = s_queue[QSTD + idx];
+      for (uint32_t idx = (uint32_t)(31 - lane); idx < qu; idx += 32) {
+        const uint32_t e1 = wq[QSTDW + idx];
         const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
         s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, true);
       }
     }
     PF_TICK(9);  // drain
-    __syncthreads();
-    if (tid == 0) s_qctl[0] = 0;  // next written by the push of the next tile, two barriers from here
+    __syncthreads();  // the whole tile (omega_{k+1}, u rows) is final: the transposed passes below read across warps
     PF_TICK(10);  // barrier
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
@@ -645,10 +657,23 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   flush_item_stats();
 
   // ---- flush CTA accumulators ----
-  atomicAdd(&s_scal[SC_LL_BERN], acc_ll_bern);
-  if (q == 0) atomicAdd(&s_scal[SC_LL_STRUCT], acc_ll_struct);
-  atomicAdd(&s_scal[SC_PG_DEFER], (double)acc_defer);
-  if (q == 0) atomicAdd(&s_scal[SC_PG_CELLS], (double)acc_cells);
+  {  // warp totals by shuffle, then one shared-memory atomic per warp and quantity (f64 shared atomics are CAS loops)
+    double v0 = acc_ll_bern, v1 = acc_ll_struct;
+    uint32_t c0 = acc_defer, c1 = acc_cells;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_scal[SC_LL_BERN], v0);
+      atomicAdd(&s_scal[SC_LL_STRUCT], v1);
+      atomicAdd(&s_scal[SC_PG_DEFER], (double)c0);
+      atomicAdd(&s_scal[SC_PG_CELLS], (double)c1);
+    }
+  }
   __syncthreads();
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) {
     const int j = t % Jp;

@@ -111,10 +111,10 @@ __device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.appro
 // f32 uses the approximate reciprocal / rsqrt (well inside the 1e-5 contract), f64 the IEEE operations
 __device__ __forceinline__ float rdiv(float a, float b) { return a * fast_rcp(b); }
 __device__ __forceinline__ double rdiv(double a, double b) { return a / b; }
-__device__ __forceinline__ float rsqrt_of(float x) { return x * fast_rsqrt(x); }  // sqrt(x), x > 0
+__device__ __forceinline__ float sqrt_of(float x) { return x * fast_rsqrt(x); }  // sqrt(x), x > 0
 __device__ __forceinline__ float rlog(float x) { return 0.6931471805599453f * fast_lg2(x); }
 __device__ __forceinline__ double rlog(double x) { return log(x); }
-__device__ __forceinline__ double rsqrt_of(double x) { return sqrt(x); }
+__device__ __forceinline__ double sqrt_of(double x) { return sqrt(x); }
 
 // Box-Muller cosine branch
 __device__ __forceinline__ double normal2(uint32_t w0, uint32_t w1) {
@@ -210,7 +210,7 @@ __device__ __forceinline__ R ig_msh(R mu, R lam, R z, R u) {
   R y = z * z;
   if (!isfinite(mu)) return rdiv(lam, y);
   R w = mu * y;
-  R x1 = rdiv(R(2) * lam * mu, R(2) * lam + w + rsqrt_of(w * (R(4) * lam + w) + R(1e-30)));
+  R x1 = rdiv(R(2) * lam * mu, R(2) * lam + w + sqrt_of(w * (R(4) * lam + w) + R(1e-30)));
   return (u * (mu + x1) <= mu) ? x1 : rdiv(mu * mu, x1);
 }
 

@@ -127,7 +127,11 @@ int erirt_get_data(erirt_handle* h, double* Y, int64_t ldY, double* logT, int64_
 
 /* Initial / current values of one InputPara field (float64, Julia layout: beta is vec(β) column-major,
  * SIGMA_P is vec(Σp), NU is n_subj (LatentQr) or n_subj x n_item column-major (CrossQr), OMEGA n_subj x n_item).
- * CrossQr draws NU before reading it, so setting it only matters for erirt_loglik_current. */
+ * CrossQr draws NU before reading it, so setting it only matters for erirt_loglik_current.
+ * One-sweep lookahead: the engine pipelines the person draws of sweep n with the item / structural draws of sweep n+1, so
+ * after erirt_sample has run n sweeps erirt_get_state returns theta_n, zeta_n together with a, b, lambda, sigma2, beta,
+ * Sigma_p (rho) of sweep n+1 and the auxiliaries omega_{n+1}, nu_{n+1} (the state the next sweep continues from).  The
+ * parameters of sweep n itself are the last trace row (erirt_get_trace). */
 int erirt_set_state(erirt_handle* h, int32_t field, const double* v, int64_t n);
 int erirt_get_state(erirt_handle* h, int32_t field, double* out, int64_t n);
 
@@ -146,7 +150,8 @@ int64_t erirt_trace_width(erirt_handle* h, int32_t which);
 int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n);
 
 /* getLogLikelihood*(Cond, Data; P) of the state currently held by the handle (every InputPara field as last set
- * with erirt_set_state, or as left by erirt_sample): used for DIC's D-hat at Post.mean,
+ * with erirt_set_state, or as left by erirt_sample -- with the one-sweep lookahead described at erirt_set_state): used for
+ * DIC's D-hat at Post.mean,
  * src/GibbsRtIrt.pl.jl:432-472.  No draw is made and nothing is modified.  CrossQr (getLogLikelihoodRtIrtCrossQr,
  * src/GibbsRtIrtCross.pl.jl:240-258) reads the N x J weights last set with erirt_set_state(ERIRT_NU) or left by erirt_sample. */
 int erirt_loglik_current(erirt_handle* h, double* out);
@@ -156,7 +161,8 @@ int erirt_get_stats(erirt_handle* h, erirt_stats* out);
 /* ---- checkpoint / resume: state, auxiliaries, Philox sweep counter, running moments and traces of the chain ----
  * erirt_checkpoint_save writes erirt_checkpoint_size(h) bytes into the caller's buffer (the caller persists them).
  * erirt_checkpoint_load restores them into a handle created with the SAME erirt_config (model, dimensions, dtype, n_iter,
- * n_chain, n_burnin, person_trace, shard, seed, chain -- checked, ERIRT_E_ARG otherwise) after erirt_set_data; the data is not
+ * n_chain, n_burnin, person_trace, shard, seed, chain, q_rt, intercept, itemtype_1pl, cov2one, compat, nu_cell_moments -- all
+ * checked, ERIRT_E_ARG otherwise) after erirt_set_data; the data is not
  * part of the checkpoint.  The resumed chain continues bit for bit as if it had never stopped.  Sharded chains: every rank
  * saves and loads its own shard. */
 int64_t erirt_checkpoint_size(erirt_handle* h);

@@ -61,6 +61,23 @@ def test_pg_distribution_ks(oracle, z):
     assert p > 1e-3, (d, p)
 
 
+PG_KS_Z = [0.0, 1.5, 3.12, 3.13, 6.0, 12.0, 16.0, 16.5, 20.0]  # both methods, the switch |z| = 3.125, the attempt-0 limit |z| = 16
+
+
+@pytest.mark.parametrize("z", PG_KS_Z)
+def test_pg_distribution_ks_1e6(oracle, z):
+    """The mixed-envelope sampler (attempt 0 always Method A for |z| <= 16, retries by regime; oracle/pg.c) is this repository's own
+    arrangement of the Polson-Scott-Windle sampler, so its law is checked on 1e6 draws per z: KS against PG(1, z) and the mean."""
+    from helpers import ks_uniformity
+    n = 1_000_000
+    w = oracle.pg_grid(np.full((n // 100, 100), z), seed=101, sweep=3).ravel()
+    d, p = ks_uniformity(w, z)
+    assert p > 1e-3, (z, d, p)
+    m = 0.25 if z == 0 else np.tanh(z / 2) / (2 * z)
+    v = 1 / 24 if z == 0 else (np.sinh(z) - z) / (4 * z ** 3 * np.cosh(z / 2) ** 2)
+    assert abs(w.mean() - m) < 4.5 * np.sqrt(v / n)
+
+
 def test_scalar_variates(oracle):
     n = 200_000
     x = oracle.variates("normal", 1.5, 2.0, n)
