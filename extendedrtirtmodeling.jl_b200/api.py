@@ -221,11 +221,27 @@ def _collect(MCMC, eng, person_trace):
     if MCMC.model == "RtIrtCrossQr" and getattr(MCMC, "nu_cell_moments", False):
         mean.nu, sd.nu = eng.get_moments("nu")  # N x J, src/GibbsRtIrtCross.pl.jl:310
     Post.mean, Post.sd = mean, sd
-    # the reference leaves the last state in MCMC.Para
+    # The reference leaves the COMPLETE last state in MCMC.Para, so a second sample!(MCMC) continues the chain.  The engine pipelines
+    # the person draws of sweep n with the item / structural draws of sweep n+1 (erirt_b200.h, erirt_set_state), so the item and
+    # structural fields of state n are the LAST TRACE ROW, not erirt_get_state.
     Para = MCMC.Para
     Para.theta = eng.get_state("theta")
     if MCMC.has_rt:
         Para.zeta = eng.get_state("zeta")
+    last = (C.nIter - 1, slice(None), C.nChain - 1)
+    ra_last, qr_last = Post.ra[last], Post.qr[last]
+    Para.a, Para.b = ra_last[ic:ic + J].copy(), ra_last[ic + J:ic + 2 * J].copy()
+    if MCMC.has_rt:
+        rt_last = Post.rt[last]
+        Para.lambda_, Para.sigma2t = rt_last[ic:ic + J].copy(), rt_last[ic + J:ic + 2 * J].copy()
+    o = 0
+    for name, n in _qr_layout(MCMC):
+        v = qr_last[o:o + n].copy()
+        cur = getattr(Para, name, None)
+        if cur is not None and np.size(cur) == n and np.ndim(cur) > 1:
+            v = v.reshape(np.shape(cur), order="F")  # beta keeps its (nFeat+1) x 2 shape, Sigma_p its 2 x 2
+        setattr(Para, name, v)
+        o += n
 
 
 sample_bang = sample  # `sample!` is not a Python identifier

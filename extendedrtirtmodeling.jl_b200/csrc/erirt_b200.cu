@@ -629,6 +629,11 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   const char* env_occ = getenv("ERIRT_CTAS_PER_SM");
   if (env_occ && atoi(env_occ) > 0 && atoi(env_occ) < occ) occ = atoi(env_occ);
   h->grid = std::min(n_tiles, h->sm_count * occ);
+  // test hook: ERIRT_MAX_GRID caps the persistent grid, so that a small problem gives every CTA many tiles (the cross-tile register
+  // accumulators and their 16-tile fold are otherwise reached only at benchmark size); results do not depend on the grid
+  const char* env_grid = getenv("ERIRT_MAX_GRID");
+  const int max_grid = env_grid && atoi(env_grid) > 0 ? atoi(env_grid) : (1 << 30);
+  h->grid = std::min(h->grid, max_grid);
   {  // the global kernel stages the statistics in dynamic shared memory on top of its ~42 KB of static scratch
     const size_t gsm = (size_t)(h->L.s_count + 2 + (h->L.F + 1) * (h->L.F + 1) + 5 * h->L.Jp) * sizeof(double);
     ce = cudaFuncSetAttribute((const void*)global_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
@@ -638,7 +643,7 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
     int occ_gen = 0;
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gen, person_kernel_for(h, 1), CTA_THREADS, h->S_gen.total);
     if (ce != cudaSuccess || occ_gen < 1) { free_handle(h); return fail(ERIRT_E_CUDA, "generic person kernel does not fit on an SM: %s", cudaGetErrorString(ce)); }
-    h->grid_gen = std::min((int)(h->n_pad / h->S_gen.P), h->sm_count * occ_gen);
+    h->grid_gen = std::min(std::min((int)(h->n_pad / h->S_gen.P), h->sm_count * occ_gen), max_grid);
   }
   tm.mark("create: func attrs, occupancy");
   *out = h;

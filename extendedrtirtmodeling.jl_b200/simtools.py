@@ -90,12 +90,24 @@ def runSimulation(Cond, truePara, Para=("a", "b", "λ", "σ²t"), funcData=simul
     return Run
 
 
+def _drop_intercept(est, n_true):
+    """vec(β) is column-major over an (nFeat+1) x ncol matrix (ncol = 2 for GibbsRtIrt); the reference's comparePara drops row 1 of
+    EVERY column (β[2:end, :], src/SimTools.jl:505), not the first len(est) - len(true) entries of the vector."""
+    est = np.asarray(est)
+    ncol = est.shape[0] - n_true
+    if ncol <= 0 or est.shape[0] % ncol:
+        return est
+    rows = est.shape[0] // ncol
+    m = est.reshape((rows, ncol) + est.shape[1:], order="F")[1:]
+    return m.reshape((n_true,) + est.shape[1:], order="F")
+
+
 def _stack(obj, par):
     runs = sorted(k for k in obj if k != "True")
-    true = np.asarray(obj["True"][par], dtype=np.float64).ravel()
-    est = np.stack([np.asarray(obj[r][par], dtype=np.float64).ravel() for r in runs], axis=1)
+    true = np.asarray(obj["True"][par], dtype=np.float64).ravel(order="F")  # Julia's vec(): column-major
+    est = np.stack([np.asarray(obj[r][par], dtype=np.float64).ravel(order="F") for r in runs], axis=1)
     if par in ("β", "beta"):  # the reference drops the intercept row (src/SimTools.jl:505)
-        est = est[-len(true):] if est.shape[0] != len(true) else est
+        est = _drop_intercept(est, len(true))
     return true, est
 
 
@@ -123,10 +135,10 @@ def comparePara(MCMC, par="a", file=None):
     """src/SimTools.jl:389-414: estimate, truth and absolute difference, rounded to 3 digits."""
     import sys
     out = file or sys.stdout
-    true = _field(MCMC.truePara, par).ravel()
-    est = _field(MCMC.Post.mean, par).ravel()
+    true = _field(MCMC.truePara, par).ravel(order="F")  # Julia's vec(): column-major
+    est = _field(MCMC.Post.mean, par).ravel(order="F")
     if par in ("β", "beta") and est.shape[0] != true.shape[0]:
-        est = est[-len(true):]
+        est = _drop_intercept(est, true.shape[0])
     print("Esti\tTrue\t|Diff|", file=out)
     print("=======\t=======\t=======", file=out)
     for e, t in zip(est, true):

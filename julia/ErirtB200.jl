@@ -12,7 +12,7 @@ using ExtendedRtIrtModeling
 import ExtendedRtIrtModeling: sample!, InputPara, GibbsMlIrt, GibbsRtIrt, GibbsRtIrtNull, GibbsRtIrtCross, GibbsRtIrtCrossQr,
                                GibbsRtIrtLatent, GibbsRtIrtLatentQr
 
-export GibbsRtIrtQuantile
+export GibbsRtIrtQuantile, lean, LeanGibbs, LeanPost, Shard, sample_sharded!
 
 const LIB = get(ENV, "ERIRT_B200_LIB", joinpath(@__DIR__, "..", "extendedrtirtmodeling.jl_b200", "liberirt_b200.so"))
 
@@ -66,21 +66,67 @@ function _trace!(h, which, out::Array{Float64,3}, first_col)
                                  h, which, first_col, size(out, 2), out))
 end
 
-function _sample_gpu!(MCMC; intercept=false, itemtype="2pl", cov2one=true, dtype=1, seed=rand(UInt64), device=0)
+# Person columns of Post.ra / rt / qr are kept on the device (and copied back) only when nIter*nChain*3*nSubj reals fit this budget;
+# beyond it only the item / structural columns are traced and θ, ζ, ν come back as post-burn-in means and SDs (erirt_get_moments),
+# which is all Post.mean needs (SURVEY 0.10: at nSubj = 1M the reference's own trace would be 160 TB).
+const PERSON_TRACE_BUDGET_MB = parse(Int, get(ENV, "ERIRT_PERSON_TRACE_MB", "8192"))
+person_trace_fits(Cond, dtype) = 3 * Cond.nIter * Cond.nChain * Cond.nSubj * (dtype == 0 ? 4 : 8) <= PERSON_TRACE_BUDGET_MB * 2^20
+
+struct Shard                      # one rank of a person-sharded chain (INTEGRATION.md section 2)
+    rank::Int32
+    world::Int32
+    offset::Int64                 # global id of this rank's first person
+    total::Int64                  # persons of the whole chain
+    allgather::Function           # bytes::Vector{UInt8} -> concatenation over the ranks, in rank order (e.g. MPI.Allgather)
+    barrier::Function             # () -> nothing, host barrier over the ranks
+end
+
+function _moments(h, field, n)
+    m, sd = Vector{Float64}(undef, n), Vector{Float64}(undef, n)
+    GC.@preserve m sd check(ccall((:erirt_get_moments, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64), h, field, m, sd, n))
+    return m, sd
+end
+
+# item / structural columns [first_col, first_col + ncols) of Post.<which> into dest[:, dest_cols, :]
+function _trace_cols!(h, which, dest::AbstractArray{Float64,3}, dest_cols, first_col)
+    tmp = Array{Float64}(undef, size(dest, 1), length(dest_cols), size(dest, 3))
+    _trace!(h, which, tmp, first_col)
+    dest[:, dest_cols, :] .= tmp
+end
+
+"""
+Body of every `sample!` method.  `Post` is any object with `ra`, `rt`, `qr`, `logLike` arrays: the reference's OutputPost* (person
+columns present, width nSubj + 2 nItem) or a `LeanPost` (item / structural columns only).  Returns a NamedTuple with the person-level
+posterior means / SDs when the person trace was off (`nothing` entries otherwise) and CrossQr's mean weights.
+"""
+function _sample_gpu!(MCMC; intercept=false, itemtype="2pl", cov2one=true, dtype=1, seed=rand(UInt64), device=0,
+                      person_trace::Union{Bool,Nothing}=nothing, shard::Union{Shard,Nothing}=nothing, modeltype=typeof(MCMC))
     if !(itemtype in ["1pl", "2pl"])
         error("Invalid input: the item type must be '1pl' or '2pl'.")     # src/GibbsRtIrt.pl.jl:212-214
     end
     Cond, Data, Para, Post = MCMC.Cond, MCMC.Data, MCMC.Para, MCMC.Post
-    N, J, F = Cond.nSubj, Cond.nItem, Cond.nFeat
-    has_rt = !(MCMC isa GibbsMlIrt)
-    cqr = MCMC isa GibbsRtIrtCrossQr
-    cfg = ErirtConfig(1, MODEL_ID[typeof(MCMC)], N, N, 0, J, F, Cond.nIter, Cond.nChain, Cond.nBurnin, Cond.qRt,
-                      intercept, itemtype == "1pl", cov2one, dtype, seed, 0, 0, 1, device, 1, 0, cqr, ntuple(_ -> Int32(0), 6))
+    N, J, F = Cond.nSubj, Cond.nItem, Cond.nFeat      # N = persons held by THIS process (the shard's, when sharded)
+    has_rt = !(modeltype === GibbsMlIrt)
+    cqr = modeltype === GibbsRtIrtCrossQr
+    lqr = modeltype === GibbsRtIrtLatentQr
+    lean = Post isa LeanPost
+    ptrace = lean ? false : (person_trace === nothing ? person_trace_fits(Cond, dtype) : person_trace)
+    total, offset = shard === nothing ? (N, 0) : (shard.total, shard.offset)
+    cfg = ErirtConfig(1, MODEL_ID[modeltype], N, total, offset, J, F, Cond.nIter, Cond.nChain, Cond.nBurnin, Cond.qRt,
+                      intercept, itemtype == "1pl", cov2one, dtype, seed, 0, 0, ptrace, device, 1, 0, cqr, ntuple(_ -> Int32(0), 6))
     νmean = Float64[]   # CrossQr: post-burn-in mean of the N*J weights
+    person = (θ=nothing, θsd=nothing, ζ=nothing, ζsd=nothing, ν=nothing, νsd=nothing)
     href = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:erirt_create, LIB), Cint, (Ref{ErirtConfig}, Ref{Ptr{Cvoid}}), cfg, href))
     h = href[]
     try
+        if shard !== nothing      # rank / world, then the fused exchange over NVLink peer memory (no NCCL communicator)
+            check(ccall((:erirt_comm_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}), h, shard.rank, shard.world, C_NULL))
+            mine = Vector{UInt8}(undef, 64)
+            GC.@preserve mine check(ccall((:erirt_peer_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h, mine))
+            all = shard.allgather(mine)::Vector{UInt8}
+            GC.@preserve all check(ccall((:erirt_peer_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h, all))
+        end
         logT = has_rt ? Matrix{Float64}(Data.logT) : zeros(0, 0)
         X = F > 0 ? Matrix{Float64}(Data.X) : zeros(0, 0)
         if Data.Y isa Matrix{Bool}   # rand.(BernoulliLogit…) of src/SimTools.jl:165: one byte per response, passed as it lies in memory
@@ -100,77 +146,159 @@ function _sample_gpu!(MCMC; intercept=false, itemtype="2pl", cov2one=true, dtype
             _set_state(h, F_SIGMA_P, Matrix{Float64}(Para.Σp))
         end
         _set_state(h, F_BETA, Para.β)
-        (MCMC isa GibbsRtIrtCross || cqr) && _set_state(h, F_RHO, Para.ρ)
+        (modeltype === GibbsRtIrtCross || cqr) && _set_state(h, F_RHO, Para.ρ)
         check(ccall((:erirt_sample, LIB), Cint, (Ptr{Cvoid}, Int64), h, Cond.nIter * Cond.nChain))
-        # fill the pre-allocated Post arrays (same layouts, src/GibbsRtIrt.pl.jl:63-69)
-        _trace!(h, T_RA, Post.ra, 0)
-        has_rt && _trace!(h, T_RT, Post.rt, 0)
+        qw = Int(ccall((:erirt_trace_width, LIB), Int64, (Ptr{Cvoid}, Int32), h, T_QR)) - (lqr ? N : 0)   # item / structural width of qr
+        if ptrace
+            # fill the pre-allocated Post arrays (same layouts, src/GibbsRtIrt.pl.jl:63-69)
+            _trace!(h, T_RA, Post.ra, 0)
+            has_rt && _trace!(h, T_RT, Post.rt, 0)
+            if cqr
+                # the reference traces all N*J weights per sweep (src/GibbsRtIrtCross.pl.jl:65, :297); the engine keeps their running
+                # mean instead, so only the [ρ; vec Σp] columns of Post.qr are filled and Post.mean.ν comes from erirt_get_moments
+                _trace_cols!(h, T_QR, Post.qr, 1:(J + 4), 0)
+            else
+                _trace!(h, T_QR, Post.qr, 0)
+            end
+        else
+            # person trace off: item / structural columns only.  A reference OutputPost keeps its width (person columns stay
+            # unset: `undef` as allocated); a LeanPost has exactly the item / structural columns.
+            c0 = lean ? 0 : N
+            _trace_cols!(h, T_RA, Post.ra, (c0 + 1):(c0 + 2J), N)
+            has_rt && _trace_cols!(h, T_RT, Post.rt, (c0 + 1):(c0 + 2J), N)
+            _trace_cols!(h, T_QR, Post.qr, 1:qw, 0)
+            θ, θsd = _moments(h, F_THETA, N)
+            ζ, ζsd = has_rt ? _moments(h, F_ZETA, N) : (nothing, nothing)
+            ν, νsd = lqr ? _moments(h, F_NU, N) : (nothing, nothing)
+            person = (θ=θ, θsd=θsd, ζ=ζ, ζsd=ζsd, ν=ν, νsd=νsd)
+        end
         if cqr
-            # the reference traces all N*J weights per sweep (src/GibbsRtIrtCross.pl.jl:65, :297); the engine keeps their running
-            # mean instead, so only the [ρ; vec Σp] columns of Post.qr are filled and Post.mean.ν comes from erirt_get_moments
-            small = Array{Float64}(undef, Cond.nIter, J + 4, Cond.nChain)
-            _trace!(h, T_QR, small, 0)
-            Post.qr[:, 1:(J + 4), :] .= small
             νmean = Vector{Float64}(undef, N * J)
             GC.@preserve νmean check(ccall((:erirt_get_moments, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64),
                                            h, F_NU, νmean, C_NULL, N * J))
-        else
-            _trace!(h, T_QR, Post.qr, 0)
         end
         _trace!(h, T_LL, Post.logLike, 0)
+        if shard !== nothing      # unmap the peers' exchange buffers on every rank before anybody frees its own
+            check(ccall((:erirt_peer_detach, LIB), Cint, (Ptr{Cvoid},), h))
+            shard.barrier()
+        end
     finally
         ccall((:erirt_destroy, LIB), Cint, (Ptr{Cvoid},), h)
     end
-    return νmean
+    return (person=person, νcell=νmean)
 end
 
 _pm(A, r, nb) = vec(ExtendedRtIrtModeling.mean(A[(nb + 1):end, r, :], dims=(1, 3)))
+_or(x, f) = x === nothing ? f() : x     # person means from the moments when the trace was off, else from the trace columns
 
-# ---- the sample! methods: same signatures as the reference, body replaced ----
-function sample!(MCMC::GibbsMlIrt; intercept=false, itemtype::Union{String}="2pl")
-    _sample_gpu!(MCMC; intercept, itemtype)
+# ---- the sample! methods: same signatures as the reference (plus the engine's keyword options), body replaced ----
+function sample!(MCMC::GibbsMlIrt; intercept=false, itemtype::Union{String}="2pl", kw...)
+    r = _sample_gpu!(MCMC; intercept, itemtype, kw...)
     C, P = MCMC.Cond, MCMC.Post
-    P.mean = InputPara(θ=_pm(P.ra, 1:C.nSubj, C.nBurnin), a=_pm(P.ra, (C.nSubj + 1):(C.nSubj + C.nItem), C.nBurnin),
+    P.mean = InputPara(θ=_or(r.person.θ, () -> _pm(P.ra, 1:C.nSubj, C.nBurnin)), a=_pm(P.ra, (C.nSubj + 1):(C.nSubj + C.nItem), C.nBurnin),
                        b=_pm(P.ra, (C.nSubj + C.nItem + 1):size(P.ra, 2), C.nBurnin), β=_pm(P.qr, 1:(C.nFeat + 1), C.nBurnin))
     return MCMC
 end
 
-function _rt_mean!(MCMC, nβ; with_ν=false)
+function _rt_mean!(MCMC, nβ, r; with_ν=false)
     C, P = MCMC.Cond, MCMC.Post
     nb, N, J = C.nBurnin, C.nSubj, C.nItem
+    c0 = size(P.ra, 2) - 2J      # N for the reference's OutputPost, 0 for a LeanPost
     P.mean = InputPara(β=_pm(P.qr, 1:nβ, nb), Σp=_pm(P.qr, (nβ + 1):(nβ + 4), nb),
-                       ν=with_ν ? _pm(P.qr, (nβ + 5):size(P.qr, 2), nb) : Float64[],
-                       θ=_pm(P.ra, 1:N, nb), a=_pm(P.ra, (N + 1):(N + J), nb), b=_pm(P.ra, (N + J + 1):(N + 2J), nb),
-                       ζ=_pm(P.rt, 1:N, nb), λ=_pm(P.rt, (N + 1):(N + J), nb), σ²t=_pm(P.rt, (N + J + 1):(N + 2J), nb))
+                       ν=with_ν ? _or(r.person.ν, () -> _pm(P.qr, (nβ + 5):size(P.qr, 2), nb)) : Float64[],
+                       θ=_or(r.person.θ, () -> _pm(P.ra, 1:N, nb)), a=_pm(P.ra, (c0 + 1):(c0 + J), nb), b=_pm(P.ra, (c0 + J + 1):(c0 + 2J), nb),
+                       ζ=_or(r.person.ζ, () -> _pm(P.rt, 1:N, nb)), λ=_pm(P.rt, (c0 + 1):(c0 + J), nb), σ²t=_pm(P.rt, (c0 + J + 1):(c0 + 2J), nb))
     return MCMC
 end
 
-function sample!(MCMC::GibbsRtIrt; intercept=false, itemtype::Union{String}="2pl", cov2one=true)
-    _sample_gpu!(MCMC; intercept, itemtype, cov2one); _rt_mean!(MCMC, 2 * (MCMC.Cond.nFeat + 1))
+function sample!(MCMC::GibbsRtIrt; intercept=false, itemtype::Union{String}="2pl", cov2one=true, kw...)
+    r = _sample_gpu!(MCMC; intercept, itemtype, cov2one, kw...); _rt_mean!(MCMC, 2 * (MCMC.Cond.nFeat + 1), r)
 end
-function sample!(MCMC::GibbsRtIrtNull; itemtype::Union{String}="2pl", cov2one=true)
-    _sample_gpu!(MCMC; itemtype, cov2one); _rt_mean!(MCMC, 2 * (MCMC.Cond.nFeat + 1))
+function sample!(MCMC::GibbsRtIrtNull; itemtype::Union{String}="2pl", cov2one=true, kw...)
+    r = _sample_gpu!(MCMC; itemtype, cov2one, kw...); _rt_mean!(MCMC, 2 * (MCMC.Cond.nFeat + 1), r)
 end
-function _cross_mean!(MCMC; ν=Float64[])
+function _cross_mean!(MCMC, r)
     C, P = MCMC.Cond, MCMC.Post
     nb, N, J = C.nBurnin, C.nSubj, C.nItem
-    P.mean = InputPara(ρ=_pm(P.qr, 1:J, nb), Σp=_pm(P.qr, (J + 1):(J + 4), nb), ν=ν,
-                       θ=_pm(P.ra, 1:N, nb), a=_pm(P.ra, (N + 1):(N + J), nb), b=_pm(P.ra, (N + J + 1):(N + 2J), nb),
-                       ζ=_pm(P.rt, 1:N, nb), λ=_pm(P.rt, (N + 1):(N + J), nb), σ²t=_pm(P.rt, (N + J + 1):(N + 2J), nb))
+    c0 = size(P.ra, 2) - 2J
+    P.mean = InputPara(ρ=_pm(P.qr, 1:J, nb), Σp=_pm(P.qr, (J + 1):(J + 4), nb), ν=r.νcell,
+                       θ=_or(r.person.θ, () -> _pm(P.ra, 1:N, nb)), a=_pm(P.ra, (c0 + 1):(c0 + J), nb), b=_pm(P.ra, (c0 + J + 1):(c0 + 2J), nb),
+                       ζ=_or(r.person.ζ, () -> _pm(P.rt, 1:N, nb)), λ=_pm(P.rt, (c0 + 1):(c0 + J), nb), σ²t=_pm(P.rt, (c0 + J + 1):(c0 + 2J), nb))
     return MCMC
 end
-function sample!(MCMC::GibbsRtIrtCross; itemtype::Union{String}="2pl", cov2one=true)      # src/GibbsRtIrtCross.pl.jl:176
-    _sample_gpu!(MCMC; itemtype, cov2one); _cross_mean!(MCMC)
+function sample!(MCMC::GibbsRtIrtCross; itemtype::Union{String}="2pl", cov2one=true, kw...)      # src/GibbsRtIrtCross.pl.jl:176
+    r = _sample_gpu!(MCMC; itemtype, cov2one, kw...); _cross_mean!(MCMC, r)
 end
-function sample!(MCMC::GibbsRtIrtCrossQr; itemtype::Union{String}="2pl", cov2one=true)    # src/GibbsRtIrtCross.pl.jl:265
-    ν = _sample_gpu!(MCMC; itemtype, cov2one); _cross_mean!(MCMC; ν=ν)                     # Post.mean.ν, :310
+function sample!(MCMC::GibbsRtIrtCrossQr; itemtype::Union{String}="2pl", cov2one=true, kw...)    # src/GibbsRtIrtCross.pl.jl:265
+    r = _sample_gpu!(MCMC; itemtype, cov2one, kw...); _cross_mean!(MCMC, r)                       # Post.mean.ν, :310
 end
-function sample!(MCMC::GibbsRtIrtLatent; intercept=false, itemtype::Union{String}="2pl", cov2one=false)
-    _sample_gpu!(MCMC; intercept, itemtype, cov2one); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2)
+function sample!(MCMC::GibbsRtIrtLatent; intercept=false, itemtype::Union{String}="2pl", cov2one=false, kw...)
+    r = _sample_gpu!(MCMC; intercept, itemtype, cov2one, kw...); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2, r)
 end
-function sample!(MCMC::GibbsRtIrtLatentQr; intercept=false, itemtype::Union{String}="2pl", cov2one=false)
-    _sample_gpu!(MCMC; intercept, itemtype, cov2one); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2; with_ν=true)
+function sample!(MCMC::GibbsRtIrtLatentQr; intercept=false, itemtype::Union{String}="2pl", cov2one=false, kw...)
+    r = _sample_gpu!(MCMC; intercept, itemtype, cov2one, kw...); _rt_mean!(MCMC, MCMC.Cond.nFeat + 2, r; with_ν=true)
 end
+
+# ---- large nSubj: a lean model object.  The reference's constructors allocate Post.ra / rt as nIter x (nSubj + 2 nItem) x nChain
+#      (src/GibbsRtIrt.pl.jl:63-69; 160 TB at nSubj = 1M, nIter = 5000, nChain = 4) inside an inner constructor, so a model of that
+#      size cannot even be constructed.  `lean(GibbsRtIrtLatentQr, Cond; Data)` builds the same five fields with a LeanPost that holds
+#      the item / structural columns only; `sample!` fills Post.mean.θ / ζ / ν (and Post.sd) from the engine's running moments. ----
+mutable struct LeanPost
+    ra::Array{Float64,3}        # [nIter, 2 nItem, nChain]  a, b
+    rt::Array{Float64,3}        # [nIter, 2 nItem, nChain]  λ, σ²t
+    qr::Array{Float64,3}        # [nIter, qw, nChain]       β / ρ, vec Σp  (no ν block)
+    logLike::Array{Float64,3}
+    mean
+    sd                          # (θ, ζ, ν) posterior SDs from erirt_get_moments
+end
+mutable struct LeanGibbs
+    modeltype::DataType         # GibbsMlIrt, GibbsRtIrt, ..., GibbsRtIrtLatentQr
+    Cond
+    Data
+    truePara
+    Para
+    Post::LeanPost
+end
+_qw(T, J, F) = T === GibbsMlIrt ? F + 1 : (T === GibbsRtIrt || T === GibbsRtIrtNull) ? 2 * (F + 1) + 4 :
+               (T === GibbsRtIrtCross || T === GibbsRtIrtCrossQr) ? J + 4 : F + 2 + 4
+function lean(T::DataType, Cond; Data, truePara=Float64[], Para=nothing)
+    N, J, F = Cond.nSubj, Cond.nItem, Cond.nFeat
+    nβ = T === GibbsMlIrt ? (F + 1,) : (T === GibbsRtIrt || T === GibbsRtIrtNull) ? (F + 1, 2) : (F + 2,)
+    if Para === nothing        # setInitialValues of the reference (src/GibbsRtIrt.pl.jl:84-133, Cross :77-147, Latent :70-137)
+        Para = InputPara(θ=randn(N), a=ones(J), b=zeros(J), ζ=randn(N), λ=zeros(J), σ²t=ones(J),
+                         β=T === GibbsRtIrtNull ? zeros(nβ...) : randn(nβ...), ρ=randn(J), Σp=[1.0 0.0; 0.0 1.0])
+    end
+    post = LeanPost(Array{Float64}(undef, Cond.nIter, 2J, Cond.nChain), Array{Float64}(undef, Cond.nIter, 2J, Cond.nChain),
+                    Array{Float64}(undef, Cond.nIter, _qw(T, J, F), Cond.nChain), Array{Float64}(undef, Cond.nIter, 1, Cond.nChain),
+                    Float64[], nothing)
+    return LeanGibbs(T, Cond, Data, truePara, Para, post)
+end
+function sample!(MCMC::LeanGibbs; intercept=false, itemtype::Union{String}="2pl",
+                 cov2one=!(MCMC.modeltype === GibbsRtIrtLatent || MCMC.modeltype === GibbsRtIrtLatentQr), kw...)
+    T = MCMC.modeltype
+    r = _sample_gpu!(MCMC; intercept, itemtype, cov2one, modeltype=T, kw...)
+    F = MCMC.Cond.nFeat
+    if T === GibbsMlIrt
+        C, P = MCMC.Cond, MCMC.Post
+        P.mean = InputPara(θ=r.person.θ, a=_pm(P.ra, 1:C.nItem, C.nBurnin), b=_pm(P.ra, (C.nItem + 1):(2 * C.nItem), C.nBurnin),
+                           β=_pm(P.qr, 1:(F + 1), C.nBurnin))
+    elseif T === GibbsRtIrtCross || T === GibbsRtIrtCrossQr
+        _cross_mean!(MCMC, r)
+    else
+        _rt_mean!(MCMC, (T === GibbsRtIrt || T === GibbsRtIrtNull) ? 2 * (F + 1) : F + 2, r; with_ν=T === GibbsRtIrtLatentQr)
+    end
+    MCMC.Post.sd = (θ=r.person.θsd, ζ=r.person.ζsd, ν=r.person.νsd)
+    return MCMC
+end
+
+"""
+    sample_sharded!(MCMC::LeanGibbs, shard::Shard; kw...)
+
+One rank of a person-sharded chain (BASELINE configs[4]; INTEGRATION.md section 2): this process holds the rows `shard.offset + 1 :
+shard.offset + MCMC.Cond.nSubj` of Y, logT, X (its `Data`) and their initial θ, ζ, one GPU (`device`), and calls this on every rank
+with the SAME `seed`.  Item / structural traces are identical on every rank; Post.mean.θ / ζ / ν are this rank's persons.
+"""
+sample_sharded!(MCMC::LeanGibbs, shard::Shard; kw...) = sample!(MCMC; shard=shard, kw...)
 
 # ---- simulated data generated on the device (erirt_generate_data): the N x J part of setData* (src/SimTools.jl:117-368) never exists on
 #      the host.  `truePara` holds the person-level draws θ (and ζ) made by the caller as in setData*, X the covariates (or nothing);

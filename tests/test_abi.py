@@ -96,4 +96,49 @@ def test_julia_stub_matches_the_header(lib):
     called = set(re.findall(r"ccall\(\(:(\w+), LIB\)", src))
     assert called and called <= set(_declared_symbols()), called - set(_declared_symbols())
     assert {"erirt_create", "erirt_set_data", "erirt_set_data_y8", "erirt_set_state", "erirt_sample", "erirt_get_trace", "erirt_get_moments",
-            "erirt_destroy", "erirt_generate_data", "erirt_checkpoint_save", "erirt_checkpoint_load"} <= called
+            "erirt_destroy", "erirt_generate_data", "erirt_checkpoint_save", "erirt_checkpoint_load", "erirt_comm_init", "erirt_peer_export",
+            "erirt_peer_attach", "erirt_peer_detach", "erirt_trace_width"} <= called
+    # large-N and sharded entry points exist
+    for needle in ("mutable struct LeanPost", "function lean(", "sample!(MCMC::LeanGibbs", "sample_sharded!", "person_trace_fits"):
+        assert needle in src, needle
+
+
+def _c_prototypes():
+    """name -> (return type, [argument types]) of every function declared in include/erirt_b200.h (comments stripped)."""
+    src = open(os.path.join(ROOT, "include", "erirt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(?:^|\n)\s*((?:const\s+)?[a-z0-9_]+\s*\**)\s*(erirt_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        types = []
+        for a in [x.strip() for x in args.split(",")]:
+            if a in ("", "void"):
+                continue
+            a = re.sub(r"\[\d*\]", "*", a)                  # array parameters decay to pointers
+            stars = a.count("*")
+            words = [w for w in re.sub(r"\*", " ", a).split() if w != "const"]
+            base = words[0] if len(words) == 1 or words[0] not in ("unsigned",) else " ".join(words[:2])
+            types.append(base + "*" * stars)
+        protos[name] = (re.sub(r"\s+", "", ret.replace("const", "")), types)
+    return protos
+
+
+def test_julia_ccall_signatures_match_the_header(lib):
+    """Every ccall of julia/ErirtB200.jl passes the number and the kinds of arguments the C prototype declares, and reads the return
+    value with the right width (the stub cannot be executed here, so this is the static check that stands in for running it)."""
+    protos = _c_prototypes()
+    assert len(protos) >= 25
+    ok = {"erirt_handle*": {"Ptr{Cvoid}"}, "erirt_handle**": {"Ref{Ptr{Cvoid}}"}, "erirt_config*": {"Ref{ErirtConfig}"},
+          "double*": {"Ptr{Float64}"}, "uint8_t*": {"Ptr{Bool}", "Ptr{UInt8}"}, "void*": {"Ptr{UInt8}", "Ptr{Cvoid}"},
+          "int64_t": {"Int64"}, "int32_t": {"Int32", "Cint"}, "uint64_t": {"UInt64"}, "uint32_t": {"UInt32"}, "erirt_stats*": {"Ref{ErirtStats}"}}
+    ret_ok = {"int": {"Cint", "Int32"}, "int64_t": {"Int64"}, "char*": {"Cstring"}}
+    src = open(os.path.join(ROOT, "julia", "ErirtB200.jl"), encoding="utf-8").read()
+    calls = re.findall(r"ccall\(\(:(\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", src, flags=re.S)
+    assert len(calls) >= 15
+    for name, ret, args in calls:
+        cret, cargs = protos[name]
+        jargs = [a.strip() for a in args.split(",") if a.strip()]
+        assert ret in ret_ok[cret], (name, "return", ret, cret)
+        assert len(jargs) == len(cargs), (name, jargs, cargs)
+        for ja, ca in zip(jargs, cargs):
+            assert ja in ok[ca], (name, ja, ca)

@@ -192,6 +192,24 @@ def test_ragged_shapes_f32_fast_kernel(E, oracle, N, J, F):
         eng.close()
 
 
+@pytest.mark.parametrize("model,J,F", [("RtIrtLatentQr", 100, 3), ("RtIrt", 21, 2), ("MlIrt", 150, 1), ("RtIrtNull", 100, 0)])
+def test_cross_tile_register_accumulators_f32(E, oracle, monkeypatch, model, J, F):
+    """person_fast.cuh keeps the item statistics in f32 registers ACROSS tiles and folds them into the CTA's f64 accumulators every
+    16 tiles through a staging area that aliases the logT tile.  With the persistent grid capped at 3 CTAs (ERIRT_MAX_GRID, a test
+    hook) a 6.7k-person problem gives every CTA 35 tiles (TPP = 2; two 16-tile folds and the final partial one), the situation of the
+    1M x 100 benchmark, at a size the oracle does in a second.  Two sweeps, f32 tolerance."""
+    monkeypatch.setenv("ERIRT_MAX_GRID", "3")
+    pb = make_problem(model, 64 * 3 * 35 + 17, J, F, seed=23)
+    ref = run_oracle(oracle, pb, 2)
+    eng = run_engine(E, pb, 2, dtype="f32")
+    _compare_traces(eng, ref, pb, 2, 2e-5, 1e-1, frac_ok=0.995)
+    eng.close()
+    # and the generic (f64) kernel with the same grid
+    eng = run_engine(E, pb, 2, dtype="f64")
+    _compare_traces(eng, ref, pb, 2, 1e-10, 1e-3)
+    eng.close()
+
+
 def test_crossqr_cell_weights_parity(E, oracle):
     """drawQrWeightsCrossQr (Draw.pl.jl:303-320): the N x J weights nu_{k+1} held by the engine after k sweeps."""
     pb = make_problem("RtIrtCrossQr", 333, 11, 0, seed=21)

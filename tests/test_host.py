@@ -185,3 +185,25 @@ def test_set_data_on_device_draws_only_the_person_level_part():
         E.setDataOnDevice(C, E.setTrueParaRtIrtCross(C, rng=3), "RtIrtCross", type="cauchy", rng=3)
     with pytest.raises(ValueError):
         E.setDataOnDevice(C, tp1, "NoSuchModel", rng=3)
+
+
+def test_beta_intercept_rows_are_dropped_per_column():
+    """comparePara / getMetrics on β of GibbsRtIrt: vec(β) is column-major over (nFeat+1) x 2 and the reference drops row 1 of each
+    column (β[2:end, :], src/SimTools.jl:505); nFeat = 3 so that a wrong 'last len(true) entries' rule would misalign."""
+    from erirt_b200 import simtools
+    F = 3
+    true = np.arange(1.0, 2 * F + 1).reshape(F, 2, order="F")          # slopes only, F x 2
+    est = np.vstack([[100.0, 200.0], true + 0.5])                     # (F+1) x 2 with an intercept row
+    obj = {"True": {"β": true.ravel(order="F")}, "Run1": {"β": est.ravel(order="F")}, "Run2": {"β": est.ravel(order="F")}}
+    m = simtools.getMetrics(obj, par="β")
+    assert abs(m["Bias"] - 0.5) < 1e-12 and abs(m["Rmse"] - 0.5) < 1e-12
+
+    class M:
+        pass
+    mc = M()
+    mc.truePara, mc.Post = E.InputPara(), M()
+    mc.Post.mean = E.InputPara()
+    mc.truePara.beta, mc.Post.mean.beta = true, est.ravel(order="F")
+    import io
+    tab = simtools.comparePara(mc, par="β", file=io.StringIO())
+    assert np.allclose(tab[:, 2], 0.5)
