@@ -53,6 +53,32 @@ ESS_SWEEPS = 3000       # total length of the chain the ESS is taken from (secon
 LONG_RUN_SECONDS = 0.5  # minimum device time of the long timed region
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (the JSON line is the only thing on stdout)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def run_sub(name, timeout):
+    """A sub-record in a child process with a hard time limit: a configuration that misbehaves at this size (it has never been the
+    headline) must not take the bench line with it.  The child prints one JSON object on stdout."""
+    log(f"sub-record {name} (child process, limit {timeout} s)")
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--sub", name], capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout} s"}
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except Exception:
+                break
+    return {"error": f"rc={r.returncode}: {r.stderr[-400:]}"}
+
+
 def make_config(world):
     """The `config` object of the JSON line; identical for this arm and for --impl reference at the same --gpus."""
     peer = os.environ.get("ERIRT_EXCHANGE", "peer") == "peer"
@@ -304,8 +330,11 @@ def roofline_record(eng_stats, kernel_ms, kernel_name, launches):
             "frac": achieved / peak, "algorithmic_bytes_per_launch": b, "kernel_ms": kernel_ms, "launches_timed": launches}
 
 
-def sub_f64(E, dY, dT, dX, n_local, theta0, zeta0, beta0, local):
+def sub_f64(E, local):
     """The benchmarked sampler in Float64 (the reference's precision): 25 B per cell."""
+    import torch
+    dY, dT, dX, _, n_local = gen_shard_torch(true_params(), 0, 1, torch.device("cuda", local))
+    theta0, zeta0, beta0 = init_state(0, n_local)
     out = {}
     for timed in (False, True):
         eng = E.Engine("RtIrtQuantile", n_local, N_ITEM, N_FEAT, n_iter=64, n_chain=1, n_burnin=0, q_rt=Q_RT, cov2one=False, dtype="f64",
@@ -478,9 +507,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (f64, crossqr, configs, c4_chains, ess)")
     ap.add_argument("--short", action="store_true", help="profiling run: timed sweeps only, no e2e / cpu / roofline / sub-record passes")
+    ap.add_argument("--sub", default=None, choices=["f64", "crossqr", "configs"], help="(internal) run one sub-record and print it")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.sub:
+        import torch
+        import erirt_b200 as E
+        torch.cuda.set_device(0)
+        rec = {"f64": sub_f64, "crossqr": sub_crossqr, "configs": sub_configs}[args.sub](E, 0)
+        print(json.dumps(rec), flush=True)
+        return
     if args.warmup < 3:
         args.warmup = 3
 
@@ -539,6 +576,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    log("data generated; value / long run / ESS chain")
     # ---------------- device-resident throughput ("value"), the long run, the ESS chain ----------------
     cap = max(ESS_SWEEPS, 2 * (K + W)) + 4096 if extras else K + W + 8
     eng = make_engine(n_iter=cap)
@@ -568,6 +606,7 @@ def main():
     st = eng.stats()
     value = K / (ms / 1000.0)
     ll_first = [float(v) for v in eng.get_trace("logLike")[:5, 0, 0]] if rank == 0 else None
+    log(f"value {value:.1f} sweeps/s ({ms / K:.4f} ms/sweep)" + (f", long run {long_run['ms_per_step']:.4f} ms/sweep over {long_run['sweeps']}" if long_run else ""))
     ess = None
     if extras:
         if done < ESS_SWEEPS:
@@ -585,6 +624,7 @@ def main():
                 ess = {"error": str(ex)}
     close_engine(eng)
 
+    log("ESS done; f64 sharding check")
     # ---------------- sharding check in f64: logLike of sweeps 1..5 of the same chain at every GPU count ----------------
     ll64 = None
     if extras:
@@ -596,6 +636,7 @@ def main():
             ll64 = [float(v) for v in e64.get_trace("logLike")[:5, 0, 0]]
         close_engine(e64)
 
+    log("roofline pass")
     # ---------------- roofline of the person kernel (plain launches bracketed by CUDA events) ----------------
     roofline = None
     if not args.short:
@@ -619,12 +660,8 @@ def main():
 
     # ---------------- sub-records that only need one GPU ----------------
     f64_rec = crossqr_rec = configs_rec = None
-    if extras and world == 1:
-        try:
-            f64_rec = sub_f64(E, dY, dT, dX, n_local, theta0, zeta0, beta0, local)
-        except Exception as ex:
-            f64_rec = {"error": str(ex)}
 
+    log("e2e pass")
     # ---------------- end to end through the C ABI with host buffers ("e2e") ----------------
     e2e = None
     if not args.no_e2e and not args.short:
@@ -673,6 +710,7 @@ def main():
         torch.cuda.empty_cache()
         hMn = np.empty((3, 2, n_local))
 
+    log("e2e with device-generated data")
     # ---------------- the same call with the N x J data generated on the device (informational: no N x J upload) ----------------
     e2e_gen = None
     if not args.no_e2e and not args.short:
@@ -698,22 +736,20 @@ def main():
                    "note": "erirt_create + erirt_generate_data (person-level theta, zeta, X from the host; responses and log-times generated "
                            "on the device) + erirt_set_state + K sweeps + read-back + erirt_destroy"}
 
-    if extras and world == 1:
-        try:
-            crossqr_rec = sub_crossqr(E, local)
-        except Exception as ex:
-            crossqr_rec = {"error": str(ex)}
-        try:
-            configs_rec = sub_configs(E, local)
-        except Exception as ex:
-            configs_rec = {"error": str(ex)}
     chains_rec = None
     if extras:
+        log("c4_chains: 8 independent RtIrtNull chains")
         try:
             chains_rec = c4_chains(E, rank, world, local)
         except Exception as ex:
             chains_rec = {"error": str(ex)}
+    if extras and world == 1:
+        torch.cuda.empty_cache()
+        f64_rec = run_sub("f64", 180)
+        configs_rec = run_sub("configs", 240)
+        crossqr_rec = run_sub("crossqr", 240)
 
+    log("cpu baseline")
     # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and not args.short:

@@ -394,7 +394,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_acc_item = (int)o; o = align_up(o + (cqr ? 7 : (cross ? 6 : 5)) * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
   S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
-  S.off_tab = (int)o; if (fast) o = align_up(o + 2 * (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response tables of the f32 fast kernel
+  S.off_tab = (int)o; if (fast) o = align_up(o + (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response table of the f32 fast kernel
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;
   return S;
@@ -1059,6 +1059,7 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   A.onepl = h->cfg.itemtype_1pl;
   A.cov2one = h->cfg.cov2one;
   A.compat = h->cfg.compat;
+  A.kz_from_stats = (stage == 0 && h->cfg.dtype == ERIRT_F32) ? 1 : 0;  // stage 0 in f32 == person_sweep_fast_kernel (launch_person)
   const double q = h->cfg.q_rt;
   A.k1 = (1.0 - 2.0 * q) / (q * (1.0 - q));
   A.k2 = 2.0 / (q * (1.0 - q));

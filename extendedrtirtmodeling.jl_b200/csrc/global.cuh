@@ -452,15 +452,20 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     double part = 0.0;
     if (model == M_CROSSQR) {
       if (tid == 0) part = st[L.s_scal + SC_LL_RT];
-    } else if (has_rt)
+    } else if (has_rt || A.kz_from_stats)
       for (int j = tid; j < J; j += G_THREADS) {
-        const double lam = par[L.p_lambda + j], s2 = par[L.p_sigma2 + j];
-        double Q = A.T2[j] - 2.0 * lam * A.T1[j] + N * lam * lam + 2.0 * (st[L.s_C + j] - lam * Sze) + Sze2;
-        if (cross) {  // residual logT - lambda + zeta + theta rho_j  (getLogLikelihoodRtIrtCross, GibbsRtIrtCross.pl.jl:158-169)
-          const double rho = par[L.p_rho + j];
-          Q += rho * rho * Sth2 + 2.0 * rho * (st[L.s_D + j] - lam * Sth + Sthze);
+        if (has_rt) {
+          const double lam = par[L.p_lambda + j], s2 = par[L.p_sigma2 + j];
+          double Q = A.T2[j] - 2.0 * lam * A.T1[j] + N * lam * lam + 2.0 * (st[L.s_C + j] - lam * Sze) + Sze2;
+          if (cross) {  // residual logT - lambda + zeta + theta rho_j  (getLogLikelihoodRtIrtCross, GibbsRtIrtCross.pl.jl:158-169)
+            const double rho = par[L.p_rho + j];
+            Q += rho * rho * Sth2 + 2.0 * rho * (st[L.s_D + j] - lam * Sth + Sthze);
+          }
+          part += -0.5 * N * (LOG2PI + log(s2)) - 0.5 * Q / s2;
         }
-        part += -0.5 * N * (LOG2PI + log(s2)) - 0.5 * Q / s2;
+        // sum_i kappa_ij z_ij = a_j [(Ky_j - sum_i theta_i / 2) - b_j K0_j] at state k: the part of the Bernoulli term the f32
+        // person kernel leaves to its statistics (Ky = sum_i y_ij theta_i, K0 = sum_i kappa_ij)
+        if (A.kz_from_stats) part += par[L.p_a + j] * ((st[L.s_Ky + j] - 0.5 * Sth) - par[L.p_b + j] * A.K0[j]);
       }
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if ((tid & 31) == 0) sRed[tid >> 5] = part;

@@ -132,6 +132,7 @@ struct GlobalArgs {
   Layout L;
   int model, intercept, onepl, cov2one, compat;
   int stage;  // 0/2: full draw + trace + counter; 1 (Cross family): lambda, sigma2 only
+  int kz_from_stats;  // 1: SC_LL_BERN lacks sum_ij kappa_ij z_ij (f32 fast person kernel); add it from Ky, sum theta, K0 and a_k, b_k
   double k1, k2;
   PhiloxKey key;
   // one-shot peer exchange of the statistics (person-sharded chains, NVLink peer memory); peer_bufs == nullptr: not used

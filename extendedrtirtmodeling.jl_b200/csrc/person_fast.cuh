@@ -5,10 +5,12 @@
 //   * all per-cell arithmetic runs two cells per instruction on the packed FP32 pipe (FFMA2/FMUL2/FADD2, pg_fast.cuh);
 //   * attempt 0 of the PG draw decides only "certainly accepted" / "certainly rejected" with constant bounds of a_1/a_0
 //     (6 MUFU per cell instead of 10); undecided cells (0.5 %) are replayed with the a_1 term from a second work queue;
-//   * the Bernoulli log-likelihood  sum kappa z - |z|/2 - ln(1 + e^{-|z|})  is accumulated as a product of (1 + e^{-|z|})
-//     (one lg2 per row instead of one per cell) and  sum_j kappa_ij z_ij  comes from 16-entry tables indexed by the four
-//     responses of an item group (T_a[g][y] = sum_e kappa_e a_e, T_b[g][y] = -sum_e kappa_e a_e b_e), which also give the
-//     row sum  sum_j a_j kappa_ij  of drawSubjAbility (Draw.pl.jl:56) without touching the individual responses.
+//   * of the Bernoulli log-likelihood  sum kappa z - |z|/2 - ln(1 + e^{-|z|})  the kernel accumulates only the last two terms
+//     (the third as a product of (1 + e^{-|z|}): one lg2 per row instead of one per cell); the first is a function of statistics
+//     the kernel reduces anyway,  sum_ij kappa_ij z_ij = sum_j a_j [(Ky_j - sum_i theta_i / 2) - b_j K0_j],  and is added by the
+//     global kernel (GlobalArgs.kz_from_stats);
+//   * the row sum  sum_j a_j kappa_ij  of drawSubjAbility (Draw.pl.jl:56) comes from a 16-entry table per 4-item group indexed by
+//     the four responses (T_a[g][y] = sum_e kappa_e a_e), without touching the individual responses.
 #pragma once
 #include "person.cuh"
 #include "pg_fast.cuh"
@@ -63,7 +65,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   R* s_u = reinterpret_cast<R*>(smem + A.S.off_u);
   R* s_beta = reinterpret_cast<R*>(smem + A.S.off_beta);  // beta (MAXD) then vec(Sigma) (4)
   R* s_ta = reinterpret_cast<R*>(smem + A.S.off_tab);     // [G][TAB_PITCH]  sum_e kappa_e a_e
-  R* s_tb = s_ta + G * TAB_PITCH;                         // [G][TAB_PITCH] -sum_e kappa_e a_e b_e
   double* s_acc_item = reinterpret_cast<double*>(smem + A.S.off_acc_item);
   double* s_acc_gram = reinterpret_cast<double*>(smem + A.S.off_acc_gram);
   uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + A.S.off_queue);
@@ -124,14 +125,12 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
   }
   __syncthreads();
-  // response tables from the staged parameters (shared memory): T_a[g][y] = sum_e kappa_e a_e, T_b[g][y] = -sum_e kappa_e a_e b_e
+  // response table from the staged parameters (shared memory): T_a[g][y] = sum_e kappa_e a_e
   for (int t = tid; t < G * 16; t += CTA_THREADS) {
     const int g = t >> 4, yb = t & 15;
     const float4 a4 = *reinterpret_cast<const float4*>(s_par + PAR_A * Jp + 4 * g);
-    const float4 n4 = *reinterpret_cast<const float4*>(s_par + PAR_AB * Jp + 4 * g);
     const R k0 = (yb & 1) ? R(0.5) : R(-0.5), k1y = (yb & 2) ? R(0.5) : R(-0.5), k2y = (yb & 4) ? R(0.5) : R(-0.5), k3 = (yb & 8) ? R(0.5) : R(-0.5);
     s_ta[g * TAB_PITCH + yb] = fmaf(k0, a4.x, fmaf(k1y, a4.y, fmaf(k2y, a4.z, k3 * a4.w)));
-    s_tb[g * TAB_PITCH + yb] = fmaf(k0, n4.x, fmaf(k1y, n4.y, fmaf(k2y, n4.z, k3 * n4.w)));
   }
   __syncthreads();
 
@@ -435,13 +434,11 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       const bool wide = !(fmaf(z_amax, fabsf(thp), z_abmax) <= PG_Z0MAX);  // some |z| of this row may exceed the attempt-0 range
       const u64 TH = bc2(thp);
       u64 prod = bc2(1.0f);
-      R sabs = R(0), skz = R(0);
+      R sabs = R(0);
       // one 4-item group: straight-line code (no branch inside), so that the groups of an iteration interleave when scheduled
       auto do_group = [&](const int g, uint32_t& dmu, uint32_t& rmu) {
         const float4 pA = *reinterpret_cast<const float4*>(s_par + PAR_A * Jp + 4 * g);
         const float4 pN = *reinterpret_cast<const float4*>(s_par + PAR_AB * Jp + 4 * g);
-        const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * g));
-        skz += fmaf(thp, s_ta[g * TAB_PITCH + yb], s_tb[g * TAB_PITCH + yb]);  // sum_e kappa_e z_e of this group
         const u64 z01 = ffma2(pk2(pA.x, pA.y), TH, pk2(pN.x, pN.y)), z23 = ffma2(pk2(pA.z, pA.w), TH, pk2(pN.z, pN.w));
         const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
         const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
@@ -472,8 +469,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         for (int kk = 0; kk < nk; ++kk) {
           const int g = group_of<TPP>(q, kk);
           if (g >= G) continue;
-          const uint32_t yb = y_nibble(*reinterpret_cast<const uint32_t*>(my_y + 4 * g));
-          skz += fmaf(thp, s_ta[g * TAB_PITCH + yb], s_tb[g * TAB_PITCH + yb]);
           uint32_t dm = 0, rm = 0;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -490,8 +485,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           rmask |= (u64)rm << (4 * kk);
         }
       }
-      // kappa z - |z|/2 - ln(1 + e^{-|z|}); a padding cell has z = 0 and contributed -ln 2
-      const R ll_row = skz - R(0.5) * sabs - PGF_LN2 * (fast_lg2(lo2(prod)) + fast_lg2(hi2(prod)) - (R)n_pad_cells);
+      // - |z|/2 - ln(1 + e^{-|z|}) (sum kappa z is added by the global kernel); a padding cell has z = 0 and contributed -ln 2
+      const R ll_row = R(-0.5) * sabs - PGF_LN2 * (fast_lg2(lo2(prod)) + fast_lg2(hi2(prod)) - (R)n_pad_cells);
       acc_ll_bern += (double)ll_row;
       dmask &= valid_mask;
       rmask &= dmask;

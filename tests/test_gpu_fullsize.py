@@ -130,7 +130,7 @@ def test_benchmark_size_parity_f32_and_f64(E, oracle, N, J, ns):
 def test_forced_queue_overflow_and_wide_rows_f32(E, oracle, a_hi, a_rest, note):
     """person_fast.cuh: `wide` rows (some |z| = |a (theta - b)| > 16) and the QCAP overflow branch of the push are not reached with
     sane parameters.  Start the chain from a = 7 for three items (|theta| > 2.3 gives |z| > 16, ~2 % of the rows) and optionally a = 4
-    for the rest (|z| > 3.125 for most cells: Method-B regime, attempt 0 rarely accepted, > 768 + 256 deferred cells per tile), one sweep
+    for the rest (|z| > 3.125 for most cells: Method-B regime, attempt 0 rarely accepted, more deferred cells than a warp's queues hold), one sweep
     so that the state every draw conditions on is exactly the oracle's."""
     N, J = 20_000, 100
     a0 = np.full(J, a_rest)
@@ -153,6 +153,6 @@ def test_forced_queue_overflow_and_wide_rows_f32(E, oracle, a_hi, a_rest, note):
     compare(eng, ref, pb, 1, [1e-5], 1e-4, 0.99, f"f32 forced a_hi={a_hi} a_rest={a_rest}")
     st = eng.stats()
     print(f"[fullsize] forced branches ({note}): deferred fraction {st['pg_deferred_frac']:.3f} (prologue {st0['pg_deferred_frac']:.3f})", flush=True)
-    if a_rest > 3:
-        assert st["pg_deferred_frac"] > (768 + 256) / 6400.0, "the queues did not overflow"
+    if a_rest > 3:  # the prologue drew omega_1 with a = 4: a warp's queues hold 192 + 64 of its 1600 cells
+        assert st0["pg_deferred_frac"] > (192 + 64) / 1600.0, "the queues did not overflow"
     eng.close()
