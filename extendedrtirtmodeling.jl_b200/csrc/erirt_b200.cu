@@ -15,6 +15,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/erirt_b200.h"
@@ -363,6 +364,7 @@ struct erirt_handle {
   uint32_t* dXseq = nullptr;
   int xstride = 0;
   bool peer_ready = false;
+  int peer_cache_slot = -1;           // >= 0: xbuf / dPeerBufs / dXseq / the peer mappings belong to g_peer_cache[slot], not to the handle
   // graph
   cudaGraphExec_t graph_exec = nullptr;
   cudaGraphExec_t graph_multi = nullptr;  // ERIRT_GRAPH_SWEEPS sweeps in one graph (experimental)
@@ -456,16 +458,52 @@ static int beta_len(int model, int F) {
 extern "C" int erirt_version(void) { return ERIRT_ABI_VERSION; }
 extern "C" const char* erirt_last_error(void) { return g_err.c_str(); }
 
+// Exchange buffers and their CUDA IPC mappings are kept for the next handle of the process (same device, rank, world and slot size):
+// opening the seven peer mappings of an 8-GPU chain costs ~40 ms per erirt_create + attach, more than 100 sweeps of the benchmark.
+// The stamps are sequence numbers that simply keep counting (xseq is cached with the buffer), so a reused buffer needs no reset;
+// every rank of a sharded program makes the same calls, hence the same reuse decisions.  ERIRT_PEER_CACHE=0 disables the cache;
+// erirt_trim_pool releases the entries that are not in use.
+struct PeerCacheEntry {
+  int device = -1, world = 0, rank = -1, xstride = 0;
+  double* xbuf = nullptr;
+  double** dPeerBufs = nullptr;
+  uint32_t* dXseq = nullptr;
+  std::vector<void*> opened;
+  std::vector<char> handles;  // world x 64 bytes the mappings were opened from
+  bool in_use = false;
+};
+static std::mutex g_peer_mu;
+static std::vector<PeerCacheEntry> g_peer_cache;
+static bool peer_cache_enabled() {
+  const char* e = getenv("ERIRT_PEER_CACHE");
+  return !(e && atoi(e) == 0);
+}
+static void peer_cache_release_entry(PeerCacheEntry& c) {
+  for (void* p : c.opened) cudaIpcCloseMemHandle(p);
+  c.opened.clear();
+  c.handles.clear();
+  if (c.xbuf) cudaFree(c.xbuf);
+  if (c.dPeerBufs) cudaFree(c.dPeerBufs);
+  if (c.dXseq) cudaFree(c.dXseq);
+  c.xbuf = nullptr; c.dPeerBufs = nullptr; c.dXseq = nullptr; c.device = -1;
+}
+
 static int free_handle(erirt_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->graph_multi) cudaGraphExecDestroy(h->graph_multi);
   if (h->comm && nccl::comm_destroy) nccl::comm_destroy(h->comm);
-  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
-  if (h->xbuf) cudaFree(h->xbuf);
-  if (h->dPeerBufs) cudaFree(h->dPeerBufs);
-  if (h->dXseq) cudaFree(h->dXseq);
+  if (h->peer_cache_slot >= 0) {  // buffers and mappings stay with the cache
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    g_peer_cache[h->peer_cache_slot].in_use = false;
+  } else {
+    for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+    if (h->xbuf) cudaFree(h->xbuf);
+    if (h->dPeerBufs) cudaFree(h->dPeerBufs);
+    if (h->dXseq) cudaFree(h->dXseq);
+  }
   if (h->arena && h->stream) {  // all device buffers of the handle: back to the pool
     cudaFreeAsync(h->arena, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -657,6 +695,11 @@ extern "C" int erirt_trim_pool(int32_t device) {
   CU(cudaDeviceGetDefaultMemPool(&pool, device));
   CU(cudaDeviceSynchronize());
   CU(cudaMemPoolTrimTo(pool, 0));
+  {
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    for (PeerCacheEntry& c : g_peer_cache)
+      if (!c.in_use && c.device == device) peer_cache_release_entry(c);
+  }
   return 0;
 }
 
@@ -1485,6 +1528,20 @@ extern "C" int erirt_peer_export(erirt_handle* h, void* ipc_handle64) {
   CU(cudaSetDevice(h->cfg.device));
   if (!h->xbuf) {
     h->xstride = (int)align_up((size_t)std::max(h->L.s_count, h->c_count), 16);  // the statistics per sweep, the ingest constants once
+    if (peer_cache_enabled()) {
+      std::lock_guard<std::mutex> lk(g_peer_mu);
+      for (size_t t = 0; t < g_peer_cache.size(); ++t) {
+        PeerCacheEntry& c = g_peer_cache[t];
+        if (!c.in_use && c.device == h->cfg.device && c.world == h->world && c.rank == h->rank && c.xstride == h->xstride && c.xbuf) {
+          c.in_use = true;
+          h->peer_cache_slot = (int)t;
+          h->xbuf = c.xbuf; h->dPeerBufs = c.dPeerBufs; h->dXseq = c.dXseq;
+          break;
+        }
+      }
+    }
+  }
+  if (!h->xbuf) {
     const size_t bytes = (size_t)2 * h->world * h->xstride * sizeof(double) + (size_t)2 * h->world * sizeof(uint32_t) + 256;
     CU(cudaMalloc((void**)&h->xbuf, bytes));
     CU(cudaMemset(h->xbuf, 0, bytes));
@@ -1492,6 +1549,14 @@ extern "C" int erirt_peer_export(erirt_handle* h, void* ipc_handle64) {
     CU(cudaMalloc((void**)&h->dXseq, sizeof(uint32_t)));
     CU(cudaMemset(h->dXseq, 0, sizeof(uint32_t)));
     CU(cudaDeviceSynchronize());
+    if (peer_cache_enabled()) {
+      std::lock_guard<std::mutex> lk(g_peer_mu);
+      PeerCacheEntry c;
+      c.device = h->cfg.device; c.world = h->world; c.rank = h->rank; c.xstride = h->xstride;
+      c.xbuf = h->xbuf; c.dPeerBufs = h->dPeerBufs; c.dXseq = h->dXseq; c.in_use = true;
+      g_peer_cache.push_back(c);
+      h->peer_cache_slot = (int)g_peer_cache.size() - 1;
+    }
   }
   cudaIpcMemHandle_t hd;
   CU(cudaIpcGetMemHandle(&hd, h->xbuf));
@@ -1503,16 +1568,39 @@ extern "C" int erirt_peer_attach(erirt_handle* h, const void* ipc_handles) {
   if (!h->xbuf) return fail(ERIRT_E_STATE, "erirt_peer_export has not been called");
   if (h->prologue_done) return fail(ERIRT_E_STATE, "erirt_peer_attach must precede erirt_sample");
   CU(cudaSetDevice(h->cfg.device));
+  if (h->peer_cache_slot >= 0) {
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    PeerCacheEntry& c = g_peer_cache[h->peer_cache_slot];
+    if (c.handles.size() == (size_t)64 * h->world && memcmp(c.handles.data(), ipc_handles, c.handles.size()) == 0) {
+      h->peer_ready = true;  // same peers, same buffers: the mappings (and the device table of their addresses) are still in place
+      return 0;
+    }
+    for (void* p : c.opened) cudaIpcCloseMemHandle(p);  // the peers changed (a rank restarted): map afresh
+    c.opened.clear();
+    c.handles.clear();
+  }
   std::vector<double*> ptrs(h->world, nullptr);
+  std::vector<void*> opened;
   for (int r = 0; r < h->world; ++r) {
     if (r == h->rank) { ptrs[r] = h->xbuf; continue; }
     cudaIpcMemHandle_t hd;
     memcpy(&hd, (const char*)ipc_handles + (size_t)64 * r, 64);
     void* p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (the GPUs must be peers on one node, one process each)", r, cudaGetErrorString(e));
-    h->peer_opened.push_back(p);
+    if (e != cudaSuccess) {
+      for (void* q : opened) cudaIpcCloseMemHandle(q);
+      return fail(ERIRT_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (the GPUs must be peers on one node, one process each)", r, cudaGetErrorString(e));
+    }
+    opened.push_back(p);
     ptrs[r] = (double*)p;
+  }
+  if (h->peer_cache_slot >= 0) {
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    PeerCacheEntry& c = g_peer_cache[h->peer_cache_slot];
+    c.opened = opened;
+    c.handles.assign((const char*)ipc_handles, (const char*)ipc_handles + (size_t)64 * h->world);
+  } else {
+    h->peer_opened = opened;
   }
   CU(cudaMemcpy(h->dPeerBufs, ptrs.data(), h->world * sizeof(double*), cudaMemcpyHostToDevice));
   h->peer_ready = true;
@@ -1523,7 +1611,7 @@ extern "C" int erirt_peer_detach(erirt_handle* h) {
   if (!h) return fail(ERIRT_E_ARG, "null handle");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->stream));
-  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);  // (mappings of a cached exchange buffer stay open for the next handle)
   h->peer_opened.clear();
   // Later sweeps go through ncclAllReduce when the chain has an NCCL communicator; a chain created with
   // erirt_comm_init(..., NULL) has no exchange left and launch_global refuses to run (ERIRT_E_STATE) instead of drawing

@@ -23,9 +23,16 @@ static_assert(FMD_ABMAX < MD_COUNT, "misc block too small");
 
 constexpr int TAB_PITCH = 20;  // floats per item group in the response tables: groups g and g+4 fall on disjoint banks
 constexpr int FAST_FLUSH_TILES = 16;  // item statistics live in f32 registers and are folded into the f64 accumulators every 16 tiles
-// Work queues of the cells that leave the fast path are WARP-LOCAL: a warp serves its own persons from the row sums to the
+// ERIRT_QUEUE_MODE 0 (default): one two-ended work queue per tile (CTA), [0, QSTD) certainly-rejected cells, [QSTD, QCAP) undecided /
+// Method-B cells, filled with one shared-memory atomic per warp and drained by all four warps after a CTA barrier.
+// ERIRT_QUEUE_MODE 1 (experiment, measured 7 % slower at C5: the per-warp remainders cost more than the two barriers save):
+// work queues of the cells that leave the fast path are WARP-LOCAL: a warp serves its own persons from the row sums to the
 // drain, so nothing between the tile load and the transposed statistics pass needs a CTA barrier.  Region of a warp:
 // QW entries, [0, QSTDW) certainly-rejected cells (standard), [QSTDW, QW) undecided / Method-B cells (special).
+#ifndef ERIRT_QUEUE_MODE
+#define ERIRT_QUEUE_MODE 0
+#endif
+constexpr int QSTD = 768;
 constexpr int QW = QCAP / (CTA_THREADS / 32);
 constexpr int QSTDW = (QW * 3) / 4;
 
@@ -71,6 +78,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   double* s_miscd = reinterpret_cast<double*>(smem + A.S.off_misc);  // MD_COUNT + SC_COUNT doubles
   double* s_scal = s_miscd + MD_COUNT;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scal + SC_COUNT);
+  uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);  // [0]: packed counts of the CTA queue (low 16 bits standard, high 16 bits special)
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
   if (*A.status <= -1000) return;  // a peer of the sharded chain timed out: the chain is dead, do not spin through queued sweeps
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       s_miscd[FMD_AMAX] = amax;
       s_miscd[FMD_ABMAX] = abmax;
       mbar_init(s_bar, 1);
+      s_qctl[0] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -501,6 +510,94 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       }
     }
     PF_TICK(6);  // PG main pass
+#if ERIRT_QUEUE_MODE == 0
+    {
+      // ---- hand the cells that left the fast path to the tile's work queues: one shared-memory atomic per WARP reserves the
+      //      slots of all its lanes in both queues (packed counts, warp prefix sum), then every lane writes its entries ----
+      const u64 smask = dmask & rmask, umask = dmask & ~rmask;  // standard (certainly rejected) / special (undecided)
+      const uint32_t n_std = (uint32_t)__popcll(smask), n_spc = (uint32_t)__popcll(umask);
+      acc_defer += n_std + n_spc;
+      uint32_t pre = n_std | (n_spc << 16);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+        if ((tid & 31) >= o) pre += t;
+      }
+      const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
+      uint32_t wbase = 0;
+      if ((tid & 31) == 31 && wtotal) wbase = atomicAdd(&s_qctl[0], wtotal);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      uint32_t slot_s = (wbase & 0xffffu) + (pre & 0xffffu) - n_std;
+      uint32_t slot_u = (wbase >> 16) + (pre >> 16) - n_spc;
+      // bit 4*kk+e of a mask -> item index: the thread owns 32/TPP consecutive items in every block of 32
+      constexpr int BPB = 32 / TPP;
+      auto push = [&](uint32_t m, int bit0, uint32_t& slot, const uint32_t cap, const uint32_t qbase, const uint32_t flag) {
+        while (m) {
+          const int bit = bit0 + __ffs((int)m) - 1;
+          m &= m - 1u;
+          const int j = ((bit / BPB) << 5) + q * BPB + (bit % BPB);
+          if (slot < cap) s_queue[qbase + slot] = ((uint32_t)p << 16) | (uint32_t)j | flag;
+          else {  // queue overflow: finish the cell here
+            const float z = fmaf(s_par[PAR_A * Jp + j], thp, s_par[PAR_AB * Jp + j]);
+            my_om[j] = pg_resolve_f32(A.key, gid, k + 1, j, z, flag != 0u);
+          }
+          ++slot;
+        }
+      };
+      if (wtotal) {
+        push((uint32_t)smask, 0, slot_s, (uint32_t)QSTD, 0u, 0u);
+        push((uint32_t)(smask >> 32), 32, slot_s, (uint32_t)QSTD, 0u, 0u);
+        push((uint32_t)umask, 0, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
+        push((uint32_t)(umask >> 32), 32, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
+      }
+    }
+    PF_TICK(7);  // queue push
+    __syncthreads();
+    PF_TICK(8);  // barrier
+
+    {
+      // ---- drain, one phase over the CTA's queue (the load of the four warps is balanced: a warp-local queue was measured 7 %
+      //      slower, r02 profiles): standard entries (Method-A retry rounds, two cells in flight per thread) are dealt from
+      //      thread 0 upwards, special entries (undecided attempt 0: replay it with the a_1 term) from the last thread downwards ----
+      const uint32_t qc = s_qctl[0];
+      const uint32_t qn = min(qc & 0xffffu, (uint32_t)QSTD), qu = min(qc >> 16, (uint32_t)(QCAP - QSTD));
+      for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
+        const bool has2 = idx + CTA_THREADS < qn;
+        const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
+        const int j1 = (int)(e1 & 0xffffu), p1 = (int)(e1 >> 16), j2 = (int)(e2 & 0xffffu), p2 = (int)(e2 >> 16);
+        const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
+        const float z2 = fmaf(s_par[PAR_A * Jp + j2], s_u[p2 * Dgp + F + 1], s_par[PAR_AB * Jp + j2]);
+        const uint32_t g1 = A.person_offset + (uint32_t)(row0 + p1), g2 = A.person_offset + (uint32_t)(row0 + p2);
+        const bool b1 = !(0.5f * fabsf(z1) <= (float)PG_CSWITCH), b2 = !(0.5f * fabsf(z2) <= (float)PG_CSWITCH);  // Method B or NaN
+        float om1 = b1 ? 0.0f : -2.0f, om2 = (has2 && !b2) ? -2.0f : 0.0f;
+#pragma unroll 1
+        for (uint32_t r = 1; r < PG_MAX_ATTEMPTS && (om1 < 0.f || om2 < 0.f); ++r) {
+          const uint4 w1 = philox(A.sched, g1, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j1), r);
+          const uint4 w2 = philox(A.sched, g2, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j2), r);
+          const float o1 = pg_exact_pair(z1, w1.x, w1.y, w1.z, w1.w);
+          const float o2 = pg_exact_pair(z2, w2.x, w2.y, w2.z, w2.w);
+          if (om1 < 0.f) om1 = o1;
+          if (om2 < 0.f) om2 = o2;
+        }
+        if (om1 < 0.f) om1 = 0.25f * (float)PG_T;
+        if (om2 < 0.f) om2 = 0.25f * (float)PG_T;
+        if (b1) om1 = pg_resolve_f32(A.key, g1, k + 1, j1, z1, false);  // rare: Method-B regime (or NaN state)
+        if (has2 && b2) om2 = pg_resolve_f32(A.key, g2, k + 1, j2, z2, false);
+        s_om[p1 * Jp + j1] = om1;
+        if (has2) s_om[p2 * Jp + j2] = om2;
+      }
+      for (uint32_t idx = (uint32_t)(CTA_THREADS - 1 - tid); idx < qu; idx += CTA_THREADS) {
+        const uint32_t e1 = s_queue[QSTD + idx];
+        const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
+        const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
+        s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, true);
+      }
+    }
+    PF_TICK(9);  // drain
+    __syncthreads();  // the whole tile (omega_{k+1}, u rows) is final: the transposed passes below read across warps
+    if (tid == 0) s_qctl[0] = 0;  // next written by the push of the next tile, two barriers from here
+    PF_TICK(10);  // barrier
+#else
     uint32_t wq_counts;  // packed entry counts of this warp's queues (low 16 bits standard, high 16 bits special)
     uint32_t* const wq = s_queue + (tid >> 5) * QW;
     {
@@ -584,6 +681,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     PF_TICK(9);  // drain
     __syncthreads();  // the whole tile (omega_{k+1}, u rows) is final: the transposed passes below read across warps
     PF_TICK(10);  // barrier
+#endif
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
     if (e_active) {

@@ -17,11 +17,20 @@ def _tnorm_pos(rng, mu, sd, size, upper=np.inf, lower=0.0):
     mu_b = np.broadcast_to(mu, out.shape).reshape(-1)
     sd_b = np.broadcast_to(sd, out.shape).reshape(-1)
     todo = np.arange(flat.size)
-    while todo.size:
+    rounds = 0
+    while todo.size and rounds < 8:
         v = rng.normal(mu_b[todo], sd_b[todo])
         ok = (v > lower) & (v < upper)
         flat[todo[ok]] = v[ok]
         todo = todo[~ok]
+        rounds += 1
+    if todo.size:
+        # far tails (mean many SDs outside the interval: plain rejection would never end; Distributions.jl's Truncated{Normal}
+        # switches to a tail sampler there too): exact inverse-CDF draw in the standardised interval
+        from scipy import stats
+        a = (lower - mu_b[todo]) / sd_b[todo]
+        b = (upper - mu_b[todo]) / sd_b[todo]
+        flat[todo] = stats.truncnorm.rvs(a, b, loc=mu_b[todo], scale=sd_b[todo], random_state=rng)
     return out
 
 

@@ -202,7 +202,10 @@ def test_cross_tile_register_accumulators_f32(E, oracle, monkeypatch, model, J, 
     pb = make_problem(model, 64 * 3 * 35 + 17, J, F, seed=23)
     ref = run_oracle(oracle, pb, 2)
     eng = run_engine(E, pb, 2, dtype="f32")
-    _compare_traces(eng, ref, pb, 2, 2e-5, 1e-1, frac_ok=0.995)
+    # Item columns: one PG accept/reject decision that f32 rounding takes the other way (the oracle decides in f64) changes that
+    # cell's omega by O(0.1), i.e. the item's statistics by ~0.1 / (0.2 N) = 7e-5 relative at N = 6.7k: 1e-4, against 1e-5 for a sweep
+    # without a flipped cell (measured: all but one of the 600 item values of this test within 1e-6)
+    _compare_traces(eng, ref, pb, 2, 1e-4, 1e-1, frac_ok=0.995)
     eng.close()
     # and the generic (f64) kernel with the same grid
     eng = run_engine(E, pb, 2, dtype="f64")
