@@ -340,6 +340,8 @@ struct erirt_handle {
   char* arena = nullptr;  // the one device allocation every pointer below is a slice of
   uint8_t* dY = nullptr;
   void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
+  double* dStatsPrev = nullptr;  // reduced statistics of the previous sweep: input of the global kernel's rehearsal pass
+  uint32_t* dTileCtr = nullptr;  // work counter of the person launches (dynamic tile dealing)
   double *dMom = nullptr, *dParams = nullptr, *dStats = nullptr, *dConstsLocal = nullptr, *dConsts = nullptr, *dDerived = nullptr;
   double* dLlOut = nullptr;
   double* dNuMom = nullptr;    // CrossQr with cfg.nu_cell_moments: [2][n_pad][Jp] running sum / sum of squares of the cell weights
@@ -373,6 +375,8 @@ struct erirt_handle {
 
 static int launch_person(erirt_handle* h, int stage);
 static int launch_global(erirt_handle* h, int stage);
+static bool pdl_enabled();
+static bool global_rehearsal_enabled();
 static int finalize_constants(erirt_handle* h);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -625,6 +629,8 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
     if (cfg->person_trace) want(&h->dPtrace, (size_t)h->cap * 3 * vec);
     want((void**)&h->dParams, (size_t)h->L.p_count * D);
     want((void**)&h->dStats, (size_t)(h->L.s_count + 2) * D);
+    want((void**)&h->dStatsPrev, (size_t)(h->L.s_count + 2) * D);
+    want((void**)&h->dTileCtr, sizeof(uint32_t));
     want((void**)&h->dConstsLocal, (size_t)h->c_count * D);
     want((void**)&h->dConsts, (size_t)h->c_count * D);
     want((void**)&h->dDerived, 4 * D);
@@ -1057,6 +1063,7 @@ static PersonArgs<R> make_person_args(erirt_handle* h, int stage) {
   A.params = h->dParams;
   A.stats = h->dStats;
   A.sweep_ctr = h->dSweep;
+  A.tile_ctr = h->dTileCtr;
   A.status = h->dStatus;
   A.n_local = h->cfg.n_subj;
   A.n_pad = h->n_pad;
@@ -1081,6 +1088,9 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   A.stage = stage;
   A.params = h->dParams;
   A.stats = h->dStats;
+  A.stats_prev = h->dStatsPrev;
+  A.rehearse = global_rehearsal_enabled() ? 1 : 0;
+  A.tile_ctr = h->dTileCtr;
   A.sweep_ctr = h->dSweep;
   A.T1 = h->dConsts + h->c_T1;
   A.T2 = h->dConsts + h->c_T2;
@@ -1115,16 +1125,42 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   return A;
 }
 
+// Every kernel of the sweep chain is launched with programmatic stream serialization (griddep_wait / griddep_launch in the
+// kernels, layout.cuh): a kernel's CTAs may become resident, and run what does not depend on its predecessor, while the predecessor
+// is still running.  ERIRT_PDL=0 switches the attribute off (plain stream order; the device-side calls are then no-ops).
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("ERIRT_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+// ERIRT_G_REHEARSE=0 switches the instruction-cache rehearsal of the global kernel off (global.cuh); it needs the early residency PDL gives
+static bool global_rehearsal_enabled() {
+  static const bool on = [] { const char* e = getenv("ERIRT_G_REHEARSE"); return pdl_enabled() && !(e && atoi(e) == 0); }();
+  return on;
+}
+static cudaError_t launch_chain_kernel(const void* kfn, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelExC(&lc, kfn, args);
+}
+
 static int launch_person(erirt_handle* h, int stage) {
   const void* kfn = person_kernel_for(h, stage == 0 ? 0 : 1);
   if (h->cfg.dtype == ERIRT_F32) {
     PersonArgs<float> A = make_person_args<float>(h, stage);
     void* args[] = {&A};
-    CU(cudaLaunchKernel(kfn, dim3(stage == 0 ? h->grid : h->grid_gen), dim3(CTA_THREADS), args, A.S.total, h->stream));
+    CU(launch_chain_kernel(kfn, dim3(stage == 0 ? h->grid : h->grid_gen), dim3(CTA_THREADS), args, A.S.total, h->stream));
   } else {
     PersonArgs<double> A = make_person_args<double>(h, stage);
     void* args[] = {&A};
-    CU(cudaLaunchKernel(kfn, dim3(stage == 0 ? h->grid : h->grid_gen), dim3(CTA_THREADS), args, A.S.total, h->stream));
+    CU(launch_chain_kernel(kfn, dim3(stage == 0 ? h->grid : h->grid_gen), dim3(CTA_THREADS), args, A.S.total, h->stream));
   }
   return 0;
 }
@@ -1135,8 +1171,8 @@ static int launch_global(erirt_handle* h, int stage) {
     NC(nccl::all_reduce(h->dStats, h->dStats, (size_t)h->L.s_count, nccl::kFloat64, nccl::kSum, h->comm, h->stream));
   GlobalArgs G = make_global_args(h, stage);
   const size_t gsm = (size_t)(h->L.s_count + 2 + (h->L.F + 1) * (h->L.F + 1) + 5 * h->L.Jp) * sizeof(double);  // staged statistics, X'X, raw variates
-  global_draw_kernel<<<1, G_THREADS, gsm, h->stream>>>(G);
-  CU(cudaGetLastError());
+  void* args[] = {&G};
+  CU(launch_chain_kernel((const void*)global_draw_kernel, dim3(1), dim3(G_THREADS), args, gsm, h->stream));
   return 0;
 }
 
@@ -1202,7 +1238,7 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
     };
     if (!h->graph_exec && (rc = capture(1, &h->graph_exec))) return rc;
     const char* env_gs = getenv("ERIRT_GRAPH_SWEEPS");
-    const int gs = env_gs ? std::max(1, std::min(64, atoi(env_gs))) : 1;
+    const int gs = env_gs ? std::max(1, std::min(64, atoi(env_gs))) : 16;  // the kernels of one graph overlap their neighbours (PDL edges); graph boundaries serialise
     int64_t left = n_sweeps;
     if (gs > 1 && left >= gs) {
       if (h->graph_multi && h->graph_multi_sweeps != gs) { cudaGraphExecDestroy(h->graph_multi); h->graph_multi = nullptr; }

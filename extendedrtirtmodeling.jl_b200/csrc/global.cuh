@@ -19,94 +19,108 @@
 
 namespace erirt {
 
-constexpr int G_THREADS = 512;  // warp 0: structural block (one lane); warps 1..15: item draws; all warps: raw variates, reductions
+// warp 0: structural block (cooperatively); warps 1..7: item draws; all warps: raw variates, reductions.  256 threads at <= 96
+// registers fit beside two resident person CTAs of the hot configuration, i.e. as soon as ONE person CTA of some SM has finished
+// its tiles, so the parameter-independent part of this kernel (everything before griddep_wait) runs beside the person kernel's tail.
+constexpr int G_THREADS = 256;
 
-// ---- small dense SPD helpers (column-major, executed by one thread on shared-memory scratch).  Every loop is kept rolled
-//      (#pragma unroll 1): this code runs once per sweep on one lane, so unrolled straight-line code would only turn into
-//      instruction-cache misses (measured: 7 k cycles for a 25-element copy before, see profiles/) ----
-__device__ inline bool chol_lower(int n, const double* A, double* Lm) {
-  #pragma unroll 1
-  for (int t = 0; t < n * n; ++t) Lm[t] = 0.0;
+// ---- small dense SPD helpers, warp-cooperative: all 32 lanes of ONE warp call them at the same point with the same arguments;
+//      matrices are column-major in shared memory, n <= 32 = MAXD, lane i owns row i (or column i).  The structural block is a
+//      dependent chain that sits on the critical path of every sweep (the person kernels wait for it): on one lane a 12 x 12
+//      solve took 29 us (profiles/r02e_sweep_timeline.txt), spread over the lanes its depth is O(n^2) shared-memory round trips.
+//      The Cholesky factor and the forward substitution subtract their products in the same order as the textbook serial loops
+//      (bitwise the same factor); the back substitution and the inverse accumulate in a different order (1e-16 relative). ----
+__device__ inline bool chol_lower(int n, const double* A, double* Lm, int lane) {
+  // right-looking: Lm starts as the lower triangle of A, column j is scaled and its outer product leaves the trailing rows
+  for (int t = lane; t < n * n; t += 32) {
+    const int r = t % n, c = t / n;
+    Lm[t] = r >= c ? A[t] : 0.0;
+  }
+  bool ok = true;
   #pragma unroll 1
   for (int j = 0; j < n; ++j) {
-    double d = A[j + n * j];
-    #pragma unroll 1
-    for (int k = 0; k < j; ++k) d -= Lm[j + n * k] * Lm[j + n * k];
-    if (!(d > 0.0)) return false;
+    __syncwarp();
+    double d = Lm[j + n * j];
+    if (!(d > 0.0)) { ok = false; break; }  // uniform: every lane reads the same element
     d = sqrt(d);
-    Lm[j + n * j] = d;
-    #pragma unroll 1
-    for (int i = j + 1; i < n; ++i) {
-      double s = A[i + n * j];
+    double lij = 0.0;
+    if (lane > j && lane < n) lij = Lm[lane + n * j] / d;
+    __syncwarp();
+    if (lane == j) Lm[j + n * j] = d;
+    if (lane > j && lane < n) Lm[lane + n * j] = lij;
+    __syncwarp();  // column j is final
+    if (lane > j && lane < n) {
       #pragma unroll 1
-      for (int k = 0; k < j; ++k) s -= Lm[i + n * k] * Lm[j + n * k];
-      Lm[i + n * j] = s / d;
+      for (int c = j + 1; c <= lane; ++c) Lm[lane + n * c] -= lij * Lm[c + n * j];
     }
   }
+  __syncwarp();
+  return ok;
+}
+// sol = A^{-1} rhs through the Cholesky factor (Lm: n*n scratch).  sol may alias rhs.
+__device__ inline bool spd_solve(int n, const double* A, const double* rhs, double* sol, double* Lm, int lane) {
+  if (!chol_lower(n, A, Lm, lane)) return false;
+  double sv = lane < n ? rhs[lane] : 0.0;
+  #pragma unroll 1
+  for (int k = 0; k < n; ++k) {  // forward: y_k = s_k / L_kk, rows below lose L_ik y_k
+    const double yk = __shfl_sync(0xffffffffu, sv, k) / Lm[k + n * k];
+    if (lane == k) sv = yk;
+    else if (lane > k && lane < n) sv -= Lm[lane + n * k] * yk;
+  }
+  #pragma unroll 1
+  for (int k = n - 1; k >= 0; --k) {  // backward: x_k = s_k / L_kk, rows above lose L_ki x_k
+    const double xk = __shfl_sync(0xffffffffu, sv, k) / Lm[k + n * k];
+    if (lane == k) sv = xk;
+    else if (lane < k) sv -= Lm[k + n * lane] * xk;
+  }
+  __syncwarp();
+  if (lane < n) sol[lane] = sv;
+  __syncwarp();
   return true;
 }
-// Ainv = A^{-1} through the Cholesky factor; Lm and Li are n*n scratch, none of the four may alias
-__device__ inline bool spd_inverse(int n, const double* A, double* Ainv, double* Lm, double* Li) {
-  if (!chol_lower(n, A, Lm)) return false;
-  #pragma unroll 1
-  for (int t = 0; t < n * n; ++t) Li[t] = 0.0;
-  #pragma unroll 1
-  for (int j = 0; j < n; ++j) {
-    Li[j + n * j] = 1.0 / Lm[j + n * j];
+// Ainv = A^{-1}: lane j solves A x = e_j (column j) by the two substitutions; Lm and Y are n*n scratch, none of the four may alias
+__device__ inline bool spd_inverse(int n, const double* A, double* Ainv, double* Lm, double* Y, int lane) {
+  if (!chol_lower(n, A, Lm, lane)) return false;
+  if (lane < n) {
+    double* y = Y + n * lane;     // column `lane` of L^{-1}
+    double* x = Ainv + n * lane;  // column `lane` of A^{-1}
     #pragma unroll 1
-    for (int i = j + 1; i < n; ++i) {
-      double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double sacc = i == lane ? 1.0 : 0.0;
       #pragma unroll 1
-      for (int k = j; k < i; ++k) s -= Lm[i + n * k] * Li[k + n * j];
-      Li[i + n * j] = s / Lm[i + n * i];
+      for (int k = 0; k < i; ++k) sacc -= Lm[i + n * k] * y[k];
+      y[i] = sacc / Lm[i + n * i];
+    }
+    #pragma unroll 1
+    for (int i = n - 1; i >= 0; --i) {
+      double sacc = y[i];
+      #pragma unroll 1
+      for (int k = i + 1; k < n; ++k) sacc -= Lm[k + n * i] * x[k];
+      x[i] = sacc / Lm[i + n * i];
     }
   }
-  #pragma unroll 1
-  for (int i = 0; i < n; ++i)
-    #pragma unroll 1
-    for (int j = 0; j < n; ++j) {
-      double s = 0.0;
-      #pragma unroll 1
-      for (int k = (i > j ? i : j); k < n; ++k) s += Li[k + n * i] * Li[k + n * j];
-      Ainv[i + n * j] = s;
-    }
+  __syncwarp();
   return true;
 }
-__device__ inline bool spd_solve(int n, const double* A, const double* rhs, double* sol, double* Lm, double* y) {
-  if (!chol_lower(n, A, Lm)) return false;
-  #pragma unroll 1
-  for (int i = 0; i < n; ++i) {
-    double s = rhs[i];
-    #pragma unroll 1
-    for (int k = 0; k < i; ++k) s -= Lm[i + n * k] * y[k];
-    y[i] = s / Lm[i + n * i];
-  }
-  #pragma unroll 1
-  for (int i = n - 1; i >= 0; --i) {
-    double s = y[i];
-    #pragma unroll 1
-    for (int k = i + 1; k < n; ++k) s -= Lm[k + n * i] * sol[k];
-    sol[i] = s / Lm[i + n * i];
-  }
-  return true;
+// sum over the lanes of a warp (butterfly: every lane gets the total)
+__device__ inline double warp_sum(double v) {
+  #pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
-// quadratic form b' M b and bilinear b' v
-__device__ inline double quad_form(int n, const double* M, const double* b) {
-  double acc = 0.0;
-  #pragma unroll 1
-  for (int r = 0; r < n; ++r) {
+// quadratic form b' M b and bilinear a' b (every lane returns the result)
+__device__ inline double quad_form(int n, const double* M, const double* b, int lane) {
+  double t = 0.0;
+  if (lane < n) {
     double x = 0.0;
     #pragma unroll 1
-    for (int q = 0; q < n; ++q) x += M[r + n * q] * b[q];
-    acc += b[r] * x;
+    for (int q = 0; q < n; ++q) x += M[lane + n * q] * b[q];
+    t = b[lane] * x;
   }
-  return acc;
+  return warp_sum(t);
 }
-__device__ inline double dotn(int n, const double* a, const double* b) {
-  double acc = 0.0;
-  #pragma unroll 1
-  for (int r = 0; r < n; ++r) acc += a[r] * b[r];
-  return acc;
+__device__ inline double dotn(int n, const double* a, const double* b, int lane) {
+  return warp_sum(lane < n ? a[lane] * b[lane] : 0.0);
 }
 
 __device__ inline void cov2one_2x2(double* S) {  // Draw.pl.jl:507-511
@@ -201,16 +215,16 @@ struct GScratch {
   double graw[6];   // attempt-0 raw material of the Sigma site: (normal, uniform) of units 0, 1, 2
 };
 
-// mean + chol(V).L * z with z_t ~ N(0,1) at the global beta site; returns false if V is not SPD
-__device__ inline bool mvn_draw(const GlobalArgs& A, uint32_t s, int d, GScratch& w) {
-  if (!chol_lower(d, w.V, w.Lc)) return false;
-  #pragma unroll 1
-  for (int r = 0; r < d; ++r) {
-    double acc = w.mean[r];
+// mean + chol(V).L * z with z_t ~ N(0,1) at the global beta site; returns false if V is not SPD (warp-cooperative)
+__device__ inline bool mvn_draw(int d, GScratch& w, int lane) {
+  if (!chol_lower(d, w.V, w.Lc, lane)) return false;
+  if (lane < d) {
+    double acc = w.mean[lane];
     #pragma unroll 1
-    for (int q = 0; q <= r; ++q) acc += w.Lc[r + d * q] * w.zn[q];
-    w.beta[r] = acc;
+    for (int q = 0; q <= lane; ++q) acc += w.Lc[lane + d * q] * w.zn[q];
+    w.beta[lane] = acc;
   }
+  __syncwarp();
   return true;
 }
 
@@ -229,7 +243,10 @@ __device__ inline void latent_prebuild(const GlobalArgs& A, const double* XtX, c
   }
 }
 
-__device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, uint32_t s, const GramView& Gm, const GramView& Gw, GScratch& w) {
+// Structural draws of sweep s, executed by the 32 lanes of warp 0 together: vector work is dealt over the lanes, scalar work is
+// computed redundantly by every lane (same values), results are left in w.beta / w.Sigma.
+__device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, uint32_t s, const GramView& Gm, const GramView& Gw, GScratch& w,
+                                        int lane) {
   const Layout& L = A.L;
   const int F = L.F, pb = F + 1, model = A.model;
   const double N = (double)A.n_total;
@@ -237,101 +254,95 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
   const double Sth2 = Gm.at(TH, TH), Sze2 = Gm.at(ZE, ZE), Sthze = Gm.at(TH, ZE);
   const double add = (A.compat & 1) ? 0.0 : 1.0;  // `1/σβ₀^2 .+ M` adds to EVERY element (Draw.pl.jl:386,410; quirk Q1)
   bool ok = true;
+  double Sig[4] = {w.Sigma[0], w.Sigma[1], w.Sigma[2], w.Sigma[3]};
+  __syncwarp();
   if (model == M_MLIRT) {
-    #pragma unroll 1
-    for (int r = 0; r < pb; ++r) w.rhs[r] = Gm.at(r, TH);
-    ok = spd_solve(pb, XtX, w.rhs, w.beta, w.Lc, w.z);  // getSubjCoefficientsMlIrt
-    if (!A.intercept) w.beta[0] = 0.0;
+    if (lane < pb) w.rhs[lane] = Gm.at(lane, TH);
+    __syncwarp();
+    ok = spd_solve(pb, XtX, w.rhs, w.beta, w.Lc, lane);  // getSubjCoefficientsMlIrt
+    if (!A.intercept && lane == 0) w.beta[0] = 0.0;
   } else if (model == M_RTIRT) {
     const int d = 2 * pb;
-    const double S11 = w.Sigma[0], S12 = w.Sigma[2], S22 = w.Sigma[3], det = S11 * S22 - S12 * S12;
+    const double S11 = Sig[0], S12 = Sig[2], S22 = Sig[3], det = S11 * S22 - S12 * S12;
     const double iO[4] = {S22 / det, -S12 / det, -S12 / det, S11 / det};
-    #pragma unroll 1
-    for (int br = 0; br < 2; ++br)
-      #pragma unroll 1
-      for (int bc = 0; bc < 2; ++bc)
-        #pragma unroll 1
-        for (int r = 0; r < pb; ++r)
-          #pragma unroll 1
-          for (int q = 0; q < pb; ++q) w.M[(br * pb + r) + d * (bc * pb + q)] = iO[br + 2 * bc] * XtX[r + pb * q] + add;
-    if (add == 0.0)
-      #pragma unroll 1
-      for (int t = 0; t < d; ++t) w.M[t + d * t] += 1.0;
-    ok = spd_inverse(d, w.M, w.V, w.Lc, w.T);
-    #pragma unroll 1
-    for (int c = 0; c < 2; ++c)  // vec(x'η invΩ')
-      #pragma unroll 1
-      for (int r = 0; r < pb; ++r) w.rhs[c * pb + r] = Gm.at(r, TH) * iO[c + 0] + Gm.at(r, ZE) * iO[c + 2];
-    #pragma unroll 1
-    for (int r = 0; r < d; ++r) {
+    for (int t = lane; t < d * d; t += 32) {
+      const int rr = t % d, cc = t / d, br = rr / pb, r = rr % pb, bc = cc / pb, q = cc % pb;
+      w.M[t] = iO[br + 2 * bc] * XtX[r + pb * q] + add + ((add == 0.0 && rr == cc) ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    ok = spd_inverse(d, w.M, w.V, w.Lc, w.T, lane);
+    if (lane < d) {  // vec(x'η invΩ')
+      const int c = lane / pb, r = lane % pb;
+      w.rhs[lane] = Gm.at(r, TH) * iO[c + 0] + Gm.at(r, ZE) * iO[c + 2];
+    }
+    __syncwarp();
+    if (lane < d) {
       double acc = 0.0;
       #pragma unroll 1
-      for (int q = 0; q < d; ++q) acc += w.V[r + d * q] * w.rhs[q];
-      w.mean[r] = acc;
+      for (int q = 0; q < d; ++q) acc += w.V[lane + d * q] * w.rhs[q];
+      w.mean[lane] = acc;
     }
-    ok = ok && mvn_draw(A, s, d, w);
-    if (!A.intercept) { w.beta[0] = 0.0; w.beta[pb] = 0.0; }
+    __syncwarp();
+    ok = ok && mvn_draw(d, w, lane);
+    if (!A.intercept && lane == 0) { w.beta[0] = 0.0; w.beta[pb] = 0.0; }
+    __syncwarp();
     // e'e, e = [θ ζ] - xβ   (drawSubjCovariance)
     const double* b1 = w.beta;
     const double* b2 = w.beta + pb;
     double q11 = 0, q12 = 0, q22 = 0, l1t = 0, l1z = 0, l2t = 0, l2z = 0;
-    #pragma unroll 1
-    for (int r = 0; r < pb; ++r) {
+    if (lane < pb) {
+      const int r = lane;
       double x1 = 0, x2 = 0;
       #pragma unroll 1
       for (int q = 0; q < pb; ++q) { x1 += XtX[r + pb * q] * b1[q]; x2 += XtX[r + pb * q] * b2[q]; }
-      q11 += b1[r] * x1; q12 += b1[r] * x2; q22 += b2[r] * x2;
-      l1t += b1[r] * Gm.at(r, TH); l1z += b1[r] * Gm.at(r, ZE);
-      l2t += b2[r] * Gm.at(r, TH); l2z += b2[r] * Gm.at(r, ZE);
+      q11 = b1[r] * x1; q12 = b1[r] * x2; q22 = b2[r] * x2;
+      l1t = b1[r] * Gm.at(r, TH); l1z = b1[r] * Gm.at(r, ZE);
+      l2t = b2[r] * Gm.at(r, TH); l2z = b2[r] * Gm.at(r, ZE);
     }
+    q11 = warp_sum(q11); q12 = warp_sum(q12); q22 = warp_sum(q22);
+    l1t = warp_sum(l1t); l1z = warp_sum(l1z); l2t = warp_sum(l2t); l2z = warp_sum(l2z);
     const double E11 = Sth2 - 2.0 * l1t + q11, E12 = Sthze - l1z - l2t + q12, E22 = Sze2 - 2.0 * l2z + q22;
     const double Psi[4] = {E11 + 1.0, E12, E12, E22 + 1.0};
-    inv_wishart2(A.key, s, N + 3.0, Psi, w.Sigma, w.graw);
-    if (A.cov2one) cov2one_2x2(w.Sigma);
+    inv_wishart2(A.key, s, N + 3.0, Psi, Sig, w.graw);
+    if (A.cov2one) cov2one_2x2(Sig);
   } else if (model == M_NULL) {
-    #pragma unroll 1
-    for (int t = 0; t < 2 * pb; ++t) w.beta[t] = 0.0;
+    for (int t = lane; t < 2 * pb; t += 32) w.beta[t] = 0.0;
     const double Psi[4] = {Sth2 + 1.0, Sthze, Sthze, Sze2 + 1.0};
-    inv_wishart2(A.key, s, N + 3.0, Psi, w.Sigma, w.graw);  // drawSubjCovarianceNull
-    if (A.cov2one) cov2one_2x2(w.Sigma);
+    inv_wishart2(A.key, s, N + 3.0, Psi, Sig, w.graw);  // drawSubjCovarianceNull
+    if (A.cov2one) cov2one_2x2(Sig);
   } else if (model == M_CROSS || model == M_CROSSQR) {
     // drawSubjCovarianceCross, Draw.pl.jl:542-557
     const double parA = 1e-3 + N / 2.0, parB = 1e-3 + Sze2 / 2.0;
     const double sv = parB / gamma_from_raw(A.key, 0, s, make_site(DOM_GLOBAL, GK_SIGMAP), parA, w.graw[0], w.graw[1]);
-    w.Sigma[0] = 1.0; w.Sigma[1] = 0.0; w.Sigma[2] = 0.0; w.Sigma[3] = sv;
-    if (A.cov2one) cov2one_2x2(w.Sigma);
+    Sig[0] = 1.0; Sig[1] = 0.0; Sig[2] = 0.0; Sig[3] = sv;
+    if (A.cov2one) cov2one_2x2(Sig);
   } else if (model == M_LATENT || model == M_LATENTQR) {
     const int d = F + 2;
     const bool qrm = model == M_LATENTQR;
     // x = [1 X θ]: x'x (ingest constant bordered by the θ column of the Gram) and x'y, y = ζ (Latent) or ζ - k1 ν (LatentQr),
     // were built by all lanes in latent_prebuild
-    S_TICK(7);
     double yy = Sze2;
     if (qrm) yy += -2.0 * A.k1 * Gm.at(ZE, NU) + A.k1 * A.k1 * Gm.at(NU, NU);
     if (!qrm) {  // drawSubjCoefficientsLatent
-      const double iO = 1.0 / w.Sigma[3];
-      #pragma unroll 1
-      for (int t = 0; t < d * d; ++t) w.M[t] = iO * w.XX[t] + add;
-      if (add == 0.0)
-        #pragma unroll 1
-        for (int t = 0; t < d; ++t) w.M[t + d * t] += 1.0;
-      ok = spd_inverse(d, w.M, w.V, w.Lc, w.T);
-      #pragma unroll 1
-      for (int r = 0; r < d; ++r) {
+      const double iO = 1.0 / Sig[3];
+      for (int t = lane; t < d * d; t += 32) w.M[t] = iO * w.XX[t] + add + ((add == 0.0 && t % d == t / d) ? 1.0 : 0.0);
+      __syncwarp();
+      ok = spd_inverse(d, w.M, w.V, w.Lc, w.T, lane);
+      if (lane < d) {
         double acc = 0.0;
         #pragma unroll 1
-        for (int q = 0; q < d; ++q) acc += w.V[r + d * q] * (w.rhs[q] * iO);
-        w.mean[r] = acc;
+        for (int q = 0; q < d; ++q) acc += w.V[lane + d * q] * (w.rhs[q] * iO);
+        w.mean[lane] = acc;
       }
-      ok = ok && mvn_draw(A, s, d, w);
+      __syncwarp();
+      ok = ok && mvn_draw(d, w, lane);
     } else {  // getSubjCoefficientsLatentQr: the tall Kronecker system collapses to OLS
-      ok = spd_solve(d, w.XX, w.rhs, w.beta, w.Lc, w.z);
+      ok = spd_solve(d, w.XX, w.rhs, w.beta, w.Lc, lane);
     }
-    S_TICK(8);
-    if (!A.intercept) w.beta[0] = 0.0;
+    if (!A.intercept && lane == 0) w.beta[0] = 0.0;
+    __syncwarp();
     // residual sum of squares r = y - xβ
-    const double ss = yy - 2.0 * dotn(d, w.beta, w.rhs) + quad_form(d, w.XX, w.beta);
-    S_TICK(9);
+    const double ss = yy - 2.0 * dotn(d, w.beta, w.rhs, lane) + quad_form(d, w.XX, w.beta, lane);
     double parA, parB;
     if (!qrm) {
       parA = 1e-3 + N / 2.0;
@@ -342,14 +353,11 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
       double scale;
       if (A.compat & 2) {
         // Σ r_i²/(2 k2 ν_i) from the 1/ν-weighted Gram: y/ν terms
-        #pragma unroll 1
-        for (int r = 0; r < d; ++r)
-          #pragma unroll 1
-          for (int q = 0; q < d; ++q) w.T[r + d * q] = Gw.at(r, q);
-        #pragma unroll 1
-        for (int r = 0; r < d; ++r) w.mean[r] = Gw.at(r, ZE) - A.k1 * Gm.at(0, r);  // Σ x (ζ - k1 ν)/ν
+        for (int t = lane; t < d * d; t += 32) w.T[t] = Gw.at(t % d, t / d);
+        if (lane < d) w.mean[lane] = Gw.at(lane, ZE) - A.k1 * Gm.at(0, lane);  // Σ x (ζ - k1 ν)/ν
+        __syncwarp();
         const double yyw = Gw.at(ZE, ZE) - 2.0 * A.k1 * Gm.at(0, ZE) + A.k1 * A.k1 * Snu;
-        const double ssw = yyw - 2.0 * dotn(d, w.beta, w.mean) + quad_form(d, w.T, w.beta);
+        const double ssw = yyw - 2.0 * dotn(d, w.beta, w.mean, lane) + quad_form(d, w.T, w.beta, lane);
         scale = ssw / (2.0 * A.k2);
       } else {
         // as written: sum(r.^2 / (2 k2e)) with vector / vector (quirk Q2, Draw.pl.jl:594)
@@ -357,16 +365,40 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
       }
       parB = 1e-3 + scale + Snu;
     }
-    S_TICK(10);
     const double sv = parB / gamma_from_raw(A.key, 0, s, make_site(DOM_GLOBAL, GK_SIGMAP), parA, w.graw[0], w.graw[1]);
-    w.Sigma[0] = 1.0; w.Sigma[1] = 0.0; w.Sigma[2] = 0.0; w.Sigma[3] = sv;
-    if (A.cov2one) cov2one_2x2(w.Sigma);
-    S_TICK(11);
+    Sig[0] = 1.0; Sig[1] = 0.0; Sig[2] = 0.0; Sig[3] = sv;
+    if (A.cov2one) cov2one_2x2(Sig);
   }
+  __syncwarp();
+  if (lane == 0) { w.Sigma[0] = Sig[0]; w.Sigma[1] = Sig[1]; w.Sigma[2] = Sig[2]; w.Sigma[3] = Sig[3]; }
   return ok;
 }
 
-__global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs A) {
+__device__ inline void global_raw_variates(const GlobalArgs& A, uint32_t s, double* sRaw, GScratch& w, int tid) {
+  // attempt-0 raw material of every site of sweep s, one task per lane: it does not depend on the parameters, and an f64 Box-Muller
+  // (log, sqrt, cospi) is a long dependent chain
+  const int J = A.L.J, Jp = A.L.Jp;
+  for (int t = tid; t < 4 * J + MAXD + 3; t += G_THREADS) {
+    if (t < 4 * J) {
+      const int j = t >> 2, kind = t & 3;
+      const uint32_t ik = kind == 0 ? IK_B : (kind == 1 ? IK_A : (kind == 2 ? IK_LAMBDA : IK_SIGMA2));
+      const uint4 wd = philox(A.key, (uint32_t)j, s, make_site(DOM_ITEM, ik), 0);
+      if (kind < 3) sRaw[kind * Jp + j] = normal2(wd.x, wd.y);
+      else { sRaw[3 * Jp + j] = normal2(wd.x, wd.y); sRaw[4 * Jp + j] = u01d(wd.z); }
+    } else if (t < 4 * J + MAXD) {
+      const int u = t - 4 * J;
+      const uint4 wd = philox(A.key, (uint32_t)u, s, make_site(DOM_GLOBAL, GK_BETA), 0);
+      w.zn[u] = normal2(wd.x, wd.y);
+    } else {
+      const int u = t - 4 * J - MAXD;
+      const uint4 wd = philox(A.key, (uint32_t)u, s, make_site(DOM_GLOBAL, GK_SIGMAP), 0);
+      w.graw[2 * u] = normal2(wd.x, wd.y);
+      w.graw[2 * u + 1] = u01d(wd.z);
+    }
+  }
+}
+
+__global__ void __maxnreg__(96) global_draw_kernel(const GlobalArgs A) {
 #ifdef ERIRT_TICKS
   const long long _g0 = clock64();
   if (threadIdx.x == 0) g_g0 = _g0;
@@ -377,9 +409,6 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   const int J = L.J, F = L.F, Dg = L.Dg, tid = threadIdx.x;
   const int model = A.model;
   const bool has_rt = model != M_MLIRT;
-  if (*A.status <= -1000) return;   // a peer timed out in an earlier exchange: no draws from partial sums, no further 10 s waits
-  const uint32_t k = *A.sweep_ctr;  // person launch P(k) just finished
-  const uint32_t s = k + 1;         // sweep whose parameters are drawn now
   const double N = (double)A.n_total;
   double* par = A.params;
   // Stage the reduced statistics and X'X in shared memory first: the structural block reads them element by element in
@@ -389,17 +418,50 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
   double* sXtX = g_dyn + L.s_count + 2;   // [(F+1)^2]
   double* sRaw = sXtX + (F + 1) * (F + 1);  // [5][Jp] attempt-0 raw material of the item sites: z_b, z_a, z_lambda, x_sigma2, u_sigma2
   const int Jp = L.Jp;
-  if (A.peer_bufs) {
-    peer_allreduce_sum(A.peer_bufs, A.xseq, A.world, A.rank, A.xstride, A.stats, L.s_count, st, A.status, tid, G_THREADS);
-    if (*reinterpret_cast<volatile int*>(A.status) <= -1000) return;  // timed out in this exchange (uniform: written before the CTA barrier)
-  } else {
-    for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats[t];
-  }
+  // ---- 0. before the dependency wait: what does not depend on the person launch P(k) that may still be running.  The sweep
+  //      counter and the parameters were written by the previous global kernel, which completed before any CTA of P(k) let this
+  //      kernel be scheduled (P's griddep_launch follows its own griddep_wait). ----
+  TL_DECL(tl_entry);
+  const uint32_t k = *A.sweep_ctr;  // person launch P(k)
+  const uint32_t s = k + 1;         // sweep whose parameters are drawn now
   for (int t = tid; t < (F + 1) * (F + 1); t += G_THREADS) sXtX[t] = A.XtX[t];
+  if (A.stage == 0 || A.stage == 2) global_raw_variates(A, s, sRaw, w, tid);
+  // Two passes over the body below.  Pass 0 is a REHEARSAL that runs before the dependency wait, on the reduced statistics of the
+  // previous sweep (A.stats_prev) and with every global store suppressed: this kernel runs once per sweep on an SM whose instruction
+  // caches the person kernel has flushed, and its ~4000 executed instructions are fetched cold (measured: 16 us after the wait, of
+  // which the arithmetic is a fraction).  The rehearsal pulls exactly the code (and the constants T1, T2, K0) the real pass needs
+  // into the caches while the person kernel is still finishing its last tiles; pass 1 is the real one.
+  const int first_pass = (A.rehearse && (A.stage == 0 || A.stage == 2) && k >= 1) ? 0 : 1;
+#pragma unroll 1
+  for (int pass = first_pass; pass < 2; ++pass) {
+  const bool real = pass == 1;
+  __syncthreads();  // the previous pass has finished with the shared scratch
   if (tid < MAXD) w.beta[tid] = par[L.p_beta + tid];  // one lane each: a single lane copying global -> shared pays a round trip per element
   if (tid >= 64 && tid < 68) w.Sigma[tid - 64] = par[L.p_Sigma + tid - 64];
+  if (real) {
+#ifdef ERIRT_TIMELINE
+    __syncthreads();
+    if (tid == 0) { g_timeline[k % TL_SLOTS][4] = tl_entry; g_timeline[k % TL_SLOTS][5] = tl_now(); }
+#endif
+    griddep_wait();  // P(k) has completed: its statistics (and, sharded, nothing else) are visible
+#ifdef ERIRT_TIMELINE
+    if (tid == 0) g_timeline[k % TL_SLOTS][6] = tl_now();
+#endif
+    if (*A.status <= -1000) return;   // a peer timed out in an earlier exchange: no draws from partial sums, no further 10 s waits
+    if (A.peer_bufs) {
+      peer_allreduce_sum(A.peer_bufs, A.xseq, A.world, A.rank, A.xstride, A.stats, L.s_count, st, A.status, tid, G_THREADS);
+      if (*reinterpret_cast<volatile int*>(A.status) <= -1000) return;  // timed out in this exchange (uniform: written before the CTA barrier)
+    } else {
+      for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats[t];
+    }
+  } else {
+    for (int t = tid; t < L.s_count; t += G_THREADS) st[t] = A.stats_prev[t];
+  }
   __syncthreads();
   G_TICK(0, 0);  // staging done
+#ifdef ERIRT_TIMELINE
+  if (real && tid == 0) g_timeline[k % TL_SLOTS][7] = tl_now();
+#endif
   const GramView Gm{st + L.s_gram, Dg, F};
   const GramView Gw{st + L.s_gramw, Dg, F};
   const double Sth = Gm.at(0, Gm.th()), Sth2 = Gm.at(Gm.th(), Gm.th()), Sthze = Gm.at(Gm.th(), Gm.ze());
@@ -444,6 +506,7 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
     }
     __syncthreads();
     for (int t = tid; t < L.s_count; t += G_THREADS) A.stats[t] = 0.0;
+    if (tid == 0) *A.tile_ctr = 0u;
     return;
   }
 
@@ -480,41 +543,25 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
       if (tid == 0) *A.ll_out = st[L.s_scal + SC_LL_BERN] + sRed[0] + st[L.s_scal + SC_LL_STRUCT];
       __syncthreads();
       for (int t = tid; t < L.s_count; t += G_THREADS) A.stats[t] = 0.0;
+      if (tid == 0) *A.tile_ctr = 0u;
       return;
     }
-    if (tid == 0 && (int)(k - 1) < A.cap) A.tr_ll[k - 1] = st[L.s_scal + SC_LL_BERN] + sRed[0] + st[L.s_scal + SC_LL_STRUCT];
+    if (real && tid == 0 && (int)(k - 1) < A.cap) A.tr_ll[k - 1] = st[L.s_scal + SC_LL_BERN] + sRed[0] + st[L.s_scal + SC_LL_STRUCT];
   }
 
   G_TICK(1, 0);  // log-likelihood done
-  // ---- 2.0 raw variates of attempt 0 of every site of sweep s, one task per lane: they do not depend on the parameters, and
-  //      an f64 Box-Muller (log, sqrt, cospi) is a long dependent chain that would otherwise run 4 + 2 times in a row per lane ----
-  for (int t = tid; t < 4 * J + MAXD + 3; t += G_THREADS) {
-    if (t < 4 * J) {
-      const int j = t >> 2, kind = t & 3;
-      const uint32_t ik = kind == 0 ? IK_B : (kind == 1 ? IK_A : (kind == 2 ? IK_LAMBDA : IK_SIGMA2));
-      const uint4 wd = philox(A.key, (uint32_t)j, s, make_site(DOM_ITEM, ik), 0);
-      if (kind < 3) sRaw[kind * Jp + j] = normal2(wd.x, wd.y);
-      else { sRaw[3 * Jp + j] = normal2(wd.x, wd.y); sRaw[4 * Jp + j] = u01d(wd.z); }
-    } else if (t < 4 * J + MAXD) {
-      const int u = t - 4 * J;
-      const uint4 wd = philox(A.key, (uint32_t)u, s, make_site(DOM_GLOBAL, GK_BETA), 0);
-      w.zn[u] = normal2(wd.x, wd.y);
-    } else {
-      const int u = t - 4 * J - MAXD;
-      const uint4 wd = philox(A.key, (uint32_t)u, s, make_site(DOM_GLOBAL, GK_SIGMAP), 0);
-      w.graw[2 * u] = normal2(wd.x, wd.y);
-      w.graw[2 * u + 1] = u01d(wd.z);
-    }
-  }
+#ifdef ERIRT_TIMELINE
+  if (real && tid == 0) g_timeline[k % TL_SLOTS][8] = tl_now();
+#endif
   if (model == M_LATENT || model == M_LATENTQR) latent_prebuild(A, sXtX, Gm, w, tid, G_THREADS);
   __syncthreads();
   G_TICK(6, 0);  // raw variates done
-  // ---- 2a. structural draws (thread 0), 2b. item draws (warps 1..) ----
-  if (tid == 0) {
-    if (!structural_draws(A, sXtX, s, Gm, Gw, w)) atomicExch(A.status, (int)s);
+  // ---- 2a. structural draws (warp 0, cooperatively), 2b. item draws (warps 1..) ----
+  if (tid < 32) {
+    if (!structural_draws(A, sXtX, s, Gm, Gw, w, tid) && tid == 0 && real) atomicExch(A.status, (int)s);
     G_TICK(2, 0);  // structural block done
   }
-  // item draws on warps 1..: the structural lane of warp 0 runs concurrently.  Two tasks per item, dealt so that a warp holds one
+  // item draws on warps 1..: the structural block of warp 0 runs concurrently.  Two tasks per item, dealt so that a warp holds one
   // kind: (b, a) [MlIrt: (a, b)] and the response-time pair (lambda, sigma2) [Cross family: rho], which do not depend on each other
   for (int t = tid - 32; t >= 0 && t < 2 * J; t += G_THREADS - 32) {
     const int part = t / J, j = t - part * J;
@@ -536,8 +583,10 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
       };
       if (model == M_MLIRT) { draw_a(); draw_b(); }  // GibbsRtIrt.pl.jl:233-237 (quirk Q8)
       else { draw_b(); draw_a(); }
-      par[L.p_a + j] = a;
-      par[L.p_b + j] = b;
+      if (real) {
+        par[L.p_a + j] = a;
+        par[L.p_b + j] = b;
+      }
     } else if (cross) {  // drawSubjCorrCross, Draw.pl.jl:463-469 (state k: theta_k, zeta_k, lambda_k, sigma2_k)
       const double s2 = par[L.p_sigma2 + j], lam = par[L.p_lambda + j];
       double parV, parM;
@@ -549,7 +598,8 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
         parV = 1.0 / (1.0 + A3 / (s2 * A.k2));
         parM = parV * (0.0 + (lam * A1 - A2 + A.k1 * Sth) / (s2 * A.k2));
       }
-      par[L.p_rho + j] = parM + sqrt(parV) * site_normal(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_RHO));
+      const double rho_new = parM + sqrt(parV) * site_normal(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_RHO));
+      if (real) par[L.p_rho + j] = rho_new;
     } else if (has_rt) {
       const double s2 = par[L.p_sigma2 + j];
       const double T1 = A.T1[j], T2 = A.T2[j], C = st[L.s_C + j];
@@ -562,41 +612,67 @@ __global__ void __launch_bounds__(G_THREADS) global_draw_kernel(const GlobalArgs
       const double Q = T2 - 2.0 * lam * T1 + N * lam * lam + 2.0 * (C - lam * Sze) + Sze2;
       const double parA = 1e-3 + N / 2.0, parB = 1e-3 + Q / 2.0;
       const double s2n = parB / gamma_from_raw(A.key, (uint32_t)j, s, make_site(DOM_ITEM, IK_SIGMA2), parA, sRaw[3 * Jp + j], sRaw[4 * Jp + j]);
-      par[L.p_lambda + j] = lam;
-      par[L.p_sigma2 + j] = s2n;
+      if (real) {
+        par[L.p_lambda + j] = lam;
+        par[L.p_sigma2 + j] = s2n;
+      }
     }
   }
   G_TICK(3, 32);  // item draws of lane 32 done
   __syncthreads();
   G_TICK(4, 0);
-  if (tid < MAXD) par[L.p_beta + tid] = w.beta[tid];
-  if (tid >= 64 && tid < 68) par[L.p_Sigma + tid - 64] = w.Sigma[tid - 64];
+  if (real) griddep_launch();  // the CTAs of the next person launch become resident and arm their barriers while the trace row is written
+#ifdef ERIRT_TIMELINE
+  if (real && tid == 0) g_timeline[k % TL_SLOTS][9] = tl_now();
+#endif
+  if (real) {
+    if (tid < MAXD) par[L.p_beta + tid] = w.beta[tid];
+    if (tid >= 64 && tid < 68) par[L.p_Sigma + tid - 64] = w.Sigma[tid - 64];
+  }
   __syncthreads();
 
   // ---- 3. trace row of sweep s, statistics reset ----
   if ((int)k < A.cap) {
     for (int j = tid; j < J; j += G_THREADS) {
-      A.tr_items_ra[(size_t)k * 2 * J + j] = par[L.p_a + j];
-      A.tr_items_ra[(size_t)k * 2 * J + J + j] = par[L.p_b + j];
+      const double va = par[L.p_a + j], vb = par[L.p_b + j];
+      if (real) {
+        A.tr_items_ra[(size_t)k * 2 * J + j] = va;
+        A.tr_items_ra[(size_t)k * 2 * J + J + j] = vb;
+      }
       if (has_rt && !cross) {
-        A.tr_items_rt[(size_t)k * 2 * J + j] = par[L.p_lambda + j];
-        A.tr_items_rt[(size_t)k * 2 * J + J + j] = par[L.p_sigma2 + j];
+        const double vl = par[L.p_lambda + j], vs = par[L.p_sigma2 + j];
+        if (real) {
+          A.tr_items_rt[(size_t)k * 2 * J + j] = vl;
+          A.tr_items_rt[(size_t)k * 2 * J + J + j] = vs;
+        }
       }
     }
     const int nb = cross ? J : ((model == M_MLIRT) ? F + 1 : ((model == M_RTIRT || model == M_NULL) ? 2 * (F + 1) : F + 2));
     for (int t = tid; t < A.qw; t += G_THREADS) {
       double v = t < nb ? (cross ? par[L.p_rho + t] : par[L.p_beta + t]) : par[L.p_Sigma + (t - nb)];
-      A.tr_qr[(size_t)k * A.qw + t] = v;
+      if (real) A.tr_qr[(size_t)k * A.qw + t] = v;
     }
   }
+  }  // pass
   if (tid == 0) {
     A.stats[L.s_count] = st[L.s_scal + SC_PG_DEFER];      // keep the diagnostics of the last sweep
     A.stats[L.s_count + 1] = st[L.s_scal + SC_PG_CELLS];
   }
   __syncthreads();
-  for (int t = tid; t < L.s_count; t += G_THREADS) A.stats[t] = 0.0;
+  for (int t = tid; t < L.s_count; t += G_THREADS) {
+    A.stats[t] = 0.0;
+    if (A.stats_prev) A.stats_prev[t] = st[t];  // the next launch rehearses on these
+  }
   G_TICK(5, 0);  // trace + reset done
-  if (tid == 0) *A.sweep_ctr = k + 1;
+  if (tid == 0) { *A.sweep_ctr = k + 1; *A.tile_ctr = 0u; }
+#ifdef ERIRT_TIMELINE
+  if (tid == 0) {
+    g_timeline[k % TL_SLOTS][10] = tl_now();
+    // slots of the person launch of sweep k+1 start from their identity values
+    g_timeline[(k + 1) % TL_SLOTS][0] = ~0ull; g_timeline[(k + 1) % TL_SLOTS][1] = ~0ull;
+    g_timeline[(k + 1) % TL_SLOTS][2] = 0ull; g_timeline[(k + 1) % TL_SLOTS][3] = 0ull;
+  }
+#endif
 }
 
 }  // namespace erirt

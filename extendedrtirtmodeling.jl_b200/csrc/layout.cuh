@@ -34,6 +34,32 @@ struct Layout {
   int s_S0, s_S1, s_S2, s_Ky, s_C, s_D, s_V, s_gram, s_gramw, s_scal, s_count;
 };
 
+// Programmatic dependent launch (sm_90+): the kernels of a chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization,
+// so a kernel's CTAs may become resident while its predecessor still runs.  Everything that reads what the predecessor wrote comes
+// after griddep_wait() (returns once the predecessor grid has completed and its writes are visible); griddep_launch() lets the
+// successor's CTAs be scheduled.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Sweep timeline of the diagnostic build (-DERIRT_TIMELINE, tools/make_tick_build.py): %globaltimer stamps (ns) per sweep slot
+#ifdef ERIRT_TIMELINE
+#define TL_SLOTS 256
+#define TL_N 12
+__device__ unsigned long long g_timeline[TL_SLOTS][TL_N];
+#define TL_CTAS 1024
+#define TL_CTA_SWEEP 60
+__device__ unsigned long long g_tl_cta[TL_CTAS][4];  // person launch of sweep TL_CTA_SWEEP: per CTA smid, past-wait, last-tile start, end
+__device__ __forceinline__ unsigned tl_smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TL_DECL(v) unsigned long long v = tl_now()
+#define TL_MIN(k, i, v) atomicMin(&g_timeline[(k) % TL_SLOTS][i], (v))
+#define TL_MAX(k, i, v) atomicMax(&g_timeline[(k) % TL_SLOTS][i], (v))
+#else
+#define TL_DECL(v)
+#define TL_MIN(k, i, v)
+#define TL_MAX(k, i, v)
+#endif
+
 __host__ __device__ inline int tri_index(int r, int c, int Dg) {  // r <= c, row-major upper triangle
   return r * Dg - (r * (r - 1)) / 2 + (c - r);
 }
@@ -97,6 +123,7 @@ struct PersonArgs {
   const double* params;
   double* stats;
   const uint32_t* sweep_ctr;  // k: this launch draws theta_k, zeta_k (k >= 1) and omega_{k+1}, nu_{k+1}
+  uint32_t* tile_ctr;         // work counter of the launch: tile blockIdx.x first, then gridDim.x + atomicAdd(tile_ctr, 1); the global kernel zeroes it
   const int* status;          // sticky error flag of the chain; <= -1000: a peer of the sharded chain timed out, every launch returns at once
   int64_t n_local, n_pad;
   uint32_t person_offset;
@@ -113,6 +140,9 @@ struct PersonArgs {
 struct GlobalArgs {
   double* params;
   double* stats;
+  double* stats_prev;  // reduced statistics of the previous sweep (input of the instruction-cache rehearsal, global.cuh), or nullptr
+  int rehearse;        // 1: run the rehearsal pass before the dependency wait
+  uint32_t* tile_ctr;  // work counter of the person launches, zeroed at the end of every global kernel
   uint32_t* sweep_ctr;
   // constants from ingest (already all-reduced over shards)
   const double* T1;   // sum_i logT_ij

@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);         // fast queue [0] count [1] head, exact queue [2] count [3] head
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  griddep_wait();    // parameters, sweep counter and cleared statistics come from the preceding global kernel (layout.cuh)
   if (*A.status <= -1000) return;  // a peer of the sharded chain timed out: the chain is dead
   const uint32_t k = *A.sweep_ctr;
   const bool do_draws = k >= 1 || (FAM == 1 && A.stage == 3);
@@ -268,15 +269,20 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   };
 
   int tiles_done = 0;
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tiles_done) {
+  // tiles are dealt dynamically (see person_fast.cuh): tile blockIdx.x first, then from the device-wide counter
+  volatile int* s_next = reinterpret_cast<volatile int*>(&s_miscd[MD_COUNT - 1]);  // spare slot of the misc block
+  int tile = blockIdx.x;
+  for (; tile < A.n_tiles; ++tiles_done) {
     const int64_t row0 = (int64_t)tile * P;
     if (tid == 0) {
+      const uint32_t nxt = (uint32_t)gridDim.x + atomicAdd(A.tile_ctr, 1u);
       tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
       mbar_expect_tx(s_bar, load_bytes);
       if (load_om) tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (load_nc) tma_load_1d(s_nc, A.nu_cell + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
+      *s_next = (int)nxt;
       s_qctl[0] = 0;
     }
     // ---- person phase, part 1 (one thread per person, coalesced): state k-1 and regression means ----
@@ -467,6 +473,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       if (pvalid && do_pg) acc_cells += (uint32_t)J;
     }
     __syncthreads();
+    const int next_tile = *s_next;  // written by thread 0 at the top of this tile; next written after at least one more barrier
+    if (next_tile >= A.n_tiles - (int)gridDim.x) griddep_launch();  // last tile of this CTA: the global kernel may become resident once every CTA is here
 
     if (cqr && (do_pg || eval)) {
       // ---- CrossQr cell pass (thread per person row): response-time log-likelihood of state k with nu_k
@@ -754,6 +762,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
       if (cqr) tma_store_1d(A.nu_cell + row0 * Jp, s_nc, (uint32_t)A.S.tile_real_bytes);
     }
+    tile = next_tile;
   }
   flush_item_stats();
 

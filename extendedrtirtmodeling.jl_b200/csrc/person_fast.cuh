@@ -81,12 +81,29 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);  // [0]: packed counts of the CTA queue (low 16 bits standard, high 16 bits special)
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  TL_DECL(tl_entry);
+  // ---- before the dependency wait (overlaps the tail of the preceding global kernel): clear the accumulators, arm the barrier ----
+  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
+  for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
+  if (tid < SC_COUNT) s_scal[tid] = 0.0;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    s_qctl[0] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  griddep_wait();    // parameters of state k, the sweep counter and the cleared statistics come from the preceding global kernel
   if (*A.status <= -1000) return;  // a peer of the sharded chain timed out: the chain is dead, do not spin through queued sweeps
   const uint32_t k = *A.sweep_ctr;
+#ifdef ERIRT_TIMELINE
+  if (tid == 0) {
+    TL_MIN(k, 0, tl_entry); const unsigned long long t = tl_now(); TL_MIN(k, 1, t); TL_MAX(k, 2, t);
+    if (k == TL_CTA_SWEEP && blockIdx.x < TL_CTAS) { g_tl_cta[blockIdx.x][0] = tl_smid(); g_tl_cta[blockIdx.x][1] = t; }
+  }
+#endif
   const bool do_draws = k >= 1;
   const double* par = A.params;
 
-  // ---- stage item / structural parameters (state k), the response tables, and clear the accumulators ----
+  // ---- stage item / structural parameters (state k) and the response tables ----
   for (int j = tid; j < Jp; j += CTA_THREADS) {
     double a = 0, b = 0, is2 = 0;
     if (j < J) {
@@ -102,9 +119,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   }
   if (tid < MAXD) s_beta[tid] = (R)par[L.p_beta + tid];
   if (tid < 4) s_beta[MAXD + tid] = has_rt ? (R)par[L.p_Sigma + tid] : (tid == 0 || tid == 3 ? R(1) : R(0));
-  for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
-  for (int t = tid; t < 2 * L.ntri; t += CTA_THREADS) s_acc_gram[t] = 0.0;
-  if (tid < SC_COUNT) s_scal[tid] = 0.0;
   if (tid < 32) {  // sum_j 1/sigma2_j, sum_j lambda_j/sigma2_j (f64), and the bound |z_ij| <= max|a| |theta_i| + max|a b|
     double s1 = 0, s2 = 0, amax = 0, abmax = 0;
     for (int j = tid; j < J; j += 32) {
@@ -128,9 +142,6 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       s_miscd[FMD_SUM_LAM_IS2] = s2;
       s_miscd[FMD_AMAX] = amax;
       s_miscd[FMD_ABMAX] = abmax;
-      mbar_init(s_bar, 1);
-      s_qctl[0] = 0;
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
   __syncthreads();
@@ -217,27 +228,27 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 
   int tiles_done = 0;
   PF_TICK_DECL();
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tiles_done) {
+  // Tiles are dealt dynamically: every CTA starts with tile blockIdx.x and then draws from a device-wide counter, so an SM that runs
+  // slower (the finishing times of statically dealt CTAs were spread over five tile times, profiles/r02e_sweep_timeline.txt) simply
+  // takes fewer tiles.  Results do not depend on who processes a tile, except for the rounding of the per-CTA partial sums.
+  int tile = blockIdx.x;
+  for (; tile < A.n_tiles; ++tiles_done) {
     const int64_t row0 = (int64_t)tile * P;
     PF_TICK(13);  // tile-loop overhead / previous store issue
     if (tid == 0) {
+      const uint32_t nxt = (uint32_t)gridDim.x + atomicAdd(A.tile_ctr, 1u);  // in flight while the store below drains
       tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
       mbar_expect_tx(s_bar, load_bytes);
       tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
-      if (tile + (int)gridDim.x < A.n_tiles) {  // pull the next tile of this CTA into L2 while this one is processed
-        const int64_t rown = row0 + (int64_t)gridDim.x * P;
+      s_qctl[1] = nxt;
+      if (nxt < (uint32_t)A.n_tiles) {  // pull the next tile of this CTA into L2 while this one is processed
+        const int64_t rown = (int64_t)nxt * P;
         l2_prefetch(A.omega + rown * Jp, (uint32_t)A.S.tile_real_bytes);
         if (has_rt) l2_prefetch(A.logT + rown * Jp, (uint32_t)A.S.tile_real_bytes);
         l2_prefetch(A.Y + rown * Jp, (uint32_t)A.S.tile_y_bytes);
       }
-    }
-    if (tid >= 32 && tid < 32 + 3 + F && tile + (int)gridDim.x < A.n_tiles) {  // ... and its person vectors (theta, zeta, nu, X columns)
-      const int a = tid - 32;
-      const int64_t rown = row0 + (int64_t)gridDim.x * P;
-      const R* src = a == 0 ? A.theta : (a == 1 ? A.zeta : (a == 2 ? A.nu : A.X + (int64_t)(a - 3) * A.n_pad));
-      l2_prefetch(src + rown, (uint32_t)(P * sizeof(R)));
     }
     // ---- person phase, part 1 (the first of the TPP lanes of a person): state k-1, regression means, the person's variates.
     //      Every warp serves its own persons, so nothing up to the work queues needs a CTA barrier ----
@@ -554,6 +565,15 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     PF_TICK(7);  // queue push
     __syncthreads();
     PF_TICK(8);  // barrier
+    const int next_tile = (int)s_qctl[1];  // written by thread 0 at the top of this tile; next written after two more barriers
+    // the deal has reached its last round: once every CTA is here the global kernel of the sweep may become resident beside the
+    // person CTAs (about two tile times before the end) and rehearse; released earlier it would only slow its SM down
+    if (next_tile >= A.n_tiles - (int)gridDim.x) griddep_launch();
+    if (next_tile < A.n_tiles && tid >= 32 && tid < 32 + 3 + F) {      // person vectors of the next tile (theta, zeta, nu, X columns) towards L2
+      const int a = tid - 32;
+      const R* src = a == 0 ? A.theta : (a == 1 ? A.zeta : (a == 2 ? A.nu : A.X + (int64_t)(a - 3) * A.n_pad));
+      l2_prefetch(src + (int64_t)next_tile * P, (uint32_t)(P * sizeof(R)));
+    }
 
     {
       // ---- drain, one phase over the CTA's queue (the load of the four warps is balanced: a warp-local queue was measured 7 %
@@ -681,6 +701,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     PF_TICK(9);  // drain
     __syncthreads();  // the whole tile (omega_{k+1}, u rows) is final: the transposed passes below read across warps
     PF_TICK(10);  // barrier
+    const int next_tile = (int)s_qctl[1];
+    if (next_tile >= A.n_tiles - (int)gridDim.x) griddep_launch();
 #endif
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
@@ -745,6 +767,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) tma_store_1d(A.omega + row0 * Jp, s_om, (uint32_t)A.S.tile_real_bytes);
+    tile = next_tile;
   }
   PF_TICK_FLUSH();
   flush_item_stats();
@@ -776,6 +799,14 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     if (t < L.ntri || qr) atomicAdd(&A.stats[L.s_gram + t], s_acc_gram[t]);
   if (tid < SC_COUNT) atomicAdd(&A.stats[L.s_scal + tid], s_scal[tid]);
   if (tid == 0) tma_store_wait_all();
+#ifdef ERIRT_TIMELINE
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long t = tl_now();
+    TL_MAX(k, 3, t);
+    if (k == TL_CTA_SWEEP && blockIdx.x < TL_CTAS) g_tl_cta[blockIdx.x][3] = t;
+  }
+#endif
 }
 
 // ---------------- parity / distribution-test kernel of the f32 PG path: the same functions as the sampler ----------------

@@ -1,0 +1,76 @@
+"""Sweep timeline of the diagnostic build diag_timeline.so (ERIRT_TIMELINE_BUILD=1 python tools/make_tick_build.py): %globaltimer
+stamps of the person launch P(k) and the global kernel G(k+1) per sweep.  usage: python tools/gpu_timeline.py [C5|C5s8|C1|C2|C3]"""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["ERIRT_B200_LIB"] = os.path.join(ROOT, "diag_timeline.so")
+import numpy as np, torch
+import erirt_b200 as E
+import bench
+
+which = sys.argv[1] if len(sys.argv) > 1 else "C5"
+dev = torch.device("cuda", 0)
+K = 48
+if which.startswith("C5"):
+    tp = bench.true_params()
+    world = 8 if which == "C5s8" else 1  # C5s8: the shard of one of eight GPUs (no exchange: timing of the local part only)
+    dY, dT, dX, off, n = bench.gen_shard_torch(tp, 0, world, dev)
+    th, ze, be = bench.init_state(off, n)
+    eng = E.Engine("RtIrtQuantile", n, bench.N_ITEM, bench.N_FEAT, n_iter=200, n_chain=1, n_burnin=0, q_rt=bench.Q_RT, cov2one=False,
+                   dtype="f32", seed=1, person_trace=False, use_graph=True)
+    eng.set_data_device(dY.data_ptr(), n, dT.data_ptr(), n, dX.data_ptr(), n)
+    eng.set_state(theta=th, zeta=ze, beta=be)
+else:
+    rng = np.random.default_rng(3)
+    if which == "C1":
+        Cond = E.setCond(nSubj=1000, nItem=15, nFeat=3, nIter=200, nChain=1)
+        D = E.setDataMlIrt(Cond, E.setTrueParaMlIrt(Cond, rng=1), rng=1)
+        model, N, J, F, init = "MlIrt", 1000, 15, 3, dict(theta=rng.standard_normal(1000), beta=rng.standard_normal(4))
+    elif which == "C2":
+        Cond = E.setCond(nSubj=10_000, nItem=30, nFeat=3, nIter=200, nChain=1)
+        D = E.setDataRtIrt(Cond, E.setTrueParaRtIrt(Cond, rng=1), rng=1)
+        model, N, J, F = "RtIrt", 10_000, 30, 3
+        init = dict(theta=rng.standard_normal(N), zeta=rng.standard_normal(N), beta=rng.standard_normal(8))
+    else:
+        Cond = E.setCond(nSubj=631, nItem=14, nFeat=10, nIter=200, nChain=1, qRt=0.85)
+        D = E.setDataRtIrtLatent(Cond, E.setTrueParaRtIrtLatent(Cond, rng=1), type="norm", rng=1)
+        model, N, J, F = "RtIrtLatentQr", 631, 14, 10
+        init = dict(theta=rng.standard_normal(N), zeta=rng.standard_normal(N), beta=rng.standard_normal(12))
+    eng = E.Engine(model, N, J, F, n_iter=200, n_chain=1, n_burnin=0, q_rt=0.85, cov2one=(model != "RtIrtLatentQr"), dtype="f32", seed=1,
+                   person_trace=False, use_graph=True)
+    eng.set_data(D.Y, None if model == "MlIrt" else D.logT, D.X if F > 0 else None)
+    eng.set_state(**init)
+eng.sample(40)
+eng.sample(K)
+print(which, "ms per sweep", eng.stats()["last_sample_ms"] / K, "PDL", os.environ.get("ERIRT_PDL", "1"), "REHEARSE", os.environ.get("ERIRT_G_REHEARSE", "1"))
+buf = (ctypes.c_ulonglong * (256 * 12))()
+eng.lib.erirt_diag_timeline(buf)
+t = np.array(list(buf), dtype=np.float64).reshape(256, 12)
+ks = np.arange(48, 40 + K - 2)  # sweeps well inside the second sample() call
+names = ["P first CTA entry", "P first CTA past wait", "P last CTA past wait", "P last CTA done", "G entry", "G pre-wait part done",
+         "G past wait", "G statistics staged", "G log-likelihood done", "G draws done", "G end"]
+rows = []
+for k in ks:
+    base = t[k, 0]
+    rows.append([(t[k, i] - base) / 1e3 for i in range(11)] + [(t[k + 1, 0] - base) / 1e3, (t[k + 1, 2] - base) / 1e3])
+m = np.median(np.array(rows), axis=0)
+for nm, v in zip(names + ["next P first CTA entry", "next P last CTA past wait"], m):
+    print(f"  {nm:28s} {v:9.2f} us")
+
+if os.environ.get("TL_CTAS"):
+    cb = (ctypes.c_ulonglong * (1024 * 4))()
+    eng.lib.erirt_diag_cta_timeline(cb)
+    c = np.array(list(cb), dtype=np.float64).reshape(1024, 4)
+    c = c[c[:, 1] > 0]
+    t0 = c[:, 1].min()
+    print("per-CTA view of sweep 60:", len(c), "CTAs on", len(set(c[:, 0])), "SMs")
+    print("  past wait: min %.2f max %.2f us" % (0.0, (c[:, 1].max() - t0) / 1e3))
+    end = (c[:, 3] - t0) / 1e3
+    print("  end: quantiles", np.round(np.quantile(end, [0, .1, .5, .8, .9, .99, 1]), 1))
+    late = end > np.quantile(end, 0.8)
+    sm_counts = {}
+    for smid in c[late, 0]: sm_counts[int(smid)] = sm_counts.get(int(smid), 0) + 1
+    hist = {}
+    for v in sm_counts.values(): hist[v] = hist.get(v, 0) + 1
+    print("  CTAs in the slowest 20 %% per SM (count of SMs by how many such CTAs they hold):", hist)
+    print("  block 0..7 -> SM", [int(x) for x in c[:8, 0]], " blocks 148..151 -> SM", [int(x) for x in c[148:152, 0]])
