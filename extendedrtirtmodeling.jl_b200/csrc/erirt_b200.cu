@@ -673,6 +673,10 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
   const char* env_occ = getenv("ERIRT_CTAS_PER_SM");
   if (env_occ && atoi(env_occ) > 0 && atoi(env_occ) < occ) occ = atoi(env_occ);
   h->grid = std::min(n_tiles, h->sm_count * occ);
+  // A full grid leaves ONE slot free: with dynamic tile dealing no person CTA exits before the last round, so the global kernel of the
+  // sweep (256 threads, 80 registers, ~55 KB) could otherwise not become resident early enough to finish its rehearsal pass
+  // (global.cuh) before the person kernel ends; the slot costs 1/444 of the person kernel's throughput
+  if (global_rehearsal_enabled() && h->grid == h->sm_count * occ && h->grid > 1) h->grid -= 1;
   // test hook: ERIRT_MAX_GRID caps the persistent grid, so that a small problem gives every CTA many tiles (the cross-tile register
   // accumulators and their 16-tile fold are otherwise reached only at benchmark size); results do not depend on the grid
   const char* env_grid = getenv("ERIRT_MAX_GRID");
@@ -1203,7 +1207,6 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
   CU(cudaSetDevice(h->cfg.device));
   int rc = finalize_constants(h);
   if (rc) return rc;
-  CU(cudaEventRecord(h->ev0, h->stream));
   if (!h->prologue_done) {
     CU(cudaMemsetAsync(h->dSweep, 0, sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->dStats, 0, (h->L.s_count + 2) * sizeof(double), h->stream));
@@ -1220,9 +1223,13 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
       h->kev.push_back(e);
     }
   }
-  if (h->cfg.use_graph && !h->cfg.time_kernels && n_sweeps > 0) {
-    // one graph = one sweep (2 or 4 kernel nodes); ERIRT_GRAPH_SWEEPS=k additionally captures k sweeps into one graph, so that small
-    // problems, whose sweep is shorter than a graph launch, pay the launch once per k sweeps (experimental, default 1)
+  const bool graphs = h->cfg.use_graph && !h->cfg.time_kernels && n_sweeps > 0;
+  // The sweeps are replayed from two CUDA graphs: one of `gs` sweeps (ERIRT_GRAPH_SWEEPS, default 16) and one of a single sweep for the
+  // remainder.  Inside a graph the kernels overlap their neighbours through the programmatic-dependent-launch edges; a graph boundary
+  // serialises, so the long graph also keeps the launch-bound small problems busy.  Both are captured on the first call, before the
+  // timed region of this call starts.
+  int gs = 1;
+  if (graphs) {
     auto capture = [&](int sweeps, cudaGraphExec_t* exec) -> int {
       cudaGraph_t graph;
       CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1238,16 +1245,20 @@ extern "C" int erirt_sample(erirt_handle* h, int64_t n_sweeps) {
     };
     if (!h->graph_exec && (rc = capture(1, &h->graph_exec))) return rc;
     const char* env_gs = getenv("ERIRT_GRAPH_SWEEPS");
-    const int gs = env_gs ? std::max(1, std::min(64, atoi(env_gs))) : 16;  // the kernels of one graph overlap their neighbours (PDL edges); graph boundaries serialise
-    int64_t left = n_sweeps;
-    if (gs > 1 && left >= gs) {
+    gs = env_gs ? std::max(1, std::min(64, atoi(env_gs))) : 16;
+    if (gs > 1) {
       if (h->graph_multi && h->graph_multi_sweeps != gs) { cudaGraphExecDestroy(h->graph_multi); h->graph_multi = nullptr; }
       if (!h->graph_multi) {
         if ((rc = capture(gs, &h->graph_multi))) return rc;
         h->graph_multi_sweeps = gs;
       }
-      for (; left >= gs; left -= gs) CU(cudaGraphLaunch(h->graph_multi, h->stream));
     }
+  }
+  CU(cudaEventRecord(h->ev0, h->stream));
+  if (graphs) {
+    int64_t left = n_sweeps;
+    if (gs > 1)
+      for (; left >= gs; left -= gs) CU(cudaGraphLaunch(h->graph_multi, h->stream));
     for (; left > 0; --left) CU(cudaGraphLaunch(h->graph_exec, h->stream));
   } else {
     for (int64_t t = 0; t < n_sweeps; ++t) {

@@ -19,8 +19,8 @@
 
 namespace erirt {
 
-// warp 0: structural block (cooperatively); warps 1..7: item draws; all warps: raw variates, reductions.  256 threads at <= 96
-// registers fit beside two resident person CTAs of the hot configuration, i.e. as soon as ONE person CTA of some SM has finished
+// warp 0: structural block (cooperatively); warps 1..7: item draws; all warps: raw variates, reductions.  256 threads at <= 80
+// registers fit beside two resident person CTAs of the hot configuration (168 registers each), i.e. as soon as ONE person CTA of some SM has finished
 // its tiles, so the parameter-independent part of this kernel (everything before griddep_wait) runs beside the person kernel's tail.
 constexpr int G_THREADS = 256;
 
@@ -398,7 +398,7 @@ __device__ inline void global_raw_variates(const GlobalArgs& A, uint32_t s, doub
   }
 }
 
-__global__ void __maxnreg__(96) global_draw_kernel(const GlobalArgs A) {
+__global__ void __maxnreg__(80) global_draw_kernel(const GlobalArgs A) {
 #ifdef ERIRT_TICKS
   const long long _g0 = clock64();
   if (threadIdx.x == 0) g_g0 = _g0;

@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     }
     __syncthreads();
     const int next_tile = *s_next;  // written by thread 0 at the top of this tile; next written after at least one more barrier
-    if (next_tile >= A.n_tiles - (int)gridDim.x) griddep_launch();  // last tile of this CTA: the global kernel may become resident once every CTA is here
+    if (next_tile >= A.n_tiles - 2 * (int)gridDim.x) griddep_launch();  // last tile of this CTA: the global kernel may become resident once every CTA is here
 
     if (cqr && (do_pg || eval)) {
       // ---- CrossQr cell pass (thread per person row): response-time log-likelihood of state k with nu_k

@@ -237,11 +237,12 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     PF_TICK(13);  // tile-loop overhead / previous store issue
     if (tid == 0) {
       const uint32_t nxt = (uint32_t)gridDim.x + atomicAdd(A.tile_ctr, 1u);  // in flight while the store below drains
-      tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
       mbar_expect_tx(s_bar, load_bytes);
-      tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
+      // the logT and Y buffers are free (every warp is past the statistics pass): their loads travel while the omega store drains
       if (has_rt) tma_load_1d(s_lt, A.logT + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       tma_load_1d(s_y, A.Y + row0 * Jp, (uint32_t)A.S.tile_y_bytes, s_bar);
+      tma_store_wait_read();  // previous tile's omega store has finished reading shared memory
+      tma_load_1d(s_om, A.omega + row0 * Jp, (uint32_t)A.S.tile_real_bytes, s_bar);
       s_qctl[1] = nxt;
       if (nxt < (uint32_t)A.n_tiles) {  // pull the next tile of this CTA into L2 while this one is processed
         const int64_t rown = (int64_t)nxt * P;
@@ -317,37 +318,42 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 
     if (do_draws) {
       // ---- row sums over items (Draw.pl.jl:55-56, 137-138), TPP threads per person, two items per instruction ----
-      u64 sA2 = 0ull, sAB = 0ull, sLT = 0ull;
+      u64 sA2 = 0ull, sAB = 0ull, sLT = 0ull, sA2b = 0ull, sABb = 0ull, sLTb = 0ull;  // two chains per sum
       R sAK = R(0);
       constexpr int CHUNK = 8 / TPP;  // consecutive groups owned by this thread inside each block of 8
-      for (int g0 = q * CHUNK; g0 < G; g0 += 8) {
-        const R* r_om = my_om + 4 * g0;
-        const R* r_lt = my_lt + 4 * g0;
-        const uint8_t* r_y = my_y + 4 * g0;
-        const R* r_par = s_par + 4 * g0;
-        const R* r_ta = s_ta + g0 * TAB_PITCH;
-#pragma unroll
-        for (int cc = 0; cc < CHUNK; ++cc) {
-          if (g0 + cc < G) {
-            const float4 om = *reinterpret_cast<const float4*>(r_om + 4 * cc);
-            const float4 pA2 = *reinterpret_cast<const float4*>(r_par + PAR_A2 * Jp + 4 * cc);
-            const float4 pA2B = *reinterpret_cast<const float4*>(r_par + PAR_A2B * Jp + 4 * cc);
-            const uint32_t yw = *reinterpret_cast<const uint32_t*>(r_y + 4 * cc);
-            const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w);
-            sA2 = ffma2(pk2(pA2.x, pA2.y), o01, sA2);
-            sA2 = ffma2(pk2(pA2.z, pA2.w), o23, sA2);
-            sAB = ffma2(pk2(pA2B.x, pA2B.y), o01, sAB);
-            sAB = ffma2(pk2(pA2B.z, pA2B.w), o23, sAB);
-            sAK += r_ta[cc * TAB_PITCH + y_nibble(yw)];
-            if (has_rt) {
-              const float4 lt = *reinterpret_cast<const float4*>(r_lt + 4 * cc);
-              const float4 pI = *reinterpret_cast<const float4*>(r_par + PAR_IS2 * Jp + 4 * cc);
-              sLT = ffma2(pk2(pI.x, pI.y), pk2(lt.x, lt.y), sLT);
-              sLT = ffma2(pk2(pI.z, pI.w), pk2(lt.z, lt.w), sLT);
-            }
-          }
+      auto row_group = [&](const int g) {  // one 4-item group of this person's row
+        const float4 om = *reinterpret_cast<const float4*>(my_om + 4 * g);
+        const float4 pA2 = *reinterpret_cast<const float4*>(s_par + PAR_A2 * Jp + 4 * g);
+        const float4 pA2B = *reinterpret_cast<const float4*>(s_par + PAR_A2B * Jp + 4 * g);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
+        const u64 o01 = pk2(om.x, om.y), o23 = pk2(om.z, om.w);
+        sA2 = ffma2(pk2(pA2.x, pA2.y), o01, sA2);
+        sA2b = ffma2(pk2(pA2.z, pA2.w), o23, sA2b);
+        sAB = ffma2(pk2(pA2B.x, pA2B.y), o01, sAB);
+        sABb = ffma2(pk2(pA2B.z, pA2B.w), o23, sABb);
+        sAK += s_ta[g * TAB_PITCH + y_nibble(yw)];
+        if (has_rt) {
+          const float4 lt = *reinterpret_cast<const float4*>(my_lt + 4 * g);
+          const float4 pI = *reinterpret_cast<const float4*>(s_par + PAR_IS2 * Jp + 4 * g);
+          sLT = ffma2(pk2(pI.x, pI.y), pk2(lt.x, lt.y), sLT);
+          sLTb = ffma2(pk2(pI.z, pI.w), pk2(lt.z, lt.w), sLTb);
         }
+      };
+      // whole chunks of CHUNK consecutive groups run without a branch inside (their shared-memory loads are issued together and the
+      // six accumulator chains interleave); only the last, partial chunk of the row is guarded
+      int g0 = q * CHUNK;
+      for (; g0 + CHUNK <= G; g0 += 8) {
+#pragma unroll
+        for (int cc = 0; cc < CHUNK; ++cc) row_group(g0 + cc);
       }
+      if (g0 < G) {
+#pragma unroll
+        for (int cc = 0; cc < CHUNK; ++cc)
+          if (g0 + cc < G) row_group(g0 + cc);
+      }
+      sA2 = fadd2(sA2, sA2b);
+      sAB = fadd2(sAB, sABb);
+      sLT = fadd2(sLT, sLTb);
       R rA2 = lo2(sA2) + hi2(sA2), rAB = lo2(sAB) + hi2(sAB), rLT = lo2(sLT) + hi2(sLT);
 #pragma unroll
       for (int o = 1; o < TPP; o <<= 1) {
@@ -567,8 +573,8 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     PF_TICK(8);  // barrier
     const int next_tile = (int)s_qctl[1];  // written by thread 0 at the top of this tile; next written after two more barriers
     // the deal has reached its last round: once every CTA is here the global kernel of the sweep may become resident beside the
-    // person CTAs (about two tile times before the end) and rehearse; released earlier it would only slow its SM down
-    if (next_tile >= A.n_tiles - (int)gridDim.x) griddep_launch();
+    // person CTAs (about two and a half tile times before the end: its rehearsal pass takes one) and rehearse; released earlier it would only slow its SM down
+    if (next_tile >= A.n_tiles - 2 * (int)gridDim.x) griddep_launch();
     if (next_tile < A.n_tiles && tid >= 32 && tid < 32 + 3 + F) {      // person vectors of the next tile (theta, zeta, nu, X columns) towards L2
       const int a = tid - 32;
       const R* src = a == 0 ? A.theta : (a == 1 ? A.zeta : (a == 2 ? A.nu : A.X + (int64_t)(a - 3) * A.n_pad));
@@ -702,7 +708,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     __syncthreads();  // the whole tile (omega_{k+1}, u rows) is final: the transposed passes below read across warps
     PF_TICK(10);  // barrier
     const int next_tile = (int)s_qctl[1];
-    if (next_tile >= A.n_tiles - (int)gridDim.x) griddep_launch();
+    if (next_tile >= A.n_tiles - 2 * (int)gridDim.x) griddep_launch();
 #endif
 
     // ---- per-item statistics: thread per (item group, person class), tile read transposed, sums kept in registers ----
