@@ -1589,7 +1589,7 @@ extern "C" int erirt_peer_export(erirt_handle* h, void* ipc_handle64) {
     }
   }
   if (!h->xbuf) {
-    const size_t bytes = (size_t)2 * h->world * h->xstride * sizeof(double) + (size_t)2 * h->world * sizeof(uint32_t) + 256;
+    const size_t bytes = (size_t)2 * h->world * h->xstride * 16 + 256;  // [2 parities][world][xstride] 16-byte packets (global.cuh)
     CU(cudaMalloc((void**)&h->xbuf, bytes));
     CU(cudaMemset(h->xbuf, 0, bytes));
     CU(cudaMalloc((void**)&h->dPeerBufs, h->world * sizeof(double*)));

@@ -163,42 +163,47 @@ struct GramView {  // accessors into the upper-triangular Gram of u = [1, X(1..F
 };
 
 // ---- fused one-shot all-reduce over NVLink peer memory (one CTA; all its threads call it at the same point) ----
-// Push `count` doubles of `src` into slot [parity][rank] of every GPU's exchange buffer, publish the sequence stamp, wait for the
-// peers' stamps, sum the slots in rank order into `dst` (shared or global; bitwise the same result on every GPU).
-// Two parities suffice: a GPU can only be two exchanges ahead of a slot it overwrites after the owner has published the stamp of
-// the exchange in between, i.e. after the owner has finished reading that slot.
+// Every GPU owns an exchange buffer of 16-byte packets [2 parities][world slots][S]; a double travels as two self-validating 8-byte
+// words {low 32 bits, seq} {high 32 bits, seq} (the LL protocol of NCCL: an aligned 8-byte store is delivered whole, so a word whose
+// flag equals the sequence number of this exchange carries this exchange's data).  A thread stores its elements into slot
+// [parity][rank] of EVERY GPU's buffer (fire and forget over NVLink), then polls the world slots of its OWN buffer and sums them in
+// rank order (bitwise the same result on every GPU).  No fence, no separate flag, no CTA barrier between sending and receiving: the
+// latency of the exchange is one NVLink store.  Two parities suffice: a GPU writes a slot again two exchanges later, and it cannot
+// finish the exchange in between before the slot's owner has sent its data for it, i.e. has finished reading the earlier one.
 __device__ inline void peer_allreduce_sum(double* const* peer_bufs, uint32_t* xseq, int world, int rank, int S, const double* src,
                                           int count, double* dst, int* status, int tid, int nthreads) {
   const uint32_t seq = *xseq + 1u;
   const int par = (int)(seq & 1u);
-  for (int r = 0; r < world; ++r) {
-    double* slot = peer_bufs[r] + ((size_t)par * world + rank) * S;
-    for (int t = tid; t < count; t += nthreads) slot[t] = src[t];
+  for (int t = tid; t < count; t += nthreads) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(src[t]);
+    const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)seq << 32), w1 = (bits >> 32) | ((unsigned long long)seq << 32);
+    for (int r = 0; r < world; ++r) {
+      ulonglong2* slot = reinterpret_cast<ulonglong2*>(peer_bufs[r]) + ((size_t)par * world + rank) * S + t;
+      asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+    }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < world) {
-    uint32_t* theirs = reinterpret_cast<uint32_t*>(peer_bufs[tid] + (size_t)2 * world * S) + par * world + rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_bufs[rank] + (size_t)2 * world * S) + par * world + tid;
-    uint32_t got;
-    const long long t_start = clock64();
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
-      if (got != seq && clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
-        atomicExch(status, -1000 - tid);
-        break;
-      }
-    } while (got != seq);
-  }
-  __syncthreads();
-  const double* slots = peer_bufs[rank] + (size_t)par * world * S;
+  const ulonglong2* mine = reinterpret_cast<const ulonglong2*>(peer_bufs[rank]) + (size_t)par * world * S;
+  const long long t_start = clock64();
+  bool dead = false;
   for (int t = tid; t < count; t += nthreads) {
     double acc = 0.0;
-    for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * S + t);
+    for (int r = 0; r < world; ++r) {
+      const ulonglong2* pk = mine + (size_t)r * S + t;
+      unsigned long long w0, w1;
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(pk) : "memory");
+        if ((uint32_t)(w0 >> 32) == seq && (uint32_t)(w1 >> 32) == seq) break;
+        if (dead || clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
+          if (!dead) atomicExch(status, -1000 - r);
+          dead = true;
+          break;
+        }
+      }
+      acc += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
     dst[t] = acc;
   }
-  __syncthreads();  // every thread has read *xseq and the slots
+  __syncthreads();  // every thread has read *xseq; dst is complete
   if (tid == 0) *xseq = seq;
 }
 // the same exchange on its own, for the one-time ingest constants

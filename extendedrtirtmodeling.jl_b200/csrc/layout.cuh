@@ -166,7 +166,7 @@ struct GlobalArgs {
   double k1, k2;
   PhiloxKey key;
   // one-shot peer exchange of the statistics (person-sharded chains, NVLink peer memory); peer_bufs == nullptr: not used
-  double* const* peer_bufs;  // [world] base of every GPU's exchange buffer: data [2][world][xstride] doubles, then stamps [2][world] u32
+  double* const* peer_bufs;  // [world] base of every GPU's exchange buffer: [2 parities][world][xstride] 16-byte packets (global.cuh)
   uint32_t* xseq;            // exchanges completed so far (identical on every GPU)
   int world, rank, xstride;
 };

@@ -174,8 +174,9 @@ int erirt_nccl_unique_id(void* id128);                 /* rank 0 creates 128 byt
 int erirt_comm_init(erirt_handle* h, int32_t rank, int32_t world, const void* id128);  /* id128 == NULL: no NCCL communicator,
                                                                 the peer exchange below must be attached before erirt_sample */
 /* One-shot exchange over NVLink peer memory, fused into the global draw kernel (replaces the per-sweep ncclAllReduce):
- * every GPU stores its statistics vector into a slot of every peer's exchange buffer, publishes a sequence stamp, waits
- * for the peers' stamps and sums the slots in rank order (bitwise identical on every GPU).  One process per GPU on one
+ * every GPU stores its statistics vector into a slot of every peer's exchange buffer as self-validating 8-byte words
+ * {32 data bits, sequence number} (no fence, no separate flag), polls its own buffer until the words of this exchange have
+ * arrived and sums the slots in rank order (bitwise identical on every GPU).  One process per GPU on one
  * node: erirt_peer_export allocates this GPU's exchange buffer and returns its 64-byte CUDA IPC handle; the caller
  * all-gathers the handles (any transport) and passes the world*64 bytes, in rank order, to erirt_peer_attach.
  * erirt_comm_init must have been called first (it fixes rank/world; with a NULL id no NCCL communicator is created and the
