@@ -399,7 +399,20 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
   S.off_beta = (int)o; o = align_up(o + (size_t)(MAXD + 4) * rsz, 128);
   S.off_acc_item = (int)o; o = align_up(o + (cqr ? 7 : (cross ? 6 : 5)) * L.Jp * sizeof(double), 128);
   S.off_acc_gram = (int)o; o = align_up(o + 2 * L.ntri * sizeof(double), 128);
-  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + QCAP * sizeof(uint32_t), 128);
+  // Work queue of the cells that leave the PG fast path.  4 % of the cells do at the benchmark configuration, but attempt 0 is always a
+  // Method-A attempt and its acceptance falls with |z|: data with a wide ability distribution (the regression models with |beta| ~ 1:
+  // BASELINE configs 1 and 2) defer 15-30 % of their cells.  Small tiles therefore get a queue of up to 45 % of their cells as long
+  // as the plan stays below 64 KB (three CTAs per SM either way); an overflowing queue is still handled inline, cell by cell.
+  S.qcap = QCAP;
+  if (fast) {
+    size_t rest = 0;  // what follows the queue in the plan
+    rest += align_up((size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128) + align_up((MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
+    const size_t budget = 64 * 1024;
+    const int want = (int)align_up((size_t)(0.45 * S.P * L.Jp), 256);
+    while (S.qcap < want && S.qcap < 16384 && o + (size_t)(S.qcap + 256) * sizeof(uint32_t) + rest <= budget) S.qcap += 256;
+  }
+  S.qstd = (S.qcap * 3) / 4;
+  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + (size_t)S.qcap * sizeof(uint32_t), 128);
   S.off_tab = (int)o; if (fast) o = align_up(o + (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response table of the f32 fast kernel
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;

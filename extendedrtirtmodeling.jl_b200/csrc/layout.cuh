@@ -48,7 +48,7 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 __device__ unsigned long long g_timeline[TL_SLOTS][TL_N];
 #define TL_CTAS 1024
 #define TL_CTA_SWEEP 60
-__device__ unsigned long long g_tl_cta[TL_CTAS][4];  // person launch of sweep TL_CTA_SWEEP: per CTA smid, past-wait, last-tile start, end
+__device__ unsigned long long g_tl_cta[TL_CTAS][6];  // person launch of sweep TL_CTA_SWEEP: per CTA smid, past-wait, tile loop start, end, tile loop end, tiles
 __device__ __forceinline__ unsigned tl_smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 __device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TL_DECL(v) unsigned long long v = tl_now()
@@ -103,6 +103,7 @@ struct SmemPlan {
   int tile_real_bytes, tile_y_bytes;
   int off_omega, off_logt, off_nuc, off_y, off_par, off_u, off_sum, off_beta, off_acc_item, off_acc_gram, off_queue, off_tab, off_misc, total;
   int Dgp;  // pitch of the U tile (elements)
+  int qcap, qstd;  // f32 fast kernel: entries of the tile's work queue, and how many of them belong to the standard end
 };
 
 template <typename R>

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   uint32_t* s_qctl = reinterpret_cast<uint32_t*>(s_bar + 1);  // [0]: packed counts of the CTA queue (low 16 bits standard, high 16 bits special)
 
   const int tid = threadIdx.x, p = tid / TPP, q = tid % TPP;
+  const uint32_t qcap = (uint32_t)A.S.qcap, qstd = (uint32_t)A.S.qstd;  // work-queue capacity of this plan (erirt_b200.cu, make_smem_plan)
   TL_DECL(tl_entry);
   // ---- before the dependency wait (overlaps the tail of the preceding global kernel): clear the accumulators, arm the barrier ----
   for (int t = tid; t < 5 * Jp; t += CTA_THREADS) s_acc_item[t] = 0.0;
@@ -232,6 +233,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   // slower (the finishing times of statically dealt CTAs were spread over five tile times, profiles/r02e_sweep_timeline.txt) simply
   // takes fewer tiles.  Results do not depend on who processes a tile, except for the rounding of the per-CTA partial sums.
   int tile = blockIdx.x;
+#ifdef ERIRT_TIMELINE
+  if (tid == 0 && k == TL_CTA_SWEEP && blockIdx.x < TL_CTAS) g_tl_cta[blockIdx.x][2] = tl_now();
+#endif
   for (; tile < A.n_tiles; ++tiles_done) {
     const int64_t row0 = (int64_t)tile * P;
     PF_TICK(13);  // tile-loop overhead / previous store issue
@@ -562,10 +566,10 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         }
       };
       if (wtotal) {
-        push((uint32_t)smask, 0, slot_s, (uint32_t)QSTD, 0u, 0u);
-        push((uint32_t)(smask >> 32), 32, slot_s, (uint32_t)QSTD, 0u, 0u);
-        push((uint32_t)umask, 0, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
-        push((uint32_t)(umask >> 32), 32, slot_u, (uint32_t)(QCAP - QSTD), (uint32_t)QSTD, 0x80000000u);
+        push((uint32_t)smask, 0, slot_s, qstd, 0u, 0u);
+        push((uint32_t)(smask >> 32), 32, slot_s, qstd, 0u, 0u);
+        push((uint32_t)umask, 0, slot_u, qcap - qstd, qstd, 0x80000000u);
+        push((uint32_t)(umask >> 32), 32, slot_u, qcap - qstd, qstd, 0x80000000u);
       }
     }
     PF_TICK(7);  // queue push
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       //      slower, r02 profiles): standard entries (Method-A retry rounds, two cells in flight per thread) are dealt from
       //      thread 0 upwards, special entries (undecided attempt 0: replay it with the a_1 term) from the last thread downwards ----
       const uint32_t qc = s_qctl[0];
-      const uint32_t qn = min(qc & 0xffffu, (uint32_t)QSTD), qu = min(qc >> 16, (uint32_t)(QCAP - QSTD));
+      const uint32_t qn = min(qc & 0xffffu, qstd), qu = min(qc >> 16, qcap - qstd);
       for (uint32_t idx = tid; idx < qn; idx += 2 * CTA_THREADS) {
         const bool has2 = idx + CTA_THREADS < qn;
         const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
@@ -594,26 +598,26 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
         const float z2 = fmaf(s_par[PAR_A * Jp + j2], s_u[p2 * Dgp + F + 1], s_par[PAR_AB * Jp + j2]);
         const uint32_t g1 = A.person_offset + (uint32_t)(row0 + p1), g2 = A.person_offset + (uint32_t)(row0 + p2);
-        const bool b1 = !(0.5f * fabsf(z1) <= (float)PG_CSWITCH), b2 = !(0.5f * fabsf(z2) <= (float)PG_CSWITCH);  // Method B or NaN
-        float om1 = b1 ? 0.0f : -2.0f, om2 = (has2 && !b2) ? -2.0f : 0.0f;
+        // retry block r carries two Method-A attempts (c <= 1/t) or one Method-B attempt (c > 1/t: with a wide ability distribution a
+        // third of the queued cells); a poisoned (NaN) state is passed through instead of spinning
+        const bool b1 = 0.5f * fabsf(z1) > (float)PG_CSWITCH, b2 = 0.5f * fabsf(z2) > (float)PG_CSWITCH;
+        float om1 = (z1 == z1) ? -2.0f : z1, om2 = (has2 && z2 == z2) ? -2.0f : (has2 ? z2 : 0.0f);
 #pragma unroll 1
         for (uint32_t r = 1; r < PG_MAX_ATTEMPTS && (om1 < 0.f || om2 < 0.f); ++r) {
           const uint4 w1 = philox(A.sched, g1, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j1), r);
           const uint4 w2 = philox(A.sched, g2, k + 1, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j2), r);
-          const float o1 = pg_exact_pair(z1, w1.x, w1.y, w1.z, w1.w);
-          const float o2 = pg_exact_pair(z2, w2.x, w2.y, w2.z, w2.w);
+          const float o1 = b1 ? pg_fast_attemptB(z1, w1) : pg_exact_pair(z1, w1.x, w1.y, w1.z, w1.w);
+          const float o2 = b2 ? pg_fast_attemptB(z2, w2) : pg_exact_pair(z2, w2.x, w2.y, w2.z, w2.w);
           if (om1 < 0.f) om1 = o1;
           if (om2 < 0.f) om2 = o2;
         }
         if (om1 < 0.f) om1 = 0.25f * (float)PG_T;
         if (om2 < 0.f) om2 = 0.25f * (float)PG_T;
-        if (b1) om1 = pg_resolve_f32(A.key, g1, k + 1, j1, z1, false);  // rare: Method-B regime (or NaN state)
-        if (has2 && b2) om2 = pg_resolve_f32(A.key, g2, k + 1, j2, z2, false);
         s_om[p1 * Jp + j1] = om1;
         if (has2) s_om[p2 * Jp + j2] = om2;
       }
       for (uint32_t idx = (uint32_t)(CTA_THREADS - 1 - tid); idx < qu; idx += CTA_THREADS) {
-        const uint32_t e1 = s_queue[QSTD + idx];
+        const uint32_t e1 = s_queue[qstd + idx];
         const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
         s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, true);
@@ -776,6 +780,9 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
     tile = next_tile;
   }
   PF_TICK_FLUSH();
+#ifdef ERIRT_TIMELINE
+  if (tid == 0 && k == TL_CTA_SWEEP && blockIdx.x < TL_CTAS) { g_tl_cta[blockIdx.x][4] = tl_now(); g_tl_cta[blockIdx.x][5] = (unsigned long long)tiles_done; }
+#endif
   flush_item_stats();
 
   // ---- flush CTA accumulators ----

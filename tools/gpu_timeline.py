@@ -3,7 +3,8 @@ stamps of the person launch P(k) and the global kernel G(k+1) per sweep.  usage:
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["ERIRT_B200_LIB"] = os.path.join(ROOT, "diag_timeline.so")
+TICKS = bool(os.environ.get("TICKS"))  # TICKS=1: the clock64() phase timers of diag_tick.so instead of the timeline
+os.environ["ERIRT_B200_LIB"] = os.path.join(ROOT, "diag_tick.so" if TICKS else "diag_timeline.so")
 import numpy as np, torch
 import erirt_b200 as E
 import bench
@@ -41,6 +42,20 @@ else:
     eng.set_data(D.Y, None if model == "MlIrt" else D.logT, D.X if F > 0 else None)
     eng.set_state(**init)
 eng.sample(40)
+if TICKS:
+    tb = (ctypes.c_ulonglong * 16)()
+    eng.lib.erirt_diag_ticks(tb, 1)
+    eng.sample(K)
+    eng.lib.erirt_diag_ticks(tb, 0)
+    t = np.array(list(tb), dtype=np.float64)
+    st = eng.stats()
+    print(which, "ms per sweep", st["last_sample_ms"] / K, "deferred PG fraction", st.get("pg_deferred_frac"), "tpp", st.get("tpp"), "grid", st.get("grid"))
+    names = ["issue+person part1", "mbar wait (TMA)", "row sums", "-", "person part 2 + u rows", "-", "PG main pass", "queue push", "barrier 3", "drain",
+             "barrier 4", "statistics pass", "flush + Gram", "loop top / store issue", "-", "-"]
+    tot = t.sum()
+    for nm, v in zip(names, t):
+        if v: print(f"  {nm:28s} {v / K:14.0f} warp-cycles per sweep  {100 * v / tot:5.1f} %")
+    sys.exit(0)
 eng.sample(K)
 print(which, "ms per sweep", eng.stats()["last_sample_ms"] / K, "PDL", os.environ.get("ERIRT_PDL", "1"), "REHEARSE", os.environ.get("ERIRT_G_REHEARSE", "1"))
 buf = (ctypes.c_ulonglong * (256 * 12))()
@@ -58,15 +73,20 @@ for nm, v in zip(names + ["next P first CTA entry", "next P last CTA past wait"]
     print(f"  {nm:28s} {v:9.2f} us")
 
 if os.environ.get("TL_CTAS"):
-    cb = (ctypes.c_ulonglong * (1024 * 4))()
+    cb = (ctypes.c_ulonglong * (1024 * 6))()
     eng.lib.erirt_diag_cta_timeline(cb)
-    c = np.array(list(cb), dtype=np.float64).reshape(1024, 4)
+    c = np.array(list(cb), dtype=np.float64).reshape(1024, 6)
     c = c[c[:, 1] > 0]
     t0 = c[:, 1].min()
     print("per-CTA view of sweep 60:", len(c), "CTAs on", len(set(c[:, 0])), "SMs")
     print("  past wait: min %.2f max %.2f us" % (0.0, (c[:, 1].max() - t0) / 1e3))
     end = (c[:, 3] - t0) / 1e3
     print("  end: quantiles", np.round(np.quantile(end, [0, .1, .5, .8, .9, .99, 1]), 1))
+    pro = (c[:, 2] - c[:, 1]) / 1e3
+    loop = (c[:, 4] - c[:, 2]) / 1e3
+    epi = (c[:, 3] - c[:, 4]) / 1e3
+    print("  prologue (wait -> tile loop): median %.2f max %.2f us; tile loop: median %.2f max %.2f us (tiles per CTA: median %d, max %d); epilogue (loop end -> CTA end): median %.2f max %.2f us"
+          % (np.median(pro), pro.max(), np.median(loop), loop.max(), np.median(c[:, 5]), c[:, 5].max(), np.median(epi), epi.max()))
     late = end > np.quantile(end, 0.8)
     sm_counts = {}
     for smid in c[late, 0]: sm_counts[int(smid)] = sm_counts.get(int(smid), 0) + 1

@@ -24,7 +24,7 @@ extern "C" int erirt_diag_timeline(unsigned long long* out) {
   return TL_SLOTS * TL_N;
 }
 extern "C" int erirt_diag_cta_timeline(unsigned long long* out) {
-  cudaMemcpyFromSymbol(out, erirt::g_tl_cta, sizeof(unsigned long long) * TL_CTAS * 4);
+  cudaMemcpyFromSymbol(out, erirt::g_tl_cta, sizeof(unsigned long long) * TL_CTAS * 6);
   return TL_CTAS;
 }
 #endif
