@@ -19,7 +19,7 @@ COMPAT_LATENTQR_SCALE_ELEMENTWISE = 2
 
 EXPORTED = ["erirt_version", "erirt_last_error", "erirt_create", "erirt_destroy", "erirt_set_data",
             "erirt_set_data_device", "erirt_trim_pool", "erirt_generate_data", "erirt_get_data", "erirt_set_data_y8", "erirt_checkpoint_size", "erirt_checkpoint_save", "erirt_checkpoint_load", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
-            "erirt_trace_width", "erirt_get_moments", "erirt_loglik_current", "erirt_get_stats",
+            "erirt_trace_width", "erirt_get_moments", "erirt_loglik_current", "erirt_get_stats", "erirt_debug_check_guards",
             "erirt_nccl_unique_id", "erirt_comm_init", "erirt_peer_export", "erirt_peer_attach", "erirt_peer_detach", "erirt_k_pg", "erirt_k_nu_person", "erirt_k_philox"]
 
 
@@ -80,6 +80,8 @@ def load():
     L.erirt_get_moments.argtypes = [vp, C.c_int32, dp, dp, C.c_int64]
     L.erirt_loglik_current.argtypes = [vp, C.POINTER(C.c_double)]
     L.erirt_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.erirt_debug_check_guards.argtypes = [vp]
+    L.erirt_debug_check_guards.restype = C.c_int64
     L.erirt_nccl_unique_id.argtypes = [vp]
     L.erirt_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.erirt_peer_export.argtypes = [vp, vp]
@@ -91,7 +93,7 @@ def load():
                                     C.c_int32, C.c_int32, dp]
     L.erirt_k_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_uint32)]
     for name in EXPORTED:
-        if name not in ("erirt_last_error", "erirt_trace_width", "erirt_version", "erirt_checkpoint_size"):
+        if name not in ("erirt_last_error", "erirt_trace_width", "erirt_version", "erirt_checkpoint_size", "erirt_debug_check_guards"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

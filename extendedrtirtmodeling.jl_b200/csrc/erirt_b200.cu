@@ -338,6 +338,7 @@ struct erirt_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // device buffers
   char* arena = nullptr;  // the one device allocation every pointer below is a slice of
+  std::vector<size_t> guard_offs;  // ERIRT_GUARDS=1: offsets of the 256-byte guard zones that follow every slice (erirt_debug_check_guards)
   uint8_t* dY = nullptr;
   void *dNuCell = nullptr, *dLogT = nullptr, *dOmega = nullptr, *dTheta = nullptr, *dZeta = nullptr, *dNu = nullptr, *dX = nullptr, *dPtrace = nullptr;
   double* dStatsPrev = nullptr;  // reduced statistics of the previous sweep: input of the global kernel's rehearsal pass
@@ -655,15 +656,27 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
     want((void**)&h->dSweep, sizeof(uint32_t));
     want((void**)&h->dStatus, sizeof(int));
     want((void**)&h->dLlOut, D);
+    // ERIRT_GUARDS=1 (debugging; compute-sanitizer is not available on every pool): every slice is followed by a 256-byte guard zone
+    // filled with 0xA5, and erirt_debug_check_guards() counts the guard bytes a kernel, a bulk copy or an ingest pass has overwritten
+    const char* env_guard = getenv("ERIRT_GUARDS");
+    const size_t guard = (env_guard && atoi(env_guard) > 0) ? 256 : 0;
     size_t total = 0;
-    for (const Req& r : reqs) total += r.bytes;
+    for (const Req& r : reqs) total += r.bytes + guard;
     tm.mark("create: stream, events");
     cudaError_t ae = cudaMallocAsync((void**)&h->arena, total, h->stream);
     tm.mark("create: cudaMallocAsync");
     if (ae == cudaSuccess) ae = cudaMemsetAsync(h->arena, 0, total, h->stream);
     if (ae != cudaSuccess) { free_handle(h); return fail(ERIRT_E_CUDA, "allocating %zu bytes of device memory: %s", total, cudaGetErrorString(ae)); }
     size_t off = 0;
-    for (const Req& r : reqs) { *r.p = h->arena + off; off += r.bytes; }
+    for (const Req& r : reqs) {
+      *r.p = h->arena + off;
+      off += r.bytes;
+      if (guard) {
+        cudaMemsetAsync(h->arena + off, 0xA5, guard, h->stream);
+        h->guard_offs.push_back(off);
+        off += guard;
+      }
+    }
   }
   // default parameters == setInitialValues (a = 1, sigma2 = 1, Sigma = I; src/GibbsRtIrt.pl.jl:122-133)
   {
@@ -1425,6 +1438,20 @@ extern "C" int erirt_loglik_current(erirt_handle* h, double* out) {
   CU(cudaMemcpyAsync(out, h->dLlOut, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+extern "C" int64_t erirt_debug_check_guards(erirt_handle* h) {
+  if (!h) return fail(ERIRT_E_ARG, "null handle");
+  if (h->guard_offs.empty()) return -1;  // the handle was created without ERIRT_GUARDS=1
+  cudaSetDevice(h->cfg.device);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(ERIRT_E_CUDA, "stream synchronize failed");
+  int64_t bad = 0;
+  std::vector<unsigned char> buf(256);
+  for (size_t off : h->guard_offs) {
+    if (cudaMemcpy(buf.data(), h->arena + off, 256, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(ERIRT_E_CUDA, "guard read-back failed");
+    for (unsigned char c : buf) bad += c != 0xA5;
+  }
+  return bad;
 }
 
 extern "C" int erirt_get_stats(erirt_handle* h, erirt_stats* out) {

@@ -174,6 +174,7 @@ __device__ inline void peer_allreduce_sum(double* const* peer_bufs, uint32_t* xs
                                           int count, double* dst, int* status, int tid, int nthreads) {
   const uint32_t seq = *xseq + 1u;
   const int par = (int)(seq & 1u);
+  ERIRT_CHECK(count <= S && rank >= 0 && rank < world);
   for (int t = tid; t < count; t += nthreads) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(src[t]);
     const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)seq << 32), w1 = (bits >> 32) | ((unsigned long long)seq << 32);
@@ -429,6 +430,7 @@ __global__ void __maxnreg__(80) global_draw_kernel(const GlobalArgs A) {
   TL_DECL(tl_entry);
   const uint32_t k = *A.sweep_ctr;  // person launch P(k)
   const uint32_t s = k + 1;         // sweep whose parameters are drawn now
+  ERIRT_CHECK(2 * (F + 1) <= MAXD && F + 2 <= MAXD && L.J <= L.Jp);
   for (int t = tid; t < (F + 1) * (F + 1); t += G_THREADS) sXtX[t] = A.XtX[t];
   if (A.stage == 0 || A.stage == 2) global_raw_variates(A, s, sRaw, w, tid);
   // Two passes over the body below.  Pass 0 is a REHEARSAL that runs before the dependency wait, on the reduced statistics of the

@@ -41,6 +41,14 @@ struct Layout {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Index checks of the diagnostic build (-DERIRT_CHECKS, tools/make_tick_build.py): a failing check traps the kernel (device assert)
+#ifdef ERIRT_CHECKS
+#include <cassert>
+#define ERIRT_CHECK(c) assert(c)
+#else
+#define ERIRT_CHECK(c)
+#endif
+
 // Sweep timeline of the diagnostic build (-DERIRT_TIMELINE, tools/make_tick_build.py): %globaltimer stamps (ns) per sweep slot
 #ifdef ERIRT_TIMELINE
 #define TL_SLOTS 256

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 
   // transposed-statistics role of this thread: item group eg, person class er (G <= CTA_THREADS is enforced by the host)
   const int Rc = CTA_THREADS / G;
+  ERIRT_CHECK(G >= 1 && G <= CTA_THREADS && Rc >= 1 && (size_t)A.S.off_misc + (MD_COUNT + SC_COUNT) * sizeof(double) + 24 <= (size_t)A.S.total);
   const bool e_active = tid < G * Rc;
   const int eg = tid % G, er = tid / G;
   u64 a0l = 0ull, a0h = 0ull, a1l = 0ull, a1h = 0ull, a2l = 0ull, a2h = 0ull, acl = 0ull, ach = 0ull;  // {items 0,1} / {items 2,3}
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 #endif
   for (; tile < A.n_tiles; ++tiles_done) {
     const int64_t row0 = (int64_t)tile * P;
+    ERIRT_CHECK(tile >= 0 && tile < A.n_tiles && row0 + P <= A.n_pad);
     PF_TICK(13);  // tile-loop overhead / previous store issue
     if (tid == 0) {
       const uint32_t nxt = (uint32_t)gridDim.x + atomicAdd(A.tile_ctr, 1u);  // in flight while the store below drains
@@ -557,6 +559,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
           const int bit = bit0 + __ffs((int)m) - 1;
           m &= m - 1u;
           const int j = ((bit / BPB) << 5) + q * BPB + (bit % BPB);
+          ERIRT_CHECK(j >= 0 && j < J && qbase + cap <= qcap);
           if (slot < cap) s_queue[qbase + slot] = ((uint32_t)p << 16) | (uint32_t)j | flag;
           else {  // queue overflow: finish the cell here
             const float z = fmaf(s_par[PAR_A * Jp + j], thp, s_par[PAR_AB * Jp + j]);
@@ -595,6 +598,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
         const bool has2 = idx + CTA_THREADS < qn;
         const uint32_t e1 = s_queue[idx], e2 = s_queue[has2 ? idx + CTA_THREADS : idx];
         const int j1 = (int)(e1 & 0xffffu), p1 = (int)(e1 >> 16), j2 = (int)(e2 & 0xffffu), p2 = (int)(e2 >> 16);
+        ERIRT_CHECK(j1 < J && p1 < P && j2 < J && p2 < P);
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
         const float z2 = fmaf(s_par[PAR_A * Jp + j2], s_u[p2 * Dgp + F + 1], s_par[PAR_AB * Jp + j2]);
         const uint32_t g1 = A.person_offset + (uint32_t)(row0 + p1), g2 = A.person_offset + (uint32_t)(row0 + p2);
@@ -619,6 +623,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       for (uint32_t idx = (uint32_t)(CTA_THREADS - 1 - tid); idx < qu; idx += CTA_THREADS) {
         const uint32_t e1 = s_queue[qstd + idx];
         const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
+        ERIRT_CHECK(qstd + idx < qcap && j1 < J && p1 < P && (e1 >> 31));
         const float z1 = fmaf(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], s_par[PAR_AB * Jp + j1]);
         s_om[p1 * Jp + j1] = pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, true);
       }

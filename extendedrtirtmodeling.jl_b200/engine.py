@@ -170,6 +170,10 @@ class Engine:
         check(self.lib.erirt_get_stats(self.h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in _lib.Stats._fields_}
 
+    def check_guards(self) -> int:
+        """Guard bytes overwritten since erirt_create (handles created with ERIRT_GUARDS=1 in the environment); -1 without guards."""
+        return int(self.lib.erirt_debug_check_guards(self.h))
+
     # ---- multi-GPU ----
     def comm_init(self, rank, world, unique_id=None):
         """unique_id: 128 bytes of an NCCL id (ncclAllReduce exchange), or None when the peer exchange is attached next."""

@@ -157,6 +157,10 @@ int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, 
 int erirt_loglik_current(erirt_handle* h, double* out);
 
 int erirt_get_stats(erirt_handle* h, erirt_stats* out);
+/* Debugging aid (compute-sanitizer is not available everywhere): a handle created with ERIRT_GUARDS=1 in the environment places a
+ * 256-byte guard zone after every device buffer; this returns how many guard bytes have been overwritten since (0 = clean), or -1
+ * when the handle has no guard zones.  No counterpart in the reference. */
+int64_t erirt_debug_check_guards(erirt_handle* h);
 
 /* ---- checkpoint / resume: state, auxiliaries, Philox sweep counter, running moments and traces of the chain ----
  * erirt_checkpoint_save writes erirt_checkpoint_size(h) bytes into the caller's buffer (the caller persists them).

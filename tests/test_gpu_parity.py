@@ -727,3 +727,24 @@ def test_sharded_chain_equals_single_gpu_chain(E):
            "--master-port", "29533", os.path.join(root, "tools", "check_sharded.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0 and "SHARDING_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,dtype,N,J,F", [("RtIrtLatentQr", "f32", 700, 100, 3), ("RtIrt", "f32", 3000, 30, 3), ("MlIrt", "f32", 1000, 15, 3),
+                                               ("RtIrtCrossQr", "f32", 150, 13, 0), ("RtIrtLatentQr", "f64", 200, 21, 2), ("RtIrtCross", "f64", 129, 7, 0)])
+def test_guard_zones_stay_clean(E, monkeypatch, model, dtype, N, J, F):
+    """ERIRT_GUARDS=1 places a 256-byte guard zone after every device buffer of the handle: ingest, sampling (bulk tile loads and stores,
+    statistics, traces, moments) and the read-backs must not touch any of them (the repo's stand-in for compute-sanitizer memcheck,
+    which is closed on the GPU pool: profiles/r02_sanitizer_unavailable.txt)."""
+    monkeypatch.setenv("ERIRT_GUARDS", "1")
+    pb = make_problem(model, N, J, F, seed=7)
+    eng = run_engine(E, pb, 4, dtype=dtype, person_trace=True)
+    assert eng.check_guards() == 0
+    eng.get_trace("ra")
+    eng.get_moments("theta")
+    assert eng.check_guards() == 0
+    eng.close()
+    monkeypatch.delenv("ERIRT_GUARDS")
+    eng = run_engine(E, pb, 1, dtype=dtype)
+    assert eng.check_guards() == -1
+    eng.close()

@@ -33,8 +33,8 @@ tmp = os.path.join(CSRC, "_tick_build.cu")
 open(tmp, "w").write(src)
 try:
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-                           "-DERIRT_TICKS" if not os.environ.get("ERIRT_TIMELINE_BUILD") else "-DERIRT_TIMELINE"] + os.environ.get("ERIRT_NVCC_EXTRA", "").split() +
-                          ["-o", os.path.join(ROOT, "diag_timeline.so" if os.environ.get("ERIRT_TIMELINE_BUILD") else "diag_tick.so"), tmp, "-ldl"])
+                           ("-DERIRT_CHECKS" if os.environ.get("ERIRT_CHECKS_BUILD") else "-DERIRT_TIMELINE" if os.environ.get("ERIRT_TIMELINE_BUILD") else "-DERIRT_TICKS")] + os.environ.get("ERIRT_NVCC_EXTRA", "").split() +
+                          ["-o", os.path.join(ROOT, "diag_checks.so" if os.environ.get("ERIRT_CHECKS_BUILD") else "diag_timeline.so" if os.environ.get("ERIRT_TIMELINE_BUILD") else "diag_tick.so"), tmp, "-ldl"])
 finally:
     os.remove(tmp)
 print("built")

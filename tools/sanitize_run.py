@@ -1,4 +1,9 @@
-"""Small driver for compute-sanitizer (memcheck / racecheck / synccheck), one tool per gpurun call:
+"""Small driver for compute-sanitizer (memcheck / racecheck / synccheck), one tool per gpurun call, and for the repo's own
+substitute where compute-sanitizer is closed (profiles/r02_sanitizer_unavailable.txt):
+
+    ERIRT_CHECKS_BUILD=1 python tools/make_tick_build.py          # diag_checks.so: device-side index asserts (-DERIRT_CHECKS)
+    ERIRT_B200_LIB=$PWD/diag_checks.so ERIRT_GUARDS=1 python tools/sanitize_run.py    # + 256-byte guard zones after every device buffer
+
 
     compute-sanitizer --tool racecheck python tools/sanitize_run.py            # single GPU
     compute-sanitizer --tool memcheck --target-processes all \
@@ -28,7 +33,9 @@ if world > 1:
 
 # (model, N, J, F, dtype, max_grid)
 cases = [("RtIrtLatentQr", 300, 13, 2, "f32", 0), ("RtIrtLatentQr", 200, 100, 3, "f32", 0), ("RtIrt", 150, 150, 1, "f32", 0), ("MlIrt", 130, 21, 0, "f32", 0),
-         ("RtIrtLatentQr", 200, 21, 2, "f64", 0), ("RtIrtCrossQr", 150, 13, 0, "f32", 0),
+         ("RtIrtLatentQr", 200, 21, 2, "f64", 0), ("RtIrtCrossQr", 150, 13, 0, "f32", 0), ("RtIrtCross", 129, 7, 0, "f64", 0),
+         ("RtIrtNull", 1000, 40, 0, "f32", 0), ("RtIrtLatent", 257, 33, 4, "f32", 0), ("RtIrtCrossQr", 131, 9, 0, "f64", 0),
+         ("RtIrt", 3000, 30, 3, "f32", 0), ("MlIrt", 1000, 15, 3, "f64", 0),
          ("RtIrtLatentQr", 64 * 2 * 18 * world + 5, 100, 3, "f32", 2)]  # 18 tiles per CTA on every rank: one 16-tile fold + the final one
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
@@ -59,12 +66,16 @@ for model, N, J, F, dt, max_grid in cases:
     eng.sample(3)
     a = eng.get_trace("ra", n, 2 * J)[:3, :, 0]
     assert np.all(np.isfinite(a)), (model, dt)
+    eng.get_moments("theta")
+    eng.loglik_current() if hasattr(eng, "loglik_current") else None
+    guards = eng.check_guards()
+    assert guards in (0, -1), f"{guards} guard bytes overwritten ({model} {dt})"
     if world > 1:
         D.close_sharded(eng)
     else:
         eng.close()
     if rank == 0:
-        print("ok", model, N, J, F, dt, "max_grid", max_grid, "world", world, flush=True)
+        print("ok", model, N, J, F, dt, "max_grid", max_grid, "world", world, "guard bytes overwritten:", guards, flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
