@@ -191,10 +191,14 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   // Folding the f32 register sums into the CTA's f64 accumulators: the Rc person classes of an item group would collide on the
   // same 500 addresses (f64 shared atomics are CAS loops), so each class writes its 20 sums into its own slab of a staging area
   // -- the logT tile, dead between the statistics pass and the next tile's load -- and the slabs are added without atomics.
-  const bool stage_flush = has_rt && (size_t)Rc * 5 * Jp * sizeof(R) <= (size_t)A.S.tile_real_bytes;
-  auto flush_item_stats = [&]() {  // called by all threads of the CTA at the same point
+  // (MlIrt has no logT tile: inside the tile loop its folds go through the atomics below, the fold after the last tile uses the omega
+  // tile once its store has drained -- with one tile per CTA, the launch-bound README problem, the atomics were 10 us of a 30 us sweep)
+  const bool stage_fits = (size_t)Rc * 5 * Jp * sizeof(R) <= (size_t)A.S.tile_real_bytes;
+  auto flush_item_stats = [&](const bool last) {  // called by all threads of the CTA at the same point
+    const bool stage_flush = stage_fits && (has_rt || last);
     if (stage_flush) {
-      R* stg = s_lt;
+      R* stg = has_rt ? s_lt : s_om;
+      if (!has_rt && tid == 0) tma_store_wait_read();  // the last tile's omega store no longer reads the buffer
       __syncthreads();  // every warp is done reading logT in the statistics pass
       if (e_active) {
         R* d = stg + (size_t)er * 5 * Jp + 4 * eg;
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
       }
     }
     PF_TICK(11);  // statistics pass
-    if ((tiles_done % FAST_FLUSH_TILES) == FAST_FLUSH_TILES - 1) flush_item_stats();
+    if ((tiles_done % FAST_FLUSH_TILES) == FAST_FLUSH_TILES - 1) flush_item_stats(false);
     // Gram of u = [1 X theta zeta nu] and its 1/nu-weighted twin: entry t is shared by the 4 lanes of a quad (persons
     // pp = lane mod 4 (mod 4)), so that all four warps of the CTA take part instead of one
     for (int t0 = 0; t0 < L.ntri; t0 += CTA_THREADS / 4) {
@@ -788,7 +792,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
 #ifdef ERIRT_TIMELINE
   if (tid == 0 && k == TL_CTA_SWEEP && blockIdx.x < TL_CTAS) { g_tl_cta[blockIdx.x][4] = tl_now(); g_tl_cta[blockIdx.x][5] = (unsigned long long)tiles_done; }
 #endif
-  flush_item_stats();
+  flush_item_stats(true);
 
   // ---- flush CTA accumulators ----
   {  // warp totals by shuffle, then one shared-memory atomic per warp and quantity (f64 shared atomics are CAS loops)
