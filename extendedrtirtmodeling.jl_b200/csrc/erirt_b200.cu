@@ -1124,7 +1124,14 @@ static GlobalArgs make_global_args(erirt_handle* h, int stage) {
   A.params = h->dParams;
   A.stats = h->dStats;
   A.stats_prev = h->dStatsPrev;
-  A.rehearse = global_rehearsal_enabled() ? 1 : 0;
+  {
+    // The rehearsal pays when the person launch in front of this kernel is long enough to hide it (about 20 us) and big enough to
+    // have flushed the instruction caches: more than one tile per CTA.  Behind a one-round launch (the small problems) it would only
+    // delay the real pass.
+    const bool generic = stage != 0 || h->cfg.dtype != ERIRT_F32;
+    const int64_t tiles = h->n_pad / (generic ? h->S_gen.P : h->S.P);
+    A.rehearse = (global_rehearsal_enabled() && tiles > (generic ? h->grid_gen : h->grid)) ? 1 : 0;
+  }
   A.tile_ctr = h->dTileCtr;
   A.sweep_ctr = h->dSweep;
   A.T1 = h->dConsts + h->c_T1;

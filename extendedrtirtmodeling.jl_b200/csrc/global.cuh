@@ -28,9 +28,13 @@ constexpr int G_THREADS = 256;
 //      matrices are column-major in shared memory, n <= 32 = MAXD, lane i owns row i (or column i).  The structural block is a
 //      dependent chain that sits on the critical path of every sweep (the person kernels wait for it): on one lane a 12 x 12
 //      solve took 29 us (profiles/r02e_sweep_timeline.txt), spread over the lanes its depth is O(n^2) shared-memory round trips.
-//      The Cholesky factor and the forward substitution subtract their products in the same order as the textbook serial loops
-//      (bitwise the same factor); the back substitution and the inverse accumulate in a different order (1e-16 relative). ----
-__device__ inline bool chol_lower(int n, const double* A, double* Lm, int lane) {
+//      Products are subtracted in the order of the textbook serial loops in the factor and the forward substitution, in another
+//      order in the back substitution and the inverse, and divisions by the diagonal are multiplications by its reciprocal: the
+//      results are within a few ulp of the oracle's serial code (the parity tests hold 1e-9 over whole chains). ----
+// idiag (n doubles) receives 1 / L_jj: the substitutions below multiply by it instead of dividing (an f64 division is ~100 cycles of
+// a dependent chain that every sweep waits for).  (Rows kept in registers with the columns travelling by shuffle were measured no
+// faster: the structural block is bound by its many short dependent f64 chains, not by this factorisation; profiles/r02_summary.md.)
+__device__ inline bool chol_lower(int n, const double* A, double* Lm, double* idiag, int lane) {
   // right-looking: Lm starts as the lower triangle of A, column j is scaled and its outer product leaves the trailing rows
   for (int t = lane; t < n * n; t += 32) {
     const int r = t % n, c = t / n;
@@ -40,13 +44,13 @@ __device__ inline bool chol_lower(int n, const double* A, double* Lm, int lane) 
   #pragma unroll 1
   for (int j = 0; j < n; ++j) {
     __syncwarp();
-    double d = Lm[j + n * j];
-    if (!(d > 0.0)) { ok = false; break; }  // uniform: every lane reads the same element
-    d = sqrt(d);
+    const double djj = Lm[j + n * j];
+    if (!(djj > 0.0)) { ok = false; break; }  // uniform: every lane reads the same element
+    const double d = sqrt(djj), id = 1.0 / d;
     double lij = 0.0;
-    if (lane > j && lane < n) lij = Lm[lane + n * j] / d;
+    if (lane > j && lane < n) lij = Lm[lane + n * j] * id;
     __syncwarp();
-    if (lane == j) Lm[j + n * j] = d;
+    if (lane == j) { Lm[j + n * j] = d; idiag[j] = id; }
     if (lane > j && lane < n) Lm[lane + n * j] = lij;
     __syncwarp();  // column j is final
     if (lane > j && lane < n) {
@@ -57,19 +61,19 @@ __device__ inline bool chol_lower(int n, const double* A, double* Lm, int lane) 
   __syncwarp();
   return ok;
 }
-// sol = A^{-1} rhs through the Cholesky factor (Lm: n*n scratch).  sol may alias rhs.
-__device__ inline bool spd_solve(int n, const double* A, const double* rhs, double* sol, double* Lm, int lane) {
-  if (!chol_lower(n, A, Lm, lane)) return false;
+// sol = A^{-1} rhs through the Cholesky factor (Lm: n*n scratch, idiag: n).  sol may alias rhs.
+__device__ inline bool spd_solve(int n, const double* A, const double* rhs, double* sol, double* Lm, double* idiag, int lane) {
+  if (!chol_lower(n, A, Lm, idiag, lane)) return false;
   double sv = lane < n ? rhs[lane] : 0.0;
   #pragma unroll 1
   for (int k = 0; k < n; ++k) {  // forward: y_k = s_k / L_kk, rows below lose L_ik y_k
-    const double yk = __shfl_sync(0xffffffffu, sv, k) / Lm[k + n * k];
+    const double yk = __shfl_sync(0xffffffffu, sv, k) * idiag[k];
     if (lane == k) sv = yk;
     else if (lane > k && lane < n) sv -= Lm[lane + n * k] * yk;
   }
   #pragma unroll 1
   for (int k = n - 1; k >= 0; --k) {  // backward: x_k = s_k / L_kk, rows above lose L_ki x_k
-    const double xk = __shfl_sync(0xffffffffu, sv, k) / Lm[k + n * k];
+    const double xk = __shfl_sync(0xffffffffu, sv, k) * idiag[k];
     if (lane == k) sv = xk;
     else if (lane < k) sv -= Lm[k + n * lane] * xk;
   }
@@ -79,24 +83,26 @@ __device__ inline bool spd_solve(int n, const double* A, const double* rhs, doub
   return true;
 }
 // Ainv = A^{-1}: lane j solves A x = e_j (column j) by the two substitutions; Lm and Y are n*n scratch, none of the four may alias
-__device__ inline bool spd_inverse(int n, const double* A, double* Ainv, double* Lm, double* Y, int lane) {
-  if (!chol_lower(n, A, Lm, lane)) return false;
+__device__ inline bool spd_inverse(int n, const double* A, double* Ainv, double* Lm, double* Y, double* idiag, int lane) {
+  if (!chol_lower(n, A, Lm, idiag, lane)) return false;
   if (lane < n) {
-    double* y = Y + n * lane;     // column `lane` of L^{-1}
+    double* y = Y + n * lane;     // column `lane` of L^{-1}: zero above its diagonal, so the rows start there
     double* x = Ainv + n * lane;  // column `lane` of A^{-1}
     #pragma unroll 1
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < lane; ++i) y[i] = 0.0;
+    #pragma unroll 1
+    for (int i = lane; i < n; ++i) {
       double sacc = i == lane ? 1.0 : 0.0;
       #pragma unroll 1
-      for (int k = 0; k < i; ++k) sacc -= Lm[i + n * k] * y[k];
-      y[i] = sacc / Lm[i + n * i];
+      for (int k = lane; k < i; ++k) sacc -= Lm[i + n * k] * y[k];
+      y[i] = sacc * idiag[i];
     }
     #pragma unroll 1
     for (int i = n - 1; i >= 0; --i) {
       double sacc = y[i];
       #pragma unroll 1
       for (int k = i + 1; k < n; ++k) sacc -= Lm[k + n * i] * x[k];
-      x[i] = sacc / Lm[i + n * i];
+      x[i] = sacc * idiag[i];
     }
   }
   __syncwarp();
@@ -217,13 +223,14 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(double* const* peer
 struct GScratch {
   double M[MAXD * MAXD], V[MAXD * MAXD], Lc[MAXD * MAXD], T[MAXD * MAXD], XX[MAXD * MAXD];
   double rhs[MAXD], mean[MAXD], z[MAXD], beta[MAXD], Sigma[4];
+  double idiag[MAXD];  // reciprocal diagonal of the current Cholesky factor
   double zn[MAXD];  // N(0,1) of the global beta site, unit t (precomputed on separate lanes)
   double graw[6];   // attempt-0 raw material of the Sigma site: (normal, uniform) of units 0, 1, 2
 };
 
 // mean + chol(V).L * z with z_t ~ N(0,1) at the global beta site; returns false if V is not SPD (warp-cooperative)
 __device__ inline bool mvn_draw(int d, GScratch& w, int lane) {
-  if (!chol_lower(d, w.V, w.Lc, lane)) return false;
+  if (!chol_lower(d, w.V, w.Lc, w.idiag, lane)) return false;
   if (lane < d) {
     double acc = w.mean[lane];
     #pragma unroll 1
@@ -265,7 +272,7 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
   if (model == M_MLIRT) {
     if (lane < pb) w.rhs[lane] = Gm.at(lane, TH);
     __syncwarp();
-    ok = spd_solve(pb, XtX, w.rhs, w.beta, w.Lc, lane);  // getSubjCoefficientsMlIrt
+    ok = spd_solve(pb, XtX, w.rhs, w.beta, w.Lc, w.idiag, lane);  // getSubjCoefficientsMlIrt
     if (!A.intercept && lane == 0) w.beta[0] = 0.0;
   } else if (model == M_RTIRT) {
     const int d = 2 * pb;
@@ -276,7 +283,7 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
       w.M[t] = iO[br + 2 * bc] * XtX[r + pb * q] + add + ((add == 0.0 && rr == cc) ? 1.0 : 0.0);
     }
     __syncwarp();
-    ok = spd_inverse(d, w.M, w.V, w.Lc, w.T, lane);
+    ok = spd_inverse(d, w.M, w.V, w.Lc, w.T, w.idiag, lane);
     if (lane < d) {  // vec(x'η invΩ')
       const int c = lane / pb, r = lane % pb;
       w.rhs[lane] = Gm.at(r, TH) * iO[c + 0] + Gm.at(r, ZE) * iO[c + 2];
@@ -333,7 +340,7 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
       const double iO = 1.0 / Sig[3];
       for (int t = lane; t < d * d; t += 32) w.M[t] = iO * w.XX[t] + add + ((add == 0.0 && t % d == t / d) ? 1.0 : 0.0);
       __syncwarp();
-      ok = spd_inverse(d, w.M, w.V, w.Lc, w.T, lane);
+      ok = spd_inverse(d, w.M, w.V, w.Lc, w.T, w.idiag, lane);
       if (lane < d) {
         double acc = 0.0;
         #pragma unroll 1
@@ -343,7 +350,7 @@ __device__ inline bool structural_draws(const GlobalArgs& A, const double* XtX, 
       __syncwarp();
       ok = ok && mvn_draw(d, w, lane);
     } else {  // getSubjCoefficientsLatentQr: the tall Kronecker system collapses to OLS
-      ok = spd_solve(d, w.XX, w.rhs, w.beta, w.Lc, lane);
+      ok = spd_solve(d, w.XX, w.rhs, w.beta, w.Lc, w.idiag, lane);
     }
     if (!A.intercept && lane == 0) w.beta[0] = 0.0;
     __syncwarp();
@@ -562,11 +569,17 @@ __global__ void __maxnreg__(80) global_draw_kernel(const GlobalArgs A) {
 #endif
   if (model == M_LATENT || model == M_LATENTQR) latent_prebuild(A, sXtX, Gm, w, tid, G_THREADS);
   __syncthreads();
+#ifdef ERIRT_TIMELINE
+  if (real && tid == 0) g_timeline[k % TL_SLOTS][13] = tl_now();
+#endif
   G_TICK(6, 0);  // raw variates done
   // ---- 2a. structural draws (warp 0, cooperatively), 2b. item draws (warps 1..) ----
   if (tid < 32) {
     if (!structural_draws(A, sXtX, s, Gm, Gw, w, tid) && tid == 0 && real) atomicExch(A.status, (int)s);
     G_TICK(2, 0);  // structural block done
+#ifdef ERIRT_TIMELINE
+    if (real && tid == 0) g_timeline[k % TL_SLOTS][11] = tl_now();
+#endif
   }
   // item draws on warps 1..: the structural block of warp 0 runs concurrently.  Two tasks per item, dealt so that a warp holds one
   // kind: (b, a) [MlIrt: (a, b)] and the response-time pair (lambda, sigma2) [Cross family: rho], which do not depend on each other
@@ -626,6 +639,10 @@ __global__ void __maxnreg__(80) global_draw_kernel(const GlobalArgs A) {
     }
   }
   G_TICK(3, 32);  // item draws of lane 32 done
+#ifdef ERIRT_TIMELINE
+  if (real && tid == 32) g_timeline[k % TL_SLOTS][12] = tl_now();
+  if (real && tid == G_THREADS - 1) g_timeline[k % TL_SLOTS][14] = tl_now();
+#endif
   __syncthreads();
   G_TICK(4, 0);
   if (real) griddep_launch();  // the CTAs of the next person launch become resident and arm their barriers while the trace row is written

@@ -52,7 +52,7 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 // Sweep timeline of the diagnostic build (-DERIRT_TIMELINE, tools/make_tick_build.py): %globaltimer stamps (ns) per sweep slot
 #ifdef ERIRT_TIMELINE
 #define TL_SLOTS 256
-#define TL_N 12
+#define TL_N 16
 __device__ unsigned long long g_timeline[TL_SLOTS][TL_N];
 #define TL_CTAS 1024
 #define TL_CTA_SWEEP 60

@@ -32,6 +32,11 @@ else:
         D = E.setDataRtIrt(Cond, E.setTrueParaRtIrt(Cond, rng=1), rng=1)
         model, N, J, F = "RtIrt", 10_000, 30, 3
         init = dict(theta=rng.standard_normal(N), zeta=rng.standard_normal(N), beta=rng.standard_normal(8))
+    elif which == "C4":
+        Cond = E.setCond(nSubj=100_000, nItem=40, nFeat=0, nIter=200, nChain=1)
+        D = E.setDataRtIrtNull(Cond, E.setTrueParaRtIrt(Cond, rng=1), rng=1)
+        model, N, J, F = "RtIrtNull", 100_000, 40, 0
+        init = dict(theta=rng.standard_normal(N), zeta=rng.standard_normal(N))
     else:
         Cond = E.setCond(nSubj=631, nItem=14, nFeat=10, nIter=200, nChain=1, qRt=0.85)
         D = E.setDataRtIrtLatent(Cond, E.setTrueParaRtIrtLatent(Cond, rng=1), type="norm", rng=1)
@@ -58,18 +63,20 @@ if TICKS:
     sys.exit(0)
 eng.sample(K)
 print(which, "ms per sweep", eng.stats()["last_sample_ms"] / K, "PDL", os.environ.get("ERIRT_PDL", "1"), "REHEARSE", os.environ.get("ERIRT_G_REHEARSE", "1"))
-buf = (ctypes.c_ulonglong * (256 * 12))()
+buf = (ctypes.c_ulonglong * (256 * 16))()
 eng.lib.erirt_diag_timeline(buf)
-t = np.array(list(buf), dtype=np.float64).reshape(256, 12)
+t = np.array(list(buf), dtype=np.float64).reshape(256, 16)
 ks = np.arange(48, 40 + K - 2)  # sweeps well inside the second sample() call
 names = ["P first CTA entry", "P first CTA past wait", "P last CTA past wait", "P last CTA done", "G entry", "G pre-wait part done",
          "G past wait", "G statistics staged", "G log-likelihood done", "G draws done", "G end"]
 rows = []
 for k in ks:
     base = t[k, 0]
-    rows.append([(t[k, i] - base) / 1e3 for i in range(11)] + [(t[k + 1, 0] - base) / 1e3, (t[k + 1, 2] - base) / 1e3])
+    rows.append([(t[k, i] - base) / 1e3 for i in range(11)] + [(t[k + 1, 0] - base) / 1e3, (t[k + 1, 2] - base) / 1e3] +
+                [(t[k, i] - base) / 1e3 for i in (13, 11, 12, 14)])
 m = np.median(np.array(rows), axis=0)
-for nm, v in zip(names + ["next P first CTA entry", "next P last CTA past wait"], m):
+for nm, v in zip(names + ["next P first CTA entry", "next P last CTA past wait", "G  prebuild done", "G  structural warp done", "G  item lane 32 done",
+                          "G  item lane 255 done"], m):
     print(f"  {nm:28s} {v:9.2f} us")
 
 if os.environ.get("TL_CTAS"):
