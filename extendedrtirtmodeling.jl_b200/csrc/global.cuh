@@ -194,19 +194,33 @@ __device__ inline void peer_allreduce_sum(double* const* peer_bufs, uint32_t* xs
   bool dead = false;
   for (int t = tid; t < count; t += nthreads) {
     double acc = 0.0;
-    for (int r = 0; r < world; ++r) {
-      const ulonglong2* pk = mine + (size_t)r * S + t;
-      unsigned long long w0, w1;
-      for (;;) {
-        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(pk) : "memory");
-        if ((uint32_t)(w0 >> 32) == seq && (uint32_t)(w1 >> 32) == seq) break;
-        if (dead || clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
-          if (!dead) atomicExch(status, -1000 - r);
-          dead = true;
-          break;
+    for (int r0 = 0; r0 < world; r0 += 8) {
+      // the packets of eight ranks are requested together (one L2 round trip instead of eight in a row: polled one by one the
+      // receive loop was ~8 us of the sweep at 8 GPUs), then each is validated and re-polled until it carries this exchange
+      unsigned long long w0[8], w1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        w0[i] = w1[i] = 0ull;
+        if (r0 + i < world) {
+          const ulonglong2* pk = mine + (size_t)(r0 + i) * S + t;
+          asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[i]), "=l"(w1[i]) : "l"(pk) : "memory");
         }
       }
-      acc += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r0 + i < world) {
+          const ulonglong2* pk = mine + (size_t)(r0 + i) * S + t;
+          while ((uint32_t)(w0[i] >> 32) != seq || (uint32_t)(w1[i] >> 32) != seq) {
+            if (dead || clock64() - t_start > 20000000000LL) {  // ~10 s: a peer is gone; flag it instead of hanging the GPU
+              if (!dead) atomicExch(status, -1000 - (r0 + i));
+              dead = true;
+              break;
+            }
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[i]), "=l"(w1[i]) : "l"(pk) : "memory");
+          }
+          acc += __longlong_as_double((long long)((w0[i] & 0xffffffffull) | (w1[i] << 32)));
+        }
+      }
     }
     dst[t] = acc;
   }
