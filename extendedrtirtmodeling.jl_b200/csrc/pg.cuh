@@ -63,7 +63,7 @@ __device__ __forceinline__ double inv_normal_tail<double>(double y) {
   double z = 1.0 / ((double)rf * (double)xq_poly(rf));
   // the polynomial start is within 3e-7 (relative) of the root and Newton on ln Phic converges quadratically with a constant below
   // one: two steps reach the rounding level of erfc / log (the oracle iterates to convergence from its own start; 1e-15 apart).
-  // The steps are 53 % of the instructions of the f64 person kernel (profiles/r02f_person_kernel_f64_ncu_breakdown.txt, four steps).
+  // The steps are 53 % of the instructions of the f64 person kernel (profiles/earlier/r02f_person_kernel_f64_ncu_breakdown.txt, four steps).
 #pragma unroll 1
   for (int it = 0; it < 2; ++it) {
     double sf = 0.5 * erfc(z * 0.70710678118654752440);
