@@ -125,15 +125,28 @@ __device__ __noinline__ double pg_draw_cell_f64(PhiloxKey key, uint32_t gid, uin
 constexpr int STAT_FLUSH_TILES = 8;  // item statistics live in registers and are folded into f64 every 8 tiles
 
 // resident CTAs per SM the register allocation is tuned for: the tile of TPP=2 leaves room for 3 CTAs, TPP=4 for 5, TPP=8 for 7
+#ifndef ERIRT_MINCTAS_TPP4  // experiment hook (tools/gpu_ab.sh): residency the TPP = 4 instantiations are compiled for
+#define ERIRT_MINCTAS_TPP4 (ERIRT_CTA_THREADS == 128 ? 5 : 3)
+#endif
 template <int TPP>
 constexpr int min_ctas_per_sm() {
-  return CTA_THREADS == 128 ? (TPP >= 8 ? 7 : (TPP == 4 ? 5 : 3)) : (TPP >= 8 ? 4 : (TPP == 4 ? 3 : 1));
+  return CTA_THREADS == 128 ? (TPP >= 8 ? 7 : (TPP == 4 ? ERIRT_MINCTAS_TPP4 : 3)) : (TPP >= 8 ? 4 : (TPP == 4 ? ERIRT_MINCTAS_TPP4 : 1));
+}
+
+// Float64: a tile row costs 17 bytes per cell, so shared memory holds three CTAs at most where TPP = 4 is chosen (J = 100: 54 KB);
+// compiled for five the kernel had 96 registers and 684 bytes of spills in its cell loop
+#ifndef ERIRT_MINCTAS_F64
+#define ERIRT_MINCTAS_F64 3
+#endif
+template <int TPP>
+constexpr int min_ctas_f64() {
+  return CTA_THREADS == 128 ? (TPP >= 8 ? 4 : ERIRT_MINCTAS_F64) : 1;
 }
 
 // FAM = 0: the one-launch-per-sweep models (MlIrt, RtIrt, RtIrtNull, Latent, LatentQr) -- the hot configuration, with the
 // Cross-family / evaluation code compiled out; FAM = 1: everything (Cross, CrossQr stages 1/2, stage 3 evaluation).
 template <typename R, int TPP, int FAM>
-__global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sweep_kernel(const PersonArgs<R> A) {
+__global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TPP>() : min_ctas_per_sm<TPP>())) person_sweep_kernel(const PersonArgs<R> A) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int P = CTA_THREADS / TPP;
   constexpr bool F32 = sizeof(R) == 4;

@@ -92,46 +92,63 @@ __device__ __forceinline__ bool series_accept(R U, R x, bool right) {
   return false;
 }
 
+// One Method-A attempt up to the alternating-series test: the proposal x, the uniform U the series is compared with and the piece
+// (`right`: exponential tail); false = already rejected by the tilt.  The series test itself has ONE call site per attempt (the f64
+// person kernel is bound by instruction fetch: every inlined copy of exp / log / erfc counts, profiles/r02h_person_kernel_f64_*).
 template <typename R>
-__device__ __forceinline__ bool pg_attempt_A(R c, uint32_t wa, uint32_t wb, R& X) {
+__device__ __forceinline__ bool pg_propose_A(R c, uint32_t wa, uint32_t wb, R& x, R& U, bool& right) {
   const R um = u01<R>(wa), up = u01<R>(wb);
   const R K = R(PI_D * PI_D / 8.0) + R(0.5) * c * c;
   const R Rm1 = R(2.0 * PG_Q0 / PI_D) * K * exp(K * R(PG_T));  // q0 / p
   const R v = um * (R(1) + Rm1);
-  if (v < R(1)) {
-    R x = R(PG_T) - log(up) / K;
-    if (!series_accept<R>(v, x, true)) return false;
-    X = x;
+  right = v < R(1);
+  if (right) {
+    x = R(PG_T) - log(up) / K;
+    U = v;
     return true;
   }
   const R Z = inv_normal_tail<R>(up * R(PG_P0));
-  const R x = R(1) / (Z * Z);
+  x = R(1) / (Z * Z);
   const R ua = (v - R(1)) / Rm1;
   const R tilt = exp(R(-0.5) * c * c * x);
   if (ua >= tilt) return false;
-  if (!series_accept<R>(ua / tilt, x, false)) return false;
+  U = ua / tilt;
+  return true;
+}
+template <typename R>
+__device__ __forceinline__ bool pg_attempt_A(R c, uint32_t wa, uint32_t wb, R& X) {
+  R x, U;
+  bool right;
+  if (!pg_propose_A<R>(c, wa, wb, x, U, right)) return false;
+  if (!series_accept<R>(U, x, right)) return false;
   X = x;
   return true;
 }
 
 template <typename R>
-__device__ __forceinline__ bool pg_attempt_B(R c, uint4 w, R& X) {
+__device__ __forceinline__ bool pg_propose_B(R c, uint4 w, R& x, R& U, bool& right) {
   const R um = u01<R>(w.x);
   const R K = R(PI_D * PI_D / 8.0) + R(0.5) * c * c;
   const R p = (R(PI_D) / (R(2) * K)) * exp(-K * R(PG_T));
   const R ql = R(2) * exp(-c);
   const R Pr = p / (p + ql);
-  if (um < Pr) {
-    R x = R(PG_T) - log(u01<R>(w.y)) / K;
-    if (!series_accept<R>(um / Pr, x, true)) return false;
-    X = x;
+  right = um < Pr;
+  if (right) {
+    x = R(PG_T) - log(u01<R>(w.y)) / K;
+    U = um / Pr;
     return true;
   }
-  const R ua = (um - Pr) / (R(1) - Pr);
+  U = (um - Pr) / (R(1) - Pr);
   const R z = normal2r<R>(w.y, w.z);
-  const R x = ig_msh<R>(R(1) / c, R(1), z, u01<R>(w.w));
-  if (!(x < R(PG_T))) return false;
-  if (!series_accept<R>(ua, x, false)) return false;
+  x = ig_msh<R>(R(1) / c, R(1), z, u01<R>(w.w));
+  return x < R(PG_T);
+}
+template <typename R>
+__device__ __forceinline__ bool pg_attempt_B(R c, uint4 w, R& X) {
+  R x, U;
+  bool right;
+  if (!pg_propose_B<R>(c, w, x, U, right)) return false;
+  if (!series_accept<R>(U, x, right)) return false;
   X = x;
   return true;
 }
@@ -155,29 +172,31 @@ __device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint3
     if (n_attempts) *n_attempts = 0;
     return z;
   }
+  // ONE loop over the attempts with one call site per function: the lanes of a warp sit at different attempt numbers of different
+  // cells and still run the same instructions, and the code of an attempt exists once (it was inlined three times)
+  const bool method_b = !(c <= R(PG_CSWITCH));
+  uint32_t r = (!skip_attempt0 && fabs(z) <= R(PG_Z0MAX_D)) ? 0u : 1u;  // block number: 0 = the cell pair's block, r >= 1 = retry block r
+  bool second = false;  // Method A: the second attempt of retry block r (words 2, 3)
   bool done = false;
-  if (!skip_attempt0 && fabs(z) <= R(PG_Z0MAX_D)) {
-    uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)), 0);
+  uint4 w = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+  while (!done && r < PG_MAX_ATTEMPTS) {
+    if (!second) w = philox(key, person, sweep, r == 0u ? make_site(DOM_PERSON, PK_PG, (uint32_t)(j >> 1)) : make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), r);
     ++used;
-    done = (j & 1) ? pg_attempt_A<R>(c, w.z, w.w, X) : pg_attempt_A<R>(c, w.x, w.y, X);
-  }
-  if (c <= R(PG_CSWITCH)) {
-#pragma unroll 1
-    for (uint32_t r = 1u; !done && r < PG_MAX_ATTEMPTS; ++r) {
-      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), r);
-      ++used;
-      done = pg_attempt_A<R>(c, w.x, w.y, X);
-      if (!done) {
-        ++used;
-        done = pg_attempt_A<R>(c, w.z, w.w, X);
-      }
+    R x, U;
+    bool right, alive;
+    if (r != 0u && method_b) {
+      alive = pg_propose_B<R>(c, w, x, U, right);
+      ++r;
+    } else {
+      const bool hi = r == 0u ? (j & 1) != 0 : second;
+      alive = pg_propose_A<R>(c, hi ? w.z : w.x, hi ? w.w : w.y, x, U, right);
+      if (r == 0u || second) { ++r; second = false; }
+      else second = true;
     }
-  } else {
-#pragma unroll 1
-    for (uint32_t r = 1u; !done && r < PG_MAX_ATTEMPTS; ++r) {
-      uint4 w = philox(key, person, sweep, make_site(DOM_PERSON, PK_PG_RETRY, (uint32_t)j), r);
-      ++used;
-      done = pg_attempt_B<R>(c, w, X);
+    if (alive && series_accept<R>(U, x, right)) {
+      X = x;
+      done = true;
     }
   }
   if (n_attempts) *n_attempts = used;
