@@ -30,6 +30,7 @@ constexpr double PG_R1MAX_LEFT = 0.005791362408683128;   // 3 exp(-4/t):    boun
 
 __device__ __constant__ const float c_xq[ERIRT_XQ_DEG + 1] = ERIRT_XQ_COEFFS;
 __device__ __constant__ const float c_l1p[ERIRT_L1P_DEG + 1] = ERIRT_L1P_COEFFS;
+__device__ __constant__ const double c_xqd[ERIRT_XQD_DEG + 1] = ERIRT_XQD_COEFFS;
 
 // s/Z as a polynomial in r = 1/s, s = sqrt(-2 ln y), Z = Phic^{-1}(y), y in (0, PG_P0]
 __device__ __forceinline__ float xq_poly(float r) {
@@ -48,7 +49,7 @@ __device__ __forceinline__ float log1p_poly(float w) {
   return p * w;
 }
 
-// Phic^{-1}(y) for y in (0, PG_P0]: f32 = polynomial; f64 = polynomial start + Newton on ln Phic(Z) = ln y
+// Phic^{-1}(y) for y in (0, PG_P0]: a polynomial in 1/sqrt(-2 ln y), to the rounding level of the working precision
 template <typename R>
 __device__ __forceinline__ R inv_normal_tail(R y);
 template <>
@@ -58,19 +59,16 @@ __device__ __forceinline__ float inv_normal_tail<float>(float y) {
 }
 template <>
 __device__ __forceinline__ double inv_normal_tail<double>(double y) {
-  double ly = log(y);
-  float rf = rsqrtf((float)(-2.0 * ly));
-  double z = 1.0 / ((double)rf * (double)xq_poly(rf));
-  // the polynomial start is within 3e-7 (relative) of the root and Newton on ln Phic converges quadratically with a constant below
-  // one: two steps reach the rounding level of erfc / log (the oracle iterates to convergence from its own start; 1e-15 apart).
-  // The steps are 53 % of the instructions of the f64 person kernel (profiles/earlier/r02f_person_kernel_f64_ncu_breakdown.txt, four steps).
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    double sf = 0.5 * erfc(z * 0.70710678118654752440);
-    double pdf = 0.39894228040143267794 * exp(-0.5 * z * z);
-    z += (log(sf) - ly) * sf / pdf;
-  }
-  return z;
+  // s/Z as a degree-24 polynomial in r = 1/s, s = sqrt(-2 ln y), fitted in 40-digit arithmetic (tools/gen_coeffs.py: 5.5e-16 relative
+  // error of Z against the exact root when evaluated in Float64, i.e. the rounding level of log and rsqrt; the oracle finds the root by
+  // Newton steps on ln Phic to convergence, 1e-15 apart).  Until round 2 the f64 path refined the f32 start by two Newton steps on
+  // erfc / exp / log: 40 % of the instructions of the f64 person kernel (profiles/r02i_person_kernel_f64_ncu_breakdown.txt).
+  const double r = rsqrt(-2.0 * log(y));
+  const double x = fma(r, ERIRT_XQD_A, ERIRT_XQD_B);
+  double p = c_xqd[ERIRT_XQD_DEG];
+#pragma unroll
+  for (int k = ERIRT_XQD_DEG - 1; k >= 0; --k) p = fma(p, x, c_xqd[k]);
+  return 1.0 / (r * p);
 }
 
 // alternating-series acceptance: U <= sum_n (-1)^n a_n(x)/a_0(x) ?
