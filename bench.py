@@ -249,16 +249,12 @@ def ncu_traffic(key="dram_bytes_per_launch"):
 
 
 def bulk_ess(columns):
-    """min / median rank-normalised bulk ESS (Vehtari et al. 2021; diagnostics.ess_rhat) over the non-constant columns."""
-    from erirt_b200.diagnostics import ess_rhat
-    ess = []
-    for arr in columns:
-        for c in range(arr.shape[1]):
-            x = arr[:, c]
-            if np.ptp(x) > 0 and np.all(np.isfinite(x)):
-                ess.append(ess_rhat(x)[0])
-    ess = np.asarray(ess)
-    return float(np.nanmin(ess)), float(np.nanmedian(ess)), int(ess.size)
+    """min / median rank-normalised bulk ESS (Vehtari et al. 2021) over the non-constant columns, by the engine's CUDA kernel
+    (erirt_ess_rhat, csrc/diagnostics.cuh; one CTA per column)."""
+    from erirt_b200.diagnostics import ess_rhat_device
+    ess = np.concatenate([ess_rhat_device(arr[:, :, None])[0] for arr in columns])
+    ess = ess[~np.isnan(ess)]
+    return float(np.min(ess)), float(np.median(ess)), int(ess.size)
 
 
 def item_struct_traces(eng, first, n, qw):
@@ -462,7 +458,7 @@ def c4_chains(E, rank, world, local, n_chains=8, n_iter=1000):
     device time) and the cross-chain split R-hat of the item parameters from the second half of the n_iter sweeps."""
     import torch
     from erirt_b200 import distributed as D
-    from erirt_b200.diagnostics import ess_rhat
+    from erirt_b200.diagnostics import ess_rhat_device
     N, J = 100_000, 40
     Cond = E.setCond(nSubj=N, nItem=J, nFeat=0, nIter=n_iter, nChain=1)
     tp = E.setTrueParaRtIrt(Cond, rng=SEED)
@@ -490,7 +486,7 @@ def c4_chains(E, rank, world, local, n_chains=8, n_iter=1000):
     if rank != 0:
         return None
     arr = np.stack([traces[c] for c in range(n_chains)], axis=2)  # [iter, param, chain]
-    rhat = [ess_rhat(arr[:, p, :])[1] for p in range(arr.shape[1])]
+    rhat = ess_rhat_device(arr, device=local)[1]  # CUDA kernel, one CTA per column
     return {"workload": f"{n_chains} independent GibbsRtIrtNull chains 100k x 40, {n_iter} sweeps each, chain c on rank c mod {world}",
             "value": n_chains * n_iter / (ms_total / 1e3), "unit": "chain-sweeps/s", "chains": n_chains, "sweeps_per_chain": n_iter,
             "seconds_max_over_ranks": ms_total / 1e3, "rhat_max": float(np.nanmax(rhat)), "rhat_median": float(np.nanmedian(rhat)),

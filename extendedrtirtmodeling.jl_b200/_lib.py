@@ -19,7 +19,7 @@ COMPAT_LATENTQR_SCALE_ELEMENTWISE = 2
 
 EXPORTED = ["erirt_version", "erirt_last_error", "erirt_create", "erirt_destroy", "erirt_set_data",
             "erirt_set_data_device", "erirt_trim_pool", "erirt_generate_data", "erirt_get_data", "erirt_set_data_y8", "erirt_checkpoint_size", "erirt_checkpoint_save", "erirt_checkpoint_load", "erirt_set_state", "erirt_get_state", "erirt_sample", "erirt_get_trace",
-            "erirt_trace_width", "erirt_get_moments", "erirt_loglik_current", "erirt_get_stats", "erirt_debug_check_guards",
+            "erirt_trace_width", "erirt_get_moments", "erirt_trace_ess_rhat", "erirt_ess_rhat", "erirt_loglik_current", "erirt_get_stats", "erirt_debug_check_guards",
             "erirt_nccl_unique_id", "erirt_comm_init", "erirt_peer_export", "erirt_peer_attach", "erirt_peer_detach", "erirt_k_pg", "erirt_k_nu_person", "erirt_k_philox"]
 
 
@@ -78,6 +78,8 @@ def load():
     L.erirt_trace_width.argtypes = [vp, C.c_int32]
     L.erirt_trace_width.restype = C.c_int64
     L.erirt_get_moments.argtypes = [vp, C.c_int32, dp, dp, C.c_int64]
+    L.erirt_trace_ess_rhat.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, dp, dp]
+    L.erirt_ess_rhat.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, dp, dp]
     L.erirt_loglik_current.argtypes = [vp, C.POINTER(C.c_double)]
     L.erirt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.erirt_debug_check_guards.argtypes = [vp]

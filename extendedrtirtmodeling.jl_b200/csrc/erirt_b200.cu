@@ -20,6 +20,7 @@
 
 #include "../../include/erirt_b200.h"
 #include "global.cuh"
+#include "diagnostics.cuh"
 #include "layout.cuh"
 #include "person.cuh"
 #include "person_fast.cuh"
@@ -379,6 +380,7 @@ static int launch_global(erirt_handle* h, int stage);
 static bool pdl_enabled();
 static bool global_rehearsal_enabled();
 static int finalize_constants(erirt_handle* h);
+static int pick_device(int32_t device);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // `fast`: plan of person_sweep_fast_kernel (f32, one-launch models): the generic plan plus the response tables
@@ -1401,6 +1403,106 @@ extern "C" int erirt_get_trace(erirt_handle* h, int32_t which, int64_t first_col
   cudaFreeAsync(tmp, h->stream);
   if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "get_trace: %s", cudaGetErrorString(e));
   return 0;
+}
+
+// ---- convergence diagnostics on the device (diagnostics.cuh) ----
+// dx: device block [n_chain][n_cols][n_iter]; results copied to the host arrays ess / rhat (n_cols each)
+static int run_ess_rhat(const double* dx, int64_t n_iter, int64_t n_cols, int64_t n_chain, int64_t skip, int64_t n_used, cudaStream_t st,
+                        double* ess, double* rhat) {
+  if (n_cols == 0) return 0;
+  const int64_t n = n_used / 2, N = 2 * n_chain * n;
+  int64_t npad = 2;
+  while (npad < N) npad <<= 1;
+  DiagArgs A{};
+  A.x = dx; A.n_iter = n_iter; A.n_cols = n_cols; A.skip = skip; A.n_used = n_used; A.n_chain = (int)n_chain; A.npad = npad;
+  const size_t smem = (size_t)npad * (sizeof(double) + sizeof(uint32_t));
+  A.use_smem = smem <= (size_t)200 * 1024 ? 1 : 0;
+  double* scratch = nullptr;
+  const size_t zb = align_up((size_t)n_cols * (size_t)std::max<int64_t>(N, 1) * sizeof(double), 256);
+  const size_t kb = A.use_smem ? 0 : align_up((size_t)n_cols * npad * sizeof(double), 256);
+  const size_t ib = A.use_smem ? 0 : align_up((size_t)n_cols * npad * sizeof(uint32_t), 256);
+  const size_t ob = align_up((size_t)2 * n_cols * sizeof(double), 256);
+  CU(cudaMallocAsync((void**)&scratch, zb + kb + ib + ob, st));
+  unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+  A.z = scratch;
+  A.keys = reinterpret_cast<double*>(base + zb);
+  A.idx = reinterpret_cast<uint32_t*>(base + zb + kb);
+  A.ess = reinterpret_cast<double*>(base + zb + kb + ib);
+  A.rhat = A.ess + n_cols;
+  cudaError_t e = cudaSuccess;
+  if (A.use_smem) e = cudaFuncSetAttribute((const void*)ess_rhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    ess_rhat_kernel<<<(unsigned)n_cols, DIAG_THREADS, A.use_smem ? smem : 0, st>>>(A);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ess, A.ess, (size_t)n_cols * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rhat, A.rhat, (size_t)n_cols * sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(scratch, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "ess_rhat: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int erirt_ess_rhat(const double* x, int64_t n_iter, int64_t n_cols, int64_t n_chain, int64_t skip, int32_t device,
+                              double* ess, double* rhat) {
+  if (!x || !ess || !rhat) return fail(ERIRT_E_ARG, "null argument");
+  if (n_iter < 1 || n_cols < 0 || n_chain < 1 || n_chain > 32 || skip < 0 || skip > n_iter) return fail(ERIRT_E_ARG, "ess_rhat: bad dimensions (1 <= n_chain <= 32, 0 <= skip <= n_iter)");
+  if (n_cols > 2147483647LL) return fail(ERIRT_E_ARG, "ess_rhat: too many columns");
+  if (int prc = pick_device(device)) return prc;
+  double* dx = nullptr;
+  const size_t bytes = (size_t)n_iter * n_cols * n_chain * sizeof(double);
+  if (bytes == 0) return 0;
+  CU(cudaMallocAsync((void**)&dx, bytes, 0));
+  cudaError_t e = cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, 0);
+  int rc = 0;
+  if (e == cudaSuccess) rc = run_ess_rhat(dx, n_iter, n_cols, n_chain, skip, n_iter - skip, 0, ess, rhat);
+  cudaFreeAsync(dx, 0);
+  cudaStreamSynchronize(0);
+  if (e != cudaSuccess) return fail(ERIRT_E_CUDA, "ess_rhat: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+extern "C" int erirt_trace_ess_rhat(erirt_handle* h, int32_t which, int64_t first_col, int64_t n_cols, int64_t skip, double* ess, double* rhat) {
+  if (!h || !ess || !rhat) return fail(ERIRT_E_ARG, "null argument");
+  const int64_t W = full_width(h, which);
+  if (W <= 0) return fail(ERIRT_E_ARG, "trace %d does not exist for this model", which);
+  if (first_col < 0 || n_cols < 0 || first_col + n_cols > W) return fail(ERIRT_E_ARG, "columns [%lld,%lld) outside [0,%lld)", (long long)first_col, (long long)(first_col + n_cols), (long long)W);
+  CU(cudaSetDevice(h->cfg.device));
+  const int64_t N = h->cfg.n_subj, J = h->cfg.n_item, nIter = h->cfg.n_iter, nChain = h->cfg.n_chain;
+  const int64_t done = h->sweeps_done, done_iter = done / nChain;  // complete iterations (every chain has drawn)
+  if (nChain > 32) return fail(ERIRT_E_ARG, "ess_rhat: at most 32 chains");
+  if (skip < 0 || skip > done_iter) return fail(ERIRT_E_ARG, "skip %lld outside [0, %lld] completed iterations", (long long)skip, (long long)done_iter);
+  int pfield = -1;
+  int64_t pcol0 = 0, small0 = 0, small_w = 0;
+  const double* dsmall = nullptr;
+  if (which == ERIRT_TRACE_RA) { pfield = 0; small0 = N; dsmall = h->dTrRa; small_w = 2 * J; }
+  else if (which == ERIRT_TRACE_RT) { pfield = 1; small0 = N; dsmall = h->dTrRt; small_w = 2 * J; }
+  else if (which == ERIRT_TRACE_QR) { dsmall = h->dTrQr; small_w = h->qw; if (h->cfg.model == ERIRT_RTIRT_LATENTQR) { pfield = 2; pcol0 = h->qw; } }
+  else { dsmall = h->dTrLl; small_w = 1; }
+  if (pfield >= 0 && first_col < pcol0 + N && first_col + n_cols > pcol0 && !h->dPtrace)
+    return fail(ERIRT_E_STATE, "person columns requested but person_trace = 0");
+  if (n_cols == 0) return 0;
+  // the columns are gathered into [chain][column][iteration] in chunks of <= 256 MB and never leave the device
+  const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(n_cols, ((int64_t)256 << 20) / (nIter * nChain * (int64_t)sizeof(double))));
+  double* tmp = nullptr;
+  CU(cudaMallocAsync((void**)&tmp, (size_t)nIter * chunk_cols * nChain * sizeof(double), h->stream));
+  int rc = 0;
+  for (int64_t c0 = 0; c0 < n_cols && rc == 0; c0 += chunk_cols) {
+    const int64_t nc = std::min(chunk_cols, n_cols - c0);
+    const int grid = (int)std::min<int64_t>((nIter * nc + 255) / 256, (int64_t)h->sm_count * 16);
+    for (int64_t l = 0; l < nChain; ++l) {
+      if (h->rsz == 4)
+        trace_gather_kernel<float><<<grid, 256, 0, h->stream>>>(tmp + nIter * nc * l, nIter, nc, first_col + c0, l, nChain, done, dsmall, small0, small_w,
+                                                                (const float*)h->dPtrace, pfield < 0 ? 0 : pfield, pfield < 0 ? -1 : pcol0, pfield < 0 ? 0 : N, h->n_pad);
+      else
+        trace_gather_kernel<double><<<grid, 256, 0, h->stream>>>(tmp + nIter * nc * l, nIter, nc, first_col + c0, l, nChain, done, dsmall, small0, small_w,
+                                                                 (const double*)h->dPtrace, pfield < 0 ? 0 : pfield, pfield < 0 ? -1 : pcol0, pfield < 0 ? 0 : N, h->n_pad);
+    }
+    rc = run_ess_rhat(tmp, nIter, nc, nChain, skip, done_iter - skip, h->stream, ess + c0, rhat + c0);
+  }
+  cudaFreeAsync(tmp, h->stream);
+  cudaStreamSynchronize(h->stream);
+  return rc;
 }
 
 extern "C" int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n) {

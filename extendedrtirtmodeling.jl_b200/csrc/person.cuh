@@ -124,9 +124,11 @@ __device__ __noinline__ double pg_draw_cell_f64(PhiloxKey key, uint32_t gid, uin
 #endif
 constexpr int STAT_FLUSH_TILES = 8;  // item statistics live in registers and are folded into f64 every 8 tiles
 
-// resident CTAs per SM the register allocation is tuned for: the tile of TPP=2 leaves room for 3 CTAs, TPP=4 for 5, TPP=8 for 7
-#ifndef ERIRT_MINCTAS_TPP4  // experiment hook (tools/gpu_ab.sh): residency the TPP = 4 instantiations are compiled for
-#define ERIRT_MINCTAS_TPP4 (ERIRT_CTA_THREADS == 128 ? 5 : 3)
+// resident CTAs per SM the register allocation is tuned for: the tile of TPP=2 leaves room for 3 CTAs, TPP=4 for 5, TPP=8 for 7.
+// TPP = 4 is compiled for four (128 registers, no spills): measured against five (102 registers) CrossQr 1M x 100 runs 1.77 -> 1.70 ms
+// per sweep and the fast kernel forced to TPP = 4 0.80 -> 0.75 ms (gpurun_out/ab_r02i.log, cqr_r02i.log); three (144 registers) is slower
+#ifndef ERIRT_MINCTAS_TPP4  // experiment hook (tools/gpu_ab2.sh)
+#define ERIRT_MINCTAS_TPP4 (ERIRT_CTA_THREADS == 128 ? 4 : 3)
 #endif
 template <int TPP>
 constexpr int min_ctas_per_sm() {

@@ -128,3 +128,20 @@ def ess_rhat_batched(arr, device=None):
     ess = torch.where(bad | (n < 4), nan, ess)
     rhat = torch.where(bad | (n < 4), nan, rhat)
     return ess.cpu().numpy(), rhat.cpu().numpy()
+
+
+def ess_rhat_device(arr, skip=0, device=0):
+    """Bulk ESS and R-hat of arr (draws, params, chains) by the CUDA kernel of the engine (erirt_ess_rhat, csrc/diagnostics.cuh:
+    one CTA per parameter: bitonic sort for the ranks, direct autocovariances, Geyer's sequence), first `skip` draws discarded.
+    Same estimator as ess_rhat above, which is its checker in the GPU tests.  Raises when the CUDA library or a GPU is missing."""
+    import ctypes as C
+    from . import _lib
+    x = np.asarray(arr, dtype=np.float64)
+    if x.ndim == 2:
+        x = x[:, :, None]
+    n, P, m = x.shape
+    xf = np.ascontiguousarray(x.transpose(2, 1, 0))  # [chain][param][draw] == Julia's column-major [nIter, P, nChain]
+    ess, rhat = np.empty(P), np.empty(P)
+    dp = C.POINTER(C.c_double)
+    _lib.check(_lib.load().erirt_ess_rhat(xf.ctypes.data_as(dp), n, P, m, int(skip), int(device), ess.ctypes.data_as(dp), rhat.ctypes.data_as(dp)))
+    return ess, rhat

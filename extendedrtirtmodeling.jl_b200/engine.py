@@ -150,6 +150,17 @@ class Engine:
             return mean.reshape((self.N, self.J), order="F"), sd.reshape((self.N, self.J), order="F")
         return mean, sd
 
+    def trace_ess_rhat(self, which, first_col=0, n_cols=None, skip=0):
+        """Rank-normalised split bulk ESS and R-hat of columns [first_col, first_col + n_cols) of Post.<which>, iterations after the
+        first `skip` (checkConvergence, src/SimTools.jl:419-443), computed by a CUDA kernel on the traces where they lie
+        (erirt_trace_ess_rhat, csrc/diagnostics.cuh).  Returns (ess, rhat), NaN for constant columns."""
+        w = int(self.lib.erirt_trace_width(self.h, _lib.TRACES[which]))
+        if n_cols is None:
+            n_cols = w - first_col
+        ess, rhat = np.empty(n_cols), np.empty(n_cols)
+        check(self.lib.erirt_trace_ess_rhat(self.h, _lib.TRACES[which], first_col, n_cols, skip, _dp(ess), _dp(rhat)))
+        return ess, rhat
+
     # ---- checkpoint / resume ----
     def checkpoint(self) -> np.ndarray:
         """State, auxiliaries, Philox sweep counter, running moments and traces of the chain as one byte array."""

@@ -7,13 +7,14 @@ replication r runs on rank r mod world (one process per GPU), results are gather
 import numpy as np
 
 from . import api, simulate
-from .diagnostics import ess_rhat_batched
+from .diagnostics import ess_rhat_batched, ess_rhat_device
 
 
 def checkConvergence(MCMC, device=None):
     """src/SimTools.jl:419-443: share of the traced columns of Post.ra / Post.rt / Post.qr with ESS > 400 and R-hat < 1.1
-    after burn-in (constant columns give NaN and are not counted, as with MCMCChains).  One batched computation per block;
-    device="cuda" keeps it on the GPU."""
+    after burn-in (constant columns give NaN and are not counted, as with MCMCChains).  One batched computation per block:
+    device="cuda" (or a device index) runs the CUDA kernel of the engine (erirt_ess_rhat, one CTA per column), device=None the
+    same estimator in torch on the host (reporting on a machine without a GPU)."""
     nb = MCMC.Cond.nBurnin
     ess_ok = rhat_ok = n_ess = n_rhat = 0
     for name in ("ra", "rt", "qr"):
@@ -24,7 +25,10 @@ def checkConvergence(MCMC, device=None):
         keep = np.all(np.isfinite(arr), axis=(0, 2))  # person columns are NaN when person_trace=False
         if not keep.any():
             continue
-        ess, rhat = ess_rhat_batched(arr[:, keep, :], device=device)
+        if device is None:
+            ess, rhat = ess_rhat_batched(arr[:, keep, :], device=None)
+        else:
+            ess, rhat = ess_rhat_device(arr[:, keep, :], device=0 if device == "cuda" else int(str(device).split(":")[-1]))
         ok = ~np.isnan(ess)
         n_ess += int(ok.sum())
         n_rhat += int((~np.isnan(rhat)).sum())

@@ -149,6 +149,18 @@ int64_t erirt_trace_width(erirt_handle* h, int32_t which);
  * n_subj x n_item column-major and needs erirt_config.nu_cell_moments). */
 int erirt_get_moments(erirt_handle* h, int32_t field, double* mean, double* sd, int64_t n);
 
+/* Convergence diagnostics on the device: rank-normalised split-chain bulk ESS and R-hat (Vehtari et al. 2021) of every requested
+ * column, the estimator behind `Chains(...) |> ess_rhat` in checkConvergence (src/SimTools.jl:419-443; gate ESS > 400, R-hat < 1.1).
+ * One CTA per column (csrc/diagnostics.cuh); ess / rhat are host arrays of n_cols values, NaN for constant or non-finite columns
+ * and for fewer than 8 draws per chain.
+ *   erirt_trace_ess_rhat: columns [first_col, first_col + n_cols) of Post.<which> as erirt_get_trace orders them, iterations
+ *                         skip+1 ... of the completed ones (skip = nBurnin in the reference's use); the traces never leave the device.
+ *   erirt_ess_rhat:       any host array in Julia's layout x[m + n_iter*(c + n_cols*l)] (nIter x P x nChain), first `skip`
+ *                         iterations of every chain discarded. */
+int erirt_trace_ess_rhat(erirt_handle* h, int32_t which, int64_t first_col, int64_t n_cols, int64_t skip, double* ess, double* rhat);
+int erirt_ess_rhat(const double* x, int64_t n_iter, int64_t n_cols, int64_t n_chain, int64_t skip, int32_t device, double* ess,
+                   double* rhat);
+
 /* getLogLikelihood*(Cond, Data; P) of the state currently held by the handle (every InputPara field as last set
  * with erirt_set_state, or as left by erirt_sample -- with the one-sweep lookahead described at erirt_set_state): used for
  * DIC's D-hat at Post.mean,

@@ -12,7 +12,7 @@ using ExtendedRtIrtModeling
 import ExtendedRtIrtModeling: sample!, InputPara, GibbsMlIrt, GibbsRtIrt, GibbsRtIrtNull, GibbsRtIrtCross, GibbsRtIrtCrossQr,
                                GibbsRtIrtLatent, GibbsRtIrtLatentQr
 
-export GibbsRtIrtQuantile, lean, LeanGibbs, LeanPost, Shard, sample_sharded!
+export GibbsRtIrtQuantile, lean, LeanGibbs, LeanPost, Shard, sample_sharded!, ess_rhat_gpu, checkConvergence_gpu
 
 const LIB = get(ENV, "ERIRT_B200_LIB", joinpath(@__DIR__, "..", "extendedrtirtmodeling.jl_b200", "liberirt_b200.so"))
 
@@ -324,5 +324,42 @@ function checkpoint(h)::Vector{UInt8}
 end
 restore!(h, buf::Vector{UInt8}) =
     GC.@preserve buf check(ccall((:erirt_checkpoint_load, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h, buf, length(buf)))
+
+# ---- convergence diagnostics on the device (erirt_ess_rhat, csrc/diagnostics.cuh): the estimator behind `Chains(...) |> ess_rhat` in
+#      checkConvergence (src/SimTools.jl:419-443), one CTA per column.  `post` is any Post.ra / Post.rt / Post.qr block
+#      [nIter, P, nChain]; returns (ess, rhat), NaN for constant columns (MCMCChains gives missing / NaN there as well) ----
+function ess_rhat_gpu(post::Array{Float64,3}; skip::Integer=0, device::Integer=0)
+    ess, rhat = Vector{Float64}(undef, size(post, 2)), Vector{Float64}(undef, size(post, 2))
+    GC.@preserve post ess rhat check(ccall((:erirt_ess_rhat, LIB), Cint,
+        (Ptr{Float64}, Int64, Int64, Int64, Int64, Int32, Ptr{Float64}, Ptr{Float64}),
+        post, size(post, 1), size(post, 2), size(post, 3), skip, device, ess, rhat))
+    return ess, rhat
+end
+# the same on the traces of a live handle, without copying them to the host: columns first_col+1 ... first_col+ncols of Post.<which>
+function ess_rhat_gpu(h::Ptr{Cvoid}, which::Integer, first_col::Integer, ncols::Integer; skip::Integer=0)
+    ess, rhat = Vector{Float64}(undef, ncols), Vector{Float64}(undef, ncols)
+    GC.@preserve ess rhat check(ccall((:erirt_trace_ess_rhat, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}), h, which, first_col, ncols, skip, ess, rhat))
+    return ess, rhat
+end
+"""
+    checkConvergence(MCMC; device=0)
+
+src/SimTools.jl:419-443 with the ESS / R-hat of every traced column computed on the GPU: share of the columns of Post.ra / rt / qr
+(after nBurnin) with ESS > 400 and R-hat < 1.1.
+"""
+function checkConvergence_gpu(MCMC; device::Integer=0)
+    nb = MCMC.Cond.nBurnin
+    essOk = rhatOk = n = 0
+    for post in (MCMC.Post.ra, MCMC.Post.rt, MCMC.Post.qr)
+        (post === nothing || isempty(post)) && continue
+        ess, rhat = ess_rhat_gpu(Array{Float64,3}(post); skip=nb, device=device)
+        keep = .!isnan.(ess)
+        n += count(keep)
+        essOk += count(ess[keep] .> 400)
+        rhatOk += count(rhat[keep] .< 1.1)
+    end
+    return (ess=100 * essOk / max(n, 1), rhat=100 * rhatOk / max(n, 1), essN="$(essOk) / $(n)", rhatN="$(rhatOk) / $(n)")
+end
 
 end # module

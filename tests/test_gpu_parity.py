@@ -748,3 +748,68 @@ def test_guard_zones_stay_clean(E, monkeypatch, model, dtype, N, J, F):
     eng = run_engine(E, pb, 1, dtype=dtype)
     assert eng.check_guards() == -1
     eng.close()
+
+
+@pytest.mark.gpu
+def test_ess_rhat_kernel_matches_the_host_estimator(E):
+    """checkConvergence's diagnostics (src/SimTools.jl:419-443) as a CUDA kernel (csrc/diagnostics.cuh) against the numpy statement of
+    the same estimator: AR(1) chains of several lengths and chain counts, an odd draw count, a column with ties, a constant column, a
+    column with a NaN, a shifted chain (R-hat > 1), and a column too long for shared memory (the global-scratch sort)."""
+    from erirt_b200 import diagnostics as Dg
+    rng = np.random.default_rng(5)
+
+    def ar1(n, m, phi):
+        e = rng.standard_normal((n, m))
+        x = np.empty((n, m))
+        x[0] = e[0]
+        for t in range(1, n):
+            x[t] = phi * x[t - 1] + np.sqrt(1 - phi * phi) * e[t]
+        return x
+
+    for n, m in ((64, 1), (501, 3), (2500, 2), (5000, 3)):
+        cols = [ar1(n, m, phi) for phi in (0.0, 0.5, 0.9, 0.99, -0.5)]
+        cols.append(np.round(ar1(n, m, 0.7), 1))          # ties
+        cols.append(np.ones((n, m)))                       # constant
+        bad = ar1(n, m, 0.3); bad[n // 3, 0] = np.nan
+        cols.append(bad)
+        sh = ar1(n, m, 0.2); sh[:, 0] += 3.0
+        cols.append(sh)
+        arr = np.stack(cols, axis=1)                       # (draws, params, chains)
+        for skip in (0, n // 5):
+            ess, rhat = Dg.ess_rhat_device(arr, skip=skip)
+            for c in range(arr.shape[1]):
+                e0, r0 = Dg.ess_rhat(arr[skip:, c, :])
+                if np.isnan(e0):
+                    assert np.isnan(ess[c]) and np.isnan(rhat[c]), (n, m, c)
+                else:
+                    assert abs(ess[c] - e0) <= 1e-8 * e0 and abs(rhat[c] - r0) <= 1e-10 * r0, (n, m, c, ess[c], e0, rhat[c], r0)
+    long = ar1(30000, 1, 0.95)[:, None, :]                 # N = 30000 > 16384: sorted in global scratch
+    ess, rhat = Dg.ess_rhat_device(long)
+    e0, r0 = Dg.ess_rhat(long[:, 0, :])
+    assert abs(ess[0] - e0) <= 1e-8 * e0 and abs(rhat[0] - r0) <= 1e-10 * r0
+    with pytest.raises(E.ErirtError):
+        Dg.ess_rhat_device(np.zeros((10, 2, 40)))          # more than 32 chains
+
+
+@pytest.mark.gpu
+def test_trace_ess_rhat_reads_the_device_traces(E):
+    """erirt_trace_ess_rhat works on the traces where they lie: equal to the host estimator applied to erirt_get_trace's copy, for the
+    item columns of ra / rt, the structural columns of qr, with burn-in skipped and chains interleaved as the engine stores them."""
+    from erirt_b200 import diagnostics as Dg
+    N, J, F, n_iter, n_chain = 300, 6, 2, 400, 2
+    Cond = E.setCond(nSubj=N, nItem=J, nFeat=F, nIter=n_iter, nChain=n_chain)
+    tp = E.setTrueParaRtIrt(Cond, rng=3)
+    Data = E.setDataRtIrt(Cond, tp, rng=3)
+    eng = E.Engine("RtIrt", N, J, F, n_iter=n_iter, n_chain=n_chain, n_burnin=100, dtype="f64", seed=11, person_trace=True)
+    eng.set_data(Data.Y, Data.logT, Data.X)
+    eng.sample(n_iter * n_chain)
+    for which, c0, nc in (("ra", N, 2 * J), ("rt", N, 2 * J), ("qr", 0, None), ("ra", 5, 3)):
+        ess, rhat = eng.trace_ess_rhat(which, c0, nc, skip=100)
+        tr = eng.get_trace(which, c0, len(ess))
+        for c in range(len(ess)):
+            e0, r0 = Dg.ess_rhat(tr[100:, c, :])
+            if np.isnan(e0):
+                assert np.isnan(ess[c])
+            else:
+                assert abs(ess[c] - e0) <= 1e-8 * e0 and abs(rhat[c] - r0) <= 1e-10 * r0, (which, c, ess[c], e0)
+    eng.close()
