@@ -598,8 +598,12 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
       // Float64 (the generic kernel): a cell costs thousands of instructions, so a problem with fewer tiles than two per SM is
       // spread over more, smaller tiles (measured at BASELINE configs 1-3: 2x the sweeps/s from TPP 1 -> 8; the f32 kernels, whose
       // sweep is bound by the per-tile latency chain, gain nothing: profiles/r02_summary.md)
-      if (!fast && h->rsz == 8)
+      if (!fast && h->rsz == 8) {
         while (tpp < 8 && (int64_t)align_up((size_t)cfg->n_subj, 128) / (CTA_THREADS / tpp) < 2 * (int64_t)h->sm_count) tpp *= 2;
+        // and a large one runs on the smaller tile as long as every thread keeps three item groups: more resident warps hide the long
+        // dependent f64 chains (J = 100: TPP 4 -> 8, 12 -> 16 warps per SM, 8.08 -> 7.55 ms per sweep at 1M x 100)
+        while (tpp < 8 && n_groups >= 3 * 2 * tpp) tpp *= 2;
+      }
     }
     if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) return "ERIRT_TPP must be 1, 2, 4 or 8";
     if (n_groups > 16 * tpp) return "too many items for this TPP (at most 64*TPP - 4)";
