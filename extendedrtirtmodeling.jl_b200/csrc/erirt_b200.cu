@@ -415,7 +415,7 @@ static SmemPlan make_smem_plan(const Layout& L, int tpp, size_t rsz, bool has_rt
     while (S.qcap < want && S.qcap < 16384 && o + (size_t)(S.qcap + 256) * sizeof(uint32_t) + rest <= budget) S.qcap += 256;
   }
   S.qstd = (S.qcap * 3) / 4;
-  S.off_queue = (int)o; if (rsz == 4) o = align_up(o + (size_t)S.qcap * sizeof(uint32_t), 128);
+  S.off_queue = (int)o; o = align_up(o + (size_t)S.qcap * sizeof(uint32_t), 128);
   S.off_tab = (int)o; if (fast) o = align_up(o + (size_t)(L.Jp / 4) * TAB_PITCH * rsz, 128);  // response table of the f32 fast kernel
   S.off_misc = (int)o; o = align_up(o + (MD_COUNT + SC_COUNT) * sizeof(double) + 8 + 16, 128);
   S.total = (int)o;
@@ -598,12 +598,10 @@ extern "C" int erirt_create(const erirt_config* cfg, erirt_handle** out) {
       // Float64 (the generic kernel): a cell costs thousands of instructions, so a problem with fewer tiles than two per SM is
       // spread over more, smaller tiles (measured at BASELINE configs 1-3: 2x the sweeps/s from TPP 1 -> 8; the f32 kernels, whose
       // sweep is bound by the per-tile latency chain, gain nothing: profiles/r02_summary.md)
-      if (!fast && h->rsz == 8) {
+      // (for a large problem TPP = 8 was 7 % faster while the cell loop was one divergent exact draw per cell; with the branch-free
+      // attempt 0 the 168-register TPP = 4 instantiation wins, 4.0 against 5.3 ms per sweep at 1M x 100)
+      if (!fast && h->rsz == 8)
         while (tpp < 8 && (int64_t)align_up((size_t)cfg->n_subj, 128) / (CTA_THREADS / tpp) < 2 * (int64_t)h->sm_count) tpp *= 2;
-        // and a large one runs on the smaller tile as long as every thread keeps three item groups: more resident warps hide the long
-        // dependent f64 chains (J = 100: TPP 4 -> 8, 12 -> 16 warps per SM, 8.08 -> 7.55 ms per sweep at 1M x 100)
-        while (tpp < 8 && n_groups >= 3 * 2 * tpp) tpp *= 2;
-      }
     }
     if (tpp != 1 && tpp != 2 && tpp != 4 && tpp != 8) return "ERIRT_TPP must be 1, 2, 4 or 8";
     if (n_groups > 16 * tpp) return "too many items for this TPP (at most 64*TPP - 4)";

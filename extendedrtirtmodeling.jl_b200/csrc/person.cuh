@@ -308,12 +308,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
     R zn_theta = R(0), zn_zeta = R(0), zn_nu = R(0), un_nu = R(0);  // variates drawn while the tile is in flight
     if (tid < P) {
       if (do_draws && !eval) {
-        const uint4 w = philox(A.key, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
+        const uint4 w = philox(A.sched, pgid, k, make_site(DOM_PERSON, PK_NORMALS), 0);
         zn_theta = normal2r<R>(w.x, w.y);
         zn_zeta = normal2r<R>(w.z, w.w);
       }
       if (qr && !eval) {
-        const uint4 w = philox(A.key, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
+        const uint4 w = philox(A.sched, pgid, k + 1, make_site(DOM_PERSON, PK_NU), 0);
         zn_nu = normal2r<R>(w.x, w.y);
         un_nu = u01<R>(w.z);
       }
@@ -513,8 +513,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
         const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
         R zn[4] = {R(0), R(0), R(0), R(0)}, un[4] = {R(0.5), R(0.5), R(0.5), R(0.5)};
         if (!eval) {
-          const uint4 wA = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g)), 0);
-          const uint4 wB = philox(A.key, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g + 1)), 0);
+          const uint4 wA = philox(A.sched, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g)), 0);
+          const uint4 wB = philox(A.sched, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g + 1)), 0);
           normal_pair(wA.x, wA.y, zn[0], zn[1]);
           normal_pair(wB.x, wB.y, zn[2], zn[3]);
           un[0] = u01<R>(wA.z); un[1] = u01<R>(wA.w); un[2] = u01<R>(wB.z); un[3] = u01<R>(wB.w);
@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
         const Quad<R> pAB = ld4(s_par + PAR_AB * Jp + 4 * g);
         const uint32_t yw = *reinterpret_cast<const uint32_t*>(my_y + 4 * g);
         if constexpr (F32) {
-          const uint4 wA = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
-          const uint4 wB = philox(A.key, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
+          const uint4 wA = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g)), 0);
+          const uint4 wB = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + 1)), 0);
           const int npad = 4 * g + 4 - J;  // > 0 only in groups holding padding cells
           float zs[4];
   #pragma unroll
@@ -607,22 +607,38 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
           defer_mask |= (unsigned long long)dm << (4 * kk);
           rej_mask |= (unsigned long long)rm << (4 * kk);
         } else {
+          // Float64: attempt 0 of every cell without a branch (pg_attempt0_f64: both envelope pieces, first term of the series); the
+          // cells it does not accept (4 %) go to the tile's work queue and are drawn by the exact loop, dealt over the whole CTA
+          uint32_t dm = 0;
   #pragma unroll 1
-          for (int e = 0; e < 4; ++e) {
-            const int j = 4 * g + e;
-            if (j >= J) { out.v[e] = R(0); continue; }
-            const R z = fma(pA.v[e], thp, -pAB.v[e]);
-            const R y = ((yw >> (8 * e)) & 0xffu) ? R(1) : R(0);
-            const R az = fabs(z);
+          for (int h = 0; h < 2; ++h) {  // one Philox block = the cell pair (4g + 2h, 4g + 2h + 1); rolled: one copy of the code
+            const uint4 w = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + h)), 0);
+            const R a0 = h ? pA.v[2] : pA.v[0], a1 = h ? pA.v[3] : pA.v[1];
+            const R ab0 = h ? pAB.v[2] : pAB.v[0], ab1 = h ? pAB.v[3] : pAB.v[1];
+            const uint32_t y2 = yw >> (16 * h);
+            const R z0 = fma(a0, thp, -ab0), z1 = fma(a1, thp, -ab1);
+            double om0 = pg_attempt0_f64((double)z0, w.x, w.y), om1 = pg_attempt0_f64((double)z1, w.z, w.w);
+            const int j0 = 4 * g + 2 * h;
             // y z - ln(1 + e^z) = y z - (z + |z|)/2 - ln(1 + e^{-|z|}); the last term as a product per row: one log per thread and row
             // instead of a log1p per cell (14 % of the instructions of the f64 kernel, profiles/r02j_person_kernel_f64_ncu_breakdown.txt)
-            ll_lin += (double)(y * z - R(0.5) * (z + az));
-            ll_prodd *= 1.0 + exp(-(double)az);
-            uint32_t na;
-            out.v[e] = (R)pg_draw_cell_f64(A.key, gid, k + 1, j, (double)z, &na);
-            my_defer += na > 1u;
+            if (j0 < J) {
+              const R az = fabs(z0);
+              ll_lin += (double)(((y2 & 0xffu) ? z0 : R(0)) - R(0.5) * (z0 + az));
+              ll_prodd *= 1.0 + exp(-(double)az);
+              if (om0 < 0.0) dm |= 1u << (2 * h);
+            } else om0 = 0.0;
+            if (j0 + 1 < J) {
+              const R az = fabs(z1);
+              ll_lin += (double)((((y2 >> 8) & 0xffu) ? z1 : R(0)) - R(0.5) * (z1 + az));
+              ll_prodd *= 1.0 + exp(-(double)az);
+              if (om1 < 0.0) dm |= 2u << (2 * h);
+            } else om1 = 0.0;
+            my_om[j0] = (R)om0;
+            my_om[j0 + 1] = (R)om1;
           }
+          defer_mask |= (unsigned long long)dm << (4 * kk);
         }
+        if constexpr (!F32) continue;
         st4(my_om + 4 * g, out);
       }
       if constexpr (!F32) {
@@ -631,6 +647,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
       if constexpr (F32) {
         // kappa z - |z|/2 - ln(1 + e^{-|z|}); a padding cell has z = 0 and contributed -ln 2 through the product
         if (valid) acc_ll_bern += (double)(ll_tile - 0.5f * ll_sabs - PGF_LN2 * (fast_lg2(lo2(ll_prod)) + fast_lg2(hi2(ll_prod)) - (float)ll_npad));
+      }
+      {
         // ---- hand the cells that left the fast path to the tile's work queue: one shared-memory atomic per WARP reserves the
         //      slots of all its lanes (warp prefix sum), then every lane writes its own entries (bit 31: replay attempt 0) ----
         my_defer = (uint32_t)__popcll(defer_mask);
@@ -652,25 +670,34 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
           const int j = 4 * group_of<TPP>(q, bit >> 2) + (bit & 3);
           if (slot < (uint32_t)QCAP) s_queue[slot] = ((uint32_t)p << 16) | (uint32_t)j | (replay0 ? 0x80000000u : 0u);
           else {  // queue overflow: finish the cell here
-            const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
-            my_om[j] = (R)pg_resolve_f32(A.key, gid, k + 1, j, z, replay0);
+            if constexpr (F32) {
+              const float z = fmaf((float)s_par[PAR_A * Jp + j], (float)thp, -(float)s_par[PAR_AB * Jp + j]);
+              my_om[j] = (R)pg_resolve_f32(A.key, gid, k + 1, j, z, replay0);
+            } else {
+              uint32_t na;
+              my_om[j] = (R)pg_draw_cell_f64(A.key, gid, k + 1, j, (double)fma(s_par[PAR_A * Jp + j], thp, -s_par[PAR_AB * Jp + j]), &na);
+            }
           }
           ++slot;
         }
-      } else {
-        acc_ll_bern += (double)ll_tile;
       }
       acc_defer += my_defer;
       __syncthreads();
 
-      if constexpr (F32) {
+      {
         // ---- drain: a strided share of the queue per thread ----
         const uint32_t qn = min(s_qctl[0], (uint32_t)QCAP);
         for (uint32_t idx = tid; idx < qn; idx += CTA_THREADS) {
           const uint32_t e1 = s_queue[idx];
           const int j1 = (int)(e1 & 0xffffu), p1 = (int)((e1 >> 16) & 0x7fffu);
-          const float z1 = fmaf((float)s_par[PAR_A * Jp + j1], (float)s_u[p1 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j1]);
-          s_om[p1 * Jp + j1] = (R)pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, (e1 >> 31) != 0u);
+          if constexpr (F32) {
+            const float z1 = fmaf((float)s_par[PAR_A * Jp + j1], (float)s_u[p1 * Dgp + F + 1], -(float)s_par[PAR_AB * Jp + j1]);
+            s_om[p1 * Jp + j1] = (R)pg_resolve_f32(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, z1, (e1 >> 31) != 0u);
+          } else {  // the exact loop from attempt 0 on; z is the expression of the main pass (same operands, same rounding)
+            uint32_t na;
+            const R z1 = fma(s_par[PAR_A * Jp + j1], s_u[p1 * Dgp + F + 1], -s_par[PAR_AB * Jp + j1]);
+            s_om[p1 * Jp + j1] = (R)pg_draw_cell_f64(A.key, A.person_offset + (uint32_t)(row0 + p1), k + 1, j1, (double)z1, &na);
+          }
         }
         __syncthreads();
       }

@@ -151,6 +151,42 @@ __device__ __forceinline__ bool pg_attempt_B(R c, uint4 w, R& X) {
   return true;
 }
 
+// ---- Float64 fast path: attempt 0 of one cell without a branch ----
+// Both pieces of the Method-A envelope are evaluated and the piece is selected at the end (a warp whose lanes sit in different pieces
+// runs one instruction stream), and the alternating series is cut after its first term.  Returns omega >= 0 when attempt 0 is
+// accepted at the first partial sum, U <= 1 - a_1/a_0 -- which is also the first exit of series_accept, and a cell that the exact
+// loop would carry to the third partial sum instead (a rounding-level difference in U) is accepted there as well, because
+// S_3 - S_1 = 5 e^{6e} - 7 e^{12e} > 0 by far more than a rounding error.  Returns -2 otherwise (rejected by the tilt, not decided
+// by one term, |z| beyond the attempt-0 range, NaN): those cells are drawn by pg_draw_exact from attempt 0 on.  The accepted
+// value is the same expression as in pg_propose_A up to the log of the left piece, ln(up P0) = ln up + ln P0 (one rounding).
+constexpr double PG_LN_P0 = -2.2476256772143173;
+constexpr double PG_Z0MAX_D_FAST = 16.0;           // == PG_Z0MAX_D (declared below)  // ln(PG_P0) = -PG_M2LNP0 / 2
+__device__ __forceinline__ double pg_attempt0_f64(double z, uint32_t wa, uint32_t wb) {
+  const double c = 0.5 * fabs(z);
+  const double cc = c * c;
+  const double um = u01d(wa), up = u01d(wb);
+  const double K = (PI_D * PI_D / 8.0) + 0.5 * cc;
+  const double Rm1 = (2.0 * PG_Q0 / PI_D) * K * exp(K * PG_T);  // q0 / p
+  const double v = um * (1.0 + Rm1);
+  const bool right = v < 1.0;
+  const double lu = log(up);
+  const double xr = PG_T - lu / K;                                // exponential tail
+  const double r = rsqrt(-2.0 * (lu + PG_LN_P0));
+  const double t = fma(r, ERIRT_XQD_A, ERIRT_XQD_B);
+  double p = c_xqd[ERIRT_XQD_DEG];
+#pragma unroll
+  for (int k = ERIRT_XQD_DEG - 1; k >= 0; --k) p = fma(p, t, c_xqd[k]);
+  const double rp = r * p;                                        // 1 / Z
+  const double xl = rp * rp;                                      // truncated Levy piece, 1 / Z^2
+  const double tilt = exp(-0.5 * cc * xl);
+  const double e = right ? (-0.5 * PI_D * PI_D) * xr : -2.0 / xl;
+  const double S1 = 1.0 - 3.0 * exp(2.0 * e);                     // first partial sum of the alternating series
+  // right: v <= S1;  left: ua = (v - 1) / Rm1 < tilt and ua / tilt <= S1, i.e. v - 1 <= S1 tilt Rm1 (S1 < 1)
+  const bool acc = right ? v <= S1 : (v - 1.0) <= S1 * tilt * Rm1;
+  const double x = right ? xr : xl;
+  return (acc && fabs(z) <= PG_Z0MAX_D_FAST) ? 0.25 * x : -2.0;
+}
+
 constexpr uint32_t PG_MAX_ATTEMPTS = 2000u;  // bound on every device loop; acceptance is >= 0.2, so 0.8^2000 never happens
 
 // Complete draw of omega_ij ~ PG(1, z).  Stream layout (identical in oracle/pg.c):
