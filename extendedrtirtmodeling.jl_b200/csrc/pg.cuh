@@ -49,6 +49,23 @@ __device__ __forceinline__ float log1p_poly(float w) {
   return p * w;
 }
 
+// XQD(r) (pg_coeffs.h), degree 24, by Estrin's scheme: the dependent chain is 6 fused multiply-adds deep instead of 24 (the f64
+// kernels are bound by the latency of dependent DFMAs at 12 warps per SM)
+__device__ __forceinline__ double xqd_poly(double r) {
+  static_assert(ERIRT_XQD_DEG == 24, "xqd_poly is written for degree 24");
+  const double t = fma(r, ERIRT_XQD_A, ERIRT_XQD_B);
+  const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4, t16 = t8 * t8;
+  double q[13];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) q[i] = fma(c_xqd[2 * i + 1], t, c_xqd[2 * i]);
+  q[12] = c_xqd[24];
+  const double r0 = fma(q[1], t2, q[0]), r1 = fma(q[3], t2, q[2]), r2 = fma(q[5], t2, q[4]), r3 = fma(q[7], t2, q[6]);
+  const double r4 = fma(q[9], t2, q[8]), r5 = fma(q[11], t2, q[10]), r6 = q[12];
+  const double s0 = fma(r1, t4, r0), s1 = fma(r3, t4, r2), s2 = fma(r5, t4, r4), s3 = r6;
+  const double u0 = fma(s1, t8, s0), u1 = fma(s3, t8, s2);
+  return fma(u1, t16, u0);
+}
+
 // Phic^{-1}(y) for y in (0, PG_P0]: a polynomial in 1/sqrt(-2 ln y), to the rounding level of the working precision
 template <typename R>
 __device__ __forceinline__ R inv_normal_tail(R y);
@@ -64,11 +81,7 @@ __device__ __forceinline__ double inv_normal_tail<double>(double y) {
   // Newton steps on ln Phic to convergence, 1e-15 apart).  Until round 2 the f64 path refined the f32 start by two Newton steps on
   // erfc / exp / log: 40 % of the instructions of the f64 person kernel (profiles/r02i_person_kernel_f64_ncu_breakdown.txt).
   const double r = rsqrt(-2.0 * log(y));
-  const double x = fma(r, ERIRT_XQD_A, ERIRT_XQD_B);
-  double p = c_xqd[ERIRT_XQD_DEG];
-#pragma unroll
-  for (int k = ERIRT_XQD_DEG - 1; k >= 0; --k) p = fma(p, x, c_xqd[k]);
-  return 1.0 / (r * p);
+  return 1.0 / (r * xqd_poly(r));
 }
 
 // alternating-series acceptance: U <= sum_n (-1)^n a_n(x)/a_0(x) ?
@@ -170,16 +183,13 @@ __device__ __forceinline__ double pg_attempt0_f64(double z, uint32_t wa, uint32_
   const double v = um * (1.0 + Rm1);
   const bool right = v < 1.0;
   const double lu = log(up);
-  const double xr = PG_T - lu / K;                                // exponential tail
   const double r = rsqrt(-2.0 * (lu + PG_LN_P0));
-  const double t = fma(r, ERIRT_XQD_A, ERIRT_XQD_B);
-  double p = c_xqd[ERIRT_XQD_DEG];
-#pragma unroll
-  for (int k = ERIRT_XQD_DEG - 1; k >= 0; --k) p = fma(p, t, c_xqd[k]);
-  const double rp = r * p;                                        // 1 / Z
+  const double rp = r * xqd_poly(r);                              // 1 / Z
   const double xl = rp * rp;                                      // truncated Levy piece, 1 / Z^2
+  const double inv = 1.0 / (K * xl);                              // one division for 1/K and 1/xl
+  const double xr = fma(-lu, xl * inv, PG_T);                     // exponential tail, t - ln(up) / K
   const double tilt = exp(-0.5 * cc * xl);
-  const double e = right ? (-0.5 * PI_D * PI_D) * xr : -2.0 / xl;
+  const double e = right ? (-0.5 * PI_D * PI_D) * xr : -2.0 * (K * inv);
   const double S1 = 1.0 - 3.0 * exp(2.0 * e);                     // first partial sum of the alternating series
   // right: v <= S1;  left: ua = (v - 1) / Rm1 < tilt and ua / tilt <= S1, i.e. v - 1 <= S1 tilt Rm1 (S1 < 1)
   const bool acc = right ? v <= S1 : (v - 1.0) <= S1 * tilt * Rm1;
