@@ -610,7 +610,11 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
           // Float64: attempt 0 of every cell without a branch (pg_attempt0_f64: both envelope pieces, first term of the series); the
           // cells it does not accept (4 %) go to the tile's work queue and are drawn by the exact loop, dealt over the whole CTA
           uint32_t dm = 0;
-  #pragma unroll 1
+#ifndef ERIRT_F64_UNROLL
+#define ERIRT_F64_UNROLL 1
+#endif
+          constexpr int f64_unroll = ERIRT_F64_UNROLL;  // 1: one cell pair in flight (one copy of the code), 2: both pairs of the group
+  #pragma unroll f64_unroll
           for (int h = 0; h < 2; ++h) {  // one Philox block = the cell pair (4g + 2h, 4g + 2h + 1); rolled: one copy of the code
             const uint4 w = philox(A.sched, gid, k + 1, make_site(DOM_PERSON, PK_PG, (uint32_t)(2 * g + h)), 0);
             const R a0 = h ? pA.v[2] : pA.v[0], a1 = h ? pA.v[3] : pA.v[1];
