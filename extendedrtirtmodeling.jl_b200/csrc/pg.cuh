@@ -206,6 +206,7 @@ constexpr uint32_t PG_MAX_ATTEMPTS = 2000u;  // bound on every device loop; acce
 //                        c > 1/t: Method-B attempt r (all four words).
 // `skip_attempt0` resumes after an attempt 0 already known to be rejected.
 constexpr double PG_Z0MAX_D = 16.0;
+static_assert(PG_Z0MAX_D == PG_Z0MAX_D_FAST, "the branch-free Float64 attempt 0 and the exact loop must agree on the attempt-0 range");
 template <typename R>
 __device__ __forceinline__ R pg_draw_exact(PhiloxKey key, uint32_t person, uint32_t sweep, int j, R z, int skip_attempt0,
                                            uint32_t* n_attempts = nullptr) {
