@@ -28,6 +28,45 @@ def test_inverse_normal_tail(oracle):
         assert abs(oracle.inv_normal_tail(y) - stats.norm.isf(y)) < 1e-12 * stats.norm.isf(y)
 
 
+def _coeff_table(name):
+    """(A, B, coefficients) of a polynomial table of csrc/pg_coeffs.h (the generated header the device code includes)."""
+    import os, re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "extendedrtirtmodeling.jl_b200", "csrc", "pg_coeffs.h")).read()
+    A = float(re.search(rf"#define {name}_A (\S+)", src).group(1))
+    B = float(re.search(rf"#define {name}_B (\S+)", src).group(1))
+    body = src[src.index(f"#define {name}_COEFFS"):]
+    body = body[:body.index("}")]
+    return A, B, [float(v) for v in re.findall(r"(-?\d\.\d+(?:e-?\d+)?),", body)]
+
+
+def test_device_inverse_tail_tables_match_the_oracle(oracle):
+    """The committed polynomial tables of the device's Phic^-1 (f32: degree 8, 1e-7; f64: degree 24, rounding level; tools/gen_coeffs.py)
+    evaluated as the kernels evaluate them -- Horner in f32, Estrin in f64 (pg.cuh: xq_poly, xqd_poly) -- against the oracle's Newton root over
+    the whole argument range y = u P0, u in [2^-33, 1]."""
+    P0 = 0.10564977366685535
+    rng = np.random.default_rng(0)
+    u = np.concatenate([rng.random(400), 2.0 ** -rng.uniform(0, 33, 400), [1.0 - 2.0 ** -33, 2.0 ** -33]])
+    zt = np.array([oracle.inv_normal_tail(P0 * v) for v in u])
+    A, B, c = _coeff_table("ERIRT_XQD")
+    assert len(c) == 25
+    r = 1.0 / np.sqrt(-2.0 * np.log(P0 * u))
+    t = A * r + B
+    q = [c[2 * i] + c[2 * i + 1] * t for i in range(12)] + [c[24] + 0 * t]
+    t2, t4, t8, t16 = t * t, t ** 4, t ** 8, t ** 16
+    rr = [q[2 * i] + q[2 * i + 1] * t2 for i in range(6)] + [q[12]]
+    ss = [rr[0] + rr[1] * t4, rr[2] + rr[3] * t4, rr[4] + rr[5] * t4, rr[6]]
+    p = (ss[0] + ss[1] * t8) + (ss[2] + ss[3] * t8) * t16
+    assert np.max(np.abs(1.0 / (r * p) - zt) / zt) < 2e-15
+    A, B, c = _coeff_table("ERIRT_XQ")
+    assert len(c) == 9
+    r32 = r.astype(np.float32)
+    x = np.float32(A) * r32 + np.float32(B)
+    p32 = np.full_like(x, np.float32(c[8]))
+    for k in range(7, -1, -1):
+        p32 = p32 * x + np.float32(c[k])
+    assert np.max(np.abs(1.0 / (r32 * p32) - zt) / zt) < 1e-6
+
+
 @pytest.mark.parametrize("z", [0.0, 0.3, 1.0, 2.0, 3.0, 3.2, 5.0, 12.0])
 def test_pg_moments(oracle, z):
     # E = tanh(z/2)/(2z), Var = (sinh z - z)/(4 z^3 cosh^2(z/2))  (SURVEY.md section 4)
