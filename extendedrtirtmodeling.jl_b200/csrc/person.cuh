@@ -17,6 +17,7 @@
 // reduced by re-reading the tile transposed (thread per item group).  omega is updated in place and
 // written back with one TMA bulk store.  HBM traffic per cell: 1 B (Y) + 4 B (logT) + 4+4 B (omega) in f32.
 #pragma once
+#include <type_traits>
 #include "layout.cuh"
 #include "pg.cuh"
 #include "pg_fast.cuh"
@@ -501,25 +502,29 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
       const R cB = sqrt_of(R(2) * k2 + k1 * k1);
       const bool nu_acc = A.nu_mom != nullptr && post_burnin && !eval;  // Post.mean.nu of GibbsRtIrtCross.pl.jl:310 as a running sum
       R llrt = R(0);
-      for (int kk = 0; kk < nk; ++kk) {
-        const int g = group_of<TPP>(q, kk);
-        if (g >= G) continue;
+      // One 4-item group of this person's row.  FULL (a compile-time tag): the sampling pass of a complete group of a real person --
+      // no per-cell validity tests and none of the run-time mode switches (evaluation stage, prologue, running moments) inside the
+      // cell loop, the same arithmetic.  The cell-level draw was 40 % of the instructions of stage K_b, half of them control flow
+      // (profiles/r02j_crossqr_kb_kernel_ncu_breakdown.txt).
+      auto nu_group = [&](const int g, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const bool g_draws = FULL ? true : do_draws, g_eval = FULL ? false : eval;
         Quad<R> nc;
-        if (do_draws) nc = ld4(s_nc + p * Jp + 4 * g);
+        if (g_draws) nc = ld4(s_nc + p * Jp + 4 * g);
         const Quad<R> lt = ld4(my_lt + 4 * g);
         const Quad<R> pL = ld4(s_par + PAR_LAM * Jp + 4 * g);
         const Quad<R> pR = ld4(s_par + PAR_RHO * Jp + 4 * g);
         const Quad<R> pC = ld4(s_par + PAR_ISC * Jp + 4 * g);
         const Quad<R> pI = ld4(s_par + PAR_IS2 * Jp + 4 * g);
         R zn[4] = {R(0), R(0), R(0), R(0)}, un[4] = {R(0.5), R(0.5), R(0.5), R(0.5)};
-        if (!eval) {
+        if (!g_eval) {
           const uint4 wA = philox(A.sched, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g)), 0);
           const uint4 wB = philox(A.sched, cgid, k + 1, make_site(DOM_PERSON, PK_NU_CELL, (uint32_t)(2 * g + 1)), 0);
           normal_pair(wA.x, wA.y, zn[0], zn[1]);
           normal_pair(wB.x, wB.y, zn[2], zn[3]);
           un[0] = u01<R>(wA.z); un[1] = u01<R>(wA.w); un[2] = u01<R>(wB.z); un[3] = u01<R>(wB.w);
         }
-        if (nu_acc && cvalid) {  // every cell is owned by exactly one thread of one CTA: plain read-modify-write
+        if (!FULL && nu_acc && cvalid) {  // every cell is owned by exactly one thread of one CTA: plain read-modify-write
           double* m1 = A.nu_mom + (row0 + p) * (int64_t)Jp + 4 * g;
           double* m2 = m1 + A.n_pad * (int64_t)Jp;
 #pragma unroll
@@ -535,13 +540,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
         for (int e = 0; e < 4; ++e) {
           const R resid = lt.v[e] - pL.v[e] + zec + thc * pR.v[e];
           R nun = R(1);
-          if (cvalid && 4 * g + e < J) {
-            if (do_draws) {
+          if (FULL || (cvalid && 4 * g + e < J)) {
+            if (g_draws) {
               const R nu0 = nc.v[e];
               const R res = resid - k1 * nu0;
               llrt += R(-0.5) * (rlog(nu0) + res * res * rdiv(pI.v[e], nu0));
             }
-            if (!eval) {
+            if (!g_eval) {
               const R parA = fabs(resid) * pC.v[e];
               const R parB = cB * pC.v[e];
               R mu = rdiv(parB, parA);
@@ -553,7 +558,14 @@ __global__ void __launch_bounds__(CTA_THREADS, (sizeof(R) == 8 ? min_ctas_f64<TP
           }
           out.v[e] = nun;
         }
-        if (!eval) st4(s_nc + p * Jp + 4 * g, out);
+        if (!g_eval) st4(s_nc + p * Jp + 4 * g, out);
+      };
+      const bool full_row = cvalid && do_draws && !eval && !nu_acc;
+      for (int kk = 0; kk < nk; ++kk) {
+        const int g = group_of<TPP>(q, kk);
+        if (g >= G) continue;
+        if (full_row && 4 * g + 3 < J) nu_group(g, std::true_type{});
+        else nu_group(g, std::false_type{});
       }
 #pragma unroll
       for (int o = 1; o < TPP; o <<= 1) llrt += __shfl_xor_sync(0xffffffffu, llrt, o);
