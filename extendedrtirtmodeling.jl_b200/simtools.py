@@ -82,7 +82,7 @@ def runSimulation(Cond, truePara, Para=("a", "b", "λ", "σ²t"), funcData=simul
             Post["Dic"] = [api.getDic(MCMC, dtype=sample_kwargs.get("dtype", "f64"), device=device).DIC]
         except Exception:  # CrossQr has no D-hat (nu_ij is not traced)
             Post["Dic"] = [float("nan")]
-        Post["Diag"] = checkConvergence(MCMC)
+        Post["Diag"] = checkConvergence(MCMC, device=device)  # ESS / R-hat by the CUDA kernel on the GPU that sampled
         mine[run] = Post
     if dist is not None and world > 1:
         gathered = [None] * world
