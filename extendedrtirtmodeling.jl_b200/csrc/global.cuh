@@ -27,7 +27,7 @@ constexpr int G_THREADS = 256;
 // ---- small dense SPD helpers, warp-cooperative: all 32 lanes of ONE warp call them at the same point with the same arguments;
 //      matrices are column-major in shared memory, n <= 32 = MAXD, lane i owns row i (or column i).  The structural block is a
 //      dependent chain that sits on the critical path of every sweep (the person kernels wait for it): on one lane a 12 x 12
-//      solve took 29 us (profiles/r02e_sweep_timeline.txt), spread over the lanes its depth is O(n^2) shared-memory round trips.
+//      solve took 29 us (profiles/r02_sweep_timeline.txt), spread over the lanes its depth is O(n^2) shared-memory round trips.
 //      Products are subtracted in the order of the textbook serial loops in the factor and the forward substitution, in another
 //      order in the back substitution and the inverse, and divisions by the diagonal are multiplications by its reciprocal: the
 //      results are within a few ulp of the oracle's serial code (the parity tests hold 1e-9 over whole chains). ----

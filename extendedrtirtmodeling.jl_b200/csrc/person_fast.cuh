@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas_per_sm<TPP>()) person_sw
   int tiles_done = 0;
   PF_TICK_DECL();
   // Tiles are dealt dynamically: every CTA starts with tile blockIdx.x and then draws from a device-wide counter, so an SM that runs
-  // slower (the finishing times of statically dealt CTAs were spread over five tile times, profiles/r02e_sweep_timeline.txt) simply
+  // slower (the finishing times of statically dealt CTAs were spread over five tile times, profiles/r02_sweep_timeline.txt) simply
   // takes fewer tiles.  Results do not depend on who processes a tile, except for the rounding of the per-CTA partial sums.
   int tile = blockIdx.x;
 #ifdef ERIRT_TIMELINE
